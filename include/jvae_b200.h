@@ -1,0 +1,206 @@
+/*
+ * jvae_b200.h — C ABI of libjvae_sm100.so: the B200-native (sm_100a) replacement for the
+ * arithmetic of moxime/joint-vae's train/eval hot path.
+ *
+ * The reference has no FFI of its own (it is PyTorch eager code); every entry point below
+ * replaces the interior of one reference function (file:line relative to the reference root)
+ * and is called from the host-side mirror in joint-vae_b200/ through ctypes.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit sizes, `void* stream` is a cudaStream_t
+ *     (PyTorch's current stream); no torch types, no C++ exceptions across the boundary.
+ *   - every function returns 0 on success, a negative jvae_status otherwise;
+ *     jvae_last_error() gives a thread-local human-readable message.
+ *   - the library never allocates user-visible memory: outputs and workspaces are caller
+ *     allocated (PyTorch owns all tensors, as in the reference).
+ *   - dtype codes: JVAE_F32 = 0, JVAE_BF16 = 1.
+ *   - all tensors are dense row-major with the shapes given in the comments.
+ */
+#ifndef JVAE_B200_H
+#define JVAE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JVAE_ABI_VERSION 1
+
+enum jvae_status {
+  JVAE_OK = 0,
+  JVAE_ERR_INVALID = -1,    /* bad argument (shape, dtype, null pointer) */
+  JVAE_ERR_CUDA = -2,       /* a CUDA runtime/driver call failed */
+  JVAE_ERR_UNSUPPORTED = -3,/* valid request this build does not implement */
+  JVAE_ERR_NOGPU = -4       /* no sm_100 device */
+};
+
+enum jvae_dtype { JVAE_F32 = 0, JVAE_BF16 = 1 };
+
+/* prior variance parametrisation, module/priors.py:110-122 */
+enum jvae_var_dim { JVAE_VAR_SCALAR = 0, JVAE_VAR_DIAG = 1, JVAE_VAR_FULL = 2 };
+/* prior family, module/priors.py:35-52 */
+enum jvae_prior_kind { JVAE_PRIOR_GAUSSIAN = 0, JVAE_PRIOR_TILTED = 1, JVAE_PRIOR_UNIFORM = 2 };
+
+const char* jvae_last_error(void);
+int jvae_abi_version(void);
+/* number of SMs / compute capability of `device`; JVAE_ERR_NOGPU if it is not sm_100 */
+int jvae_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* how many kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t jvae_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused class-conditional Gaussian-prior ELBO  (cvae.py:626-902, module/priors.py:173-342,
+ * module/losses.py:8-27,52-86).  B samples, L latent draws (+ slab 0 = the mean), K latent
+ * dims, C classes, D = prod(input_shape) pixels.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jvae_elbo_cfg {
+  int32_t B, L, K, C, D;
+  int32_t xreco_dtype;      /* jvae_dtype of x_reco (and of d_x_reco) */
+  int32_t logits_dtype;     /* jvae_dtype of logits (and of d_logits) */
+  int32_t var_dim;          /* jvae_var_dim */
+  int32_t prior_kind;       /* jvae_prior_kind */
+  int32_t conditional;      /* 1: C class means, 0: single prior (means is (1,K)) */
+  int32_t has_xreco;        /* 0 for type 'vib' (no reconstruction term) */
+  int32_t has_logits;       /* 1 if a classifier output exists (y_is_decoded) */
+  int32_t sigma_is_log;     /* Sigma stored as log sigma (learned), layers.py:84-87 */
+  int32_t sigma_is_rmse;    /* Sigma(is_rmse): sigma^2 := batch wmse, cvae.py:662-670 */
+  float   sigma_param;      /* raw Sigma parameter value (sdim == 1) */
+  float   beta;             /* KL weight actually applied (1 unless with_beta), cvae.py:898 */
+  float   gamma_w;          /* cross_y weight actually applied (0 => not added), cvae.py:557-562 */
+  float   var_w;            /* kl_var_weighting, priors.py:323 */
+  float   tau;              /* tilted / uniform priors */
+  float   alpha;            /* uniform prior: log rho inside [-tau,tau], priors.py:423-424 */
+} jvae_elbo_cfg;
+
+/* bytes of scratch the three ELBO entry points need for `cfg` */
+size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
+
+/* Train forward (y given).  Replaces cvae.py:626-902 + priors.py:252-326 + losses.py:8-27,73-86.
+ *   x (B,D) f32; x_reco (L+1,B,D) [slab 0 is not read]; mu, log_var (B,K) f32;
+ *   logits (L+1,B,C) or NULL; y (B) int64; means (C,K) f32; inv_trans (C)|(C,K)|(C,K,K) f32.
+ *   outputs, each (B) f32 (NULL = not wanted): kl zdist var_kl wmse cross_x cross_y total dzdist.
+ *   finite_flag: 1 int32, set to 0 if any output is NaN/Inf (replaces cvae.py:2454-2457 scan). */
+int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
+                        const float* mu, const float* log_var, const void* logits, const int64_t* y,
+                        const float* means, const float* inv_trans,
+                        float* kl, float* zdist, float* var_kl, float* wmse, float* cross_x,
+                        float* cross_y, float* total, float* dzdist, int32_t* finite_flag,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Train backward of sum_b g[b]*total[b] (SURVEY.md §8a backward contract; the reference uses
+ * autograd over the same lines).  g (B) f32 (= 1/B for total.mean()).  wmse (B): saved forward output.
+ *   d_x_reco (L+1,B,D) [slab 0 written as zeros]; d_mu, d_log_var (B,K) f32: DIRECT terms only
+ *   (the path through z is added by jvae_sample_bwd); d_logits (L+1,B,C); d_means (C,K) f32;
+ *   d_inv_trans like inv_trans (NULL unless var_dim is diag/full); d_sigma: 1 f32. */
+int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x, const void* x_reco,
+                        const float* mu, const float* log_var, const void* logits, const int64_t* y,
+                        const float* means, const float* inv_trans, const float* wmse,
+                        void* d_x_reco, float* d_mu, float* d_log_var, void* d_logits,
+                        float* d_means, float* d_inv_trans, float* d_sigma,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* scores written by the eval kernel, one row of JVAE_NSCORES floats per sample
+ * (cvae.py:972-1085 batch_dist_measures; -2s / -a-p-q suffixes only select the ROC mode) */
+enum jvae_score {
+  JVAE_S_ELBO = 0,     /* 'elbo' / 'max': max_c(-total) */
+  JVAE_S_SUM = 1,      /* 'sum': logsumexp_c(-total) */
+  JVAE_S_MEAN = 2,     /* 'mean': logmeanexp_c(-total) */
+  JVAE_S_IWS = 3,      /* 'iws': logsumexp_c(iws) + log C */
+  JVAE_S_SOFTKL = 4,   /* 'soft' / 'softkl': max softmax_c(-kl) */
+  JVAE_S_ZDIST = 5,    /* 'zdist': max_c(-zdist) */
+  JVAE_S_KL = 6,       /* 'kl': max_c(-kl) */
+  JVAE_S_MSE = 7,      /* 'mse': -cross_x */
+  JVAE_S_WMSE = 8,     /* 'wmse': -wmse */
+  JVAE_S_LOGITS = 9,   /* 'logits': max_c logits */
+  JVAE_S_BASELINE = 10,/* 'baseline': max softmax(logits) */
+  JVAE_S_HYZ = 11,     /* 'hyz': sum p log p */
+  JVAE_S_STD = 12,     /* 'std': unbiased std_c(-total) */
+  JVAE_S_SOFTIWS = 13, /* 'softiws': max softmax_c(iws) */
+  JVAE_NSCORES = 16
+};
+/* predictions written by the eval kernel, JVAE_NPRED int32 per sample (cvae.py:938-970) */
+enum jvae_pred { JVAE_P_LOSS = 0, JVAE_P_ESTY = 1, JVAE_P_CLOSEST = 2, JVAE_P_IWS = 3, JVAE_NPRED = 4 };
+
+/* Eval / scoring forward (y None: losses for every class).  Replaces cvae.py:593-600,626-917,
+ * priors.py:252-342 (no (C,B,K) / (L,C,B,K) materialisation), losses.py:62-71, cvae.py:938-1085.
+ *   z (L+1,B,K) f32; eps_norm (L,B) f32 = sum_k eps^2.
+ *   per-class outputs (C,B) f32: kl zdist var_kl total iws cross_y; per-sample (B): wmse cross_x dzdist;
+ *   logits_out (B,C) f32 = mean_{l>=1} logits; scores (B,JVAE_NSCORES) f32; preds (B,JVAE_NPRED) int32.
+ *   For non-conditional priors (vae/jvae/vib) kl zdist var_kl iws are (B) and total/cross_y (C,B) only
+ *   when has_logits and gamma_w != 0. Any output pointer may be NULL. */
+int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
+                       const float* mu, const float* log_var, const float* z, const float* eps_norm,
+                       const void* logits, const float* means, const float* inv_trans,
+                       float* kl, float* zdist, float* var_kl, float* total, float* iws, float* cross_y,
+                       float* wmse, float* cross_x, float* dzdist, float* logits_out,
+                       float* scores, int32_t* preds,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reparameterisation sampler (module/vae_layers/layers.py:230-244, 388-396).
+ *   head (B,2K) f32: [mu | raw log_var] (the fused dense_mean/dense_log_var GEMM output, bias added);
+ *   eps_in (L+1,B,K) f32 or NULL (NULL => Philox4x32-10 + Box-Muller from (seed, offset));
+ *   writes mu, log_var = clip(raw,-20,20) (B,K) f32; z (L+1,B,K) f32 and optional bf16 copy z_bf16;
+ *   eps_out (L,B,K) f32 (slabs 1..L) and eps_norm (L,B).  is_sampled: layers.py:243.
+ *   uniform != 0 draws U(-sqrt3, sqrt3) instead (layers.py:237).
+ * ------------------------------------------------------------------------------------------ */
+int jvae_sample_fwd(int B, int L, int K, const float* head, const float* eps_in,
+                    uint64_t seed, uint64_t offset, int is_sampled, int uniform,
+                    float* mu, float* log_var, float* z, void* z_bf16, float* eps_out, float* eps_norm,
+                    void* stream);
+/* d_head (B,2K) = [d_mu_direct + sum_l dz | (d_lv_direct + sum_l dz*0.5*exp(lv/2)*eps) * 1[|raw|<=20]] */
+int jvae_sample_bwd(int B, int L, int K, const float* head, const float* log_var, const float* eps,
+                    const void* dz, int dz_dtype, const float* d_mu_direct, const float* d_lv_direct,
+                    int is_sampled, float* d_head, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense layers on the tcgen05 tensor cores (nn.Linear in layers.py:284-298,441-453,476-480;
+ * ConvTranspose2d on a 1x1 input, conv-models.ini:25).  bf16 operands, fp32 accumulation in TMEM.
+ *   D[M,N] = act( A[M,K] * W[N,K]^T + bias[N] )
+ * ------------------------------------------------------------------------------------------ */
+enum jvae_act { JVAE_ACT_NONE = 0, JVAE_ACT_RELU = 1, JVAE_ACT_SIGMOID = 2 };
+enum jvae_gemm_mode {
+  JVAE_GEMM_NT = 0,  /* D[M,N] = A[M,K] . B[N,K]^T   forward:  y = x W^T                       */
+  JVAE_GEMM_NN = 1,  /* D[M,N] = A[M,K] . B[K,N]     dgrad:    dx = dy W                        */
+  JVAE_GEMM_TN = 2   /* D[M,N] = A[K,M]^T . B[K,N]   wgrad:    dW = dy^T x   (reduction over rows) */
+};
+/*   a, b: bf16, leading dimensions lda/ldb in elements (multiples of 8);
+ *   out_bf16 / out_f32: either or both, leading dimension ldd; bias (N) f32 or NULL;
+ *   col_stats (2,N) f32 or NULL: += per-column sum and sum of squares of the pre-activation
+ *   (BatchNorm batch statistics, conv.py:216-217); accumulate != 0: out_f32 += result. */
+int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const void* b, int ldb,
+                   const float* bias, int act, void* out_bf16, float* out_f32, int ldd,
+                   float* col_stats, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small data-movement / elementwise kernels of the step
+ * ------------------------------------------------------------------------------------------ */
+/* f32 -> bf16 cast of n elements (weights repack, activations) */
+int jvae_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
+int jvae_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
+/* NCHW f32 -> NHWC bf16 (optionally padding channels to c_pad with zeros) and back */
+int jvae_nchw_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
+int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer (module/optimizers.py:79-81,120-121: clip_grad_norm_ then Adam with L2 weight decay)
+ * on one flat f32 parameter / gradient buffer.  grad may be the bf16 all-reduced bucket.
+ * ------------------------------------------------------------------------------------------ */
+/* norm2_out[0] += sum(grad^2) (zero it first); grad_dtype is a jvae_dtype */
+int jvae_grad_sqnorm(const void* grad, int grad_dtype, size_t n, float* norm2_out, void* stream);
+/* p,m,v (n) f32; clip_coef = min(1, max_norm/(sqrt(norm2)+1e-6)) computed on device from norm2;
+ * max_norm <= 0 disables clipping; step is the 1-based Adam step count */
+int jvae_adam_step(float* p, float* m, float* v, const void* grad, int grad_dtype, size_t n,
+                   const float* norm2, float max_norm, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, void* stream);
+
+/* self-test of the tensor-core kernels against naive CUDA-core references run on the device;
+ * prints a report to stdout, returns the number of failed cases */
+int jvae_selftest(int verbose);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JVAE_B200_H */
