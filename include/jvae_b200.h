@@ -66,7 +66,6 @@ typedef struct jvae_elbo_cfg {
   int32_t has_logits;       /* 1 if a classifier output exists (y_is_decoded) */
   int32_t sigma_is_log;     /* Sigma stored as log sigma (learned), layers.py:84-87 */
   int32_t sigma_is_rmse;    /* Sigma(is_rmse): sigma^2 := batch wmse, cvae.py:662-670 */
-  float   sigma_param;      /* raw Sigma parameter value (sdim == 1) */
   float   beta;             /* KL weight actually applied (1 unless with_beta), cvae.py:898 */
   float   gamma_w;          /* cross_y weight actually applied (0 => not added), cvae.py:557-562 */
   float   var_w;            /* kl_var_weighting, priors.py:323 */
@@ -74,17 +73,19 @@ typedef struct jvae_elbo_cfg {
   float   alpha;            /* uniform prior: log rho inside [-tau,tau], priors.py:423-424 */
 } jvae_elbo_cfg;
 
-/* bytes of scratch the three ELBO entry points need for `cfg` */
+/* bytes of scratch the three ELBO entry points need for `cfg` (contents need no initialisation) */
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
 
 /* Train forward (y given).  Replaces cvae.py:626-902 + priors.py:252-326 + losses.py:8-27,73-86.
  *   x (B,D) f32; x_reco (L+1,B,D) [slab 0 is not read]; mu, log_var (B,K) f32;
- *   logits (L+1,B,C) or NULL; y (B) int64; means (C,K) f32; inv_trans (C)|(C,K)|(C,K,K) f32.
+ *   logits (L+1,B,C) or NULL; y (B) int64; means (C,K) f32; inv_trans (C)|(C,K)|(C,K,K) f32;
+ *   sigma: 1 f32 on the device = the raw Sigma parameter (log sigma if sigma_is_log; sdim == 1), it is a
+ *   learned parameter so it is never read back to the host.
  *   outputs, each (B) f32 (NULL = not wanted): kl zdist var_kl wmse cross_x cross_y total dzdist.
  *   finite_flag: 1 int32, set to 0 if any output is NaN/Inf (replaces cvae.py:2454-2457 scan). */
 int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
                         const float* mu, const float* log_var, const void* logits, const int64_t* y,
-                        const float* means, const float* inv_trans,
+                        const float* means, const float* inv_trans, const float* sigma,
                         float* kl, float* zdist, float* var_kl, float* wmse, float* cross_x,
                         float* cross_y, float* total, float* dzdist, int32_t* finite_flag,
                         void* workspace, size_t workspace_bytes, void* stream);
@@ -96,7 +97,7 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
  *   d_inv_trans like inv_trans (NULL unless var_dim is diag/full); d_sigma: 1 f32. */
 int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x, const void* x_reco,
                         const float* mu, const float* log_var, const void* logits, const int64_t* y,
-                        const float* means, const float* inv_trans, const float* wmse,
+                        const float* means, const float* inv_trans, const float* sigma, const float* wmse,
                         void* d_x_reco, float* d_mu, float* d_log_var, void* d_logits,
                         float* d_means, float* d_inv_trans, float* d_sigma,
                         void* workspace, size_t workspace_bytes, void* stream);
@@ -132,7 +133,7 @@ enum jvae_pred { JVAE_P_LOSS = 0, JVAE_P_ESTY = 1, JVAE_P_CLOSEST = 2, JVAE_P_IW
  *   when has_logits and gamma_w != 0. Any output pointer may be NULL. */
 int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
                        const float* mu, const float* log_var, const float* z, const float* eps_norm,
-                       const void* logits, const float* means, const float* inv_trans,
+                       const void* logits, const float* means, const float* inv_trans, const float* sigma,
                        float* kl, float* zdist, float* var_kl, float* total, float* iws, float* cross_y,
                        float* wmse, float* cross_x, float* dzdist, float* logits_out,
                        float* scores, int32_t* preds,

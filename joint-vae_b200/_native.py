@@ -1,0 +1,276 @@
+"""ctypes binding of libjvae_sm100.so (the C ABI declared in include/jvae_b200.h).
+
+The host side of this package is PyTorch (device memory, streams, torch.distributed); every arithmetic
+step of the hot path goes through this module.  There is no CPU / eager fallback: if the library cannot
+be loaded, or a tensor is not on a CUDA device, calls raise.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libjvae_sm100.so')
+
+F32, BF16 = 0, 1
+VAR_DIM = {'scalar': 0, 'diag': 1, 'full': 2}
+PRIOR_KIND = {'gaussian': 0, 'tilted': 1, 'uniform': 2}
+ACT = {'none': 0, 'linear': 0, 'relu': 1, 'sigmoid': 2}
+NSCORES, NPRED = 16, 4
+SCORE_INDEX = {'elbo': 0, 'max': 0, 'sum': 1, 'mean': 2, 'iws': 3, 'soft': 4, 'softkl': 4, 'zdist': 5, 'kl': 6,
+               'mse': 7, 'wmse': 8, 'logits': 9, 'baseline': 10, 'hyz': 11, 'std': 12, 'softiws': 13}
+PRED_INDEX = {'loss': 0, 'esty': 1, 'closest': 2, 'iws': 3}
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+c_u64, c_i64 = ctypes.c_uint64, ctypes.c_int64
+
+
+class ElboCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('B', 'L', 'K', 'C', 'D', 'xreco_dtype', 'logits_dtype', 'var_dim', 'prior_kind', 'conditional',
+                 'has_xreco', 'has_logits', 'sigma_is_log', 'sigma_is_rmse')] + \
+               [(n, ctypes.c_float) for n in ('beta', 'gamma_w', 'var_w', 'tau', 'alpha')]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads the library once; raises if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f'{LIB_PATH} is not built: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          'in a container with nvcc; there is no CPU fallback')
+    L = ctypes.CDLL(LIB_PATH)
+    L.jvae_last_error.restype = ctypes.c_char_p
+    L.jvae_abi_version.restype = c_int
+    L.jvae_launch_count.restype = c_i64
+    L.jvae_device_info.argtypes = [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.jvae_elbo_workspace_bytes.restype = c_size_t
+    L.jvae_elbo_workspace_bytes.argtypes = [ctypes.POINTER(ElboCfg)]
+    P = c_void_p
+    L.jvae_elbo_train_fwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 19 + [c_size_t, P]
+    L.jvae_elbo_train_bwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 19 + [c_size_t, P]
+    L.jvae_elbo_eval_fwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 23 + [c_size_t, P]
+    L.jvae_sample_fwd.argtypes = [c_int, c_int, c_int, P, P, c_u64, c_u64, c_int, c_int, P, P, P, P, P, P, P]
+    L.jvae_sample_bwd.argtypes = [c_int, c_int, c_int, P, P, P, P, c_int, P, P, c_int, P, P]
+    L.jvae_cast_f32_bf16.argtypes = [P, P, c_size_t, P]
+    L.jvae_cast_bf16_f32.argtypes = [P, P, c_size_t, P]
+    L.jvae_nchw_to_nhwc_bf16.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P]
+    L.jvae_nhwc_bf16_to_nchw.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P]
+    L.jvae_grad_sqnorm.argtypes = [P, c_int, c_size_t, P, P]
+    L.jvae_adam_step.argtypes = [P, P, P, P, c_int, c_size_t, P, c_float, c_float, c_float, c_float, c_float,
+                                 c_float, c_int, c_float, P]
+    for name in ('jvae_gemm_bf16', 'jvae_selftest'):
+        if not hasattr(L, name):
+            raise NativeError(f'{LIB_PATH} does not export {name}: stale build')
+    L.jvae_gemm_bf16.argtypes = [c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, P, c_int, P]
+    L.jvae_selftest.argtypes = [c_int]
+    if L.jvae_abi_version() != 1:
+        raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(lib().jvae_last_error().decode() + f' (status {rc})')
+
+
+def launch_count():
+    return int(lib().jvae_launch_count())
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError('libjvae_sm100 works on CUDA tensors only (got a CPU tensor); there is no CPU fallback')
+    if not t.is_contiguous():
+        raise NativeError('non-contiguous tensor passed to the native library')
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dtype_code(t):
+    if t is None or t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise NativeError(f'unsupported dtype {t.dtype}')
+
+
+def f32c(t):
+    """contiguous float32 view/copy of t (None passes through)"""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_ws_cache = {}
+
+
+def workspace(cfg, device):
+    n = int(lib().jvae_elbo_workspace_bytes(ctypes.byref(cfg)))
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws, n
+
+
+def make_cfg(*, B, L, K, C, D, x_reco, logits, var_dim, prior_kind, conditional, sigma_is_log, sigma_is_rmse,
+             beta, gamma_w, var_w, tau=0.0, alpha=0.0):
+    return ElboCfg(B=B, L=L, K=K, C=C, D=D, xreco_dtype=dtype_code(x_reco), logits_dtype=dtype_code(logits),
+                   var_dim=VAR_DIM[var_dim], prior_kind=PRIOR_KIND[prior_kind], conditional=int(bool(conditional)),
+                   has_xreco=int(x_reco is not None), has_logits=int(logits is not None),
+                   sigma_is_log=int(bool(sigma_is_log)), sigma_is_rmse=int(bool(sigma_is_rmse)),
+                   beta=float(beta), gamma_w=float(gamma_w or 0.0), var_w=float(var_w), tau=float(tau or 0.0),
+                   alpha=float(alpha or 0.0))
+
+
+def elbo_train_fwd(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma):
+    """-> dict of (B,) f32 tensors + 'finite' int32 flag tensor.  include/jvae_b200.h: jvae_elbo_train_fwd"""
+    dev = mu.device
+    B = cfg.B
+    out = torch.empty((8, B), dtype=torch.float32, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    ws, n = workspace(cfg, dev)
+    check(lib().jvae_elbo_train_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits), ptr(y),
+                                    ptr(means), ptr(inv_trans), ptr(sigma),
+                                    *[c_void_p(out[i].data_ptr()) for i in range(8)], ptr(flag), ptr(ws), n, stream()))
+    names = ('kl', 'zdist', 'var_kl', 'wmse', 'cross_x', 'cross_y', 'total', 'dzdist')
+    res = {k: out[i] for i, k in enumerate(names)}
+    res['finite'] = flag
+    return res
+
+
+def elbo_train_bwd(cfg, g, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, wmse, need_inv_trans=False):
+    dev = mu.device
+    d_xr = torch.empty_like(x_reco) if x_reco is not None else None
+    d_mu = torch.empty_like(mu)
+    d_lv = torch.empty_like(log_var)
+    d_logits = torch.empty_like(logits) if logits is not None else None
+    d_means = torch.empty_like(means)
+    d_it = torch.empty_like(inv_trans) if need_inv_trans else None
+    d_sigma = torch.empty(1, dtype=torch.float32, device=dev) if x_reco is not None else None
+    check(lib().jvae_elbo_train_bwd(ctypes.byref(cfg), ptr(g), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits),
+                                    ptr(y), ptr(means), ptr(inv_trans), ptr(sigma), ptr(wmse), ptr(d_xr), ptr(d_mu),
+                                    ptr(d_lv), ptr(d_logits), ptr(d_means), ptr(d_it), ptr(d_sigma), None, 0, stream()))
+    return d_xr, d_mu, d_lv, d_logits, d_means, d_it, d_sigma
+
+
+def elbo_eval_fwd(cfg, x, x_reco, mu, log_var, z, eps_norm, logits, means, inv_trans, sigma, *, want_iws=True,
+                  want_scores=True):
+    """-> dict: per-class (Cp,B) kl zdist var_kl iws, total (nT,B), cross_y (C,B), per-sample wmse cross_x dzdist,
+    logits (B,C), scores (B,16), preds (B,4).  include/jvae_b200.h: jvae_elbo_eval_fwd"""
+    dev = mu.device
+    B, C = cfg.B, cfg.C
+    Cp = C if cfg.conditional else 1
+    add_cy = bool(cfg.has_logits) and cfg.gamma_w != 0.0
+    nT = Cp if Cp > 1 else (C if add_cy else 1)
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    kl, zdist, var_kl = f(Cp, B), f(Cp, B), f(Cp, B)
+    total = f(nT, B)
+    iws = f(Cp, B) if (want_iws and cfg.has_xreco and z is not None and eps_norm is not None) else None
+    cross_y = f(C, B) if cfg.has_logits else None
+    logits_out = f(B, C) if cfg.has_logits else None
+    wmse = f(B) if cfg.has_xreco else None
+    cross_x = f(B) if cfg.has_xreco else None
+    dzdist = f(B) if cfg.conditional else None
+    scores = f(B, NSCORES) if want_scores else None
+    preds = torch.empty((B, NPRED), dtype=torch.int32, device=dev) if want_scores else None
+    ws, n = workspace(cfg, dev)
+    check(lib().jvae_elbo_eval_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),
+                                   ptr(z) if iws is not None else None, ptr(eps_norm) if iws is not None else None,
+                                   ptr(logits), ptr(means), ptr(inv_trans), ptr(sigma),
+                                   ptr(kl), ptr(zdist), ptr(var_kl), ptr(total), ptr(iws), ptr(cross_y), ptr(wmse),
+                                   ptr(cross_x), ptr(dzdist), ptr(logits_out), ptr(scores), ptr(preds), ptr(ws), n,
+                                   stream()))
+    return dict(kl=kl, zdist=zdist, var_kl=var_kl, total=total, iws=iws, cross_y=cross_y, wmse=wmse, cross_x=cross_x,
+                dzdist=dzdist, logits=logits_out, scores=scores, preds=preds)
+
+
+def sample_fwd(head, L, K, eps_in=None, seed=0, offset=0, is_sampled=True, uniform=False, want_bf16=False):
+    """head (B,2K) f32 -> mu, log_var (B,K), z (L+1,B,K), z_bf16|None, eps (L,B,K), eps_norm (L,B)"""
+    dev = head.device
+    B = head.shape[0]
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    mu, lv, z, eps, en = f(B, K), f(B, K), f(L + 1, B, K), f(L, B, K), f(L, B)
+    z16 = torch.empty((L + 1, B, K), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    check(lib().jvae_sample_fwd(B, L, K, ptr(head), ptr(eps_in), seed, offset, int(is_sampled), int(uniform), ptr(mu),
+                                ptr(lv), ptr(z), ptr(z16), ptr(eps), ptr(en), stream()))
+    return mu, lv, z, z16, eps, en
+
+
+def sample_bwd(head, log_var, eps, dz, d_mu, d_lv, L, K, is_sampled=True):
+    B = head.shape[0]
+    d_head = torch.empty_like(head)
+    check(lib().jvae_sample_bwd(B, L, K, ptr(head), ptr(log_var), ptr(eps), ptr(dz), dtype_code(dz), ptr(d_mu),
+                                ptr(d_lv), int(is_sampled), ptr(d_head), stream()))
+    return d_head
+
+
+def cast_f32_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib().jvae_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream()))
+    return dst
+
+
+def cast_bf16_f32(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    check(lib().jvae_cast_bf16_f32(ptr(src), ptr(dst), src.numel(), stream()))
+    return dst
+
+
+def nchw_to_nhwc_bf16(src, c_pad=None):
+    n, c, h, w = src.shape
+    c_pad = c_pad or c
+    dst = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=src.device)
+    check(lib().jvae_nchw_to_nhwc_bf16(ptr(src), ptr(dst), n, c, h, w, c_pad, stream()))
+    return dst
+
+
+def nhwc_bf16_to_nchw(src, c=None):
+    n, h, w, c_pad = src.shape
+    c = c or c_pad
+    dst = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+    check(lib().jvae_nhwc_bf16_to_nchw(ptr(src), ptr(dst), n, c, h, w, c_pad, stream()))
+    return dst
+
+
+def grad_sqnorm(grad, out):
+    check(lib().jvae_grad_sqnorm(ptr(grad), dtype_code(grad), grad.numel(), ptr(out), stream()))
+
+
+def adam_step(p, m, v, grad, norm2, *, max_norm, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(lib().jvae_adam_step(ptr(p), ptr(m), ptr(v), ptr(grad), dtype_code(grad), p.numel(), ptr(norm2),
+                               float(max_norm or 0.0), lr, beta1, beta2, eps, weight_decay, int(step), grad_scale,
+                               stream()))
+
+
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def gemm_bf16(mode, M, N, K, a, lda, b, ldb, *, bias=None, act=0, out_bf16=None, out_f32=None, ldd=None,
+              col_stats=None, accumulate=False):
+    check(lib().jvae_gemm_bf16(mode, M, N, K, ptr(a), lda, ptr(b), ldb, ptr(bias), act, ptr(out_bf16), ptr(out_f32),
+                               ldd if ldd is not None else N, ptr(col_stats), int(accumulate), stream()))
+
+
+def selftest(verbose=1):
+    return int(lib().jvae_selftest(verbose))

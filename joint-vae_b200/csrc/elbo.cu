@@ -1,0 +1,1029 @@
+// Fused class-conditional prior / ELBO kernels (train forward, train backward, eval/scoring forward).
+//
+// Replaces the ~30 ATen kernels + host syncs of cvae.py:626-902, module/priors.py:173-342 and
+// module/losses.py:8-27,52-86 of the reference by ONE launch per direction (plus a tiny prior-statistics
+// prologue).  The kernels are HBM-bound streaming reductions over x_reco (L*D elements per sample) with a
+// latent-space epilogue executed by the last CTA that finishes a sample ("last block done" election), so
+// neither the (C,B,K) nor the (L,C,B,K) broadcast of the reference is ever materialised.
+//
+// Work decomposition: one CTA per (sample b, group g of up to LG latent draws).  Each thread keeps 8
+// pixels of x in registers and streams the matching 8 pixels of LG reconstructions with 16-byte
+// no-allocate loads (LG independent loads in flight per thread), so x is read from HBM once and x_reco
+// exactly once.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace jvae {
+
+constexpr int ELBO_THREADS = 128;
+constexpr int LG = 4;  // latent draws per CTA
+constexpr float LOG2PI_F = 1.8378770664093453f;
+
+struct ElboArgs {
+  int B, L, K, C, Cp, D, G;
+  int xr_bf16, lg_bf16, var_dim, prior_kind, conditional, has_xreco, has_logits, sigma_is_log, sigma_is_rmse;
+  float beta, gamma_w, var_w, tau, alpha;
+  const float* x;
+  const void* xr;
+  const float* mu;
+  const float* lv;
+  const float* z;
+  const float* eps_norm;
+  const void* logits;
+  const long long* y;
+  const float* means;
+  const float* inv_trans;
+  const float* sigma;
+  const float* g;
+  const float* wmse_in;
+  // outputs
+  float *kl, *zdist, *var_kl, *wmse, *cross_x, *cross_y, *total, *dzdist, *iws, *logits_out, *scores;
+  int* preds;
+  int* finite_flag;
+  void* d_xr;
+  float *d_mu, *d_lv, *d_means, *d_inv_trans, *d_sigma;
+  void* d_logits;
+  // workspace
+  unsigned int* counters;   // (B)
+  float* dict_norm_var;     // 1 (adjacent to counters, zeroed together)
+  float* ws_mse;            // (L,B) sum_d (x_reco - x)^2
+  float* dict_mean;         // (K)
+  float* logdet;            // (Cp)
+};
+
+struct WsLayout {
+  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, total;
+};
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static WsLayout ws_layout(int B, int L, int K, int Cp) {
+  WsLayout w;
+  w.counters = 0;
+  w.dnv = (size_t)B * 4;
+  w.zero_bytes = w.dnv + 4;
+  w.mse = align256(w.zero_bytes);
+  w.dict_mean = w.mse + align256((size_t)(L > 0 ? L : 1) * B * 4);
+  w.logdet = w.dict_mean + align256((size_t)K * 4);
+  w.total = w.logdet + align256((size_t)Cp * 4);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior statistics prologue: dict_mean (K), dict_norm_var, log det Sigma_c (Cp)
+//   cvae.py:747-754, priors.py:173-186
+// blocks [0, nkb): 32 latent columns each; blocks [nkb, ...): 8 classes each (one warp per class)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prior_stats_kernel(ElboArgs a, int nkb) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if ((int)blockIdx.x < nkb) {
+    const int k = blockIdx.x * 32 + lane;
+    float sum = 0.f, sq = 0.f;
+    if (k < a.K)
+      for (int c = w; c < a.Cp; c += 8) {
+        float m = a.means[(size_t)c * a.K + k];
+        sum += m;
+        sq += m * m;
+      }
+    s1[w][lane] = sum;
+    s2[w][lane] = sq;
+    __syncthreads();
+    if (w == 0) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t1 += s1[i][lane]; t2 += s2[i][lane]; }
+      float dm = t1 / (float)a.Cp;
+      float part = 0.f;
+      if (k < a.K) {
+        a.dict_mean[k] = dm;
+        part = t2 / (float)a.Cp - dm * dm;
+      }
+      part = warp_sum(part);
+      if (lane == 0) atomicAdd(a.dict_norm_var, part);
+    }
+  } else {
+    const int c = ((int)blockIdx.x - nkb) * 8 + w;
+    if (c >= a.Cp) return;
+    float v;
+    if (a.var_dim == JVAE_VAR_SCALAR) {
+      v = -2.f * (float)a.K * logf(a.inv_trans[c]);
+    } else if (a.var_dim == JVAE_VAR_DIAG) {
+      float s = 0.f;
+      for (int k = lane; k < a.K; k += 32) s += logf(fabsf(a.inv_trans[(size_t)c * a.K + k]));
+      v = -2.f * warp_sum(s);
+    } else {
+      float s = 0.f;
+      for (int k = lane; k < a.K; k += 32) s += logf(fabsf(a.inv_trans[((size_t)c * a.K + k) * a.K + k]));
+      v = -2.f * warp_sum(s);
+    }
+    if (lane == 0) a.logdet[c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming part: sum_d (x_reco[l,b,d] - x[b,d])^2 for nl <= LG draws starting at l0
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sq_acc8(float& acc, const float4& x0, const float4& x1, const uint4& r) {
+  float d;
+  d = bf16_lo(r.x) - x0.x; acc = fmaf(d, d, acc);
+  d = bf16_hi(r.x) - x0.y; acc = fmaf(d, d, acc);
+  d = bf16_lo(r.y) - x0.z; acc = fmaf(d, d, acc);
+  d = bf16_hi(r.y) - x0.w; acc = fmaf(d, d, acc);
+  d = bf16_lo(r.z) - x1.x; acc = fmaf(d, d, acc);
+  d = bf16_hi(r.z) - x1.y; acc = fmaf(d, d, acc);
+  d = bf16_lo(r.w) - x1.z; acc = fmaf(d, d, acc);
+  d = bf16_hi(r.w) - x1.w; acc = fmaf(d, d, acc);
+}
+__device__ __forceinline__ void sq_acc4(float& acc, const float4& x0, const uint4& r) {
+  float d;
+  d = __uint_as_float(r.x) - x0.x; acc = fmaf(d, d, acc);
+  d = __uint_as_float(r.y) - x0.y; acc = fmaf(d, d, acc);
+  d = __uint_as_float(r.z) - x0.z; acc = fmaf(d, d, acc);
+  d = __uint_as_float(r.w) - x0.w; acc = fmaf(d, d, acc);
+}
+
+template <bool XR_BF16>
+__device__ __forceinline__ void mse_partial(const ElboArgs& a, int b, int l0, int nl, float (&acc)[LG]) {
+  const int D = a.D;
+  const float* xb = a.x + (size_t)b * D;
+  const size_t slab = (size_t)a.B * D;  // elements per latent draw
+#pragma unroll
+  for (int j = 0; j < LG; ++j) acc[j] = 0.f;
+  const bool vec_ok = XR_BF16 ? ((D & 7) == 0) : ((D & 3) == 0);
+  if (vec_ok) {
+    if (XR_BF16) {
+      const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(a.xr) + (size_t)l0 * slab + (size_t)b * D;
+      const int nvec = D >> 3;
+#pragma unroll 2
+      for (int v = threadIdx.x; v < nvec; v += ELBO_THREADS) {
+        uint4 r[LG];
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) r[j] = ld_stream16(r0 + (size_t)j * slab + (size_t)v * 8);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xb) + 2 * v);
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(xb) + 2 * v + 1);
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) sq_acc8(acc[j], x0, x1, r[j]);
+      }
+    } else {
+      const float* r0 = reinterpret_cast<const float*>(a.xr) + (size_t)l0 * slab + (size_t)b * D;
+      const int nvec = D >> 2;
+#pragma unroll 2
+      for (int v = threadIdx.x; v < nvec; v += ELBO_THREADS) {
+        uint4 r[LG];
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) r[j] = ld_stream16(r0 + (size_t)j * slab + (size_t)v * 4);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xb) + v);
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) sq_acc4(acc[j], x0, r[j]);
+      }
+    }
+  } else {  // ragged D: scalar path
+    for (int d = threadIdx.x; d < D; d += ELBO_THREADS) {
+      const float xv = xb[d];
+#pragma unroll
+      for (int j = 0; j < LG; ++j)
+        if (j < nl) {
+          const size_t idx = (size_t)(l0 + j) * slab + (size_t)b * D + d;
+          const float rv = XR_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.xr)[idx])
+                                   : reinterpret_cast<const float*>(a.xr)[idx];
+          const float df = rv - xv;
+          acc[j] = fmaf(df, df, acc[j]);
+        }
+    }
+  }
+}
+
+// Runs the streaming part for CTA (b, g) and elects the last CTA of sample b.  Returns true in every
+// thread of the elected CTA, after which ws_mse[(l-1)*B + b] is complete for all l.
+template <bool XR_BF16>
+__device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g, float* red) {
+  __shared__ int s_last;
+  if (a.has_xreco) {
+    const int l0 = 1 + g * LG;
+    const int nl = min(LG, a.L + 1 - l0);
+    float acc[LG];
+    mse_partial<XR_BF16>(a, b, l0, nl, acc);
+#pragma unroll
+    for (int j = 0; j < LG; ++j) {
+      const float s = block_sum(acc[j], red);
+      if (threadIdx.x == 0 && j < nl) a.ws_mse[(size_t)(l0 - 1 + j) * a.B + b] = s;
+    }
+  }
+  if (a.G == 1) return true;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(&a.counters[b], 1u);
+    s_last = (old == (unsigned int)(a.G - 1));
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  return true;
+}
+
+__device__ __forceinline__ float load_logit(const void* p, size_t i, int bf16) {
+  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+
+// sigma handling of cvae.py:644-670: returns mean_l wmse_l in *wmse, log sigma in *log_sigma and the factor
+// that turns a raw sum of squares into wmse_l in *scale  (all threads compute the same values)
+__device__ __forceinline__ void sigma_terms(const ElboArgs& a, int b, float* wmse, float* log_sigma, float* scale) {
+  float raw = 0.f;
+  for (int l = 0; l < a.L; ++l) raw += __ldcg(&a.ws_mse[(size_t)l * a.B + b]);
+  const float mse = raw / ((float)a.L * (float)a.D);
+  if (a.sigma_is_rmse) {
+    *wmse = mse / mse;
+    *log_sigma = 0.5f * logf(mse);
+    *scale = 1.f / ((float)a.D * mse);
+  } else {
+    const float s = *a.sigma;
+    const float sig = a.sigma_is_log ? expf(s) : s;
+    *log_sigma = a.sigma_is_log ? s : logf(s);
+    *wmse = mse / (sig * sig);
+    *scale = 1.f / ((float)a.D * sig * sig);
+  }
+}
+
+// per-latent-dimension terms of the KL for one (sample, class) pair; accumulates into 3 running sums
+//   gaussian: dist += (T d)^2, tr += exp(lv) T^2            (priors.py:188-250)
+//   tilted:   dist only                                       (priors.py:389-408)
+//   uniform:  dist += d^2, tr += Elogq + neg, aux += Elogq + alpha   (priors.py:429-476)
+__device__ __forceinline__ void kl_dim_terms(const ElboArgs& a, float mu, float lv, float m, float T, float& dist,
+                                             float& tr, float& aux) {
+  const float d = mu - m;
+  if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+    const float tau = a.tau, c = LOG2PI_F;
+    const float span = 2.f * 1.7320508075688772f * expf(0.5f * lv);
+    const float lo = d - 0.5f * span, hi = d + 0.5f * span;
+    const float lo_ = tau * fminf(fmaxf(lo / tau, -1.f), 1.f);
+    const float hi_ = tau * fminf(fmaxf(hi / tau, -1.f), 1.f);
+    const float elogq = -0.5f * lv - 0.5f * 2.4849066497880004f;  // log 12
+    float neg = (c + d * d + span * span / 12.f) * 0.5f;
+    neg += (a.alpha - 0.5f * c) * (hi_ - lo_) / span;
+    neg -= (hi_ * hi_ * hi_ - lo_ * lo_ * lo_) / span / 6.f;
+    dist += d * d;
+    tr += elogq + neg;
+    aux += elogq + a.alpha;
+  } else {
+    const float w = T * d;
+    dist = fmaf(w, w, dist);
+    tr = fmaf(expf(lv), T * T, tr);
+  }
+}
+
+// turns the reduced sums into (kl, zdist, var_kl)
+__device__ __forceinline__ void kl_finish(const ElboArgs& a, float dist, float tr, float aux, float slv, float logdet,
+                                          float* kl, float* var_kl) {
+  if (a.prior_kind == JVAE_PRIOR_TILTED) {
+    const float n = sqrtf(dist) - a.tau;
+    *kl = 0.5f * n * n;
+    *var_kl = 0.f;
+  } else if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+    float k = fmaxf(tr, aux);
+    if (a.var_w != 1.f) k += (a.var_w - 1.f) * aux;
+    *kl = k;
+    *var_kl = 2.f * aux;
+  } else {
+    const float vk = tr - slv + logdet - (float)a.K;
+    *var_kl = vk;
+    *kl = 0.5f * (dist + a.var_w * vk);
+  }
+}
+
+// ================================================================================================
+// TRAIN FORWARD
+// ================================================================================================
+template <bool XR_BF16>
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a) {
+  __shared__ float red[32];
+  __shared__ float s_ce[ELBO_THREADS / 32];
+  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
+  if (!stream_and_elect<XR_BF16>(a, b, g, red)) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int K = a.K, C = a.C;
+  long long yb = a.y[b];
+  bool bad_label = (yb < 0 || yb >= C);
+  if (bad_label) yb = 0;
+  const int c = a.conditional ? (int)yb : 0;
+
+  // ---- reconstruction term (cvae.py:649-672, 773-789)
+  float wmse = 0.f, cross_x = 0.f;
+  if (a.has_xreco) {
+    float log_sigma, scale;
+    sigma_terms(a, b, &wmse, &log_sigma, &scale);
+    cross_x = 0.5f * (float)a.D * (2.f * log_sigma + wmse + LOG2PI_F);
+  }
+  // ---- KL to the prior of class y_b (priors.py:252-326)
+  float dist = 0.f, tr = 0.f, aux = 0.f, slv = 0.f, dzd = 0.f;
+  const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
+  for (int k = tid; k < K; k += ELBO_THREADS) {
+    const float mu = a.mu[(size_t)b * K + k], lv = a.lv[(size_t)b * K + k];
+    const float m = a.means[(size_t)c * K + k];
+    const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
+    kl_dim_terms(a, mu, lv, m, T, dist, tr, aux);
+    slv += lv;
+    if (a.conditional) {
+      const float dd = mu - a.dict_mean[k];
+      dzd = fmaf(dd, dd, dzd);
+    }
+  }
+  dist = block_sum(dist, red);
+  tr = block_sum(tr, red);
+  aux = block_sum(aux, red);
+  slv = block_sum(slv, red);
+  dzd = block_sum(dzd, red);
+  float kl, var_kl;
+  kl_finish(a, dist, tr, aux, slv, a.logdet[c], &kl, &var_kl);
+
+  // ---- cross entropy of the classifier over all L+1 draws (losses.py:73-86)
+  float cross_y = 0.f;
+  if (a.has_logits) {
+    float part = 0.f;
+    for (int r = wid; r <= a.L; r += ELBO_THREADS / 32) {
+      const size_t base = ((size_t)r * a.B + b) * C;
+      float mx = -CUDART_INF_F;
+      for (int j = lane; j < C; j += 32) mx = fmaxf(mx, load_logit(a.logits, base + j, a.lg_bf16));
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int j = lane; j < C; j += 32) se += expf(load_logit(a.logits, base + j, a.lg_bf16) - mx);
+      se = warp_sum(se);
+      part += logf(se) + mx - load_logit(a.logits, base + (size_t)yb, a.lg_bf16);
+    }
+    __syncthreads();
+    if (lane == 0) s_ce[wid] = part;
+    __syncthreads();
+    for (int i = 0; i < ELBO_THREADS / 32; ++i) cross_y += s_ce[i];
+    cross_y /= (float)(a.L + 1);
+  }
+
+  if (tid == 0) {
+    float total = a.beta * kl;
+    if (a.has_xreco) total += cross_x;
+    if (a.has_logits && a.gamma_w != 0.f) total += a.gamma_w * cross_y;
+    if (a.kl) a.kl[b] = kl;
+    if (a.zdist) a.zdist[b] = dist;
+    if (a.var_kl) a.var_kl[b] = var_kl;
+    if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
+    if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
+    if (a.cross_y && a.has_logits) a.cross_y[b] = cross_y;
+    if (a.total) a.total[b] = total;
+    if (a.dzdist && a.conditional) a.dzdist[b] = dzd + __ldcg(a.dict_norm_var);
+    if (a.finite_flag && (bad_label || !isfinite(total))) atomicExch(a.finite_flag, 0);
+  }
+}
+
+// ================================================================================================
+// TRAIN BACKWARD  (SURVEY.md §8a backward contract)
+// ================================================================================================
+template <bool XR_BF16>
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a) {
+  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float gb = a.g[b];
+  const int D = a.D, K = a.K, C = a.C;
+  float sig = 1.f;
+  if (a.has_xreco) {
+    const float s = *a.sigma;
+    sig = a.sigma_is_log ? expf(s) : s;
+  }
+  // ---- d x_reco[l,b,:] = g_b (x_reco - x) / (L sigma^2), l >= 1; slab 0 gets zeros
+  if (a.has_xreco && a.d_xr) {
+    const float coef = gb / ((float)a.L * sig * sig);
+    const int l0 = 1 + g * LG;
+    const int nl = min(LG, a.L + 1 - l0);
+    const size_t slab = (size_t)a.B * D;
+    const float* xb = a.x + (size_t)b * D;
+    const bool vec_ok = XR_BF16 ? ((D & 7) == 0) : ((D & 3) == 0);
+    if (vec_ok && XR_BF16) {
+      const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(a.xr) + (size_t)l0 * slab + (size_t)b * D;
+      __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(a.d_xr) + (size_t)l0 * slab + (size_t)b * D;
+      const int nvec = D >> 3;
+      for (int v = tid; v < nvec; v += ELBO_THREADS) {
+        uint4 r[LG];
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) r[j] = ld_stream16(r0 + (size_t)j * slab + (size_t)v * 8);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xb) + 2 * v);
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(xb) + 2 * v + 1);
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) {
+            uint4 o;
+            o.x = pack_bf16(coef * (bf16_lo(r[j].x) - x0.x), coef * (bf16_hi(r[j].x) - x0.y));
+            o.y = pack_bf16(coef * (bf16_lo(r[j].y) - x0.z), coef * (bf16_hi(r[j].y) - x0.w));
+            o.z = pack_bf16(coef * (bf16_lo(r[j].z) - x1.x), coef * (bf16_hi(r[j].z) - x1.y));
+            o.w = pack_bf16(coef * (bf16_lo(r[j].w) - x1.z), coef * (bf16_hi(r[j].w) - x1.w));
+            st_stream16(o0 + (size_t)j * slab + (size_t)v * 8, o);
+          }
+        if (g == 0) st_stream16(reinterpret_cast<__nv_bfloat16*>(a.d_xr) + (size_t)b * D + (size_t)v * 8, make_uint4(0, 0, 0, 0));
+      }
+    } else if (vec_ok) {
+      const float* r0 = reinterpret_cast<const float*>(a.xr) + (size_t)l0 * slab + (size_t)b * D;
+      float* o0 = reinterpret_cast<float*>(a.d_xr) + (size_t)l0 * slab + (size_t)b * D;
+      const int nvec = D >> 2;
+      for (int v = tid; v < nvec; v += ELBO_THREADS) {
+        uint4 r[LG];
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) r[j] = ld_stream16(r0 + (size_t)j * slab + (size_t)v * 4);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(xb) + v);
+#pragma unroll
+        for (int j = 0; j < LG; ++j)
+          if (j < nl) {
+            uint4 o;
+            o.x = __float_as_uint(coef * (__uint_as_float(r[j].x) - x0.x));
+            o.y = __float_as_uint(coef * (__uint_as_float(r[j].y) - x0.y));
+            o.z = __float_as_uint(coef * (__uint_as_float(r[j].z) - x0.z));
+            o.w = __float_as_uint(coef * (__uint_as_float(r[j].w) - x0.w));
+            st_stream16(o0 + (size_t)j * slab + (size_t)v * 4, o);
+          }
+        if (g == 0) st_stream16(reinterpret_cast<float*>(a.d_xr) + (size_t)b * D + (size_t)v * 4, make_uint4(0, 0, 0, 0));
+      }
+    } else {
+      for (int d = tid; d < D; d += ELBO_THREADS) {
+        const float xv = xb[d];
+        for (int j = 0; j < nl; ++j) {
+          const size_t idx = (size_t)(l0 + j) * slab + (size_t)b * D + d;
+          if (XR_BF16) {
+            const float rv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.xr)[idx]);
+            reinterpret_cast<__nv_bfloat16*>(a.d_xr)[idx] = __float2bfloat16(coef * (rv - xv));
+          } else {
+            reinterpret_cast<float*>(a.d_xr)[idx] = coef * (reinterpret_cast<const float*>(a.xr)[idx] - xv);
+          }
+        }
+        if (g == 0) {
+          if (XR_BF16) reinterpret_cast<__nv_bfloat16*>(a.d_xr)[(size_t)b * D + d] = __float2bfloat16(0.f);
+          else reinterpret_cast<float*>(a.d_xr)[(size_t)b * D + d] = 0.f;
+        }
+      }
+    }
+  }
+  if (g != 0) return;
+
+  // ---- latent-space gradients, once per sample
+  long long yb = a.y[b];
+  if (yb < 0 || yb >= C) yb = 0;
+  const int c = a.conditional ? (int)yb : 0;
+  if (a.has_xreco && a.d_sigma && tid == 0) {
+    // cross_x = D/2 (2 log sigma + wmse + log 2pi), wmse ~ sigma^-2
+    float ds = gb * (float)D * (1.f - a.wmse_in[b]);
+    if (!a.sigma_is_log) ds /= sig;
+    atomicAdd(a.d_sigma, ds);
+  }
+  const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
+  float tilt = 1.f;
+  if (a.prior_kind == JVAE_PRIOR_TILTED) {
+    __shared__ float red[32];
+    float dist = 0.f;
+    for (int k = tid; k < K; k += ELBO_THREADS) {
+      const float w = Tc * (a.mu[(size_t)b * K + k] - a.means[(size_t)c * K + k]);
+      dist = fmaf(w, w, dist);
+    }
+    dist = block_sum(dist, red);
+    const float n = sqrtf(dist);
+    tilt = (n > 0.f) ? (n - a.tau) / n : 0.f;
+  }
+  for (int k = tid; k < K; k += ELBO_THREADS) {
+    const float mu = a.mu[(size_t)b * K + k], lv = a.lv[(size_t)b * K + k];
+    const float m = a.means[(size_t)c * K + k];
+    const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
+    const float t2 = T * T;
+    float dmu, dlv;
+    if (a.prior_kind == JVAE_PRIOR_TILTED) {
+      dmu = gb * a.beta * tilt * t2 * (mu - m);
+      dlv = 0.f;
+    } else {
+      dmu = gb * a.beta * t2 * (mu - m);
+      dlv = gb * a.beta * 0.5f * a.var_w * (t2 * expf(lv) - 1.f);
+    }
+    if (a.d_mu) a.d_mu[(size_t)b * K + k] = dmu;
+    if (a.d_lv) a.d_lv[(size_t)b * K + k] = dlv;
+    if (a.d_means) atomicAdd(&a.d_means[(size_t)c * K + k], -dmu);
+    if (a.d_inv_trans && a.var_dim == JVAE_VAR_DIAG && a.prior_kind == JVAE_PRIOR_GAUSSIAN) {
+      // d/dT of 1/2 [ T^2 d^2 + w (exp(lv) T^2 - 2 log|T|) ]
+      const float d = mu - m;
+      atomicAdd(&a.d_inv_trans[(size_t)c * K + k], gb * a.beta * (T * d * d + a.var_w * (expf(lv) * T - 1.f / T)));
+    }
+  }
+  // ---- d logits = g gamma_w/(L+1) (softmax - onehot) for all L+1 draws
+  if (a.has_logits && a.d_logits) {
+    const float coef = (a.gamma_w != 0.f) ? gb * a.gamma_w / (float)(a.L + 1) : 0.f;
+    for (int r = wid; r <= a.L; r += ELBO_THREADS / 32) {
+      const size_t base = ((size_t)r * a.B + b) * C;
+      float mx = -CUDART_INF_F;
+      for (int j = lane; j < C; j += 32) mx = fmaxf(mx, load_logit(a.logits, base + j, a.lg_bf16));
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int j = lane; j < C; j += 32) se += expf(load_logit(a.logits, base + j, a.lg_bf16) - mx);
+      se = warp_sum(se);
+      const float inv = 1.f / se;
+      for (int j = lane; j < C; j += 32) {
+        const float p = expf(load_logit(a.logits, base + j, a.lg_bf16) - mx) * inv;
+        const float v = coef * (p - ((long long)j == yb ? 1.f : 0.f));
+        if (a.lg_bf16) reinterpret_cast<__nv_bfloat16*>(a.d_logits)[base + j] = __float2bfloat16(v);
+        else reinterpret_cast<float*>(a.d_logits)[base + j] = v;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// EVAL / SCORING FORWARD: losses for every class, importance-weighted score, logits, OOD scores, predictions
+// ================================================================================================
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -CUDART_INF_F;
+  return warp_max(r);
+}
+
+// first index attaining `target` (ties -> smallest index, like torch.argmax / argmin)
+__device__ __forceinline__ int block_first_index(const float* v, int n, float target, int* red_i) {
+  int best = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (v[i] == target) best = min(best, i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red_i[wid] = best;
+  __syncthreads();
+  int r = (lane < nw) ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+
+template <bool XR_BF16>
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  __shared__ int red_i[32];
+  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
+  if (!stream_and_elect<XR_BF16>(a, b, g, red)) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int K = a.K, C = a.C, Cp = a.Cp, L = a.L, B = a.B;
+  // dynamic shared memory carve-up
+  float* zs = sm;                       // (L+1, K): row 0 = mu, rows 1..L = z[1..L]
+  float* evar = zs + (size_t)(L + 1) * K;  // (K) log_var
+  float* base_l = evar + K;             // (L) per-draw class-independent part of log_iws
+  float* s_kl = base_l + L;             // (Cp)
+  float* s_zd = s_kl + Cp;              // (Cp)
+  float* s_vk = s_zd + Cp;              // (Cp)
+  float* s_iws = s_vk + Cp;             // (Cp)
+  float* s_tot = s_iws + Cp;            // (max(C,Cp))
+  float* s_lo = s_tot + max(C, Cp);     // (C) mean logits
+  float* s_cy = s_lo + C;               // (C) cross_y per class
+  float* s_li = s_cy + C;               // (warps, L) log importance weights of the class a warp works on
+
+  for (int k = tid; k < K; k += ELBO_THREADS) {
+    zs[k] = a.mu[(size_t)b * K + k];
+    evar[k] = a.lv[(size_t)b * K + k];
+  }
+  if (a.z)
+    for (int i = tid; i < L * K; i += ELBO_THREADS) {
+      const int l = i / K, k = i - l * K;
+      zs[(size_t)(l + 1) * K + k] = a.z[((size_t)(l + 1) * B + b) * K + k];
+    }
+  __syncthreads();
+
+  // ---- per-sample scalars
+  float slv = 0.f, dzd = 0.f;
+  for (int k = tid; k < K; k += ELBO_THREADS) {
+    slv += evar[k];
+    if (a.conditional) {
+      const float dd = zs[k] - a.dict_mean[k];
+      dzd = fmaf(dd, dd, dzd);
+    }
+  }
+  slv = block_sum(slv, red);
+  dzd = block_sum(dzd, red);
+
+  float wmse = 0.f, cross_x = 0.f, log_sigma = 0.f, scale = 0.f;
+  const bool do_iws = a.has_xreco && a.z && a.eps_norm;
+  if (a.has_xreco) {
+    sigma_terms(a, b, &wmse, &log_sigma, &scale);
+    cross_x = 0.5f * (float)a.D * (2.f * log_sigma + wmse + LOG2PI_F);
+    if (do_iws)
+      for (int l = tid; l < L; l += ELBO_THREADS) {
+        const float wl = __ldcg(&a.ws_mse[(size_t)l * B + b]) * scale;
+        // cvae.py:676-683 and 837-850
+        float v = -0.5f * (float)a.D * (wl + 2.f * log_sigma + LOG2PI_F);
+        v += 0.5f * (a.eps_norm[(size_t)l * B + b] + slv) + 0.5f * (float)K * LOG2PI_F;
+        base_l[l] = v;
+      }
+  }
+  __syncthreads();
+
+  // ---- logits: mean over draws 1..L, and per-class cross_y = -mean_l log(softmax_l + 1e-6)  (losses.py:62-71)
+  if (a.has_logits) {
+    for (int j = tid; j < C; j += ELBO_THREADS) { s_lo[j] = 0.f; s_cy[j] = 0.f; }
+    __syncthreads();
+    const int r0 = (L >= 1) ? 1 : 0, nr = (L >= 1) ? L : 1;
+    for (int r = r0 + wid; r < r0 + nr; r += ELBO_THREADS / 32) {
+      const size_t base = ((size_t)r * B + b) * C;
+      float mx = -CUDART_INF_F;
+      for (int j = lane; j < C; j += 32) mx = fmaxf(mx, load_logit(a.logits, base + j, a.lg_bf16));
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int j = lane; j < C; j += 32) se += expf(load_logit(a.logits, base + j, a.lg_bf16) - mx);
+      se = warp_sum(se);
+      const float inv = 1.f / se;
+      for (int j = lane; j < C; j += 32) {
+        const float v = load_logit(a.logits, base + j, a.lg_bf16);
+        atomicAdd(&s_lo[j], v);
+        atomicAdd(&s_cy[j], logf(expf(v - mx) * inv + 1e-6f));
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < C; j += ELBO_THREADS) {
+      s_lo[j] = s_lo[j] / (float)nr;
+      s_cy[j] = -s_cy[j] / (float)nr;
+    }
+    __syncthreads();
+  }
+
+  // ---- class loop: one warp per class, all L+1 rows of zs against mean_c
+  for (int c = wid; c < Cp; c += ELBO_THREADS / 32) {
+    const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
+    const float logdet = a.logdet[c];
+    // KL terms on mu (row 0)
+    float dist = 0.f, tr = 0.f, aux = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float m = a.means[(size_t)c * K + k];
+      const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
+      kl_dim_terms(a, zs[k], evar[k], m, T, dist, tr, aux);
+    }
+    dist = warp_sum(dist);
+    tr = warp_sum(tr);
+    aux = warp_sum(aux);
+    float kl, var_kl;
+    kl_finish(a, dist, tr, aux, slv, logdet, &kl, &var_kl);
+    // log p(z_l | c) for the L draws (priors.py:328-342, 381-383, 478-491) and the importance weights
+    float iws = 0.f;
+    if (do_iws) {
+      float* li_w = s_li + (size_t)wid * L;
+      for (int l = 0; l < L; ++l) {
+        const float* zr = zs + (size_t)(l + 1) * K;
+        float q = 0.f, nz = 0.f;
+        for (int k = lane; k < K; k += 32) {
+          const float zv = zr[k];
+          const float m = a.means[(size_t)c * K + k];
+          if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+            const float d = a.conditional ? zv - m : zv;
+            q += (fabsf(d) > a.tau) ? (-0.5f * LOG2PI_F - 0.5f * d * d) : -a.alpha;
+          } else {
+            const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
+            const float w = T * (zv - m);
+            q = fmaf(w, w, q);
+            nz = fmaf(zv, zv, nz);
+          }
+        }
+        q = warp_sum(q);
+        float logp;
+        if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+          logp = q;
+        } else {
+          logp = -0.5f * (float)K * LOG2PI_F - 0.5f * q - 0.5f * logdet;
+          if (a.prior_kind == JVAE_PRIOR_TILTED) logp -= sqrtf(warp_sum(nz));
+        }
+        if (lane == 0) li_w[l] = base_l[l] + logp;
+      }
+      __syncwarp();
+      float mxl = -CUDART_INF_F;
+      for (int l = lane; l < L; l += 32) mxl = fmaxf(mxl, li_w[l]);
+      mxl = warp_max(mxl);
+      float se = 0.f;
+      for (int l = lane; l < L; l += 32) se += expf(li_w[l] - mxl);
+      se = warp_sum(se);
+      iws = se / (float)L + mxl;  // cvae.py:870: mean_l exp(.) + max, no log
+      __syncwarp();
+    }
+    if (lane == 0) {
+      s_kl[c] = kl;
+      s_zd[c] = dist;
+      s_vk[c] = var_kl;
+      s_iws[c] = iws;
+    }
+  }
+  __syncthreads();
+
+  // ---- totals (cvae.py:744, 791, 875-902): beta is cfg.beta (1 unless with_beta)
+  const bool add_cy = a.has_logits && a.gamma_w != 0.f;
+  const int nT = (Cp > 1) ? Cp : (add_cy ? C : 1);
+  for (int j = tid; j < nT; j += ELBO_THREADS) {
+    float t = a.beta * s_kl[(Cp > 1) ? j : 0];
+    if (a.has_xreco) t += cross_x;
+    if (add_cy) t += a.gamma_w * s_cy[j];
+    s_tot[j] = t;
+  }
+  __syncthreads();
+
+  // ---- write the per-class tensors, (C,B) layout
+  for (int j = tid; j < Cp; j += ELBO_THREADS) {
+    const size_t o = (size_t)j * B + b;
+    if (a.kl) a.kl[o] = s_kl[j];
+    if (a.zdist) a.zdist[o] = s_zd[j];
+    if (a.var_kl) a.var_kl[o] = s_vk[j];
+    if (a.iws && do_iws) a.iws[o] = s_iws[j];
+  }
+  for (int j = tid; j < nT; j += ELBO_THREADS)
+    if (a.total) a.total[(size_t)j * B + b] = s_tot[j];
+  if (a.has_logits)
+    for (int j = tid; j < C; j += ELBO_THREADS) {
+      if (a.cross_y) a.cross_y[(size_t)j * B + b] = s_cy[j];
+      if (a.logits_out) a.logits_out[(size_t)b * C + j] = s_lo[j];
+    }
+  if (tid == 0) {
+    if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
+    if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
+    if (a.dzdist && a.conditional) a.dzdist[b] = dzd + __ldcg(a.dict_norm_var);
+  }
+  if (!a.scores && !a.preds) return;
+
+  // ---- fused batch_dist_measures (cvae.py:972-1085) and predict_after_evaluate (cvae.py:938-970)
+  // reductions over classes of -total, iws, -kl, -zdist and logits
+  float v_negtot = -CUDART_INF_F, v_iws = -CUDART_INF_F, v_negkl = -CUDART_INF_F, v_negzd = -CUDART_INF_F,
+        v_lo = -CUDART_INF_F;
+  for (int j = tid; j < nT; j += ELBO_THREADS) v_negtot = fmaxf(v_negtot, -s_tot[j]);
+  for (int j = tid; j < Cp; j += ELBO_THREADS) {
+    v_iws = fmaxf(v_iws, s_iws[j]);
+    v_negkl = fmaxf(v_negkl, -s_kl[j]);
+    v_negzd = fmaxf(v_negzd, -s_zd[j]);
+  }
+  if (a.has_logits)
+    for (int j = tid; j < C; j += ELBO_THREADS) v_lo = fmaxf(v_lo, s_lo[j]);
+  const float mx_negtot = block_max(v_negtot, red);
+  const float mx_iws = block_max(v_iws, red);
+  const float mx_negkl = block_max(v_negkl, red);
+  const float mx_negzd = block_max(v_negzd, red);
+  const float mx_lo = block_max(v_lo, red);
+
+  float se_tot = 0.f, s1 = 0.f, se_iws = 0.f, se_kl = 0.f, se_lo = 0.f, plogp = 0.f;
+  for (int j = tid; j < nT; j += ELBO_THREADS) {
+    se_tot += expf(-s_tot[j] - mx_negtot);
+    s1 += -s_tot[j];
+  }
+  for (int j = tid; j < Cp; j += ELBO_THREADS) {
+    se_iws += expf(s_iws[j] - mx_iws);
+    se_kl += expf(-s_kl[j] - mx_negkl);
+  }
+  if (a.has_logits)
+    for (int j = tid; j < C; j += ELBO_THREADS) se_lo += expf(s_lo[j] - mx_lo);
+  se_tot = block_sum(se_tot, red);
+  s1 = block_sum(s1, red);
+  se_iws = block_sum(se_iws, red);
+  se_kl = block_sum(se_kl, red);
+  se_lo = block_sum(se_lo, red);
+  const float mean_negtot = s1 / (float)nT;
+  float ss = 0.f;
+  for (int j = tid; j < nT; j += ELBO_THREADS) {
+    const float d = -s_tot[j] - mean_negtot;
+    ss = fmaf(d, d, ss);
+  }
+  ss = block_sum(ss, red);
+  if (a.has_logits) {
+    for (int j = tid; j < C; j += ELBO_THREADS) {
+      const float p = expf(s_lo[j] - mx_lo) / se_lo;
+      plogp += p * logf(p);
+    }
+    plogp = block_sum(plogp, red);
+  }
+  if (a.scores && tid == 0) {
+    float* s = a.scores + (size_t)b * JVAE_NSCORES;
+    s[JVAE_S_ELBO] = mx_negtot;
+    s[JVAE_S_SUM] = logf(se_tot) + mx_negtot;
+    s[JVAE_S_MEAN] = logf(se_tot / (float)nT) + mx_negtot;
+    s[JVAE_S_IWS] = (Cp > 1) ? logf(se_iws) + mx_iws + logf((float)C) : mx_iws;
+    s[JVAE_S_SOFTKL] = 1.f / se_kl;
+    s[JVAE_S_ZDIST] = mx_negzd;
+    s[JVAE_S_KL] = mx_negkl;
+    s[JVAE_S_MSE] = -cross_x;
+    s[JVAE_S_WMSE] = -wmse;
+    s[JVAE_S_LOGITS] = a.has_logits ? mx_lo : 0.f;
+    s[JVAE_S_BASELINE] = a.has_logits ? 1.f / se_lo : 0.f;
+    s[JVAE_S_HYZ] = a.has_logits ? plogp : 0.f;
+    s[JVAE_S_STD] = (nT > 1) ? sqrtf(ss / (float)(nT - 1)) : 0.f;
+    s[JVAE_S_SOFTIWS] = 1.f / se_iws;
+    s[14] = 0.f;
+    s[15] = 0.f;
+  }
+  if (a.preds) {
+    // argmin total == first index with -total == max(-total)
+    for (int j = tid; j < nT; j += ELBO_THREADS) s_tot[j] = -s_tot[j];
+    __syncthreads();
+    const int p_loss = block_first_index(s_tot, nT, mx_negtot, red_i);
+    const int p_esty = a.has_logits ? block_first_index(s_lo, C, mx_lo, red_i) : 0;
+    for (int j = tid; j < Cp; j += ELBO_THREADS) s_zd[j] = -s_zd[j];
+    __syncthreads();
+    const int p_closest = block_first_index(s_zd, Cp, mx_negzd, red_i);
+    const int p_iws = block_first_index(s_iws, Cp, mx_iws, red_i);
+    if (tid == 0) {
+      int* p = a.preds + (size_t)b * JVAE_NPRED;
+      p[JVAE_P_LOSS] = p_loss;
+      p[JVAE_P_ESTY] = p_esty;
+      p[JVAE_P_CLOSEST] = p_closest;
+      p[JVAE_P_IWS] = p_iws;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int check_cfg(const jvae_elbo_cfg* cfg, const char* fn) {
+  if (!cfg) { set_error("%s: cfg is NULL", fn); return JVAE_ERR_INVALID; }
+  if (cfg->B <= 0 || cfg->K <= 0 || cfg->C <= 0 || cfg->L < 0) {
+    set_error("%s: bad dims B=%d L=%d K=%d C=%d", fn, cfg->B, cfg->L, cfg->K, cfg->C);
+    return JVAE_ERR_INVALID;
+  }
+  if (cfg->has_xreco && (cfg->D <= 0 || cfg->L < 1)) {
+    set_error("%s: a reconstruction term needs D > 0 and L >= 1 (D=%d L=%d)", fn, cfg->D, cfg->L);
+    return JVAE_ERR_INVALID;
+  }
+  if (cfg->var_dim == JVAE_VAR_FULL) {
+    set_error("%s: var_dim='full' (inverse Cholesky) priors are not implemented in the fused kernel", fn);
+    return JVAE_ERR_UNSUPPORTED;
+  }
+  if (cfg->var_dim != JVAE_VAR_SCALAR && cfg->var_dim != JVAE_VAR_DIAG) {
+    set_error("%s: bad var_dim %d", fn, cfg->var_dim);
+    return JVAE_ERR_INVALID;
+  }
+  if (cfg->prior_kind < JVAE_PRIOR_GAUSSIAN || cfg->prior_kind > JVAE_PRIOR_UNIFORM) {
+    set_error("%s: bad prior_kind %d", fn, cfg->prior_kind);
+    return JVAE_ERR_INVALID;
+  }
+  if (cfg->prior_kind != JVAE_PRIOR_GAUSSIAN && cfg->var_dim != JVAE_VAR_SCALAR) {
+    set_error("%s: tilted / uniform priors are scalar-variance only (priors.py:44-51)", fn);
+    return JVAE_ERR_INVALID;
+  }
+  return JVAE_OK;
+}
+
+static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
+  memset(&a, 0, sizeof(a));
+  a.B = cfg->B; a.L = cfg->L; a.K = cfg->K; a.C = cfg->C; a.D = cfg->D;
+  a.Cp = cfg->conditional ? cfg->C : 1;
+  a.G = cfg->has_xreco ? (cfg->L + LG - 1) / LG : 1;
+  a.xr_bf16 = cfg->xreco_dtype == JVAE_BF16;
+  a.lg_bf16 = cfg->logits_dtype == JVAE_BF16;
+  a.var_dim = cfg->var_dim; a.prior_kind = cfg->prior_kind; a.conditional = cfg->conditional;
+  a.has_xreco = cfg->has_xreco; a.has_logits = cfg->has_logits;
+  a.sigma_is_log = cfg->sigma_is_log; a.sigma_is_rmse = cfg->sigma_is_rmse;
+  a.beta = cfg->beta; a.gamma_w = cfg->gamma_w; a.var_w = cfg->var_w; a.tau = cfg->tau; a.alpha = cfg->alpha;
+  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp);
+  char* p = reinterpret_cast<char*>(workspace);
+  a.counters = reinterpret_cast<unsigned int*>(p + w.counters);
+  a.dict_norm_var = reinterpret_cast<float*>(p + w.dnv);
+  a.ws_mse = reinterpret_cast<float*>(p + w.mse);
+  a.dict_mean = reinterpret_cast<float*>(p + w.dict_mean);
+  a.logdet = reinterpret_cast<float*>(p + w.logdet);
+}
+
+static int launch_prologue(const ElboArgs& a, cudaStream_t st) {
+  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp);
+  JVAE_CUDA(cudaMemsetAsync(a.counters, 0, w.zero_bytes, st));
+  const int nkb = (a.K + 31) / 32;
+  const int ncb = (a.Cp + 7) / 8;
+  prior_stats_kernel<<<nkb + ncb, 256, 0, st>>>(a, nkb);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+}  // namespace jvae
+
+using namespace jvae;
+
+extern "C" {
+
+size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg) {
+  if (!cfg) return 0;
+  return ws_layout(cfg->B, cfg->L, cfg->K, cfg->conditional ? cfg->C : 1).total;
+}
+
+int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco, const float* mu,
+                        const float* log_var, const void* logits, const int64_t* y, const float* means,
+                        const float* inv_trans, const float* sigma, float* kl, float* zdist, float* var_kl,
+                        float* wmse, float* cross_x, float* cross_y, float* total, float* dzdist,
+                        int32_t* finite_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg, __func__);
+  if (rc) return rc;
+  JVAE_CHECK_ARG(mu && log_var && y && means && inv_trans, "mu, log_var, y, means, inv_trans are required");
+  JVAE_CHECK_ARG(!cfg->has_xreco || (x && x_reco && sigma), "x, x_reco and sigma are required when has_xreco");
+  JVAE_CHECK_ARG(!cfg->has_logits || logits, "logits is required when has_logits");
+  JVAE_CHECK_ARG(workspace && workspace_bytes >= jvae_elbo_workspace_bytes(cfg), "workspace too small");
+  JVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x_reco & 15) == 0, "x and x_reco must be 16-byte aligned");
+  ElboArgs a;
+  fill_args(a, cfg, workspace);
+  a.x = x; a.xr = x_reco; a.mu = mu; a.lv = log_var; a.logits = logits; a.y = (const long long*)y;
+  a.means = means; a.inv_trans = inv_trans; a.sigma = sigma;
+  a.kl = kl; a.zdist = zdist; a.var_kl = var_kl; a.wmse = wmse; a.cross_x = cross_x; a.cross_y = cross_y;
+  a.total = total; a.dzdist = dzdist; a.finite_flag = finite_flag;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (finite_flag) {
+    // set to 1; the kernel clears it on the first non-finite total
+    static const int32_t one = 1;
+    JVAE_CUDA(cudaMemcpyAsync(finite_flag, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+  }
+  rc = launch_prologue(a, st);
+  if (rc) return rc;
+  const int grid = a.B * a.G;
+  if (a.xr_bf16) elbo_train_fwd_kernel<true><<<grid, ELBO_THREADS, 0, st>>>(a);
+  else elbo_train_fwd_kernel<false><<<grid, ELBO_THREADS, 0, st>>>(a);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x, const void* x_reco,
+                        const float* mu, const float* log_var, const void* logits, const int64_t* y,
+                        const float* means, const float* inv_trans, const float* sigma, const float* wmse,
+                        void* d_x_reco, float* d_mu, float* d_log_var, void* d_logits, float* d_means,
+                        float* d_inv_trans, float* d_sigma, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg, __func__);
+  if (rc) return rc;
+  if (cfg->prior_kind == JVAE_PRIOR_UNIFORM) {
+    set_error("%s: backward of the uniform-with-gaussian-tail prior is not implemented", __func__);
+    return JVAE_ERR_UNSUPPORTED;
+  }
+  if (cfg->sigma_is_rmse) {
+    set_error("%s: backward with sigma=rmse is not implemented", __func__);
+    return JVAE_ERR_UNSUPPORTED;
+  }
+  JVAE_CHECK_ARG(g && mu && log_var && y && means && inv_trans, "g, mu, log_var, y, means, inv_trans are required");
+  JVAE_CHECK_ARG(!cfg->has_xreco || (x && x_reco && sigma && wmse), "x, x_reco, sigma, wmse are required when has_xreco");
+  JVAE_CHECK_ARG(!cfg->has_logits || logits, "logits is required when has_logits");
+  JVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x_reco & 15) == 0 && ((uintptr_t)d_x_reco & 15) == 0,
+                 "x, x_reco and d_x_reco must be 16-byte aligned");
+  (void)workspace; (void)workspace_bytes;
+  ElboArgs a;
+  char dummy[4096];
+  fill_args(a, cfg, dummy);
+  a.counters = nullptr; a.dict_norm_var = nullptr; a.ws_mse = nullptr; a.dict_mean = nullptr; a.logdet = nullptr;
+  a.g = g; a.x = x; a.xr = x_reco; a.mu = mu; a.lv = log_var; a.logits = logits; a.y = (const long long*)y;
+  a.means = means; a.inv_trans = inv_trans; a.sigma = sigma; a.wmse_in = wmse;
+  a.d_xr = d_x_reco; a.d_mu = d_mu; a.d_lv = d_log_var; a.d_logits = d_logits; a.d_means = d_means;
+  a.d_inv_trans = d_inv_trans; a.d_sigma = d_sigma;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_means) JVAE_CUDA(cudaMemsetAsync(d_means, 0, (size_t)a.Cp * a.K * 4, st));
+  if (d_sigma) JVAE_CUDA(cudaMemsetAsync(d_sigma, 0, 4, st));
+  if (d_inv_trans)
+    JVAE_CUDA(cudaMemsetAsync(d_inv_trans, 0, (size_t)a.Cp * (cfg->var_dim == JVAE_VAR_DIAG ? a.K : 1) * 4, st));
+  const int grid = a.B * a.G;
+  if (a.xr_bf16) elbo_train_bwd_kernel<true><<<grid, ELBO_THREADS, 0, st>>>(a);
+  else elbo_train_bwd_kernel<false><<<grid, ELBO_THREADS, 0, st>>>(a);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco, const float* mu,
+                       const float* log_var, const float* z, const float* eps_norm, const void* logits,
+                       const float* means, const float* inv_trans, const float* sigma, float* kl, float* zdist,
+                       float* var_kl, float* total, float* iws, float* cross_y, float* wmse, float* cross_x,
+                       float* dzdist, float* logits_out, float* scores, int32_t* preds, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg, __func__);
+  if (rc) return rc;
+  JVAE_CHECK_ARG(mu && log_var && means && inv_trans, "mu, log_var, means, inv_trans are required");
+  JVAE_CHECK_ARG(!cfg->has_xreco || (x && x_reco && sigma), "x, x_reco and sigma are required when has_xreco");
+  JVAE_CHECK_ARG(!cfg->has_logits || logits, "logits is required when has_logits");
+  JVAE_CHECK_ARG(workspace && workspace_bytes >= jvae_elbo_workspace_bytes(cfg), "workspace too small");
+  JVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x_reco & 15) == 0, "x and x_reco must be 16-byte aligned");
+  ElboArgs a;
+  fill_args(a, cfg, workspace);
+  a.x = x; a.xr = x_reco; a.mu = mu; a.lv = log_var; a.z = z; a.eps_norm = eps_norm; a.logits = logits;
+  a.means = means; a.inv_trans = inv_trans; a.sigma = sigma;
+  a.kl = kl; a.zdist = zdist; a.var_kl = var_kl; a.total = total; a.iws = iws; a.cross_y = cross_y;
+  a.wmse = wmse; a.cross_x = cross_x; a.dzdist = dzdist; a.logits_out = logits_out; a.scores = scores; a.preds = preds;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cmax = a.C > a.Cp ? a.C : a.Cp;
+  const size_t smem = ((size_t)(a.L + 1) * a.K + a.K + a.L + 4 * (size_t)a.Cp + Cmax + 2 * (size_t)a.C +
+                       (size_t)(ELBO_THREADS / 32) * a.L) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("%s: (L+1)*K + 7*C floats = %zu bytes of shared memory exceed 200 KB", __func__, smem);
+    return JVAE_ERR_UNSUPPORTED;
+  }
+  rc = launch_prologue(a, st);
+  if (rc) return rc;
+  const int grid = a.B * a.G;
+  if (a.xr_bf16) {
+    if (smem > 48 * 1024)
+      JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    elbo_eval_fwd_kernel<true><<<grid, ELBO_THREADS, smem, st>>>(a);
+  } else {
+    if (smem > 48 * 1024)
+      JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    elbo_eval_fwd_kernel<false><<<grid, ELBO_THREADS, smem, st>>>(a);
+  }
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+}  // extern "C"

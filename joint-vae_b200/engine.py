@@ -1,0 +1,246 @@
+"""Execution engine: maps the reference's layer containers and loss step onto libjvae_sm100.so.
+
+Everything here is host plumbing (PyTorch owns tensors, autograd graph and streams); the arithmetic is in
+csrc/*.cu, reached through _native (ctypes, C ABI).  POLICY names, per layer family, whether the hand-written
+kernel ('native') or a vendor library call through torch ('library': cuDNN / cuBLAS, bf16) executes it.  The
+library setting exists only for layer families whose sm_100a kernel has not landed yet; it is
+never selected silently: a 'native' op that cannot run raises.
+"""
+import itertools
+import os
+
+import torch
+from torch import nn
+
+from . import _native as nat
+
+POLICY = {
+    'linear': os.environ.get('JVAE_LINEAR', 'native'),
+    'conv': os.environ.get('JVAE_CONV', 'library'),
+}
+_rng_offset = itertools.count(1)
+
+
+def _r8(n):
+    return (n + 7) & ~7
+
+
+def _bf16_ld8(t):
+    """2-D tensor -> bf16 tensor whose row stride is a multiple of 8 elements (TMA needs 16-byte strides)."""
+    M, N = t.shape
+    if N % 8 == 0:
+        if t.dtype == torch.bfloat16 and t.is_contiguous():
+            return t
+        if t.dtype == torch.float32 and t.is_contiguous():
+            return nat.cast_f32_bf16(t)
+        return t.to(torch.bfloat16).contiguous()
+    buf = torch.zeros((M, _r8(N)), dtype=torch.bfloat16, device=t.device)
+    buf[:, :N].copy_(t)
+    return buf[:, :N]
+
+
+def _ld(t):
+    return t.stride(0)
+
+
+# --------------------------------------------------------------------------------------------- dense layers
+_wcache = {}
+
+
+def _weight_bf16(w):
+    key = id(w)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == w._version and hit[1].device == w.device:
+        return hit[1]
+    wb = _bf16_ld8(w.detach())
+    _wcache[key] = (w._version, wb)
+    return wb
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on tcgen05 (csrc/gemm.cu); dgrad / wgrad reuse the same kernel with MN-major operands."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, out_dtype):
+        M, K = x.shape
+        N = w.shape[0]
+        xb = _bf16_ld8(x.detach())
+        wb = _weight_bf16(w)
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        nat.gemm_bf16(nat.GEMM_NT, M, N, K, xb, _ld(xb), wb, _ld(wb), bias=b.detach() if b is not None else None,
+                      act=nat.ACT[act], out_bf16=out if out_dtype == torch.bfloat16 else None,
+                      out_f32=out if out_dtype == torch.float32 else None, ldd=N)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xb, wb, out if act in ('relu', 'sigmoid') else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, out = ctx.saved_tensors
+        M, K = xb.shape
+        N = wb.shape[0]
+        if ctx.act == 'relu':
+            dy = dy * (out > 0)
+        elif ctx.act == 'sigmoid':
+            o = out.float()
+            dy = dy.float() * o * (1 - o)
+        dzb = _bf16_ld8(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=ctx.x_dtype, device=dy.device)
+            nat.gemm_bf16(nat.GEMM_NN, M, K, N, dzb, _ld(dzb), wb, _ld(wb),
+                          out_bf16=dx if dx.dtype == torch.bfloat16 else None,
+                          out_f32=dx if dx.dtype == torch.float32 else None, ldd=K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+            nat.gemm_bf16(nat.GEMM_TN, N, K, M, dzb, _ld(dzb), xb, _ld(xb), out_f32=dw, ldd=K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum(0)
+        return dx, dw, db, None, None
+
+
+def linear(x, w, b, act='linear', out_dtype=torch.bfloat16):
+    """x (M,K) -> act(x W^T + b) (M,N).  act in linear|relu|sigmoid."""
+    if not x.is_cuda:
+        raise nat.NativeError('joint-vae_b200 runs on CUDA devices only (there is no CPU fallback); got a CPU tensor')
+    if POLICY['linear'] == 'native':
+        return _LinearFn.apply(x, w, b, act, out_dtype)
+    y = torch.nn.functional.linear(x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16) if b is not None else None)
+    if act == 'relu':
+        y = torch.relu(y)
+    elif act == 'sigmoid':
+        y = torch.sigmoid(y)
+    return y.to(out_dtype)
+
+
+_ACT_OF = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Identity: 'linear'}
+_CONV_TYPES = (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d, nn.UpsamplingNearest2d)
+
+
+def run_sequential(seq, x, out_dtype=None):
+    """Executes an nn.Sequential container built by the reference-style constructors.
+    Linear(+ReLU/Sigmoid/Identity) pairs become one fused GEMM; conv-type runs go to run_conv_stack."""
+    mods = list(seq)
+    i = 0
+    n = len(mods)
+    if n == 0:
+        return x
+    while i < n:
+        m = mods[i]
+        last_linear = isinstance(m, nn.Linear) and not any(isinstance(k, nn.Linear) for k in mods[i + 1:])
+        if isinstance(m, nn.Linear):
+            act = 'linear'
+            if i + 1 < n and type(mods[i + 1]) in _ACT_OF:
+                act = _ACT_OF[type(mods[i + 1])]
+                i += 1
+            dt = out_dtype if (last_linear and out_dtype is not None) else torch.bfloat16
+            x = linear(x, m.weight, m.bias, act=act, out_dtype=dt)
+        elif isinstance(m, _CONV_TYPES):
+            j = i
+            while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF or isinstance(mods[j], nn.LeakyReLU)):
+                j += 1
+            x = run_conv_stack(mods[i:j], x)
+            i = j - 1
+        elif isinstance(m, nn.Dropout):
+            x = torch.nn.functional.dropout(x, m.p, seq.training)
+        elif isinstance(m, nn.LeakyReLU):
+            x = torch.nn.functional.leaky_relu(x, m.negative_slope)
+        elif type(m) in _ACT_OF:
+            x = m(x)
+        else:
+            x = m(x)     # Reshape and other shape-only modules
+        i += 1
+    if out_dtype is not None and x.dtype != out_dtype:
+        x = x.to(out_dtype)
+    return x
+
+
+def run_conv_stack(mods, x):
+    """x NCHW.  'library' policy: the layers run as cuDNN / ATen calls in bf16 channels_last (interim path, see
+    DESIGN.md 'what is native'); 'native': the tcgen05 implicit-GEMM kernels of csrc/conv.cu."""
+    if POLICY['conv'] == 'native':
+        from . import conv_engine
+        return conv_engine.run(mods, x)
+    with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
+        x = x.contiguous(memory_format=torch.channels_last)
+        for m in mods:
+            x = m(x)
+    return x
+
+
+# --------------------------------------------------------------------------------------------- sampler
+class _SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, eps_in, L, is_sampled, uniform, seed, offset):
+        K = head.shape[1] // 2
+        head = nat.f32c(head.detach())
+        mu, lv, z, _, eps, en = nat.sample_fwd(head, L, K, eps_in=nat.f32c(eps_in), seed=seed, offset=offset,
+                                               is_sampled=is_sampled, uniform=uniform)
+        ctx.save_for_backward(head, lv, eps)
+        ctx.dims = (L, K, is_sampled)
+        ctx.mark_non_differentiable(eps, en)
+        ctx.set_materialize_grads(False)
+        return mu, lv, z, eps, en
+
+    @staticmethod
+    def backward(ctx, d_mu, d_lv, dz, _de, _den):
+        head, lv, eps = ctx.saved_tensors
+        L, K, is_sampled = ctx.dims
+        if dz is not None and dz.dtype not in (torch.float32, torch.bfloat16):
+            dz = dz.float()
+        d_head = nat.sample_bwd(head, lv, eps, dz.contiguous() if dz is not None else None, nat.f32c(d_mu),
+                                nat.f32c(d_lv), L, K, is_sampled)
+        return d_head, None, None, None, None, None, None
+
+
+def sample(head, L, eps_in=None, is_sampled=True, uniform=False):
+    """head (B,2K) = [mean | raw log_var] -> mean, clip(log_var), z (L+1,B,K), eps (L,B,K), |eps|^2 (L,B).
+    csrc/sampler.cu; eps_in (L+1,B,K) injects the noise, else Philox4x32-10 keyed by torch's seed."""
+    if not head.is_cuda:
+        raise nat.NativeError('joint-vae_b200 runs on CUDA devices only (there is no CPU fallback); got a CPU tensor')
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    return _SampleFn.apply(head, eps_in, L, is_sampled, uniform, seed, next(_rng_offset))
+
+
+# --------------------------------------------------------------------------------------------- fused ELBO
+class _ElboTrainFn(torch.autograd.Function):
+    """Forward: jvae_elbo_train_fwd; backward of `total` only (what the reference differentiates, cvae.py:2450)."""
+
+    @staticmethod
+    def forward(ctx, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, cfg):
+        out = nat.elbo_train_fwd(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma)
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, out['wmse'])
+        ctx.set_materialize_grads(False)
+        names = ('kl', 'zdist', 'var_kl', 'wmse', 'cross_x', 'cross_y', 'total', 'dzdist')
+        ctx.mark_non_differentiable(out['finite'])
+        return tuple(out[k] for k in names) + (out['finite'],)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        g_total = grads[6]
+        if any(g is not None for i, g in enumerate(grads) if i != 6):
+            raise NotImplementedError('the fused ELBO differentiates `total` only (as the reference trains on '
+                                      'total.mean()); detach the other loss terms')
+        x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, wmse = ctx.saved_tensors
+        cfg = ctx.cfg
+        need_it = ctx.needs_input_grad[7] and cfg.var_dim == nat.VAR_DIM['diag']
+        d_xr, d_mu, d_lv, d_lg, d_means, d_it, d_sigma = nat.elbo_train_bwd(
+            cfg, g_total.contiguous(), x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, wmse,
+            need_inv_trans=need_it)
+        if ctx.needs_input_grad[7] and not need_it and inv_trans.requires_grad:
+            raise NotImplementedError('gradient of the prior variance is implemented for var_dim="diag" only')
+        ng = ctx.needs_input_grad
+        return (None, d_xr if ng[1] else None, d_mu if ng[2] else None, d_lv if ng[3] else None,
+                d_lg if ng[4] else None, None, d_means if ng[6] else None, d_it if ng[7] else None,
+                d_sigma.view_as(sigma) if (ng[8] and d_sigma is not None) else None, None)
+
+
+def elbo_train(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma):
+    return _ElboTrainFn.apply(x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, cfg)
+
+
+def elbo_eval(cfg, x, x_reco, mu, log_var, z, eps_norm, logits, means, inv_trans, sigma, **kw):
+    return nat.elbo_eval_fwd(cfg, x, x_reco, mu, log_var, z, eps_norm, logits, means, inv_trans, sigma, **kw)

@@ -21,3 +21,10 @@ def golden_names():
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope='session')
+def pkg():
+    """the product package (joint-vae_b200/), with libjvae_sm100.so built/loaded"""
+    import __graft_entry__ as g
+    return g.build()
