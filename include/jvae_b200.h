@@ -82,7 +82,8 @@ size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
  *   sigma: 1 f32 on the device = the raw Sigma parameter (log sigma if sigma_is_log; sdim == 1), it is a
  *   learned parameter so it is never read back to the host.
  *   outputs, each (B) f32 (NULL = not wanted): kl zdist var_kl wmse cross_x cross_y total dzdist.
- *   finite_flag: 1 int32, set to 0 if any output is NaN/Inf (replaces cvae.py:2454-2457 scan). */
+ *   finite_flag: 1 int32, non-zero after the call unless some total is NaN/Inf or a label is out of range, then 0
+ *   (replaces the per-parameter isnan scan of cvae.py:2454-2457). */
 int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
                         const float* mu, const float* log_var, const void* logits, const int64_t* y,
                         const float* means, const float* inv_trans, const float* sigma,

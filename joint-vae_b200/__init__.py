@@ -8,7 +8,7 @@ The directory name is not an importable identifier; load it with `__graft_entry_
     jointvae_b200._native                                   <- ctypes binding of libjvae_sm100.so (include/jvae_b200.h)
 """
 from . import _native, engine            # noqa: F401
-from . import cvae                        # noqa: F401
+from . import cvae, distributed           # noqa: F401
 from .module import losses, priors, optimizers, vae_layers   # noqa: F401
 
 ClassificationVariationalNetwork = cvae.ClassificationVariationalNetwork

@@ -92,8 +92,8 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise NativeError('libjvae_sm100 works on CUDA tensors only (got a CPU tensor); there is no CPU fallback')
-    if not t.is_contiguous():
-        raise NativeError('non-contiguous tensor passed to the native library')
+    if not (t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))):
+        raise NativeError('non-dense tensor passed to the native library')
     return c_void_p(t.data_ptr())
 
 
@@ -119,6 +119,27 @@ def f32c(t):
 
 
 _ws_cache = {}
+
+# bench.py sets PROFILE = {'elbo_train_fwd': [], ...}: CUDA event pairs recorded on the launching stream around the
+# named entry point (the roofline's per-launch duration is measured live inside the timed region)
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.on = PROFILE is not None and name in PROFILE
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            PROFILE[self.name].append((self.a, self.b))
 
 
 def workspace(cfg, device):
@@ -148,9 +169,10 @@ def elbo_train_fwd(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sig
     out = torch.empty((8, B), dtype=torch.float32, device=dev)
     flag = torch.empty(1, dtype=torch.int32, device=dev)
     ws, n = workspace(cfg, dev)
-    check(lib().jvae_elbo_train_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits), ptr(y),
-                                    ptr(means), ptr(inv_trans), ptr(sigma),
-                                    *[c_void_p(out[i].data_ptr()) for i in range(8)], ptr(flag), ptr(ws), n, stream()))
+    with _timed('elbo_train_fwd'):
+        check(lib().jvae_elbo_train_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits),
+                                        ptr(y), ptr(means), ptr(inv_trans), ptr(sigma),
+                                        *[c_void_p(out[i].data_ptr()) for i in range(8)], ptr(flag), ptr(ws), n, stream()))
     names = ('kl', 'zdist', 'var_kl', 'wmse', 'cross_x', 'cross_y', 'total', 'dzdist')
     res = {k: out[i] for i, k in enumerate(names)}
     res['finite'] = flag
@@ -166,9 +188,11 @@ def elbo_train_bwd(cfg, g, x, x_reco, mu, log_var, logits, y, means, inv_trans, 
     d_means = torch.empty_like(means)
     d_it = torch.empty_like(inv_trans) if need_inv_trans else None
     d_sigma = torch.empty(1, dtype=torch.float32, device=dev) if x_reco is not None else None
-    check(lib().jvae_elbo_train_bwd(ctypes.byref(cfg), ptr(g), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits),
-                                    ptr(y), ptr(means), ptr(inv_trans), ptr(sigma), ptr(wmse), ptr(d_xr), ptr(d_mu),
-                                    ptr(d_lv), ptr(d_logits), ptr(d_means), ptr(d_it), ptr(d_sigma), None, 0, stream()))
+    with _timed('elbo_train_bwd'):
+        check(lib().jvae_elbo_train_bwd(ctypes.byref(cfg), ptr(g), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),
+                                        ptr(logits), ptr(y), ptr(means), ptr(inv_trans), ptr(sigma), ptr(wmse), ptr(d_xr),
+                                        ptr(d_mu), ptr(d_lv), ptr(d_logits), ptr(d_means), ptr(d_it), ptr(d_sigma), None, 0,
+                                        stream()))
     return d_xr, d_mu, d_lv, d_logits, d_means, d_it, d_sigma
 
 
@@ -193,7 +217,8 @@ def elbo_eval_fwd(cfg, x, x_reco, mu, log_var, z, eps_norm, logits, means, inv_t
     scores = f(B, NSCORES) if want_scores else None
     preds = torch.empty((B, NPRED), dtype=torch.int32, device=dev) if want_scores else None
     ws, n = workspace(cfg, dev)
-    check(lib().jvae_elbo_eval_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),
+    with _timed('elbo_eval_fwd'):
+      check(lib().jvae_elbo_eval_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),
                                    ptr(z) if iws is not None else None, ptr(eps_norm) if iws is not None else None,
                                    ptr(logits), ptr(means), ptr(inv_trans), ptr(sigma),
                                    ptr(kl), ptr(zdist), ptr(var_kl), ptr(total), ptr(iws), ptr(cross_y), ptr(wmse),

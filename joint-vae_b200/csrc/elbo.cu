@@ -928,11 +928,8 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   a.kl = kl; a.zdist = zdist; a.var_kl = var_kl; a.wmse = wmse; a.cross_x = cross_x; a.cross_y = cross_y;
   a.total = total; a.dzdist = dzdist; a.finite_flag = finite_flag;
   cudaStream_t st = (cudaStream_t)stream;
-  if (finite_flag) {
-    // set to 1; the kernel clears it on the first non-finite total
-    static const int32_t one = 1;
-    JVAE_CUDA(cudaMemcpyAsync(finite_flag, &one, sizeof(one), cudaMemcpyHostToDevice, st));
-  }
+  // non-zero = all finite so far; the kernel clears it on the first non-finite total (no host memory involved)
+  if (finite_flag) JVAE_CUDA(cudaMemsetAsync(finite_flag, 0x01, sizeof(int32_t), st));
   rc = launch_prologue(a, st);
   if (rc) return rc;
   const int grid = a.B * a.G;

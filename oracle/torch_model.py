@@ -215,3 +215,63 @@ def train_step(net, opt, x, y, eps, *, beta, gamma, clip=None):
         nn.utils.clip_grad_norm_(net.parameters(), clip)
     opt.step()
     return losses
+
+
+# --------------------------------------------------------------------------- arch description of a live model
+def describe_seq(seq):
+    """JSON-able description of an nn.Sequential made of standard torch layers (same schema as
+    tests/golden/make_golden.py:describe, which produced the fixtures' `arch`)."""
+    out = []
+    if seq is None:
+        return out
+    for m in seq:
+        if isinstance(m, nn.ConvTranspose2d):
+            out.append(dict(t='convT', cin=m.in_channels, cout=m.out_channels, k=m.kernel_size[0], s=m.stride[0],
+                            p=m.padding[0], op=m.output_padding[0]))
+        elif isinstance(m, nn.Conv2d):
+            out.append(dict(t='conv', cin=m.in_channels, cout=m.out_channels, k=m.kernel_size[0], s=m.stride[0],
+                            p=m.padding[0]))
+        elif isinstance(m, nn.BatchNorm2d):
+            out.append(dict(t='bn', n=m.num_features, eps=m.eps, momentum=m.momentum))
+        elif isinstance(m, nn.Linear):
+            out.append(dict(t='linear', cin=m.in_features, cout=m.out_features))
+        elif isinstance(m, nn.MaxPool2d):
+            out.append(dict(t='maxpool', k=m.kernel_size, s=m.stride, p=m.padding))
+        elif isinstance(m, nn.AvgPool2d):
+            out.append(dict(t='avgpool', k=m.kernel_size, s=m.stride, p=m.padding))
+        elif isinstance(m, nn.UpsamplingNearest2d):
+            out.append(dict(t='upsample', s=int(m.scale_factor)))
+        elif isinstance(m, nn.ReLU):
+            out.append(dict(t='relu'))
+        elif isinstance(m, nn.Sigmoid):
+            out.append(dict(t='sigmoid'))
+        elif isinstance(m, nn.Identity):
+            out.append(dict(t='identity'))
+        elif isinstance(m, nn.LeakyReLU):
+            out.append(dict(t='leaky'))
+        else:
+            raise TypeError(str(m))
+    return out
+
+
+def describe_model(model):
+    """(cfg, arch) for OracleNet from any model exposing the reference's attribute names."""
+    arch = {'features': describe_seq(model.features),
+            'features_out': list(model.encoder.input_shape) if model.features is not None else None,
+            'dense_projs': describe_seq(model.encoder.dense_projs),
+            'classifier': describe_seq(getattr(model, 'classifier', None)),
+            'classifier_type': model.classifier_type,
+            'sampling': bool(model.encoder.sampling.is_sampled),
+            'y_is_decoded': bool(model.y_is_decoded),
+            'sigma': {'is_log': bool(model.sigma.is_log), 'is_rmse': bool(model.sigma.is_rmse),
+                      'learned': bool(model.sigma.learned), 'sdim': int(model.sigma.sdim)},
+            'prior': {'conditional': bool(model.encoder.prior.conditional), 'var_dim': model.encoder.prior.var_dim,
+                      'distribution': model.encoder.prior.params['distribution'],
+                      'tau': getattr(model.encoder.prior, 'tau', None)}}
+    if not model.is_vib:
+        arch['decoder'] = describe_seq(model.decoder)
+        arch['imager'] = describe_seq(model.imager)
+        arch['imager_in'] = list(model.imager.input_shape)
+    cfg = {'type': model.type, 'input_shape': list(model.input_shape), 'num_labels': model.num_labels,
+           'latent_dim': model.latent_dim, 'beta': model.beta, 'gamma': model.gamma or 0.0}
+    return cfg, arch
