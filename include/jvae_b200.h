@@ -73,7 +73,8 @@ typedef struct jvae_elbo_cfg {
   float   alpha;            /* uniform prior: log rho inside [-tau,tau], priors.py:423-424 */
 } jvae_elbo_cfg;
 
-/* bytes of scratch the three ELBO entry points need for `cfg` (contents need no initialisation) */
+/* bytes of scratch the ELBO entry points need for `cfg`.  The first 4*B bytes (arrival counters) must be ZERO before
+ * the first use; every launch leaves them zero again, so one workspace can be reused without clearing. */
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
 
 /* Train forward (y given).  Replaces cvae.py:626-902 + priors.py:252-326 + losses.py:8-27,73-86.
@@ -175,6 +176,30 @@ enum jvae_gemm_mode {
 int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const void* b, int ldb,
                    const float* bias, int act, void* out_bf16, float* out_f32, int ldd,
                    float* col_stats, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolutions as implicit GEMM on tcgen05, NHWC bf16 activations (nn.Conv2d / nn.ConvTranspose2d of the
+ * features / imager stacks, module/vae_layers/conv.py:189-219, conv-models.ini:11-30).
+ *
+ * jvae_conv_gather_gemm: for every position q = (n, qy, qx) of an (N, Hq, Wq) grid
+ *     out[n, qy*out_sy + out_oy, qx*out_sx + out_ox, co] =
+ *         act( bias[co] + sum_t sum_ci in[n, qy*in_stride + tap_dy[t], qx*in_stride + tap_dx[t], ci] * W[co][t][ci] )
+ *   with out-of-image reads equal to zero.  One call is a Conv2d (stride 1 or 2), a ConvTranspose2d of stride 1
+ *   (flipped taps), ONE sub-pixel phase of a stride-2 ConvTranspose2d (out_s = 2, out_o = phase), or the data
+ *   gradient of any of them, depending on the tap table and weight arrangement the host passes.
+ *   in  (N,H,W,ld_in) bf16, Cin real channels; wmat (Cout_pad, ldw) bf16 with row co = [tap][chunk][Cblk] where
+ *   Cblk = 16/32/64 for Cin <= 16 / <= 32 / > 32 and chunk = ceil(Cin/Cblk) (zero padded); Cout_pad a multiple of 16
+ *   (of 256 above 256); out (N,Ho,Wo,ld_out) bf16, channels >= Cout up to ld_out are written as zeros.
+ * jvae_conv_wgrad: dw[t][co][ci] += sum_q dy[n,qy,qx,co] * x[n, qy*in_stride + tap_dy[t], qx*in_stride + tap_dx[t], ci]
+ *   (fp32, atomically accumulated: zero dw first); dw strides in elements.
+ * ------------------------------------------------------------------------------------------ */
+int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                          int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
+                          void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
+                          const float* bias, int act, void* stream);
+int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
+                    int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
+                    int dw_ld_co, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small data-movement / elementwise kernels of the step

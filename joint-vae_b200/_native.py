@@ -97,6 +97,17 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
+def ptr2d(t):
+    """2-D operand of the GEMM: unit inner stride, any 16-byte aligned row stride"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError('libjvae_sm100 works on CUDA tensors only (got a CPU tensor); there is no CPU fallback')
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise NativeError('GEMM operands must be 2-D with unit inner stride')
+    return c_void_p(t.data_ptr())
+
+
 def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -147,7 +158,7 @@ def workspace(cfg, device):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
-        ws = torch.empty(max(n, 1 << 16), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(n, 1 << 16), dtype=torch.uint8, device=device)    # counters start at zero
         _ws_cache[key] = ws
     return ws, n
 
@@ -293,7 +304,7 @@ GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 
 def gemm_bf16(mode, M, N, K, a, lda, b, ldb, *, bias=None, act=0, out_bf16=None, out_f32=None, ldd=None,
               col_stats=None, accumulate=False):
-    check(lib().jvae_gemm_bf16(mode, M, N, K, ptr(a), lda, ptr(b), ldb, ptr(bias), act, ptr(out_bf16), ptr(out_f32),
+    check(lib().jvae_gemm_bf16(mode, M, N, K, ptr2d(a), lda, ptr2d(b), ldb, ptr(bias), act, ptr(out_bf16), ptr(out_f32),
                                ldd if ldd is not None else N, ptr(col_stats), int(accumulate), stream()))
 
 

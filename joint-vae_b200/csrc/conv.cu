@@ -1,5 +1,651 @@
-// Implicit-GEMM convolution kernels on tcgen05 (placeholder until the kernels land).
+// Implicit-GEMM convolutions on tcgen05 for NHWC bf16 activations: Conv2d, ConvTranspose2d (stride 1, and stride 2
+// through its 4 sub-pixel phases), their data gradients (the same kernel with transformed weights / geometry) and the
+// weight gradient (second kernel, MN-major operands, split over the pixel dimension).
+//
+// Replaces nn.Conv2d / nn.ConvTranspose2d of the reference's features / imager stacks
+// (module/vae_layers/conv.py:189-219, conv-models.ini:11-30).
+//
+// Forward / dgrad kernel ("gather GEMM"): the output tile is 128 positions q = (image, y, x) of a TW x TH x NB box by
+// BN output channels.  For every tap (dy,dx) of the filter the A operand is ONE TMA box load of the NHWC input at the
+// shifted coordinate (q*stride + d): out-of-image rows / columns are zero-filled by TMA, which is the padding.  No
+// im2col buffer exists anywhere.  B is the [BN x Cblk] slice of the pre-arranged weight matrix for that tap.
+// The kernel is persistent (static round-robin over tiles) with a double-buffered TMEM accumulator so the epilogue
+// of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
+#include <vector>
+
 namespace jvae {
-int conv_selftest(int verbose) { (void)verbose; return 0; }
+
+constexpr int CONV_THREADS = 192;
+constexpr int CONV_MAX_TAPS = 64;
+
+struct ConvParams {
+  // iteration space
+  int N, Hq, Wq;               // positions q: image, row, column
+  int TW, TH, NB;              // tile box, TW*TH*NB == 128
+  int tiles_x, tiles_y, tiles_n, num_tiles, n_tiles_n;  // n_tiles_n: output-channel tiles
+  // reduction
+  int Cblk, nCk, ntaps;        // channel chunk (16/32/64 elements = swizzle span), chunks per tap, taps
+  int in_stride;               // input coordinate = q * in_stride + d
+  short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
+  int BN;                      // output channels per CTA tile (multiple of 16, <= 256)
+  // output
+  int Ho, Wo, Cout, ldc;       // output tensor (N, Ho, Wo, ldc channels); Cout real channels written
+  int out_sy, out_sx, out_oy, out_ox;   // output pixel = q * out_s + out_o
+  int act;
+  const float* bias;
+  __nv_bfloat16* out;
+  uint32_t stage_bytes, a_bytes, tx_bytes, tmem_cols;
+  int stages;
+};
+
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                        const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tile = p.ntaps * p.nCk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = p.tmem_cols >> 1;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int m = tile / p.n_tiles_n;
+        const int tx = m % p.tiles_x; m /= p.tiles_x;
+        const int ty = m % p.tiles_y; m /= p.tiles_y;
+        const int x0 = tx * p.TW * p.in_stride, y0 = ty * p.TH * p.in_stride, n0 = m * p.NB;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int c = 0; c < p.nCk; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+            tma_load_4d(sa, &tmap_in, &full_bar[s], c * p.Cblk, x0 + p.dx[t], y0 + p.dy[t], n0);
+            tma_load_2d(sa + p.a_bytes, &tmap_w, &full_bar[s], (t * p.nCk + c) * p.Cblk, nt * p.BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, false, false);
+      const uint32_t swz = (p.Cblk == 64) ? SWZ_128B : (p.Cblk == 32 ? SWZ_64B : SWZ_32B);
+      const uint32_t sbo = 8u * (uint32_t)p.Cblk * 2u;      // 8 rows of Cblk bf16
+      const int ksteps = p.Cblk >> 4;
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1;
+        mbar_wait(&tempty_bar[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        for (int kb = 0; kb < kb_per_tile; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t a_desc = make_smem_desc(sa, 16, sbo, swz);
+          const uint64_t b_desc = make_smem_desc(sa + p.a_bytes, 16, sbo, swz);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    const int mrow = q * 32 + lane;
+    const int tx_in = mrow % p.TW, ty_in = (mrow / p.TW) % p.TH, nb_in = mrow / (p.TW * p.TH);
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1;
+      const int nt = tile % p.n_tiles_n;
+      int m = tile / p.n_tiles_n;
+      const int tx = m % p.tiles_x; m /= p.tiles_x;
+      const int ty = m % p.tiles_y; m /= p.tiles_y;
+      const int qx = tx * p.TW + tx_in, qy = ty * p.TH + ty_in, n = m * p.NB + nb_in;
+      const bool ok = (n < p.N) && (qy < p.Hq) && (qx < p.Wq);
+      const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
+      __nv_bfloat16* orow = p.out + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + (size_t)nt * p.BN;
+      mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      const int ch0 = nt * p.BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (ok && (ch0 + c0 < p.Cout)) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r[j]);
+            const int ch = ch0 + c0 + j;
+            if (p.bias && ch < p.Cout) t += __ldg(&p.bias[ch]);
+            if (p.act == JVAE_ACT_RELU) t = fmaxf(t, 0.f);
+            v[j] = (ch < p.Cout) ? t : 0.f;
+          }
+          if (ch0 + c0 + 16 <= p.ldc) {
+            uint4 o0, o1;
+            o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+            o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+            *reinterpret_cast<uint4*>(orow + c0) = o0;
+            *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + c0 + j < p.ldc) orow[c0 + j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[tap][co][ci] = sum_q dY[q, co] * X[q*stride + d_tap, ci]
+// Both operands are NHWC tiles whose contiguous dimension (channels) is the M / N dimension of the GEMM and whose
+// rows (pixels) are the reduction: MN-major descriptors on the same TMA boxes the forward kernel uses.
+// Each CTA owns a slice of the pixel tiles and a group of taps; partial sums are reduced with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int N, Hq, Wq, TW, TH, NB, tiles_x, tiles_y, tiles_n, num_tiles;
+  int Cblk_y, Cblk_x;          // channel block of dY (M side, 64 max) and X (N side)
+  int cy0, cx0;                // channel offsets of this launch's blocks in dY / X
+  int M_real, N_real;          // channels actually accumulated (rest is padding)
+  int ntaps, tap0, taps_per_cta, in_stride;
+  short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
+  float* dw;                   // (ntaps_total, Cout, Cin) fp32, accumulated atomically
+  int dw_ld_tap, dw_ld_co;     // strides of dw in elements
+  uint32_t stage_bytes, a_bytes, tx_bytes, tmem_cols;
+  int stages;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* done_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap_lo = p.tap0 + blockIdx.y * p.taps_per_cta;
+  const int ntap = min(p.taps_per_cta, p.ntaps - tap_lo);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t x_bytes = 128u * (uint32_t)p.Cblk_x * 2u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int m = tile;
+        const int tx = m % p.tiles_x; m /= p.tiles_x;
+        const int ty = m % p.tiles_y; m /= p.tiles_y;
+        const int n0 = m * p.NB;
+        // stage layout: [dY tile (128 x Cblk_y)] [X tile per tap ...]: one stage = dY + ONE tap's X tile
+        for (int t = 0; t < ntap; ++t, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
+          tma_load_4d(sa, &tmap_dy, &full_bar[s], p.cy0, tx * p.TW, ty * p.TH, n0);
+          tma_load_4d(sa + p.a_bytes, &tmap_x, &full_bar[s], p.cx0, tx * p.TW * p.in_stride + p.dx[tap_lo + t],
+                      ty * p.TH * p.in_stride + p.dy[tap_lo + t], n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D[M = dY channels (64 rows), N = X channels] += dY^T[M x 128 px] * X[128 px x N]; both MN-major
+      const uint32_t idesc = make_idesc_bf16(64, p.Cblk_x, true, true);
+      const uint32_t swz_y = (p.Cblk_y == 64) ? SWZ_128B : (p.Cblk_y == 32 ? SWZ_64B : SWZ_32B);
+      const uint32_t swz_x = (p.Cblk_x == 64) ? SWZ_128B : (p.Cblk_x == 32 ? SWZ_64B : SWZ_32B);
+      const uint32_t row_y = (uint32_t)p.Cblk_y * 2u, row_x = (uint32_t)p.Cblk_x * 2u;
+      uint32_t it = 0;
+      bool first_tile = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int t = 0; t < ntap; ++t, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+          // MN-major: one block of Cblk channels wide; 8-pixel groups are 8 rows apart (SBO); LBO (next channel block)
+          // is unused for a single block but must be valid: point it at the same block
+          const uint64_t a_desc = make_smem_desc(sa, 8 * row_y, 8 * row_y, swz_y);
+          const uint64_t b_desc = make_smem_desc(sa + p.a_bytes, 8 * row_x, 8 * row_x, swz_x);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.Cblk_x);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // 128 pixels = 8 x K16
+            umma_bf16(d_tmem, a_desc + (uint64_t)((16 * row_y * k) >> 4), b_desc + (uint64_t)((16 * row_x * k) >> 4), idesc,
+                      (!first_tile || k != 0));
+          umma_commit(&empty_bar[s]);
+        }
+        first_tile = false;
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: accumulator rows = dY channels (M = 64: TMEM lanes 0..15 of each lane quarter hold rows 16q..16q+15),
+    // columns = taps x X channels
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_work = blockIdx.x < p.num_tiles;
+    for (int t = 0; t < ntap && has_work; ++t) {
+      for (int c0 = 0; c0 < p.Cblk_x; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.Cblk_x + c0), r);
+        tmem_ld_wait();
+        const int row = q * 16 + lane;     // valid for lane < 16
+        if (lane < 16 && row < p.M_real) {
+          float* o = p.dw + (size_t)(tap_lo + t) * p.dw_ld_tap + (size_t)(p.cy0 + row) * p.dw_ld_co + p.cx0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.N_real) atomicAdd(o + j, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+static void tile_shape(int Hq, int Wq, int* TW, int* TH, int* NB) {
+  int tw = pow2_floor(Wq); if (tw > 128) tw = 128;
+  if (tw < Wq && tw * 2 <= 128 && (tw * 2 - Wq) * 4 <= Wq) tw *= 2;   // e.g. W=28 -> 32 rather than 16
+  int th = pow2_ceil(Hq); if (th > 128 / tw) th = 128 / tw;
+  *TW = tw; *TH = th; *NB = 128 / (tw * th);
+}
+
+static int cblk_of(int C) { return C > 32 ? 64 : (C > 16 ? 32 : 16); }
+
+// NHWC bf16 activation map: dims {C, W, H, N}, box {Cblk, TW*s, TH*s, NB}, element strides {1, s, s, 1}
+static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C, int ldc, int Cblk, int TW, int TH, int NB,
+                    int stride) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)ldc * 2, (uint64_t)W * ldc * 2, (uint64_t)H * W * ldc * 2};
+  uint32_t box[4] = {(uint32_t)Cblk, (uint32_t)(TW * stride), (uint32_t)(TH * stride), (uint32_t)NB};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  return make_tmap_bf16(t, base, 4, dims, strides, box, es, Cblk * 2);
+}
+
+}  // namespace jvae
+
+using namespace jvae;
+
+extern "C" {
+
+int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                          int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
+                          void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
+                          const float* bias, int act, void* stream) {
+  JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
+  JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
+  JVAE_CHECK_ARG((ld_in % 8) == 0 && (ldw % 8) == 0 && (ld_out % 8) == 0, "channel strides must be multiples of 8");
+  JVAE_CHECK_ARG((Cout_pad % 16) == 0 && Cout_pad >= 16, "Cout_pad must be a multiple of 16");
+  JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
+  JVAE_CHECK_ARG((((uintptr_t)in | (uintptr_t)wmat | (uintptr_t)out) & 15) == 0, "16-byte alignment");
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.Hq = Hq; p.Wq = Wq;
+  tile_shape(Hq, Wq, &p.TW, &p.TH, &p.NB);
+  p.tiles_x = (Wq + p.TW - 1) / p.TW; p.tiles_y = (Hq + p.TH - 1) / p.TH; p.tiles_n = (N + p.NB - 1) / p.NB;
+  p.BN = Cout_pad > 256 ? 256 : Cout_pad;
+  if (Cout_pad > 256) JVAE_CHECK_ARG((Cout_pad % 256) == 0, "Cout_pad > 256 must be a multiple of 256");
+  p.n_tiles_n = Cout_pad / p.BN;
+  p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
+  p.Cblk = cblk_of(Cin); p.nCk = (Cin + p.Cblk - 1) / p.Cblk; p.ntaps = ntaps; p.in_stride = in_stride;
+  for (int t = 0; t < ntaps; ++t) { p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t]; }
+  p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
+  p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
+  p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.a_bytes = 128u * p.Cblk * 2u;
+  p.tx_bytes = p.a_bytes + (uint32_t)p.BN * p.Cblk * 2u;      // bytes the two TMA boxes deliver per stage
+  p.stage_bytes = (p.tx_bytes + 1023u) & ~1023u;
+  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (p.stages > 12) p.stages = 12;
+  JVAE_CHECK_ARG(p.stages >= 2, "tile too large for shared memory");
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.BN < 32 ? 32 : 2 * p.BN);
+  CUtensorMap tin, tw;
+  int rc = act_tmap(&tin, in, N, H, W, Cin, ld_in, p.Cblk, p.TW, p.TH, p.NB, in_stride);
+  if (rc) return rc;
+  {
+    const int Ktot = ntaps * p.nCk * p.Cblk;
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout_pad};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {(uint32_t)p.Cblk, (uint32_t)p.BN};
+    JVAE_CHECK_ARG(ldw >= Ktot, "weight matrix row shorter than taps*chunks*Cblk");
+    rc = make_tmap_bf16(&tw, wmat, 2, dims, strides, box, nullptr, p.Cblk * 2);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    JVAE_CUDA(cudaFuncSetAttribute(conv_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  ConvParams pk = p;
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_gather_gemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(tin, tw, pk);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
+                    int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
+                    int dw_ld_co, void* stream) {
+  JVAE_CHECK_ARG(dy && x && dw && tap_dy && tap_dx, "null pointer");
+  JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
+  JVAE_CHECK_ARG((ld_dy % 8) == 0 && (ld_x % 8) == 0, "channel strides must be multiples of 8");
+  JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.Hq = Hq; p.Wq = Wq;
+  tile_shape(Hq, Wq, &p.TW, &p.TH, &p.NB);
+  p.tiles_x = (Wq + p.TW - 1) / p.TW; p.tiles_y = (Hq + p.TH - 1) / p.TH; p.tiles_n = (N + p.NB - 1) / p.NB;
+  p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.Cblk_y = cblk_of(Cout); p.Cblk_x = cblk_of(Cin);
+  p.ntaps = ntaps; p.in_stride = in_stride;
+  for (int t = 0; t < ntaps; ++t) { p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t]; }
+  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co;
+  p.a_bytes = 128u * 64u * 2u;     // the M=64 MMA reads 64 channel columns: reserve a full 64-wide slot for dY
+  p.stage_bytes = p.a_bytes + 128u * (uint32_t)p.Cblk_x * 2u;
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  p.tx_bytes = 128u * (uint32_t)p.Cblk_y * 2u + 128u * (uint32_t)p.Cblk_x * 2u;
+  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  // taps per CTA limited by TMEM: taps * Cblk_x <= 512 columns
+  p.taps_per_cta = 512 / p.Cblk_x;
+  if (p.taps_per_cta > ntaps) p.taps_per_cta = ntaps;
+  const int tap_groups = (ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
+  p.tmem_cols = (uint32_t)pow2_ceil(p.taps_per_cta * p.Cblk_x < 32 ? 32 : p.taps_per_cta * p.Cblk_x);
+  CUtensorMap tdy, tx;
+  static bool attr = false;
+  if (!attr) {
+    JVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + 1024;
+  int gx = sm_count() / tap_groups;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_tiles) gx = p.num_tiles;
+  // loop over 64-wide channel blocks of dY (M) and X (N)
+  for (int cy = 0; cy < Cout; cy += p.Cblk_y) {
+    for (int cx = 0; cx < Cin; cx += p.Cblk_x) {
+      WgradParams q = p;
+      q.cy0 = cy; q.cx0 = cx;
+      q.M_real = (Cout - cy < p.Cblk_y) ? Cout - cy : p.Cblk_y;
+      q.N_real = (Cin - cx < p.Cblk_x) ? Cin - cx : p.Cblk_x;
+      int rc = act_tmap(&tdy, dy, N, Hq, Wq, Cout, ld_dy, p.Cblk_y, p.TW, p.TH, p.NB, 1);
+      if (rc) return rc;
+      rc = act_tmap(&tx, x, N, H, W, Cin, ld_x, p.Cblk_x, p.TW, p.TH, p.NB, in_stride);
+      if (rc) return rc;
+      conv_wgrad_kernel<<<dim3(gx, tap_groups), CONV_THREADS, smem, (cudaStream_t)stream>>>(tdy, tx, q);
+      JVAE_LAUNCH_CHECK();
+    }
+  }
+  return JVAE_OK;
+}
+
+}  // extern "C"
+
+namespace jvae {
+
+// ------------------------------------------------------------------------------------------------ self test
+__global__ void conv_fill_kernel(__nv_bfloat16* p, size_t n, uint32_t seed, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    p[i] = __float2bfloat16(scale * (((float)(h & 0xffff) / 32768.f) - 1.f));
+  }
+}
+
+// naive gather conv with the same tap-table semantics; one thread per (output position q, co)
+__global__ void conv_ref_kernel(const __nv_bfloat16* in, int N, int H, int W, int Cin, int ld_in, const __nv_bfloat16* wmat,
+                                int ldw, int Cblk, int nCk, int ntaps, const short* dy, const short* dx, int in_stride,
+                                int Hq, int Wq, float* out, int Ho, int Wo, int Cout, int out_sy, int out_sx, int out_oy,
+                                int out_ox, const float* bias, int act) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Hq * Wq * Cout;
+  if (idx >= total) return;
+  const int co = (int)(idx % Cout);
+  size_t r = idx / Cout;
+  const int qx = (int)(r % Wq); r /= Wq;
+  const int qy = (int)(r % Hq); r /= Hq;
+  const int n = (int)r;
+  float acc = 0.f;
+  for (int t = 0; t < ntaps; ++t) {
+    const int iy = qy * in_stride + dy[t], ix = qx * in_stride + dx[t];
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float a = __bfloat162float(in[(((size_t)n * H + iy) * W + ix) * ld_in + ci]);
+      const float w = __bfloat162float(wmat[(size_t)co * ldw + (size_t)(t * nCk + ci / Cblk) * Cblk + ci % Cblk]);
+      acc = fmaf(a, w, acc);
+    }
+  }
+  if (bias) acc += bias[co];
+  if (act == JVAE_ACT_RELU) acc = fmaxf(acc, 0.f);
+  const int oy = qy * out_sy + out_oy, ox = qx * out_sx + out_ox;
+  out[(((size_t)n * Ho + oy) * Wo + ox) * Cout + co] = acc;
+}
+
+__global__ void conv_cmp_kernel(const __nv_bfloat16* got, int ld, const float* ref, int C, size_t pixels, const float* mask,
+                                float* err) {
+  float e = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels * C; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / C;
+    const int c = (int)(i % C);
+    if (mask && mask[pix] == 0.f) continue;
+    const float g = __bfloat162float(got[pix * ld + c]), r = ref[i];
+    float d = fabsf(g - r) / (1.f + fabsf(r));
+    if (!(d == d)) d = 1e30f;
+    e = fmaxf(e, d);
+  }
+  e = warp_max(e);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(err), __float_as_int(e));
+}
+
+__global__ void wgrad_ref_kernel(const __nv_bfloat16* dyp, int N, int Hq, int Wq, int Cout, int ld_dy, const __nv_bfloat16* x,
+                                 int H, int W, int Cin, int ld_x, int ntaps, const short* dy, const short* dx, int in_stride,
+                                 float* dw) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)ntaps * Cout * Cin) return;
+  const int ci = (int)(idx % Cin);
+  const int co = (int)((idx / Cin) % Cout);
+  const int t = (int)(idx / ((size_t)Cin * Cout));
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int qy = 0; qy < Hq; ++qy)
+      for (int qx = 0; qx < Wq; ++qx) {
+        const int iy = qy * in_stride + dy[t], ix = qx * in_stride + dx[t];
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        acc = fmaf(__bfloat162float(dyp[(((size_t)n * Hq + qy) * Wq + qx) * ld_dy + co]),
+                   __bfloat162float(x[(((size_t)n * H + iy) * W + ix) * ld_x + ci]), acc);
+      }
+  dw[idx] = acc;
+}
+
+__global__ void f32_cmp_kernel(const float* a, const float* b, size_t n, float* err) {
+  float e = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float d = fabsf(a[i] - b[i]) / (1.f + fabsf(b[i]));
+    if (!(d == d)) d = 1e30f;
+    e = fmaxf(e, d);
+  }
+  e = warp_max(e);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(err), __float_as_int(e));
+}
+
+struct ConvCase { int N, H, W, Cin, Cout, k, pad, in_stride, out_s, act; };
+
+static int r8(int v) { return (v + 7) & ~7; }
+static int r16(int v) { return (v + 15) & ~15; }
+
+static int conv_case(const ConvCase& c, int verbose) {
+  // regular conv geometry when out_s == 1: q is the output position; out_s == 2 emulates one sub-pixel phase
+  const int Hq = (c.in_stride == 2) ? (c.H + 2 * c.pad - c.k) / 2 + 1 : c.H;
+  const int Wq = (c.in_stride == 2) ? (c.W + 2 * c.pad - c.k) / 2 + 1 : c.W;
+  const int Ho = Hq * c.out_s, Wo = Wq * c.out_s;
+  const int ntaps = c.k * c.k;
+  std::vector<int16_t> dy(ntaps), dx(ntaps);
+  for (int i = 0; i < ntaps; ++i) { dy[i] = (int16_t)(i / c.k - c.pad); dx[i] = (int16_t)(i % c.k - c.pad); }
+  const int ld_in = r8(c.Cin), Cblk = cblk_of(c.Cin), nCk = (c.Cin + Cblk - 1) / Cblk;
+  const int Cout_pad = c.Cout > 256 ? ((c.Cout + 255) / 256) * 256 : r16(c.Cout);
+  const int ldw = ntaps * nCk * Cblk, ld_out = r8(c.Cout);
+  const size_t in_n = (size_t)c.N * c.H * c.W * ld_in, w_n = (size_t)Cout_pad * ldw, out_pix = (size_t)c.N * Ho * Wo;
+  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *mask; short *ddy, *ddx;
+  cudaMalloc(&in, in_n * 2); cudaMalloc(&w, w_n * 2); cudaMalloc(&out, out_pix * ld_out * 2);
+  cudaMalloc(&ref, out_pix * c.Cout * 4); cudaMalloc(&bias, c.Cout * 4); cudaMalloc(&err, 4); cudaMalloc(&mask, out_pix * 4);
+  cudaMalloc(&ddy, ntaps * 2); cudaMalloc(&ddx, ntaps * 2);
+  cudaMemcpy(ddy, dy.data(), ntaps * 2, cudaMemcpyHostToDevice); cudaMemcpy(ddx, dx.data(), ntaps * 2, cudaMemcpyHostToDevice);
+  conv_fill_kernel<<<128, 256>>>(in, in_n, 17u, 1.f);
+  conv_fill_kernel<<<128, 256>>>(w, w_n, 99u, 0.25f);
+  std::vector<float> hb(c.Cout);
+  for (int i = 0; i < c.Cout; ++i) hb[i] = 0.05f * (float)(i % 13) - 0.3f;
+  cudaMemcpy(bias, hb.data(), c.Cout * 4, cudaMemcpyHostToDevice);
+  cudaMemset(out, 0, out_pix * ld_out * 2); cudaMemset(ref, 0, out_pix * c.Cout * 4); cudaMemset(err, 0, 4);
+  // mask of output pixels this launch writes (phase (0,0) only when out_s == 2)
+  std::vector<float> hm(out_pix, 0.f);
+  for (int n = 0; n < c.N; ++n) for (int y = 0; y < Hq; ++y) for (int x = 0; x < Wq; ++x)
+    hm[((size_t)n * Ho + y * c.out_s) * Wo + x * c.out_s] = 1.f;
+  cudaMemcpy(mask, hm.data(), out_pix * 4, cudaMemcpyHostToDevice);
+  int rc = jvae_conv_gather_gemm(in, c.N, c.H, c.W, c.Cin, ld_in, w, Cout_pad, ldw, ntaps, dy.data(), dx.data(), c.in_stride, Hq, Wq,
+                                 out, Ho, Wo, c.Cout, ld_out, c.out_s, c.out_s, 0, 0, bias, c.act, nullptr);
+  float h_err = -1.f;
+  if (rc == 0) {
+    const size_t total = (size_t)c.N * Hq * Wq * c.Cout;
+    conv_ref_kernel<<<(unsigned)((total + 255) / 256), 256>>>(in, c.N, c.H, c.W, c.Cin, ld_in, w, ldw, Cblk, nCk, ntaps, ddy, ddx,
+                                                             c.in_stride, Hq, Wq, ref, Ho, Wo, c.Cout, c.out_s, c.out_s, 0, 0, bias, c.act);
+    conv_cmp_kernel<<<128, 256>>>(out, ld_out, ref, c.Cout, out_pix, mask, err);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("[selftest] conv: CUDA error %s\n", cudaGetErrorString(e)); rc = -2; }
+    else cudaMemcpy(&h_err, err, 4, cudaMemcpyDeviceToHost);
+  }
+  const bool ok = rc == 0 && h_err >= 0.f && h_err < 2e-2f;
+  if (verbose || !ok)
+    printf("[selftest] conv N=%d %dx%d Cin=%d Cout=%d k=%d pad=%d in_stride=%d out_s=%d act=%d: rc=%d rel_err=%g %s%s\n", c.N, c.H,
+           c.W, c.Cin, c.Cout, c.k, c.pad, c.in_stride, c.out_s, c.act, rc, h_err, ok ? "OK" : "FAIL", rc ? jvae_last_error() : "");
+  // ---- weight gradient on the same geometry: dY := out (bf16), X := in
+  int fails = ok ? 0 : 1;
+  if (ok && c.out_s == 1) {
+    float *dw, *dwr;
+    const size_t dw_n = (size_t)ntaps * c.Cout * c.Cin;
+    cudaMalloc(&dw, dw_n * 4); cudaMalloc(&dwr, dw_n * 4);
+    cudaMemset(dw, 0, dw_n * 4); cudaMemset(err, 0, 4);
+    conv_fill_kernel<<<128, 256>>>(out, out_pix * ld_out, 5u, 0.5f);
+    rc = jvae_conv_wgrad(out, c.N, Hq, Wq, c.Cout, ld_out, in, c.H, c.W, c.Cin, ld_in, ntaps, dy.data(), dx.data(), c.in_stride, dw,
+                         c.Cout * c.Cin, c.Cin, nullptr);
+    h_err = -1.f;
+    if (rc == 0) {
+      wgrad_ref_kernel<<<(unsigned)((dw_n + 127) / 128), 128>>>(out, c.N, Hq, Wq, c.Cout, ld_out, in, c.H, c.W, c.Cin, ld_in, ntaps,
+                                                               ddy, ddx, c.in_stride, dwr);
+      f32_cmp_kernel<<<64, 256>>>(dw, dwr, dw_n, err);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("[selftest] wgrad: CUDA error %s\n", cudaGetErrorString(e)); rc = -2; }
+      else cudaMemcpy(&h_err, err, 4, cudaMemcpyDeviceToHost);
+    }
+    const bool ok2 = rc == 0 && h_err >= 0.f && h_err < 2e-2f;
+    if (verbose || !ok2)
+      printf("[selftest] wgrad same geometry: rc=%d rel_err=%g %s%s\n", rc, h_err, ok2 ? "OK" : "FAIL", rc ? jvae_last_error() : "");
+    fails += ok2 ? 0 : 1;
+    cudaFree(dw); cudaFree(dwr);
+  }
+  cudaFree(in); cudaFree(w); cudaFree(out); cudaFree(ref); cudaFree(bias); cudaFree(err); cudaFree(mask); cudaFree(ddy); cudaFree(ddx);
+  return fails;
+}
+
+int conv_selftest(int verbose) {
+  const ConvCase cases[] = {
+      {4, 8, 8, 64, 64, 3, 1, 1, 1, 0},     // SW128, NB=2
+      {3, 16, 16, 32, 32, 5, 2, 1, 1, 1},   // SW64, relu
+      {2, 32, 32, 16, 32, 5, 2, 1, 1, 0},   // SW32
+      {5, 32, 32, 3, 64, 3, 1, 1, 1, 0},    // 3 input channels (zero-filled to 16)
+      {2, 32, 32, 32, 3, 5, 2, 1, 1, 0},    // 3 output channels
+      {3, 8, 8, 128, 128, 3, 1, 1, 1, 0},   // two channel chunks
+      {2, 4, 4, 64, 512, 3, 1, 1, 1, 0},    // two output-channel tiles
+      {3, 16, 16, 32, 64, 5, 2, 2, 1, 0},   // stride-2 conv (TMA element strides)
+      {3, 8, 8, 64, 64, 3, 1, 1, 2, 0},     // sub-pixel phase store (output stride 2)
+      {70, 28, 28, 8, 24, 3, 1, 1, 1, 0},   // ragged W, many tiles
+      {2, 1, 1, 64, 64, 1, 0, 1, 1, 0},     // 1x1 spatial
+  };
+  int fails = 0;
+  for (const auto& c : cases) {
+    fails += conv_case(c, verbose);
+    if (fails > 4) { printf("[selftest] conv: too many failures, stopping\n"); break; }
+  }
+  return fails;
+}
 }  // namespace jvae

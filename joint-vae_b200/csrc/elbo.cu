@@ -12,11 +12,11 @@
 // exactly once.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace jvae {
 
 constexpr int ELBO_THREADS = 128;
-constexpr int LG = 4;  // latent draws per CTA
 constexpr float LOG2PI_F = 1.8378770664093453f;
 
 struct ElboArgs {
@@ -45,7 +45,8 @@ struct ElboArgs {
   void* d_logits;
   // workspace
   unsigned int* counters;   // (B)
-  float* dict_norm_var;     // 1 (adjacent to counters, zeroed together)
+  float* dict_norm_var;     // (ceil(K/32)) partial sums written by prior_stats_kernel
+  int nkb;
   float* ws_mse;            // (L,B) sum_d (x_reco - x)^2
   float* dict_mean;         // (K)
   float* logdet;            // (Cp)
@@ -58,9 +59,9 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static WsLayout ws_layout(int B, int L, int K, int Cp) {
   WsLayout w;
   w.counters = 0;
-  w.dnv = (size_t)B * 4;
-  w.zero_bytes = w.dnv + 4;
-  w.mse = align256(w.zero_bytes);
+  w.zero_bytes = (size_t)B * 4;
+  w.dnv = align256(w.zero_bytes);
+  w.mse = w.dnv + align256((size_t)((K + 31) / 32) * 4);
   w.dict_mean = w.mse + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.logdet = w.dict_mean + align256((size_t)K * 4);
   w.total = w.logdet + align256((size_t)Cp * 4);
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) prior_stats_kernel(ElboArgs a, int nkb) {
         part = t2 / (float)a.Cp - dm * dm;
       }
       part = warp_sum(part);
-      if (lane == 0) atomicAdd(a.dict_norm_var, part);
+      if (lane == 0) a.dict_norm_var[blockIdx.x] = part;   // summed by the consumers (nkb <= 64 partials)
     }
   } else {
     const int c = ((int)blockIdx.x - nkb) * 8 + w;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void sq_acc4(float& acc, const float4& x0, const uint
   d = __uint_as_float(r.w) - x0.w; acc = fmaf(d, d, acc);
 }
 
-template <bool XR_BF16>
+template <bool XR_BF16, int LG>
 __device__ __forceinline__ void mse_partial(const ElboArgs& a, int b, int l0, int nl, float (&acc)[LG]) {
   const int D = a.D;
   const float* xb = a.x + (size_t)b * D;
@@ -198,25 +199,40 @@ __device__ __forceinline__ void mse_partial(const ElboArgs& a, int b, int l0, in
 
 // Runs the streaming part for CTA (b, g) and elects the last CTA of sample b.  Returns true in every
 // thread of the elected CTA, after which ws_mse[(l-1)*B + b] is complete for all l.
-template <bool XR_BF16>
+template <bool XR_BF16, int LG>
 __device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g, float* red) {
   __shared__ int s_last;
+  __shared__ float s_part[ELBO_THREADS / 32][LG];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (a.has_xreco) {
     const int l0 = 1 + g * LG;
     const int nl = min(LG, a.L + 1 - l0);
     float acc[LG];
-    mse_partial<XR_BF16>(a, b, l0, nl, acc);
+    mse_partial<XR_BF16, LG>(a, b, l0, nl, acc);
 #pragma unroll
     for (int j = 0; j < LG; ++j) {
-      const float s = block_sum(acc[j], red);
-      if (threadIdx.x == 0 && j < nl) a.ws_mse[(size_t)(l0 - 1 + j) * a.B + b] = s;
+      const float s = warp_sum(acc[j]);
+      if (lane == 0) s_part[wid][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < nl) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < ELBO_THREADS / 32; ++w) s += s_part[w][threadIdx.x];
+      a.ws_mse[(size_t)(l0 - 1 + threadIdx.x) * a.B + b] = s;
     }
   }
-  if (a.G == 1) return true;
+  if (a.G == 1) {
+    __syncthreads();
+    return true;
+  }
+  // last-CTA election: every writer fences its own store, then one thread counts the arrival
+  if (threadIdx.x < LG) __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     const unsigned int old = atomicAdd(&a.counters[b], 1u);
     s_last = (old == (unsigned int)(a.G - 1));
+    if (s_last) a.counters[b] = 0;   // self-cleaning: the workspace is ready for the next launch
   }
   __syncthreads();
   if (!s_last) return false;
@@ -296,12 +312,12 @@ __device__ __forceinline__ void kl_finish(const ElboArgs& a, float dist, float t
 // ================================================================================================
 // TRAIN FORWARD
 // ================================================================================================
-template <bool XR_BF16>
+template <bool XR_BF16, int LG>
 __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a) {
   __shared__ float red[32];
   __shared__ float s_ce[ELBO_THREADS / 32];
-  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
-  if (!stream_and_elect<XR_BF16>(a, b, g, red)) return;
+  const int b = blockIdx.x % a.B, g = blockIdx.x / a.B;   // b fastest: neighbouring CTAs stream neighbouring rows
+  if (!stream_and_elect<XR_BF16, LG>(a, b, g, red)) return;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int K = a.K, C = a.C;
@@ -371,7 +387,11 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a
     if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
     if (a.cross_y && a.has_logits) a.cross_y[b] = cross_y;
     if (a.total) a.total[b] = total;
-    if (a.dzdist && a.conditional) a.dzdist[b] = dzd + __ldcg(a.dict_norm_var);
+    if (a.dzdist && a.conditional) {
+      float dnv = 0.f;
+      for (int i = 0; i < a.nkb; ++i) dnv += __ldcg(&a.dict_norm_var[i]);
+      a.dzdist[b] = dzd + dnv;
+    }
     if (a.finite_flag && (bad_label || !isfinite(total))) atomicExch(a.finite_flag, 0);
   }
 }
@@ -379,9 +399,9 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a
 // ================================================================================================
 // TRAIN BACKWARD  (SURVEY.md §8a backward contract)
 // ================================================================================================
-template <bool XR_BF16>
+template <bool XR_BF16, int LG>
 __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a) {
-  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
+  const int b = blockIdx.x % a.B, g = blockIdx.x / a.B;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float gb = a.g[b];
   const int D = a.D, K = a.K, C = a.C;
@@ -561,13 +581,13 @@ __device__ __forceinline__ int block_first_index(const float* v, int n, float ta
   return r;
 }
 
-template <bool XR_BF16>
+template <bool XR_BF16, int LG>
 __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a) {
   extern __shared__ float sm[];
   __shared__ float red[32];
   __shared__ int red_i[32];
-  const int b = blockIdx.x / a.G, g = blockIdx.x % a.G;
-  if (!stream_and_elect<XR_BF16>(a, b, g, red)) return;
+  const int b = blockIdx.x % a.B, g = blockIdx.x / a.B;
+  if (!stream_and_elect<XR_BF16, LG>(a, b, g, red)) return;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int K = a.K, C = a.C, Cp = a.Cp, L = a.L, B = a.B;
@@ -745,7 +765,11 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
   if (tid == 0) {
     if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
     if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
-    if (a.dzdist && a.conditional) a.dzdist[b] = dzd + __ldcg(a.dict_norm_var);
+    if (a.dzdist && a.conditional) {
+      float dnv = 0.f;
+      for (int i = 0; i < a.nkb; ++i) dnv += __ldcg(&a.dict_norm_var[i]);
+      a.dzdist[b] = dzd + dnv;
+    }
   }
   if (!a.scores && !a.preds) return;
 
@@ -868,11 +892,23 @@ static int check_cfg(const jvae_elbo_cfg* cfg, const char* fn) {
   return JVAE_OK;
 }
 
+// latent draws streamed per CTA (1, 2, 4 or 8); JVAE_ELBO_LG overrides the default for tuning runs
+static int elbo_lg() {
+  static int lg = 0;
+  if (lg == 0) {
+    const char* e = getenv("JVAE_ELBO_LG");
+    int v = e ? atoi(e) : 4;
+    lg = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+  }
+  return lg;
+}
+
 static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   memset(&a, 0, sizeof(a));
   a.B = cfg->B; a.L = cfg->L; a.K = cfg->K; a.C = cfg->C; a.D = cfg->D;
   a.Cp = cfg->conditional ? cfg->C : 1;
-  a.G = cfg->has_xreco ? (cfg->L + LG - 1) / LG : 1;
+  a.nkb = (cfg->K + 31) / 32;
+  a.G = cfg->has_xreco ? (cfg->L + elbo_lg() - 1) / elbo_lg() : 1;
   a.xr_bf16 = cfg->xreco_dtype == JVAE_BF16;
   a.lg_bf16 = cfg->logits_dtype == JVAE_BF16;
   a.var_dim = cfg->var_dim; a.prior_kind = cfg->prior_kind; a.conditional = cfg->conditional;
@@ -889,8 +925,6 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
 }
 
 static int launch_prologue(const ElboArgs& a, cudaStream_t st) {
-  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp);
-  JVAE_CUDA(cudaMemsetAsync(a.counters, 0, w.zero_bytes, st));
   const int nkb = (a.K + 31) / 32;
   const int ncb = (a.Cp + 7) / 8;
   prior_stats_kernel<<<nkb + ncb, 256, 0, st>>>(a, nkb);
@@ -933,8 +967,22 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   rc = launch_prologue(a, st);
   if (rc) return rc;
   const int grid = a.B * a.G;
-  if (a.xr_bf16) elbo_train_fwd_kernel<true><<<grid, ELBO_THREADS, 0, st>>>(a);
-  else elbo_train_fwd_kernel<false><<<grid, ELBO_THREADS, 0, st>>>(a);
+#define JVAE_ELBO_LAUNCH(kern, smem_)                                                              \
+  do {                                                                                           \
+    const int lg_ = elbo_lg();                                                                   \
+    if (a.xr_bf16) {                                                                             \
+      if (lg_ == 1) kern<true, 1><<<grid, ELBO_THREADS, smem_, st>>>(a);                         \
+      else if (lg_ == 2) kern<true, 2><<<grid, ELBO_THREADS, smem_, st>>>(a);                    \
+      else if (lg_ == 4) kern<true, 4><<<grid, ELBO_THREADS, smem_, st>>>(a);                    \
+      else kern<true, 8><<<grid, ELBO_THREADS, smem_, st>>>(a);                                  \
+    } else {                                                                                     \
+      if (lg_ == 1) kern<false, 1><<<grid, ELBO_THREADS, smem_, st>>>(a);                        \
+      else if (lg_ == 2) kern<false, 2><<<grid, ELBO_THREADS, smem_, st>>>(a);                   \
+      else if (lg_ == 4) kern<false, 4><<<grid, ELBO_THREADS, smem_, st>>>(a);                   \
+      else kern<false, 8><<<grid, ELBO_THREADS, smem_, st>>>(a);                                 \
+    }                                                                                            \
+  } while (0)
+  JVAE_ELBO_LAUNCH(elbo_train_fwd_kernel, 0);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }
@@ -974,8 +1022,7 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
   if (d_inv_trans)
     JVAE_CUDA(cudaMemsetAsync(d_inv_trans, 0, (size_t)a.Cp * (cfg->var_dim == JVAE_VAR_DIAG ? a.K : 1) * 4, st));
   const int grid = a.B * a.G;
-  if (a.xr_bf16) elbo_train_bwd_kernel<true><<<grid, ELBO_THREADS, 0, st>>>(a);
-  else elbo_train_bwd_kernel<false><<<grid, ELBO_THREADS, 0, st>>>(a);
+  JVAE_ELBO_LAUNCH(elbo_train_bwd_kernel, 0);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }
@@ -1010,15 +1057,13 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
   rc = launch_prologue(a, st);
   if (rc) return rc;
   const int grid = a.B * a.G;
-  if (a.xr_bf16) {
-    if (smem > 48 * 1024)
-      JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    elbo_eval_fwd_kernel<true><<<grid, ELBO_THREADS, smem, st>>>(a);
-  } else {
-    if (smem > 48 * 1024)
-      JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    elbo_eval_fwd_kernel<false><<<grid, ELBO_THREADS, smem, st>>>(a);
+  if (smem > 48 * 1024) {
+#define JVAE_EVAL_ATTR(bf, lg) JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<bf, lg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+    JVAE_EVAL_ATTR(true, 1); JVAE_EVAL_ATTR(true, 2); JVAE_EVAL_ATTR(true, 4); JVAE_EVAL_ATTR(true, 8);
+    JVAE_EVAL_ATTR(false, 1); JVAE_EVAL_ATTR(false, 2); JVAE_EVAL_ATTR(false, 4); JVAE_EVAL_ATTR(false, 8);
+#undef JVAE_EVAL_ATTR
   }
+  JVAE_ELBO_LAUNCH(elbo_eval_fwd_kernel, smem);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }

