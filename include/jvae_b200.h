@@ -190,16 +190,46 @@ int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const 
  *   in  (N,H,W,ld_in) bf16, Cin real channels; wmat (Cout_pad, ldw) bf16 with row co = [tap][chunk][Cblk] where
  *   Cblk = 16/32/64 for Cin <= 16 / <= 32 / > 32 and chunk = ceil(Cin/Cblk) (zero padded); Cout_pad a multiple of 16
  *   (of 256 above 256); out (N,Ho,Wo,ld_out) bf16, channels >= Cout up to ld_out are written as zeros.
+ *   stats (2,Cout) f32 or NULL: += per-channel sum and sum of squares of the pre-activation over the positions this
+ *   call writes, taken from the fp32 accumulators (BatchNorm2d batch statistics, conv.py:216-217).
  * jvae_conv_wgrad: dw[t][co][ci] += sum_q dy[n,qy,qx,co] * x[n, qy*in_stride + tap_dy[t], qx*in_stride + tap_dx[t], ci]
  *   (fp32, atomically accumulated: zero dw first); dw strides in elements.
  * ------------------------------------------------------------------------------------------ */
 int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                          const float* bias, int act, void* stream);
+                          const float* bias, int act, float* stats, void* stream);
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layers between the convolutions, NHWC bf16, P = N*H*W pixels (module/vae_layers/conv.py:189-227):
+ * BatchNorm2d (torch semantics: biased variance to normalise, unbiased for running_var, momentum 0.1),
+ * activation backward + bias gradient, MaxPool2d(2), UpsamplingNearest2d(2).
+ * ------------------------------------------------------------------------------------------ */
+/* stats (2,C) += per-channel sum / sum of squares of y (P,C) with leading dimension ld (zero stats first) */
+int jvae_bn_stats(const void* y, size_t P, int C, int ld, float* stats, void* stream);
+/* out = act(gamma * (y - mean) * rstd + beta).  training != 0: mean / biased var from stats (sums over P), writes
+ * save_mean_rstd (2,C), updates running_mean / running_var / num_batches (any may be NULL); training == 0: running stats */
+int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* stats, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches, int training,
+                      int act, void* out, int ld_out, float* save_mean_rstd, void* stream);
+/* backward of act(BN_train(y)) given da = dL/d(out): dy (P,C) bf16, dgamma, dbeta (C) f32 (written, any may be NULL);
+ * sums (2,C) f32 scratch */
+int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
+                const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
+                void* stream);
+/* dy = da * act'(.) expressed with the activation OUTPUT a_out (relu, sigmoid; act none: dy = da, dy may be NULL);
+ * dbias (C) f32 += sum over pixels of dy (NULL = not wanted) */
+int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t P, int C, int act, void* dy, int ld_dy,
+                 float* dbias, void* stream);
+int jvae_maxpool2_fwd(const void* in, int N, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream);
+/* gradient to the first maximum of each window (torch tie rule); `in` is the pooling input */
+int jvae_maxpool2_bwd(const void* in, int N, int H, int W, int C, int ld_in, const void* dout, int ld_dout, void* din, int ld_din,
+                      void* stream);
+/* backward == 0: dst (N,2H,2W,C) = nearest up-sampling of src (N,H,W,C); backward != 0: dst (N,H,W,C) = 2x2 block sums of src */
+int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int backward, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small data-movement / elementwise kernels of the step

@@ -72,6 +72,20 @@ def lib():
             raise NativeError(f'{LIB_PATH} does not export {name}: stale build')
     L.jvae_gemm_bf16.argtypes = [c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, P, c_int, P]
     L.jvae_selftest.argtypes = [c_int]
+    I16P = ctypes.POINTER(ctypes.c_int16)
+    L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
+                                        c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int,
+                                        P, P]
+    L.jvae_conv_wgrad.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, I16P, I16P,
+                                  c_int, P, c_int, c_int, P]
+    L.jvae_bn_stats.argtypes = [P, c_size_t, c_int, c_int, P, P]
+    L.jvae_bn_apply_fwd.argtypes = [P, c_size_t, c_int, c_int, P, P, P, c_float, c_float, P, P, P, c_int, c_int, P, c_int,
+                                    P, P]
+    L.jvae_bn_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, P, P, P, c_int, P, P, c_int, P, P, P]
+    L.jvae_act_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, c_int, P, c_int, P, P]
+    L.jvae_maxpool2_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
+    L.jvae_maxpool2_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
+    L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     if L.jvae_abi_version() != 1:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
@@ -306,6 +320,67 @@ def gemm_bf16(mode, M, N, K, a, lda, b, ldb, *, bias=None, act=0, out_bf16=None,
               col_stats=None, accumulate=False):
     check(lib().jvae_gemm_bf16(mode, M, N, K, ptr2d(a), lda, ptr2d(b), ldb, ptr(bias), act, ptr(out_bf16), ptr(out_f32),
                                ldd if ldd is not None else N, ptr(col_stats), int(accumulate), stream()))
+
+
+def rawptr(t):
+    """device pointer of a tensor the caller has laid out itself (NHWC activations with padded channel strides)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError('libjvae_sm100 works on CUDA tensors only (got a CPU tensor); there is no CPU fallback')
+    return c_void_p(t.data_ptr())
+
+
+def taps_arg(taps):
+    """list of (dy, dx) -> two ctypes int16 arrays"""
+    n = len(taps)
+    A = ctypes.c_int16 * n
+    return A(*[int(t[0]) for t in taps]), A(*[int(t[1]) for t in taps])
+
+
+def conv_gather_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, taps, in_stride, Hq, Wq, out, Ho, Wo, Cout, ld_out,
+                     out_s=(1, 1), out_o=(0, 0), bias=None, act=0, stats=None):
+    """include/jvae_b200.h: jvae_conv_gather_gemm.  taps = (dy_array, dx_array) from taps_arg"""
+    check(lib().jvae_conv_gather_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]), taps[0],
+                                      taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s[0], out_s[1],
+                                      out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), stream()))
+
+
+def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co):
+    check(lib().jvae_conv_wgrad(rawptr(dy), N, Hq, Wq, Cout, ld_dy, rawptr(x), H, W, Cin, ld_x, len(taps[0]), taps[0],
+                                taps[1], in_stride, rawptr(dw), dw_ld_tap, dw_ld_co, stream()))
+
+
+def bn_stats(y, P, C, ld, stats):
+    check(lib().jvae_bn_stats(rawptr(y), P, C, ld, rawptr(stats), stream()))
+
+
+def bn_apply_fwd(y, P, C, ld_y, stats, gamma, beta, eps, momentum, running_mean, running_var, num_batches, training, act,
+                 out, ld_out, save):
+    check(lib().jvae_bn_apply_fwd(rawptr(y), P, C, ld_y, rawptr(stats), rawptr(gamma), rawptr(beta), float(eps),
+                                  float(momentum), rawptr(running_mean), rawptr(running_var), rawptr(num_batches),
+                                  int(training), act, rawptr(out), ld_out, rawptr(save), stream()))
+
+
+def bn_bwd(da, ld_da, y, ld_y, P, C, save, gamma, beta, act, sums, dy, ld_dy, dgamma, dbeta):
+    check(lib().jvae_bn_bwd(rawptr(da), ld_da, rawptr(y), ld_y, P, C, rawptr(save), rawptr(gamma), rawptr(beta), act,
+                            rawptr(sums), rawptr(dy), ld_dy, rawptr(dgamma), rawptr(dbeta), stream()))
+
+
+def act_bwd(da, ld_da, a_out, ld_a, P, C, act, dy, ld_dy, dbias):
+    check(lib().jvae_act_bwd(rawptr(da), ld_da, rawptr(a_out), ld_a, P, C, act, rawptr(dy), ld_dy, rawptr(dbias), stream()))
+
+
+def maxpool2_fwd(inp, N, H, W, C, ld_in, out, ld_out):
+    check(lib().jvae_maxpool2_fwd(rawptr(inp), N, H, W, C, ld_in, rawptr(out), ld_out, stream()))
+
+
+def maxpool2_bwd(inp, N, H, W, C, ld_in, dout, ld_dout, din, ld_din):
+    check(lib().jvae_maxpool2_bwd(rawptr(inp), N, H, W, C, ld_in, rawptr(dout), ld_dout, rawptr(din), ld_din, stream()))
+
+
+def upsample2(src, ld_src, dst, ld_dst, N, H, W, C, backward=False):
+    check(lib().jvae_upsample2(rawptr(src), ld_src, rawptr(dst), ld_dst, N, H, W, C, int(backward), stream()))
 
 
 def selftest(verbose=1):

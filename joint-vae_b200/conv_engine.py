@@ -1,0 +1,522 @@
+"""Native execution of the reference's conv / deconv stacks (module/vae_layers/conv.py:128-244) on libjvae_sm100.so.
+
+A stack (the module list build_de_conv_layers produces: Conv2d | ConvTranspose2d, optional BatchNorm2d, activation,
+MaxPool2d / AvgPool2d, UpsamplingNearest2d) is compiled once into a list of steps and runs as ONE autograd node with a
+hand-written backward.  Activations live in HBM as NHWC bf16 (channel stride padded to a multiple of 8 elements = the
+16-byte granularity TMA needs); weights stay fp32 torch Parameters in the reference's layout (state_dict compatible) and
+are re-packed to the kernels' bf16 [Cout][tap][Cin-chunk] arrangement whenever their version changes.
+
+Every convolution flavour is one or several launches of the same tcgen05 "gather GEMM" (csrc/conv.cu):
+  Conv2d stride 1/2            taps (i-p, j-p), input stride s
+  ConvTranspose2d stride 1     taps (p-i, p-j)
+  ConvTranspose2d stride s>1   s*s sub-pixel phases, each a small stride-1 gather written with output stride s
+  data gradients               the same two forms with the roles of Conv / ConvTranspose exchanged
+  ConvTranspose2d on 1x1 input a plain GEMM (csrc/gemm.cu)
+Weight gradients use csrc/conv.cu's wgrad kernel (MN-major operands straight from the NHWC tensors).
+BatchNorm batch statistics come out of the convolution epilogue (fp32 accumulators); normalisation + activation is one
+streaming pass (csrc/norm.cu), its backward two.
+
+`K` is the kernel backend: `NativeKernels` (ctypes -> CUDA) in the product.  tests/ substitute a torch emulation of the
+same entry points to check the tap tables / weight arrangements on machines without a GPU; the product never does.
+"""
+import torch
+from torch import nn
+
+from . import _native as nat
+
+
+def r8(n):
+    return (n + 7) & ~7
+
+
+def cblk_of(c):
+    return 64 if c > 32 else (32 if c > 16 else 16)
+
+
+def cout_pad_of(c):
+    return ((c + 255) // 256) * 256 if c > 256 else ((c + 15) // 16) * 16
+
+
+_ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0}
+
+
+# ------------------------------------------------------------------------------------------------ kernel backend
+class NativeKernels:
+    """thin adaptor from NHWC tensors to the C ABI (include/jvae_b200.h)"""
+    act_dtype = torch.bfloat16
+
+    @staticmethod
+    def empty(shape, like, dtype=torch.bfloat16):
+        return torch.empty(shape, dtype=dtype, device=like.device)
+
+    @staticmethod
+    def zeros(shape, like, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=like.device)
+
+    @staticmethod
+    def to_nhwc(x, c_pad):
+        return nat.nchw_to_nhwc_bf16(x.float().contiguous(), c_pad)
+
+    @staticmethod
+    def to_nchw(t, C):
+        return nat.nhwc_bf16_to_nchw(t, C)
+
+    @staticmethod
+    def gather(x, Cin, wmat, cout_pad, taps, in_stride, Hq, Wq, out, Cout, out_s, out_o, bias, act, stats):
+        N, H, W, ld_in = x.shape
+        _, Ho, Wo, ld_out = out.shape
+        nat.conv_gather_gemm(x, N, H, W, Cin, ld_in, wmat, cout_pad, wmat.shape[1], taps, in_stride, Hq, Wq, out, Ho, Wo,
+                             Cout, ld_out, out_s, out_o, bias, act, stats)
+
+    @staticmethod
+    def wgrad(g, Cg, x, Cx, taps, in_stride, dw):
+        N, Hq, Wq, ld_g = g.shape
+        _, H, W, ld_x = x.shape
+        nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, Cg * Cx, Cx)
+
+    @staticmethod
+    def gemm(mode, M, N, K, a, b, bias=None, act=0, out_bf16=None, out_f32=None):
+        nat.gemm_bf16(mode, M, N, K, a, a.stride(0), b, b.stride(0), bias=bias, act=act, out_bf16=out_bf16, out_f32=out_f32,
+                      ldd=N)
+
+    bn_stats = staticmethod(nat.bn_stats)
+    bn_apply_fwd = staticmethod(nat.bn_apply_fwd)
+    bn_bwd = staticmethod(nat.bn_bwd)
+    act_bwd = staticmethod(nat.act_bwd)
+    maxpool2_fwd = staticmethod(nat.maxpool2_fwd)
+    maxpool2_bwd = staticmethod(nat.maxpool2_bwd)
+    upsample2 = staticmethod(nat.upsample2)
+    taps_arg = staticmethod(nat.taps_arg)
+
+
+K = NativeKernels
+
+
+# ------------------------------------------------------------------------------------------------ gather-op tables
+def conv_form(k, p, s, Hq, Wq):
+    """out[q] = sum_ij in[q*s + (i-p, j-p)] * G[:, ij, :]   (Conv2d forward, ConvTranspose2d data gradient)"""
+    taps = [(i - p, j - p) for i in range(k) for j in range(k)]
+    return [dict(taps=taps, idx=list(range(k * k)), in_stride=s, Hq=Hq, Wq=Wq, out_s=(1, 1), out_o=(0, 0))]
+
+
+def deconv_form(k, p, s, Ho, Wo):
+    """out[o] = sum over (i, j) with (o + p - i) divisible by s of in[(o + p - (i,j)) / s] * G[:, ij, :]
+    (ConvTranspose2d forward, Conv2d data gradient): one stride-1 gather per sub-pixel phase, no zero insertion."""
+    ops = []
+    for fy in range(s):
+        rows = [i for i in range(k) if (fy + p - i) % s == 0]
+        for fx in range(s):
+            cols = [j for j in range(k) if (fx + p - j) % s == 0]
+            Hq, Wq = (Ho - fy + s - 1) // s, (Wo - fx + s - 1) // s
+            if Hq <= 0 or Wq <= 0:
+                continue
+            if not rows or not cols:
+                raise NotImplementedError('transposed convolution with kernel smaller than its stride')
+            taps = [((fy + p - i) // s, (fx + p - j) // s) for i in rows for j in cols]
+            ops.append(dict(taps=taps, idx=[i * k + j for i in rows for j in cols], in_stride=1, Hq=Hq, Wq=Wq,
+                            out_s=(s, s), out_o=(fy, fx)))
+    return ops
+
+
+def pack_gather_weights(G, idx, cin):
+    """G (Cout, k*k, Cin) fp32 -> bf16 (Cout_pad, T*nCk*Cblk): row co = [tap][chunk][Cblk], zero padded"""
+    Co = G.shape[0]
+    cb = cblk_of(cin)
+    nck = (cin + cb - 1) // cb
+    g = G[:, idx, :]
+    T = g.shape[1]
+    out = torch.zeros((cout_pad_of(Co), T, nck * cb), dtype=torch.bfloat16, device=G.device)
+    out[:Co, :, :cin] = g
+    return out.view(out.shape[0], T * nck * cb)
+
+
+# ------------------------------------------------------------------------------------------------ steps
+class ConvStep:
+    """Conv2d | ConvTranspose2d [+ BatchNorm2d] [+ activation]"""
+
+    def __init__(self, conv, bn, act, in_shape, final_dense):
+        self.conv, self.bn, self.act = conv, bn, act
+        self.transposed = isinstance(conv, nn.ConvTranspose2d)
+        k, p, s = conv.kernel_size[0], conv.padding[0], conv.stride[0]
+        assert conv.kernel_size[0] == conv.kernel_size[1] and conv.padding[0] == conv.padding[1] \
+            and conv.stride[0] == conv.stride[1], 'square kernels / symmetric geometry only'
+        if conv.dilation != (1, 1) or conv.groups != 1:
+            raise NotImplementedError('dilated / grouped convolutions')
+        if k * k > 64:
+            raise NotImplementedError('kernels larger than 8x8')
+        self.k, self.p, self.s = k, p, s
+        Ci, H, W = in_shape
+        self.Ci, self.H, self.W = Ci, H, W
+        self.Co = conv.out_channels
+        if self.transposed:
+            op = conv.output_padding[0]
+            self.Ho, self.Wo = (H - 1) * s - 2 * p + k + op, (W - 1) * s - 2 * p + k + op
+        else:
+            if s > 2:
+                raise NotImplementedError('convolution stride > 2')
+            self.Ho, self.Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        self.out_shape = (self.Co, self.Ho, self.Wo)
+        self.gemm1x1 = (self.transposed and H == 1 and W == 1 and p == 0 and conv.output_padding[0] == 0
+                        and self.Co % 8 == 0)
+        self.final_dense = final_dense
+        self.ld_y = r8(self.Co) if (bn is not None or not final_dense) else self.Co
+        self.ld_a = self.Co if final_dense else r8(self.Co)
+        if self.gemm1x1:
+            self.fwd_ops = self.dgrad_ops = None
+        elif self.transposed:
+            if s > 2:
+                raise NotImplementedError('transposed convolution stride > 2 (weight gradient kernel)')
+            self.fwd_ops = deconv_form(k, p, s, self.Ho, self.Wo)
+            self.dgrad_ops = conv_form(k, p, s, H, W)
+        else:
+            self.fwd_ops = conv_form(k, p, s, self.Ho, self.Wo)
+            self.dgrad_ops = deconv_form(k, p, s, H, W)
+        self.wgrad_taps = [(i - p, j - p) for i in range(k) for j in range(k)]
+        self._packed = None
+        self._ctaps = {}
+
+    def params(self):
+        ps = [self.conv.weight, self.conv.bias]
+        if self.bn is not None:
+            ps += [self.bn.weight, self.bn.bias]
+        return ps
+
+    def _taps(self, key, taps):
+        c = self._ctaps.get(key)
+        if c is None:
+            c = self._ctaps[key] = K.taps_arg(taps)
+        return c
+
+    def _pack(self):
+        """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict)"""
+        w = self.conv.weight
+        key = (w._version, w.device, w.data_ptr())
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        wd = w.detach().float()
+        kk = self.k * self.k
+        d = {}
+        if self.gemm1x1:
+            # Bm[(y, x, co)][ci] = W[ci][co][y][x]
+            d['bm'] = wd.permute(2, 3, 1, 0).reshape(kk * self.Co, self.Ci).to(torch.bfloat16).contiguous()
+            if self.Ci % 8:
+                t = torch.zeros((kk * self.Co, r8(self.Ci)), dtype=torch.bfloat16, device=w.device)
+                t[:, :self.Ci] = d['bm']
+                d['bm'] = t[:, :self.Ci]
+            b = self.conv.bias
+            d['bias'] = b.detach().float().repeat(kk).contiguous() if b is not None else None
+        else:
+            if self.transposed:     # W (Ci, Co, k, k)
+                g_f = wd.permute(1, 2, 3, 0).reshape(self.Co, kk, self.Ci)
+                g_b = wd.permute(0, 2, 3, 1).reshape(self.Ci, kk, self.Co)
+            else:                   # W (Co, Ci, k, k)
+                g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
+                g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
+            d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
+            d['bwd'] = [pack_gather_weights(g_b, op['idx'], self.Co) for op in self.dgrad_ops]
+        self._packed = (key, d)
+        return d
+
+    # ---- forward
+    def forward(self, x, st, training):
+        N = x.shape[0]
+        pk = self._pack()
+        bn = self.bn
+        bn_train = bn is not None and (training or not bn.track_running_stats)
+        bias = self.conv.bias.detach() if self.conv.bias is not None else None
+        fused_act = self.act if bn is None else 0
+        y = K.empty((N, self.Ho, self.Wo, self.ld_y), x)
+        stats = K.zeros((2, self.Co), x) if bn_train else None
+        if self.gemm1x1:
+            kk = self.k * self.k
+            a2 = x.view(N, x.shape[-1])
+            K.gemm(nat.GEMM_NT, N, kk * self.Co, self.Ci, a2, pk['bm'], bias=pk['bias'], act=fused_act,
+                   out_bf16=y.view(N, kk * self.Co))
+            if bn_train:
+                K.bn_stats(y, N * kk, self.Co, self.ld_y, stats)
+        else:
+            for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
+                K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
+                         y, self.Co, op['out_s'], op['out_o'], bias, fused_act, stats)
+        st['x'] = x
+        if bn is None:
+            st['a'] = y
+            return y
+        P = N * self.Ho * self.Wo
+        a = K.empty((N, self.Ho, self.Wo, self.ld_a), x)
+        save = K.empty((2, self.Co), x, torch.float32) if bn_train else None
+        track = bn.track_running_stats and training
+        K.bn_apply_fwd(y, P, self.Co, self.ld_y, stats, bn.weight.detach() if bn.affine else None,
+                       bn.bias.detach() if bn.affine else None, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                       bn.running_mean if track or not bn_train else None, bn.running_var if track or not bn_train else None,
+                       bn.num_batches_tracked if track else None, bn_train, self.act, a, self.ld_a, save)
+        st['y'], st['save'], st['bn_train'] = y, save, bn_train
+        return a
+
+    # ---- backward: da = dL/d(output) NHWC bf16 -> (dx or None, [param grads])
+    def backward(self, da, st, need_dx):
+        x = st['x']
+        N = x.shape[0]
+        P = N * self.Ho * self.Wo
+        bn = self.bn
+        grads = {}
+        if bn is not None:
+            if not st['bn_train']:
+                raise NotImplementedError('backward through BatchNorm in eval mode')
+            y = st['y']
+            dy = K.empty(y.shape, x)
+            sums = K.empty((2, self.Co), x, torch.float32)
+            dg = K.empty((self.Co,), x, torch.float32) if bn.affine else None
+            db = K.empty((self.Co,), x, torch.float32) if bn.affine else None
+            K.bn_bwd(da, da.shape[-1], y, self.ld_y, P, self.Co, st['save'], bn.weight.detach() if bn.affine else None,
+                     bn.bias.detach() if bn.affine else None, self.act, sums, dy, self.ld_y, dg, db)
+            grads['bn_w'], grads['bn_b'] = dg, db
+            # the bias of a convolution followed by train-mode BatchNorm has an exactly zero gradient
+            # (BN subtracts the batch mean); the reference's autograd returns rounding noise here
+            grads['b'] = K.zeros((self.Co,), x) if self.conv.bias is not None else None
+        else:
+            dbias = K.zeros((self.Co,), x) if self.conv.bias is not None else None
+            if self.act == 0 and da.shape[-1] % 8 == 0:
+                dy = da
+                if dbias is not None:
+                    K.act_bwd(da, da.shape[-1], None, 0, P, self.Co, 0, None, 0, dbias)
+            else:
+                a = st['a']
+                dy = K.zeros((N, self.Ho, self.Wo, r8(self.Co)), x, torch.bfloat16) if r8(self.Co) != self.Co \
+                    else K.empty((N, self.Ho, self.Wo, self.Co), x)
+                K.act_bwd(da, da.shape[-1], a, a.shape[-1], P, self.Co, self.act, dy, dy.shape[-1], dbias)
+            grads['b'] = dbias
+        pk = self._pack()
+        kk = self.k * self.k
+        dx = None
+        if self.gemm1x1:
+            dy2 = dy.view(N, kk * self.Co)
+            x2 = x.view(N, x.shape[-1])
+            dbm = K.empty((kk * self.Co, self.Ci), x, torch.float32)
+            K.gemm(nat.GEMM_TN, kk * self.Co, self.Ci, N, dy2, x2, out_f32=dbm)
+            grads['w'] = dbm.view(self.k, self.k, self.Co, self.Ci).permute(3, 2, 0, 1).contiguous()
+            if need_dx:
+                ldx = x.shape[-1]
+                if ldx == self.Ci:
+                    dx = K.empty(x.shape, x)
+                    K.gemm(nat.GEMM_NN, N, self.Ci, kk * self.Co, dy2, pk['bm'], out_bf16=dx.view(N, ldx))
+                else:
+                    tmp = K.empty((N, self.Ci), x, torch.float32)
+                    K.gemm(nat.GEMM_NN, N, self.Ci, kk * self.Co, dy2, pk['bm'], out_f32=tmp)
+                    dx = K.zeros(x.shape, x, torch.bfloat16)
+                    dx.view(N, ldx)[:, :self.Ci] = tmp
+        else:
+            if self.transposed:      # grid tensor = x, gathered tensor = dy   -> dw (T, Ci, Co)
+                dw = K.zeros((kk, self.Ci, self.Co), x)
+                K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw)
+                grads['w'] = dw.permute(1, 2, 0).reshape(self.Ci, self.Co, self.k, self.k)
+            else:                    # grid tensor = dy, gathered tensor = x   -> dw (T, Co, Ci)
+                dw = K.zeros((kk, self.Co, self.Ci), x)
+                K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw)
+                grads['w'] = dw.permute(1, 2, 0).reshape(self.Co, self.Ci, self.k, self.k)
+            if need_dx:
+                dx = K.empty(x.shape, x)
+                for i, (op, wm) in enumerate(zip(self.dgrad_ops, pk['bwd'])):
+                    K.gather(dy, self.Co, wm, wm.shape[0], self._taps(('b', i), op['taps']), op['in_stride'], op['Hq'],
+                             op['Wq'], dx, self.Ci, op['out_s'], op['out_o'], None, 0, None)
+        out = [grads['w'], grads['b']]
+        if bn is not None:
+            out += [grads['bn_w'], grads['bn_b']]
+        return dx, out
+
+
+class PoolStep:
+    """MaxPool2d(2) (stride 2, no padding)"""
+
+    def __init__(self, mod, in_shape):
+        ks = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
+        stv = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
+        pad = mod.padding if isinstance(mod.padding, int) else mod.padding[0]
+        if ks != 2 or stv != 2 or pad != 0:
+            raise NotImplementedError('only MaxPool2d(2, stride 2, padding 0) has a native kernel')
+        self.C, self.H, self.W = in_shape
+        self.out_shape = (self.C, self.H // 2, self.W // 2)
+
+    def params(self):
+        return []
+
+    def forward(self, x, st, training):
+        N, _, _, ld = x.shape
+        out = K.empty((N, self.H // 2, self.W // 2, ld), x)
+        K.maxpool2_fwd(x, N, self.H, self.W, ld, ld, out, ld)      # padded channels pool to zero as well
+        st['x'] = x
+        return out
+
+    def backward(self, da, st, need_dx):
+        if not need_dx:
+            return None, []
+        x = st['x']
+        N, _, _, ld = x.shape
+        dx = K.empty(x.shape, x)
+        K.maxpool2_bwd(x, N, self.H, self.W, ld, ld, da, da.shape[-1], dx, ld)
+        return dx, []
+
+
+class UpStep:
+    """UpsamplingNearest2d(scale_factor=2)"""
+
+    def __init__(self, mod, in_shape):
+        if int(mod.scale_factor) != 2:
+            raise NotImplementedError('only 2x nearest up-sampling has a native kernel')
+        self.C, self.H, self.W = in_shape
+        self.out_shape = (self.C, 2 * self.H, 2 * self.W)
+
+    def params(self):
+        return []
+
+    def forward(self, x, st, training):
+        N, _, _, ld = x.shape
+        out = K.empty((N, 2 * self.H, 2 * self.W, ld), x)
+        K.upsample2(x, ld, out, ld, N, self.H, self.W, ld, False)
+        st['ld'] = ld
+        return out
+
+    def backward(self, da, st, need_dx):
+        if not need_dx:
+            return None, []
+        N = da.shape[0]
+        ld = st['ld']
+        dx = K.empty((N, self.H, self.W, ld), da)
+        K.upsample2(da, da.shape[-1], dx, ld, N, self.H, self.W, ld, True)
+        return dx, []
+
+
+# ------------------------------------------------------------------------------------------------ the stack
+class ConvStack:
+    def __init__(self, mods, in_shape, image_out):
+        self.in_shape = tuple(in_shape)
+        self.image_out = image_out
+        steps, shape = [], tuple(in_shape)
+        i, n = 0, len(mods)
+        groups = []
+        while i < n:
+            m = mods[i]
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                bn, act = None, 0
+                j = i + 1
+                if j < n and isinstance(mods[j], nn.BatchNorm2d):
+                    bn = mods[j]
+                    j += 1
+                if j < n and type(mods[j]) in _ACT_CODE:
+                    act = _ACT_CODE[type(mods[j])]
+                    j += 1
+                elif j < n and isinstance(mods[j], (nn.LeakyReLU,)):
+                    raise NotImplementedError('LeakyReLU has no native kernel yet')
+                groups.append(('conv', m, bn, act))
+                i = j
+            elif isinstance(m, nn.MaxPool2d):
+                groups.append(('pool', m))
+                i += 1
+            elif isinstance(m, nn.AvgPool2d):
+                ks = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+                if ks != 1:
+                    raise NotImplementedError('AvgPool2d with kernel > 1 has no native kernel yet')
+                i += 1      # AvgPool2d(1) is the identity (the vgg specs end with it)
+            elif isinstance(m, nn.UpsamplingNearest2d):
+                groups.append(('up', m))
+                i += 1
+            elif isinstance(m, nn.Identity):
+                i += 1
+            else:
+                raise NotImplementedError(f'{type(m).__name__} inside a conv stack')
+        for gi, g in enumerate(groups):
+            last = gi == len(groups) - 1
+            if g[0] == 'conv':
+                stp = ConvStep(g[1], g[2], g[3], shape, final_dense=last and image_out)
+            elif g[0] == 'pool':
+                stp = PoolStep(g[1], shape)
+            else:
+                stp = UpStep(g[1], shape)
+            steps.append(stp)
+            shape = stp.out_shape
+        self.steps = steps
+        self.out_shape = shape
+        self.parameters = [p for s in steps for p in s.params()]
+
+    def forward(self, x, training):
+        """x (N, C, H, W) fp32 / bf16 NCHW -> (output tensor, saved state)"""
+        C, H, W = self.in_shape
+        N = x.shape[0]
+        t = K.to_nhwc(x.reshape(N, C, H, W), r8(C))
+        state = []
+        for s in self.steps:
+            st = {}
+            t = s.forward(t, st, training)
+            state.append(st)
+        Co, Ho, Wo = self.out_shape
+        if self.image_out and t.shape[-1] == Co:
+            out = t.permute(0, 3, 1, 2)          # logical NCHW, channels_last memory, bf16
+        else:
+            out = K.to_nchw(t, Co)               # fp32 NCHW (feature vectors for the encoder)
+        return out, state, t.shape[-1]
+
+    def backward(self, dout, state, ld_last, need_dx):
+        Co, Ho, Wo = self.out_shape
+        N = dout.shape[0]
+        if self.image_out and ld_last == Co:
+            g = dout
+            if g.dtype != K.act_dtype:
+                g = g.to(K.act_dtype)
+            g = g.permute(0, 2, 3, 1)
+            if not g.is_contiguous():
+                g = g.contiguous()
+        else:
+            g = K.to_nhwc(dout, ld_last)
+        grads = []
+        for idx in range(len(self.steps) - 1, -1, -1):
+            s = self.steps[idx]
+            g, pg = s.backward(g, state[idx], need_dx or idx > 0)
+            grads = pg + grads
+            if g is None:
+                break
+        dx = None
+        if need_dx and g is not None:
+            C, H, W = self.in_shape
+            dx = K.to_nchw(g, C)
+        return dx, grads
+
+
+class _StackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, stack, training, *params):
+        out, state, ld_last = stack.forward(x.detach(), training)
+        ctx.stack, ctx.state, ctx.ld_last = stack, state, ld_last
+        ctx.in_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        stack = ctx.stack
+        dx, grads = stack.backward(dout, ctx.state, ctx.ld_last, ctx.needs_input_grad[0])
+        ctx.state = None
+        if dx is not None:
+            dx = dx.reshape(ctx.in_shape)
+        out = []
+        for p, g in zip(stack.parameters, grads):
+            out.append(g if (p is not None and g is not None and p.requires_grad) else None)
+        return (dx, None, None) + tuple(out)
+
+
+_stacks = {}
+
+
+def run(mods, x, image_out=False):
+    """Executes the conv-type modules `mods` (a slice of an nn.Sequential) on x (N, C, H, W)."""
+    if not x.is_cuda and K is NativeKernels:
+        raise nat.NativeError('joint-vae_b200 runs on CUDA devices only (there is no CPU fallback); got a CPU tensor')
+    key = (tuple(id(m) for m in mods), tuple(x.shape[1:]), bool(image_out))
+    stack = _stacks.get(key)
+    if stack is None:
+        stack = _stacks[key] = ConvStack(list(mods), tuple(x.shape[1:]), image_out)
+    training = any(m.training for m in mods)
+    params = [p for p in stack.parameters]
+    live = [p if p is not None else torch.empty(0, device=x.device) for p in params]
+    if torch.is_grad_enabled() and (x.requires_grad or any(p is not None and p.requires_grad for p in params)):
+        return _StackFn.apply(x, stack, training, *live)
+    out, _, _ = stack.forward(x.detach(), training)
+    return out

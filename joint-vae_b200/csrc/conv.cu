@@ -35,9 +35,37 @@ struct ConvParams {
   int act;
   const float* bias;
   __nv_bfloat16* out;
+  float* stats;                // (2, Cout) per-channel sum / sum of squares of the pre-activation, += (or null)
+  int cout_pad;                // padded channel count (size of the shared-memory statistics accumulators)
   uint32_t stage_bytes, a_bytes, tx_bytes, tmem_cols;
   int stages;
 };
+
+// Sum of v[j] over the 32 lanes of a warp for 16 values at once (16 shuffles instead of 80): after the call the
+// lane pair (2c, 2c+1) holds the warp total of v[c'] with c' = bit-reversed routing below, returned with its index.
+__device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane, int* channel) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  float w[8], u[4], t[2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = b4 ? v[j] : v[j + 8], keep = b4 ? v[j + 8] : v[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = b3 ? w[j] : w[j + 4], keep = b3 ? w[j + 4] : w[j];
+    u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = b2 ? u[j] : u[j + 2], keep = b2 ? u[j + 2] : u[j];
+    t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  float s = (b1 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, b1 ? t[0] : t[1], 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  *channel = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+  return s;
+}
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
@@ -57,9 +85,12 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
   uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][cout_pad] when p.stats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_per_tile = p.ntaps * p.nCk;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -158,17 +189,36 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
         uint32_t r[16];
         tmem_ld_32x16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (ok && (ch0 + c0 < p.Cout)) {
-          float v[16];
+        if (ch0 + c0 >= p.Cout) continue;       // warp-uniform
+        float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = __uint_as_float(r[j]);
-            const int ch = ch0 + c0 + j;
-            if (p.bias && ch < p.Cout) t += __ldg(&p.bias[ch]);
-            if (p.act == JVAE_ACT_RELU) t = fmaxf(t, 0.f);
-            v[j] = (ch < p.Cout) ? t : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          float t = __uint_as_float(r[j]);
+          const int ch = ch0 + c0 + j;
+          if (p.bias && ch < p.Cout) t += __ldg(&p.bias[ch]);
+          v[j] = (ok && ch < p.Cout) ? t : 0.f;
+        }
+        if (p.stats) {      // batch statistics of the pre-activation (BatchNorm2d in train mode), fp32 accumulators
+          float sq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+          int chn;
+          const float s1 = warp_sum16(v, lane, &chn);
+          const float s2 = warp_sum16(sq, lane, &chn);
+          if ((lane & 1) == 0 && ch0 + c0 + chn < p.Cout) {
+            atomicAdd(&s_stats[ch0 + c0 + chn], s1);
+            atomicAdd(&s_stats[p.cout_pad + ch0 + c0 + chn], s2);
           }
-          if (ch0 + c0 + 16 <= p.ldc) {
+        }
+        if (ok) {
+          if (p.act == JVAE_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == JVAE_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (ch0 + c0 + j < p.Cout) ? 1.f / (1.f + __expf(-v[j])) : 0.f;
+          }
+          if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
             uint4 o0, o1;
             o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
             o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
@@ -183,6 +233,15 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+      const int t = threadIdx.x - 64;
+      for (int i = t; i < 2 * p.cout_pad; i += 128) {
+        const int ch = i % p.cout_pad;
+        const float val = s_stats[i];
+        if (ch < p.Cout && val != 0.f) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
+      }
     }
   }
   tc_fence_before();
@@ -199,8 +258,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 struct WgradParams {
   int N, Hq, Wq, TW, TH, NB, tiles_x, tiles_y, tiles_n, num_tiles;
   int Cblk_y, Cblk_x;          // channel block of dY (M side, 64 max) and X (N side)
-  int cy0, cx0;                // channel offsets of this launch's blocks in dY / X
-  int M_real, N_real;          // channels actually accumulated (rest is padding)
+  int Cy, Cx, ncx;             // channels of dY / X; blockIdx.z = (dY block) * ncx + (X block)
   int ntaps, tap0, taps_per_cta, in_stride;
   short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
   float* dw;                   // (ntaps_total, Cout, Cin) fp32, accumulated atomically
@@ -221,6 +279,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap_lo = p.tap0 + blockIdx.y * p.taps_per_cta;
   const int ntap = min(p.taps_per_cta, p.ntaps - tap_lo);
+  const int cy0 = ((int)blockIdx.z / p.ncx) * p.Cblk_y, cx0 = ((int)blockIdx.z % p.ncx) * p.Cblk_x;
+  const int M_real = min(p.Cblk_y, p.Cy - cy0), N_real = min(p.Cblk_x, p.Cx - cx0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_dy);
@@ -255,8 +315,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
-          tma_load_4d(sa, &tmap_dy, &full_bar[s], p.cy0, tx * p.TW, ty * p.TH, n0);
-          tma_load_4d(sa + p.a_bytes, &tmap_x, &full_bar[s], p.cx0, tx * p.TW * p.in_stride + p.dx[tap_lo + t],
+          tma_load_4d(sa, &tmap_dy, &full_bar[s], cy0, tx * p.TW, ty * p.TH, n0);
+          tma_load_4d(sa + p.a_bytes, &tmap_x, &full_bar[s], cx0, tx * p.TW * p.in_stride + p.dx[tap_lo + t],
                       ty * p.TH * p.in_stride + p.dy[tap_lo + t], n0);
         }
       }
@@ -305,11 +365,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.Cblk_x + c0), r);
         tmem_ld_wait();
         const int row = q * 16 + lane;     // valid for lane < 16
-        if (lane < 16 && row < p.M_real) {
-          float* o = p.dw + (size_t)(tap_lo + t) * p.dw_ld_tap + (size_t)(p.cy0 + row) * p.dw_ld_co + p.cx0 + c0;
+        if (lane < 16 && row < M_real) {
+          float* o = p.dw + (size_t)(tap_lo + t) * p.dw_ld_tap + (size_t)(cy0 + row) * p.dw_ld_co + cx0 + c0;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.N_real) atomicAdd(o + j, __uint_as_float(r[j]));
+            if (c0 + j < N_real) atomicAdd(o + j, __uint_as_float(r[j]));
         }
       }
     }
@@ -351,11 +411,13 @@ extern "C" {
 int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                          const float* bias, int act, void* stream) {
+                          const float* bias, int act, float* stats, void* stream) {
   JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
   JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
-  JVAE_CHECK_ARG((ld_in % 8) == 0 && (ldw % 8) == 0 && (ld_out % 8) == 0, "channel strides must be multiples of 8");
-  JVAE_CHECK_ARG((Cout_pad % 16) == 0 && Cout_pad >= 16, "Cout_pad must be a multiple of 16");
+  JVAE_CHECK_ARG((ld_in % 8) == 0 && (ldw % 8) == 0, "input / weight channel strides must be multiples of 8");
+  JVAE_CHECK_ARG(ld_out >= Cout, "ld_out < Cout");
+  JVAE_CHECK_ARG((Cout_pad % 16) == 0 && Cout_pad >= 16 && Cout_pad >= Cout, "Cout_pad must be a multiple of 16, >= Cout");
+  JVAE_CHECK_ARG(!stats || Cout_pad <= 2048, "statistics epilogue supports up to 2048 channels");
   JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
   JVAE_CHECK_ARG((((uintptr_t)in | (uintptr_t)wmat | (uintptr_t)out) & 15) == 0, "16-byte alignment");
   ConvParams p;
@@ -372,10 +434,12 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.stats = stats; p.cout_pad = Cout_pad;
+  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 4u : 0u;
   p.a_bytes = 128u * p.Cblk * 2u;
   p.tx_bytes = p.a_bytes + (uint32_t)p.BN * p.Cblk * 2u;      // bytes the two TMA boxes deliver per stage
   p.stage_bytes = (p.tx_bytes + 1023u) & ~1023u;
-  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  p.stages = (int)((200u * 1024u - stats_bytes) / p.stage_bytes);
   if (p.stages > 12) p.stages = 12;
   JVAE_CHECK_ARG(p.stages >= 2, "tile too large for shared memory");
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.BN < 32 ? 32 : 2 * p.BN);
@@ -391,7 +455,7 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
     rc = make_tmap_bf16(&tw, wmat, 2, dims, strides, box, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + stats_bytes + 1024;
   static bool attr = false;
   if (!attr) {
     JVAE_CUDA(cudaFuncSetAttribute(conv_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -439,24 +503,21 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
     attr = true;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + 1024;
-  int gx = sm_count() / tap_groups;
+  // grid: x = slices of the pixel tiles, y = tap groups, z = (64-wide dY channel block) x (X channel block)
+  const int ncy = (Cout + p.Cblk_y - 1) / p.Cblk_y;
+  p.ncx = (Cin + p.Cblk_x - 1) / p.Cblk_x;
+  p.Cy = Cout; p.Cx = Cin;
+  const int nz = ncy * p.ncx;
+  JVAE_CHECK_ARG(nz <= 65535, "too many channel blocks");
+  int gx = (2 * sm_count() + tap_groups * nz - 1) / (tap_groups * nz);
   if (gx < 1) gx = 1;
   if (gx > p.num_tiles) gx = p.num_tiles;
-  // loop over 64-wide channel blocks of dY (M) and X (N)
-  for (int cy = 0; cy < Cout; cy += p.Cblk_y) {
-    for (int cx = 0; cx < Cin; cx += p.Cblk_x) {
-      WgradParams q = p;
-      q.cy0 = cy; q.cx0 = cx;
-      q.M_real = (Cout - cy < p.Cblk_y) ? Cout - cy : p.Cblk_y;
-      q.N_real = (Cin - cx < p.Cblk_x) ? Cin - cx : p.Cblk_x;
-      int rc = act_tmap(&tdy, dy, N, Hq, Wq, Cout, ld_dy, p.Cblk_y, p.TW, p.TH, p.NB, 1);
-      if (rc) return rc;
-      rc = act_tmap(&tx, x, N, H, W, Cin, ld_x, p.Cblk_x, p.TW, p.TH, p.NB, in_stride);
-      if (rc) return rc;
-      conv_wgrad_kernel<<<dim3(gx, tap_groups), CONV_THREADS, smem, (cudaStream_t)stream>>>(tdy, tx, q);
-      JVAE_LAUNCH_CHECK();
-    }
-  }
+  int rc = act_tmap(&tdy, dy, N, Hq, Wq, Cout, ld_dy, p.Cblk_y, p.TW, p.TH, p.NB, 1);
+  if (rc) return rc;
+  rc = act_tmap(&tx, x, N, H, W, Cin, ld_x, p.Cblk_x, p.TW, p.TH, p.NB, in_stride);
+  if (rc) return rc;
+  conv_wgrad_kernel<<<dim3(gx, tap_groups, nz), CONV_THREADS, smem, (cudaStream_t)stream>>>(tdy, tx, p);
+  JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }
 
@@ -549,6 +610,19 @@ __global__ void f32_cmp_kernel(const float* a, const float* b, size_t n, float* 
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(err), __float_as_int(e));
 }
 
+// per-channel sum / sum of squares of a dense (pixels, C) fp32 tensor restricted to the masked pixels; one thread per channel
+__global__ void stats_ref_kernel(const float* ref, int C, size_t pixels, const float* mask, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (size_t p = 0; p < pixels; ++p) {
+    if (mask && mask[p] == 0.f) continue;
+    const double v = ref[p * C + c];
+    s1 += v; s2 += v * v;
+  }
+  out[c] = (float)s1; out[C + c] = (float)s2;
+}
+
 struct ConvCase { int N, H, W, Cin, Cout, k, pad, in_stride, out_s, act; };
 
 static int r8(int v) { return (v + 7) & ~7; }
@@ -566,7 +640,11 @@ static int conv_case(const ConvCase& c, int verbose) {
   const int Cout_pad = c.Cout > 256 ? ((c.Cout + 255) / 256) * 256 : r16(c.Cout);
   const int ldw = ntaps * nCk * Cblk, ld_out = r8(c.Cout);
   const size_t in_n = (size_t)c.N * c.H * c.W * ld_in, w_n = (size_t)Cout_pad * ldw, out_pix = (size_t)c.N * Ho * Wo;
-  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *mask; short *ddy, *ddx;
+  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *mask, *stats = nullptr, *stats_ref = nullptr; short *ddy, *ddx;
+  if (c.act == 0) {
+    cudaMalloc(&stats, 2 * c.Cout * 4); cudaMalloc(&stats_ref, 2 * c.Cout * 4);
+    cudaMemset(stats, 0, 2 * c.Cout * 4);
+  }
   cudaMalloc(&in, in_n * 2); cudaMalloc(&w, w_n * 2); cudaMalloc(&out, out_pix * ld_out * 2);
   cudaMalloc(&ref, out_pix * c.Cout * 4); cudaMalloc(&bias, c.Cout * 4); cudaMalloc(&err, 4); cudaMalloc(&mask, out_pix * 4);
   cudaMalloc(&ddy, ntaps * 2); cudaMalloc(&ddx, ntaps * 2);
@@ -583,13 +661,17 @@ static int conv_case(const ConvCase& c, int verbose) {
     hm[((size_t)n * Ho + y * c.out_s) * Wo + x * c.out_s] = 1.f;
   cudaMemcpy(mask, hm.data(), out_pix * 4, cudaMemcpyHostToDevice);
   int rc = jvae_conv_gather_gemm(in, c.N, c.H, c.W, c.Cin, ld_in, w, Cout_pad, ldw, ntaps, dy.data(), dx.data(), c.in_stride, Hq, Wq,
-                                 out, Ho, Wo, c.Cout, ld_out, c.out_s, c.out_s, 0, 0, bias, c.act, nullptr);
+                                 out, Ho, Wo, c.Cout, ld_out, c.out_s, c.out_s, 0, 0, bias, c.act, stats, nullptr);
   float h_err = -1.f;
   if (rc == 0) {
     const size_t total = (size_t)c.N * Hq * Wq * c.Cout;
     conv_ref_kernel<<<(unsigned)((total + 255) / 256), 256>>>(in, c.N, c.H, c.W, c.Cin, ld_in, w, ldw, Cblk, nCk, ntaps, ddy, ddx,
                                                              c.in_stride, Hq, Wq, ref, Ho, Wo, c.Cout, c.out_s, c.out_s, 0, 0, bias, c.act);
     conv_cmp_kernel<<<128, 256>>>(out, ld_out, ref, c.Cout, out_pix, mask, err);
+    if (stats) {
+      stats_ref_kernel<<<(c.Cout + 63) / 64, 64>>>(ref, c.Cout, out_pix, mask, stats_ref);
+      f32_cmp_kernel<<<1, 256>>>(stats, stats_ref, 2 * (size_t)c.Cout, err);      // folded into the same error word
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("[selftest] conv: CUDA error %s\n", cudaGetErrorString(e)); rc = -2; }
     else cudaMemcpy(&h_err, err, 4, cudaMemcpyDeviceToHost);
@@ -623,6 +705,7 @@ static int conv_case(const ConvCase& c, int verbose) {
     fails += ok2 ? 0 : 1;
     cudaFree(dw); cudaFree(dwr);
   }
+  if (stats) { cudaFree(stats); cudaFree(stats_ref); }
   cudaFree(in); cudaFree(w); cudaFree(out); cudaFree(ref); cudaFree(bias); cudaFree(err); cudaFree(mask); cudaFree(ddy); cudaFree(ddx);
   return fails;
 }

@@ -1,0 +1,453 @@
+// BatchNorm2d (train / eval), activation backward, bias gradient, 2x2 max pooling and nearest 2x up-sampling on NHWC
+// bf16 activations: the layers that sit between the tcgen05 convolutions of the reference's features / imager stacks
+// (module/vae_layers/conv.py:189-227: Conv -> [BatchNorm2d] -> activation, MaxPool2d / AvgPool2d, UpsamplingNearest2d).
+//
+// All kernels are HBM-bound streaming passes over a (P pixels, C channels) matrix with leading dimension ld.  Thread
+// mapping: a thread owns ONE channel chunk (8 channels = one 16-byte vector when C and every ld are multiples of 8,
+// one channel otherwise) for the whole kernel and walks over pixels, so per-channel parameters live in registers and
+// per-channel reductions need one shared-memory + one global atomic per block.
+#include "common.cuh"
+#include <initializer_list>
+
+namespace jvae {
+
+constexpr int NORM_MAX_THREADS = 256;
+
+template <int V> struct Vec;
+template <> struct Vec<8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct Vec<1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16(v[0]); }
+};
+
+// thread geometry shared by all kernels: nchunk chunks per pixel, blockDim.x = nchunk * pixels_per_block
+struct Geo {
+  int nchunk, ppb, threads, grid;
+};
+static Geo make_geo(size_t P, int C, int V) {
+  Geo g;
+  g.nchunk = C / V;
+  g.ppb = NORM_MAX_THREADS / g.nchunk;
+  if (g.ppb < 1) g.ppb = 1;
+  g.threads = g.nchunk * g.ppb;
+  size_t want = (P + g.ppb - 1) / g.ppb;
+  const size_t cap = (size_t)sm_count() * 8;
+  g.grid = (int)(want < cap ? (want ? want : 1) : cap);
+  return g;
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == JVAE_ACT_RELU) return fmaxf(z, 0.f);
+  if (act == JVAE_ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
+  return z;
+}
+// derivative of the activation expressed with the pre-activation z
+__device__ __forceinline__ float act_grad_z(float z, int act) {
+  if (act == JVAE_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == JVAE_ACT_SIGMOID) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
+  return 1.f;
+}
+
+// per-block reduction of per-thread channel partials: s_acc[(k * C) + channel] += v, then one global atomic per value
+template <int V, int NK>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][V], int chunk, int C, float* s_acc, float* gout) {
+  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], acc[k][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) atomicAdd(&gout[i], s_acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, size_t P, int C, int ld,
+                                                                    int nchunk, int ppb, float* stats) {
+  extern __shared__ float s_acc[];
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  float acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < P; p += (size_t)gridDim.x * ppb) {
+    float v[V];
+    Vec<V>::load(y + p * ld + chunk * V, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
+  }
+  block_channel_reduce<V, 2>(acc, chunk, C, s_acc, stats);
+}
+
+// ------------------------------------------------------------------------------------------------ BN forward
+struct BnFwd {
+  const __nv_bfloat16* y; __nv_bfloat16* out;
+  size_t P; int C, ld_y, ld_out, nchunk, ppb, act, training;
+  const float* stats; const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches; float* save;
+  float eps, momentum;
+};
+
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) bn_apply_fwd_kernel(const BnFwd a) {
+  const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
+  float scale[V], shift[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = chunk * V + j;
+    float mean, rstd;
+    if (a.training) {
+      const float inv = 1.f / (float)a.P;
+      mean = a.stats[c] * inv;
+      const float var = fmaxf(a.stats[a.C + c] * inv - mean * mean, 0.f);
+      rstd = rsqrtf(var + a.eps);
+      if (blockIdx.x == 0 && pl == 0) {
+        a.save[c] = mean; a.save[a.C + c] = rstd;
+        if (a.running_mean) {   // torch: running = (1-m) running + m batch, unbiased variance
+          const float unb = a.P > 1 ? var * (float)a.P / (float)(a.P - 1) : var;
+          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unb;
+        }
+      }
+    } else {
+      mean = a.running_mean[c];
+      rstd = rsqrtf(a.running_var[c] + a.eps);
+    }
+    const float g = a.gamma ? a.gamma[c] : 1.f, b = a.beta ? a.beta[c] : 0.f;
+    scale[j] = g * rstd;
+    shift[j] = b - mean * scale[j];
+  }
+  if (a.training && a.num_batches && blockIdx.x == 0 && threadIdx.x == 0) *a.num_batches += 1;
+  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
+    float v[V];
+    Vec<V>::load(a.y + p * a.ld_y + chunk * V, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], scale[j], shift[j]), a.act);
+    Vec<V>::store(a.out + p * a.ld_out + chunk * V, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+struct BnBwd {
+  const __nv_bfloat16* da; const __nv_bfloat16* y; __nv_bfloat16* dy;
+  size_t P; int C, ld_da, ld_y, ld_dy, nchunk, ppb, act;
+  const float* save; const float* gamma; const float* beta;
+  float* sums;            // (2, C): sum g, sum g * xhat   (zeroed by the caller before the reduce kernel)
+  float* dgamma; float* dbeta;
+};
+
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_reduce_kernel(const BnBwd a) {
+  extern __shared__ float s_acc[];
+  const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
+  float mean[V], rstd[V], scale[V], shift[V], acc[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = chunk * V + j;
+    mean[j] = a.save[c]; rstd[j] = a.save[a.C + c];
+    const float g = a.gamma ? a.gamma[c] : 1.f, b = a.beta ? a.beta[c] : 0.f;
+    scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
+    acc[0][j] = acc[1][j] = 0.f;
+  }
+  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
+    float g[V], y[V];
+    Vec<V>::load(a.da + p * a.ld_da + chunk * V, g);
+    Vec<V>::load(a.y + p * a.ld_y + chunk * V, y);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
+      acc[0][j] += gz;
+      acc[1][j] += gz * (y[j] - mean[j]) * rstd[j];
+    }
+  }
+  block_channel_reduce<V, 2>(acc, chunk, a.C, s_acc, a.sums);
+}
+
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_apply_kernel(const BnBwd a) {
+  const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
+  float mean[V], rstd[V], scale[V], shift[V], k1[V], k2[V];
+  const float inv = 1.f / (float)a.P;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = chunk * V + j;
+    mean[j] = a.save[c]; rstd[j] = a.save[a.C + c];
+    const float g = a.gamma ? a.gamma[c] : 1.f, b = a.beta ? a.beta[c] : 0.f;
+    scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
+    k1[j] = a.sums[c] * inv; k2[j] = a.sums[a.C + c] * inv;
+    if (blockIdx.x == 0 && pl == 0) {
+      if (a.dbeta) a.dbeta[c] = a.sums[c];
+      if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+    }
+  }
+  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
+    float g[V], y[V];
+    Vec<V>::load(a.da + p * a.ld_da + chunk * V, g);
+    Vec<V>::load(a.y + p * a.ld_y + chunk * V, y);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
+      const float xh = (y[j] - mean[j]) * rstd[j];
+      g[j] = scale[j] * (gz - k1[j] - xh * k2[j]);
+    }
+    Vec<V>::store(a.dy + p * a.ld_dy + chunk * V, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ activation backward + bias gradient
+// dy = da * f'(a) with the derivative expressed through the OUTPUT a of the activation (relu: a > 0, sigmoid: a (1 - a));
+// dbias[c] += sum_p dy[p, c].  act == none: pure channel sum of da (dy may be null).
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int ld_da,
+                                                                   const __nv_bfloat16* __restrict__ aout, int ld_a, size_t P, int C,
+                                                                   int nchunk, int ppb, int act, __nv_bfloat16* dy, int ld_dy,
+                                                                   float* dbias) {
+  extern __shared__ float s_acc[];
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  float acc[1][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[0][j] = 0.f;
+  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < P; p += (size_t)gridDim.x * ppb) {
+    float g[V];
+    Vec<V>::load(da + p * ld_da + chunk * V, g);
+    if (act != JVAE_ACT_NONE) {
+      float o[V];
+      Vec<V>::load(aout + p * ld_a + chunk * V, o);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] *= (act == JVAE_ACT_RELU) ? (o[j] > 0.f ? 1.f : 0.f) : o[j] * (1.f - o[j]);
+    }
+    if (dy) Vec<V>::store(dy + p * ld_dy + chunk * V, g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[0][j] += g[j];
+  }
+  if (dbias) block_channel_reduce<V, 1>(acc, chunk, C, s_acc, dbias);
+}
+
+// ------------------------------------------------------------------------------------------------ pooling / up-sampling
+// 2x2 max pooling, stride 2 (floor): out (N, H/2, W/2, C)
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
+                                                                        __nv_bfloat16* __restrict__ out, int ld_out, size_t Pout,
+                                                                        int nchunk, int ppb) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  const int Ho = H / 2, Wo = W / 2;
+  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < Pout; p += (size_t)gridDim.x * ppb) {
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
+    const size_t n = p / ((size_t)Wo * Ho);
+    const __nv_bfloat16* base = in + ((n * H + 2 * oy) * W + 2 * ox) * ld_in + chunk * V;
+    float m[V], t[V];
+    Vec<V>::load(base, m);
+    Vec<V>::load(base + ld_in, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
+    Vec<V>::load(base + (size_t)W * ld_in, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
+    Vec<V>::load(base + (size_t)(W + 1) * ld_in, t);
+#pragma unroll
+    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
+    Vec<V>::store(out + p * ld_out + chunk * V, m);
+  }
+}
+
+// gradient goes to the FIRST maximum of the window in row-major order (torch's max_pool2d tie rule)
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
+                                                                        const __nv_bfloat16* __restrict__ dout, int ld_dout,
+                                                                        __nv_bfloat16* __restrict__ din, int ld_din, size_t Pout,
+                                                                        int nchunk, int ppb) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  const int Ho = H / 2, Wo = W / 2;
+  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < Pout; p += (size_t)gridDim.x * ppb) {
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
+    const size_t n = p / ((size_t)Wo * Ho);
+    const size_t pix = (n * H + 2 * oy) * W + 2 * ox;
+    const __nv_bfloat16* base = in + pix * ld_in + chunk * V;
+    float a0[V], a1[V], a2[V], a3[V], g[V];
+    Vec<V>::load(base, a0);
+    Vec<V>::load(base + ld_in, a1);
+    Vec<V>::load(base + (size_t)W * ld_in, a2);
+    Vec<V>::load(base + (size_t)(W + 1) * ld_in, a3);
+    Vec<V>::load(dout + p * ld_dout + chunk * V, g);
+    float o0[V], o1[V], o2[V], o3[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float m = fmaxf(fmaxf(a0[j], a1[j]), fmaxf(a2[j], a3[j]));
+      const int w = (a0[j] == m) ? 0 : (a1[j] == m) ? 1 : (a2[j] == m) ? 2 : 3;
+      o0[j] = w == 0 ? g[j] : 0.f; o1[j] = w == 1 ? g[j] : 0.f; o2[j] = w == 2 ? g[j] : 0.f; o3[j] = w == 3 ? g[j] : 0.f;
+    }
+    __nv_bfloat16* d = din + pix * ld_din + chunk * V;
+    Vec<V>::store(d, o0);
+    Vec<V>::store(d + ld_din, o1);
+    Vec<V>::store(d + (size_t)W * ld_din, o2);
+    Vec<V>::store(d + (size_t)(W + 1) * ld_din, o3);
+  }
+}
+
+// nearest-neighbour 2x up-sampling: out (N, 2H, 2W, C); backward sums the 2x2 block
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) upsample2_kernel(const __nv_bfloat16* __restrict__ src, int ld_src,
+                                                                     __nv_bfloat16* __restrict__ dst, int ld_dst, int H, int W,
+                                                                     size_t Pin, int nchunk, int ppb, int backward) {
+  // forward: src = small (N,H,W), dst = large (N,2H,2W).  backward: src = large gradient, dst = small gradient.
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < Pin; p += (size_t)gridDim.x * ppb) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const size_t n = p / ((size_t)W * H);
+    const size_t big = (n * 2 * H + 2 * y) * (size_t)(2 * W) + 2 * x;
+    if (!backward) {
+      float v[V];
+      Vec<V>::load(src + p * ld_src + chunk * V, v);
+      __nv_bfloat16* d = dst + big * ld_dst + chunk * V;
+      Vec<V>::store(d, v);
+      Vec<V>::store(d + ld_dst, v);
+      Vec<V>::store(d + (size_t)2 * W * ld_dst, v);
+      Vec<V>::store(d + (size_t)(2 * W + 1) * ld_dst, v);
+    } else {
+      float v[V], t[V];
+      const __nv_bfloat16* s = src + big * ld_src + chunk * V;
+      Vec<V>::load(s, v);
+      Vec<V>::load(s + ld_src, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += t[j];
+      Vec<V>::load(s + (size_t)2 * W * ld_src, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += t[j];
+      Vec<V>::load(s + (size_t)(2 * W + 1) * ld_src, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += t[j];
+      Vec<V>::store(dst + p * ld_dst + chunk * V, v);
+    }
+  }
+}
+
+static bool vec_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void*> ptrs) {
+  if (C % 8) return false;
+  for (int l : lds) if (l % 8) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  return true;
+}
+
+}  // namespace jvae
+
+using namespace jvae;
+
+#define NORM_DISPATCH(vec, kernel, geo, smem, st, ...)                                             \
+  do {                                                                                             \
+    if (vec) kernel<8><<<geo.grid, geo.threads, smem, st>>>(__VA_ARGS__);                          \
+    else kernel<1><<<geo.grid, geo.threads, smem, st>>>(__VA_ARGS__);                              \
+    JVAE_LAUNCH_CHECK();                                                                           \
+  } while (0)
+
+extern "C" {
+
+int jvae_bn_stats(const void* y, size_t P, int C, int ld, float* stats, void* stream) {
+  JVAE_CHECK_ARG(y && stats && P > 0 && C > 0 && ld >= C, "bad arguments");
+  const bool vec = vec_ok(C, {ld}, {y});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const Geo g = make_geo(P, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, bn_stats_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream,
+                reinterpret_cast<const __nv_bfloat16*>(y), P, C, ld, g.nchunk, g.ppb, stats);
+  return JVAE_OK;
+}
+
+int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* stats, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches, int training,
+                      int act, void* out, int ld_out, float* save_mean_rstd, void* stream) {
+  JVAE_CHECK_ARG(y && out && P > 0 && C > 0 && ld_y >= C && ld_out >= C, "bad arguments");
+  JVAE_CHECK_ARG(training ? (stats && save_mean_rstd) : (running_mean && running_var), "statistics missing");
+  const bool vec = vec_ok(C, {ld_y, ld_out}, {y, out});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const Geo g = make_geo(P, C, vec ? 8 : 1);
+  BnFwd a;
+  a.y = reinterpret_cast<const __nv_bfloat16*>(y); a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.P = P; a.C = C; a.ld_y = ld_y; a.ld_out = ld_out; a.nchunk = g.nchunk; a.ppb = g.ppb; a.act = act; a.training = training;
+  a.stats = stats; a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
+  a.num_batches = reinterpret_cast<long long*>(num_batches); a.save = save_mean_rstd; a.eps = eps; a.momentum = momentum;
+  NORM_DISPATCH(vec, bn_apply_fwd_kernel, g, 0, (cudaStream_t)stream, a);
+  return JVAE_OK;
+}
+
+int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
+                const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
+                void* stream) {
+  JVAE_CHECK_ARG(da && y && dy && sums && save_mean_rstd && P > 0 && C > 0, "bad arguments");
+  JVAE_CHECK_ARG(ld_da >= C && ld_y >= C && ld_dy >= C, "leading dimension < C");
+  const bool vec = vec_ok(C, {ld_da, ld_y, ld_dy}, {da, y, dy});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const Geo g = make_geo(P, C, vec ? 8 : 1);
+  BnBwd a;
+  a.da = reinterpret_cast<const __nv_bfloat16*>(da); a.y = reinterpret_cast<const __nv_bfloat16*>(y);
+  a.dy = reinterpret_cast<__nv_bfloat16*>(dy);
+  a.P = P; a.C = C; a.ld_da = ld_da; a.ld_y = ld_y; a.ld_dy = ld_dy; a.nchunk = g.nchunk; a.ppb = g.ppb; a.act = act;
+  a.save = save_mean_rstd; a.gamma = gamma; a.beta = beta; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
+  JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream));
+  NORM_DISPATCH(vec, bn_bwd_reduce_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream, a);
+  NORM_DISPATCH(vec, bn_bwd_apply_kernel, g, 0, (cudaStream_t)stream, a);
+  return JVAE_OK;
+}
+
+int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t P, int C, int act, void* dy, int ld_dy,
+                 float* dbias, void* stream) {
+  JVAE_CHECK_ARG(da && P > 0 && C > 0 && ld_da >= C, "bad arguments");
+  JVAE_CHECK_ARG(act == JVAE_ACT_NONE || (a_out && ld_a >= C), "activation output missing");
+  JVAE_CHECK_ARG(dy || dbias, "nothing to compute");
+  const bool vec = vec_ok(C, {ld_da, a_out ? ld_a : 8, dy ? ld_dy : 8}, {da, a_out, dy});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const Geo g = make_geo(P, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, act_bwd_kernel, g, C * sizeof(float), (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(da),
+                ld_da, reinterpret_cast<const __nv_bfloat16*>(a_out), ld_a, P, C, g.nchunk, g.ppb, act,
+                reinterpret_cast<__nv_bfloat16*>(dy), ld_dy, dbias);
+  return JVAE_OK;
+}
+
+int jvae_maxpool2_fwd(const void* in, int N, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream) {
+  JVAE_CHECK_ARG(in && out && N > 0 && H >= 2 && W >= 2 && C > 0 && ld_in >= C && ld_out >= C, "bad arguments");
+  const bool vec = vec_ok(C, {ld_in, ld_out}, {in, out});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const size_t Pout = (size_t)N * (H / 2) * (W / 2);
+  const Geo g = make_geo(Pout, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, maxpool2_fwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
+                reinterpret_cast<__nv_bfloat16*>(out), ld_out, Pout, g.nchunk, g.ppb);
+  return JVAE_OK;
+}
+
+int jvae_maxpool2_bwd(const void* in, int N, int H, int W, int C, int ld_in, const void* dout, int ld_dout, void* din, int ld_din,
+                      void* stream) {
+  JVAE_CHECK_ARG(in && dout && din && N > 0 && H >= 2 && W >= 2 && C > 0, "bad arguments");
+  JVAE_CHECK_ARG(ld_in >= C && ld_dout >= C && ld_din >= C, "leading dimension < C");
+  const bool vec = vec_ok(C, {ld_in, ld_dout, ld_din}, {in, dout, din});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  if ((H & 1) || (W & 1))   // rows / columns outside every window get no gradient
+    JVAE_CUDA(cudaMemsetAsync(din, 0, (size_t)N * H * W * ld_din * 2, (cudaStream_t)stream));
+  const size_t Pout = (size_t)N * (H / 2) * (W / 2);
+  const Geo g = make_geo(Pout, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, maxpool2_bwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
+                reinterpret_cast<const __nv_bfloat16*>(dout), ld_dout, reinterpret_cast<__nv_bfloat16*>(din), ld_din, Pout,
+                g.nchunk, g.ppb);
+  return JVAE_OK;
+}
+
+int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int backward, void* stream) {
+  JVAE_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && ld_src >= C && ld_dst >= C, "bad arguments");
+  const bool vec = vec_ok(C, {ld_src, ld_dst}, {src, dst});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const size_t Pin = (size_t)N * H * W;
+  const Geo g = make_geo(Pin, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, upsample2_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
+                reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, H, W, Pin, g.nchunk, g.ppb, backward);
+  return JVAE_OK;
+}
+
+}  // extern "C"

@@ -284,7 +284,7 @@ class ClassificationVariationalNetwork(nn.Module):
         z2 = z.reshape(-1, K)
         if not self.is_vib:
             u = engine.run_sequential(self.decoder, z2)
-            xr = engine.run_sequential(self.imager, u.reshape(-1, *self.imager.input_shape))
+            xr = engine.run_sequential(self.imager, u.reshape(-1, *self.imager.input_shape), image_out=True)
         if self.classifier_type in ('linear', None):
             y_output = self.classifier(z)
         else:   # 'softmax': z.m^T + |m|^2/2 (cvae.py:499)

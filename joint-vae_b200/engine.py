@@ -16,7 +16,7 @@ from . import _native as nat
 
 POLICY = {
     'linear': os.environ.get('JVAE_LINEAR', 'native'),
-    'conv': os.environ.get('JVAE_CONV', 'library'),
+    'conv': os.environ.get('JVAE_CONV', 'native'),
 }
 _rng_offset = itertools.count(1)
 
@@ -119,9 +119,11 @@ _ACT_OF = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Identity: 'linear'}
 _CONV_TYPES = (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d, nn.UpsamplingNearest2d)
 
 
-def run_sequential(seq, x, out_dtype=None):
+def run_sequential(seq, x, out_dtype=None, image_out=False):
     """Executes an nn.Sequential container built by the reference-style constructors.
-    Linear(+ReLU/Sigmoid/Identity) pairs become one fused GEMM; conv-type runs go to run_conv_stack."""
+    Linear(+ReLU/Sigmoid/Identity) pairs become one fused GEMM; conv-type runs go to run_conv_stack.
+    image_out: a conv stack that ends the container returns its result as a channels_last bf16 tensor (the layout the
+    fused ELBO kernel reads) instead of fp32 NCHW."""
     mods = list(seq)
     i = 0
     n = len(mods)
@@ -141,7 +143,7 @@ def run_sequential(seq, x, out_dtype=None):
             j = i
             while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF or isinstance(mods[j], nn.LeakyReLU)):
                 j += 1
-            x = run_conv_stack(mods[i:j], x)
+            x = run_conv_stack(mods[i:j], x, image_out=image_out and j == n)
             i = j - 1
         elif isinstance(m, nn.Dropout):
             x = torch.nn.functional.dropout(x, m.p, seq.training)
@@ -157,12 +159,13 @@ def run_sequential(seq, x, out_dtype=None):
     return x
 
 
-def run_conv_stack(mods, x):
-    """x NCHW.  'library' policy: the layers run as cuDNN / ATen calls in bf16 channels_last (interim path, see
-    DESIGN.md 'what is native'); 'native': the tcgen05 implicit-GEMM kernels of csrc/conv.cu."""
+def run_conv_stack(mods, x, image_out=False):
+    """x NCHW.  'native' (default): the tcgen05 implicit-GEMM kernels of csrc/conv.cu + csrc/norm.cu through
+    conv_engine; 'library': the same layers as cuDNN / ATen calls in bf16 channels_last, kept ONLY as the comparison
+    arm of bench.py --conv library and for layer types without a native kernel (never selected silently)."""
     if POLICY['conv'] == 'native':
         from . import conv_engine
-        return conv_engine.run(mods, x)
+        return conv_engine.run(mods, x, image_out=image_out)
     with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
         x = x.contiguous(memory_format=torch.channels_last)
         for m in mods:

@@ -1,0 +1,122 @@
+"""Host logic of the native convolution path (joint-vae_b200/conv_engine.py) without a GPU: the stack compiler, tap
+tables, sub-pixel phases of strided transposed convolutions, weight arrangements, BatchNorm forward / backward algebra
+and layouts are driven through tests/emu_kernels.py (a torch emulation of the C-ABI entry points, same arguments) and
+compared with torch.nn running the same nn.Sequential in fp32.  The CUDA kernels themselves are checked on the GPU
+(tests/test_gpu_conv.py, jvae_selftest)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from emu_kernels import EmuKernels
+
+
+@pytest.fixture()
+def ce(pkg, monkeypatch):
+    from jointvae_b200 import conv_engine
+    monkeypatch.setattr(conv_engine, 'K', EmuKernels)
+    conv_engine._stacks.clear()
+    return conv_engine
+
+
+def _rel(a, b):
+    a, b = a.detach().float().double(), b.detach().float().double()
+    return float((a - b).norm() / max(1e-9, float(b.norm())))
+
+
+CASES = [
+    # (where, spec, input shape, batch_norm, output_activation)
+    ('input', '[x3-Mx2]8-M-16-16-M-Ax1', (3, 8, 8), True, None),
+    ('input', '[x3-Mx2]8-M-24', (3, 12, 12), False, None),
+    ('input', '[x5+2]8-8:2-16-16:2-20x2+0', (3, 8, 8), True, None),
+    ('input', '16x3+1:2-8x5+2', (5, 9, 9), False, None),            # odd sizes through a stride-2 conv
+    ('output', '[x5+2]16x4+0-16-16:2++1-8-!3x5+2', (12, 1, 1), True, 'linear'),
+    ('output', '[x5+2]16x4+0-8:2++1-!3x5+2', (12, 1, 1), False, 'sigmoid'),
+    ('output', '[x3+1]8-8:2++1-!2x3+1', (6, 3, 3), True, 'sigmoid'),
+    ('output', '[!x3+1-U:2]U-!8-U-!3', (4, 2, 2), True, 'linear'),
+    ('output', '[x4+1]8x4+1:2-!3x3+1', (6, 3, 3), False, 'linear'),  # even kernel, stride 2, no output padding
+]
+
+
+# fp32 storage in the emulation isolates the host logic (only the bf16 weight packing rounds): tight tolerance.
+# bf16 storage is what the kernels do: at these tiny batch sizes BatchNorm backward and max-pool routing amplify the
+# activation rounding (the error shrinks with the number of pixels per channel), so the tolerance is loose.
+@pytest.mark.parametrize('store,tol_f,tol_g', [(torch.float32, 1e-4, 1e-3), (torch.bfloat16, 2e-2, 0.25)])
+@pytest.mark.parametrize('where,spec,shape,bn,out_act', CASES)
+def test_stack_matches_torch(pkg, ce, monkeypatch, where, spec, shape, bn, out_act, store, tol_f, tol_g):
+    monkeypatch.setattr(EmuKernels, 'store', store)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', store)
+    torch.manual_seed(0)
+    build = pkg.module.vae_layers.build_de_conv_layers
+    kw = dict(output_activation=out_act) if where == 'output' else {}
+    seq = build(shape, spec, batch_norm=bn, where=where, **kw)
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+        elif hasattr(m, 'weight'):
+            m.weight.data = m.weight.data.to(torch.bfloat16).float()      # bf16-exact weights: packing does not round
+    ref = copy.deepcopy(seq)
+    seq.train(), ref.train()
+    N = 3
+    x = torch.randn(N, *shape)
+    x = x.to(torch.bfloat16).float()          # the native path stores activations in bf16
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    xin = x.clone().requires_grad_(where == 'output')
+    got = ce.run(list(seq), xin, image_out=(where == 'output'))
+    assert tuple(got.shape) == tuple(want.shape)
+    assert _rel(got, want) < tol_f, _rel(got, want)
+    go = torch.randn_like(want)
+    want.backward(go)
+    if where == 'output':
+        g = go.to(store).contiguous(memory_format=torch.channels_last)
+        assert got.dtype == store and got.is_contiguous(memory_format=torch.channels_last)
+    else:
+        g = go
+    got.backward(g)
+    names = dict(ref.named_parameters())
+    gmax = max(float(p.grad.norm()) for p in names.values())
+    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, k
+        err = float((p.grad.double() - q.grad.double()).norm())
+        assert err <= tol_g * float(q.grad.norm()) + 0.1 * tol_g * gmax, (k, err, float(q.grad.norm()))
+    if where == 'output':
+        assert _rel(xin.grad, xr.grad) < tol_g
+    # BatchNorm running statistics follow torch's update rule
+    for m, r in zip(seq, ref):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            assert _rel(m.running_mean, r.running_mean) < 2e-2 or float((m.running_mean - r.running_mean).abs().max()) < 2e-3
+            assert _rel(m.running_var, r.running_var) < 2e-2
+            assert int(m.num_batches_tracked) == int(r.num_batches_tracked) == 1
+
+
+def test_eval_mode_uses_running_stats(pkg, ce):
+    torch.manual_seed(1)
+    seq = pkg.module.vae_layers.build_de_conv_layers((3, 8, 8), '[x3-Mx2]8-M-16', batch_norm=True, where='input')
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+    seq.eval()
+    x = torch.randn(2, 3, 8, 8).to(torch.bfloat16).float()
+    with torch.no_grad():
+        want = seq(x)
+        got = ce.run(list(seq), x)
+    assert _rel(got, want) < 2e-2
+
+
+def test_phase_tables_cover_every_tap_once(pkg):
+    from jointvae_b200 import conv_engine as c
+    for k, p, s in [(5, 2, 2), (4, 1, 2), (3, 1, 2), (5, 2, 1), (8, 0, 1)]:
+        ops = c.deconv_form(k, p, s, 16, 16)
+        idx = sorted(i for op in ops for i in op['idx'])
+        assert idx == list(range(k * k))
+        assert len(ops) == s * s
+
+
+def test_unsupported_layers_raise(pkg, ce):
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.LeakyReLU())
+    with pytest.raises(NotImplementedError):
+        ce.run(list(seq), torch.randn(1, 3, 4, 4))

@@ -1,0 +1,151 @@
+"""GPU parity of the native convolution path (csrc/conv.cu, csrc/norm.cu through conv_engine) against torch.nn running
+the same layers in fp32 on the same device.  Activations are stored in bf16 between layers, so forward results are
+compared at 2e-2 relative (north_star's bf16 tolerance) and gradients per tensor relative to the tensor's norm."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rel(a, b):
+    a, b = a.detach().float().double(), b.detach().float().double()
+    return float((a - b).norm() / max(1e-9, float(b.norm())))
+
+
+CASES = [
+    # (where, spec, input shape, batch, batch_norm, output_activation)
+    ('input', 'vgg11', (3, 32, 32), 16, True, None),
+    ('input', 'conv32', (3, 32, 32), 32, True, None),
+    ('input', 'conv32', (3, 32, 32), 8, False, None),
+    ('input', '[x3-Mx2]8-M-24-M-40', (3, 28, 28), 5, False, None),
+    ('input', '16x3+1:2-8x5+2', (5, 9, 9), 7, False, None),
+    ('output', 'deconv32', (128, 1, 1), 48, True, 'linear'),
+    ('output', 'deconv32', (64, 1, 1), 8, False, 'sigmoid'),
+    ('output', 'deconv32+', (32, 1, 1), 8, True, 'sigmoid'),
+    ('output', 'ivgg', (16, 2, 2), 6, True, 'linear'),
+    ('output', '[x4+1]8x4+1:2-!3x3+1', (6, 3, 3), 9, False, 'linear'),
+]
+
+
+@pytest.mark.parametrize('where,spec,shape,N,bn,out_act', CASES)
+def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
+    from jointvae_b200 import conv_engine as ce
+    torch.manual_seed(0)
+    kw = dict(output_activation=out_act) if where == 'output' else {}
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=bn, where=where, **kw).to(DEV)
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+        elif hasattr(m, 'weight'):
+            m.weight.data = m.weight.data.to(torch.bfloat16).float()
+    ref = copy.deepcopy(seq)
+    seq.train(), ref.train()
+    x = torch.randn(N, *shape, device=DEV).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    xin = x.clone().requires_grad_(where == 'output')
+    n0 = pkg._native.launch_count()
+    got = ce.run(list(seq), xin, image_out=(where == 'output'))
+    assert pkg._native.launch_count() > n0
+    assert tuple(got.shape) == tuple(want.shape)
+    assert torch.isfinite(got.float()).all()
+    assert _rel(got, want) < 2e-2, _rel(got, want)
+    go = torch.randn_like(want)
+    want.backward(go)
+    g = go.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if where == 'output' else go
+    got.backward(g)
+    gmax = max(float(p.grad.norm()) for p in ref.parameters())
+    worst = 0.0
+    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, k
+        assert torch.isfinite(p.grad).all(), k
+        err = float((p.grad.double() - q.grad.double()).norm())
+        assert err <= 0.12 * float(q.grad.norm()) + 0.01 * gmax, (k, err, float(q.grad.norm()))
+        worst = max(worst, err / max(float(q.grad.norm()), 0.01 * gmax))
+    if where == 'output':
+        assert _rel(xin.grad, xr.grad) < 0.12
+    for m, r in zip(seq, ref):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            assert float((m.running_mean - r.running_mean).abs().max()) < 2e-2 * max(1.0, float(r.running_mean.abs().max()))
+            assert _rel(m.running_var, r.running_var) < 2e-2
+            assert int(m.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize('C,ld', [(32, 32), (64, 64), (512, 512), (3, 8), (200, 200), (24, 24)])
+def test_batchnorm_kernels(pkg, C, ld):
+    """csrc/norm.cu against torch.nn.functional.batch_norm (+ relu) and its autograd"""
+    nat = pkg._native
+    torch.manual_seed(1)
+    P = 3000
+    y = (torch.randn(P, C, device=DEV) * 2 + 0.5).to(torch.bfloat16)
+    buf = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    buf[:, :C] = y
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV) * 0.2
+    stats = torch.zeros(2, C, device=DEV)
+    nat.bn_stats(buf, P, C, ld, stats)
+    yf = y.float()
+    assert _rel(stats[0], yf.sum(0)) < 1e-4 and _rel(stats[1], (yf * yf).sum(0)) < 1e-4
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nb = torch.zeros((), dtype=torch.long, device=DEV)
+    out = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    save = torch.empty(2, C, device=DEV)
+    nat.bn_apply_fwd(buf, P, C, ld, stats, gamma, beta, 1e-5, 0.1, rm, rv, nb, True, 1, out, ld, save)
+    yr = yf.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    want = torch.relu(torch.nn.functional.batch_norm(yr, rm2, rv2, g2, b2, True, 0.1, 1e-5))
+    assert _rel(out[:, :C], want) < 6e-3
+    assert _rel(rm, rm2) < 1e-4 and _rel(rv, rv2) < 1e-4 and int(nb) == 1
+    da = torch.randn(P, C, device=DEV).to(torch.bfloat16)
+    dab = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    dab[:, :C] = da
+    want.backward(da.float())
+    dy = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    sums = torch.empty(2, C, device=DEV)
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    nat.bn_bwd(dab, ld, buf, ld, P, C, save, gamma, beta, 1, sums, dy, ld, dg, db)
+    assert _rel(dy[:, :C], yr.grad) < 1e-2
+    assert _rel(dg, g2.grad) < 1e-3 and _rel(db, b2.grad) < 1e-3
+
+
+@pytest.mark.parametrize('C', [8, 64, 3])
+def test_pool_upsample_act_kernels(pkg, C):
+    nat = pkg._native
+    torch.manual_seed(2)
+    N, H, W = 3, 8, 6
+    ld = (C + 7) // 8 * 8
+    x = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device=DEV)
+    x[..., :C] = torch.randn(N, H, W, C, device=DEV).clamp_min(0)       # relu-like: exact ties at zero
+    out = torch.zeros(N, H // 2, W // 2, ld, dtype=torch.bfloat16, device=DEV)
+    nat.maxpool2_fwd(x, N, H, W, C, ld, out, ld)
+    xr = x[..., :C].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    want = torch.nn.functional.max_pool2d(xr, 2)
+    assert torch.equal(out[..., :C].float().permute(0, 3, 1, 2), want)
+    go = torch.randn_like(want).to(torch.bfloat16)
+    want.backward(go.float())
+    gob = torch.zeros(N, H // 2, W // 2, ld, dtype=torch.bfloat16, device=DEV)
+    gob[..., :C] = go.permute(0, 2, 3, 1)
+    din = torch.zeros_like(x)
+    nat.maxpool2_bwd(x, N, H, W, C, ld, gob, ld, din, ld)
+    assert torch.equal(din[..., :C].float().permute(0, 3, 1, 2), xr.grad)
+    up = torch.zeros(N, 2 * H, 2 * W, ld, dtype=torch.bfloat16, device=DEV)
+    nat.upsample2(x, ld, up, ld, N, H, W, C, False)
+    assert torch.equal(up[..., :C], x[..., :C].repeat_interleave(2, 1).repeat_interleave(2, 2))
+    dn = torch.zeros_like(x)
+    nat.upsample2(up, ld, dn, ld, N, H, W, C, True)
+    assert _rel(dn[..., :C], 4 * x[..., :C].float()) < 1e-2
+    # activation backward + bias gradient
+    P = N * H * W
+    da = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    da[:, :C] = torch.randn(P, C, device=DEV)
+    dy = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
+    dbias = torch.zeros(C, device=DEV)
+    nat.act_bwd(da, ld, x, ld, P, C, 1, dy, ld, dbias)
+    wantd = da[:, :C].float() * (x.view(P, ld)[:, :C] > 0)
+    assert _rel(dy[:, :C], wantd) < 1e-6 or float(wantd.norm()) == 0
+    assert _rel(dbias, wantd.sum(0)) < 1e-3
