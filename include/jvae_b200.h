@@ -224,10 +224,11 @@ int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, in
  * dbias (C) f32 += sum over pixels of dy (NULL = not wanted) */
 int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t P, int C, int act, void* dy, int ld_dy,
                  float* dbias, void* stream);
-int jvae_maxpool2_fwd(const void* in, int N, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream);
+/* MaxPool2d(k, stride >= k, padding 0, floor mode): out (N,(H-k)/stride+1,(W-k)/stride+1,C) */
+int jvae_maxpool_fwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, void* out, int ld_out, void* stream);
 /* gradient to the first maximum of each window (torch tie rule); `in` is the pooling input */
-int jvae_maxpool2_bwd(const void* in, int N, int H, int W, int C, int ld_in, const void* dout, int ld_dout, void* din, int ld_din,
-                      void* stream);
+int jvae_maxpool_bwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, const void* dout, int ld_dout,
+                     void* din, int ld_din, void* stream);
 /* backward == 0: dst (N,2H,2W,C) = nearest up-sampling of src (N,H,W,C); backward != 0: dst (N,H,W,C) = 2x2 block sums of src */
 int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int backward, void* stream);
 
@@ -256,6 +257,9 @@ int jvae_adam_step(float* p, float* m, float* v, const void* grad, int grad_dtyp
 /* self-test of the tensor-core kernels against naive CUDA-core references run on the device;
  * prints a report to stdout, returns the number of failed cases */
 int jvae_selftest(int verbose);
+/* diagnostic: which shifted / strided start addresses K-major swizzled UMMA descriptors accept on this GPU (prints a
+ * table; returns the number of baseline cases that failed) */
+int jvae_probe_descriptors(int verbose);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ def lib():
             raise NativeError(f'{LIB_PATH} does not export {name}: stale build')
     L.jvae_gemm_bf16.argtypes = [c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, P, c_int, P]
     L.jvae_selftest.argtypes = [c_int]
+    L.jvae_probe_descriptors.argtypes = [c_int]
     I16P = ctypes.POINTER(ctypes.c_int16)
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
                                         c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int,
@@ -83,8 +84,8 @@ def lib():
                                     P, P]
     L.jvae_bn_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, P, P, P, c_int, P, P, c_int, P, P, P]
     L.jvae_act_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, c_int, P, c_int, P, P]
-    L.jvae_maxpool2_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
-    L.jvae_maxpool2_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
+    L.jvae_maxpool_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
+    L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     if L.jvae_abi_version() != 1:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
@@ -371,12 +372,13 @@ def act_bwd(da, ld_da, a_out, ld_a, P, C, act, dy, ld_dy, dbias):
     check(lib().jvae_act_bwd(rawptr(da), ld_da, rawptr(a_out), ld_a, P, C, act, rawptr(dy), ld_dy, rawptr(dbias), stream()))
 
 
-def maxpool2_fwd(inp, N, H, W, C, ld_in, out, ld_out):
-    check(lib().jvae_maxpool2_fwd(rawptr(inp), N, H, W, C, ld_in, rawptr(out), ld_out, stream()))
+def maxpool_fwd(inp, N, H, W, C, ld_in, k, stride, out, ld_out):
+    check(lib().jvae_maxpool_fwd(rawptr(inp), N, H, W, C, ld_in, k, stride, rawptr(out), ld_out, stream()))
 
 
-def maxpool2_bwd(inp, N, H, W, C, ld_in, dout, ld_dout, din, ld_din):
-    check(lib().jvae_maxpool2_bwd(rawptr(inp), N, H, W, C, ld_in, rawptr(dout), ld_dout, rawptr(din), ld_din, stream()))
+def maxpool_bwd(inp, N, H, W, C, ld_in, k, stride, dout, ld_dout, din, ld_din):
+    check(lib().jvae_maxpool_bwd(rawptr(inp), N, H, W, C, ld_in, k, stride, rawptr(dout), ld_dout, rawptr(din), ld_din,
+                                 stream()))
 
 
 def upsample2(src, ld_src, dst, ld_dst, N, H, W, C, backward=False):

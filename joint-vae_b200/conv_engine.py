@@ -83,8 +83,8 @@ class NativeKernels:
     bn_apply_fwd = staticmethod(nat.bn_apply_fwd)
     bn_bwd = staticmethod(nat.bn_bwd)
     act_bwd = staticmethod(nat.act_bwd)
-    maxpool2_fwd = staticmethod(nat.maxpool2_fwd)
-    maxpool2_bwd = staticmethod(nat.maxpool2_bwd)
+    maxpool_fwd = staticmethod(nat.maxpool_fwd)
+    maxpool_bwd = staticmethod(nat.maxpool_bwd)
     upsample2 = staticmethod(nat.upsample2)
     taps_arg = staticmethod(nat.taps_arg)
 
@@ -326,24 +326,26 @@ class ConvStep:
 
 
 class PoolStep:
-    """MaxPool2d(2) (stride 2, no padding)"""
+    """MaxPool2d(k, stride >= k, padding 0): non-overlapping windows (what the reference's 'M' tokens build)"""
 
     def __init__(self, mod, in_shape):
         ks = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
         stv = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
         pad = mod.padding if isinstance(mod.padding, int) else mod.padding[0]
-        if ks != 2 or stv != 2 or pad != 0:
-            raise NotImplementedError('only MaxPool2d(2, stride 2, padding 0) has a native kernel')
+        if pad != 0 or stv < ks or mod.ceil_mode or mod.dilation not in (1, (1, 1)):
+            raise NotImplementedError('only non-overlapping, unpadded MaxPool2d has a native kernel')
+        self.k, self.s = ks, stv
         self.C, self.H, self.W = in_shape
-        self.out_shape = (self.C, self.H // 2, self.W // 2)
+        self.Ho, self.Wo = (self.H - ks) // stv + 1, (self.W - ks) // stv + 1
+        self.out_shape = (self.C, self.Ho, self.Wo)
 
     def params(self):
         return []
 
     def forward(self, x, st, training):
         N, _, _, ld = x.shape
-        out = K.empty((N, self.H // 2, self.W // 2, ld), x)
-        K.maxpool2_fwd(x, N, self.H, self.W, ld, ld, out, ld)      # padded channels pool to zero as well
+        out = K.empty((N, self.Ho, self.Wo, ld), x)
+        K.maxpool_fwd(x, N, self.H, self.W, ld, ld, self.k, self.s, out, ld)      # padded channels are pooled as well
         st['x'] = x
         return out
 
@@ -353,7 +355,7 @@ class PoolStep:
         x = st['x']
         N, _, _, ld = x.shape
         dx = K.empty(x.shape, x)
-        K.maxpool2_bwd(x, N, self.H, self.W, ld, ld, da, da.shape[-1], dx, ld)
+        K.maxpool_bwd(x, N, self.H, self.W, ld, ld, self.k, self.s, da, da.shape[-1], dx, ld)
         return dx, []
 
 

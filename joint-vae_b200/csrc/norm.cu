@@ -235,63 +235,61 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) act_bwd_kernel(const __nv_bf
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / up-sampling
-// 2x2 max pooling, stride 2 (floor): out (N, H/2, W/2, C)
+// k x k max pooling with stride s >= k, no padding, floor mode: out (N, (H-k)/s+1, (W-k)/s+1, C)
 template <int V>
-__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
-                                                                        __nv_bfloat16* __restrict__ out, int ld_out, size_t Pout,
-                                                                        int nchunk, int ppb) {
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
+                                                                       __nv_bfloat16* __restrict__ out, int ld_out, int Ho, int Wo,
+                                                                       int k, int s, size_t Pout, int nchunk, int ppb) {
   const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
-  const int Ho = H / 2, Wo = W / 2;
   for (size_t p = (size_t)blockIdx.x * ppb + pl; p < Pout; p += (size_t)gridDim.x * ppb) {
     const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
     const size_t n = p / ((size_t)Wo * Ho);
-    const __nv_bfloat16* base = in + ((n * H + 2 * oy) * W + 2 * ox) * ld_in + chunk * V;
+    const __nv_bfloat16* base = in + ((n * H + (size_t)s * oy) * W + (size_t)s * ox) * ld_in + chunk * V;
     float m[V], t[V];
     Vec<V>::load(base, m);
-    Vec<V>::load(base + ld_in, t);
+    for (int i = 0; i < k; ++i)
+      for (int j = (i == 0 ? 1 : 0); j < k; ++j) {
+        Vec<V>::load(base + ((size_t)i * W + j) * ld_in, t);
 #pragma unroll
-    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
-    Vec<V>::load(base + (size_t)W * ld_in, t);
-#pragma unroll
-    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
-    Vec<V>::load(base + (size_t)(W + 1) * ld_in, t);
-#pragma unroll
-    for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], t[j]);
+        for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], t[e]);
+      }
     Vec<V>::store(out + p * ld_out + chunk * V, m);
   }
 }
 
-// gradient goes to the FIRST maximum of the window in row-major order (torch's max_pool2d tie rule)
+// gradient goes to the FIRST maximum of the window in row-major order (torch's max_pool2d tie rule); windows do not
+// overlap (s >= k), so every input pixel inside a window is written exactly once (pixels outside: caller zero-fills)
 template <int V>
-__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
-                                                                        const __nv_bfloat16* __restrict__ dout, int ld_dout,
-                                                                        __nv_bfloat16* __restrict__ din, int ld_din, size_t Pout,
-                                                                        int nchunk, int ppb) {
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int ld_in,
+                                                                       const __nv_bfloat16* __restrict__ dout, int ld_dout,
+                                                                       __nv_bfloat16* __restrict__ din, int ld_din, int Ho, int Wo,
+                                                                       int k, int s, size_t Pout, int nchunk, int ppb) {
   const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
-  const int Ho = H / 2, Wo = W / 2;
   for (size_t p = (size_t)blockIdx.x * ppb + pl; p < Pout; p += (size_t)gridDim.x * ppb) {
     const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
     const size_t n = p / ((size_t)Wo * Ho);
-    const size_t pix = (n * H + 2 * oy) * W + 2 * ox;
+    const size_t pix = (n * H + (size_t)s * oy) * W + (size_t)s * ox;
     const __nv_bfloat16* base = in + pix * ld_in + chunk * V;
-    float a0[V], a1[V], a2[V], a3[V], g[V];
-    Vec<V>::load(base, a0);
-    Vec<V>::load(base + ld_in, a1);
-    Vec<V>::load(base + (size_t)W * ld_in, a2);
-    Vec<V>::load(base + (size_t)(W + 1) * ld_in, a3);
-    Vec<V>::load(dout + p * ld_dout + chunk * V, g);
-    float o0[V], o1[V], o2[V], o3[V];
+    float m[V], t[V], g[V];
+    int win[V];
+    Vec<V>::load(base, m);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float m = fmaxf(fmaxf(a0[j], a1[j]), fmaxf(a2[j], a3[j]));
-      const int w = (a0[j] == m) ? 0 : (a1[j] == m) ? 1 : (a2[j] == m) ? 2 : 3;
-      o0[j] = w == 0 ? g[j] : 0.f; o1[j] = w == 1 ? g[j] : 0.f; o2[j] = w == 2 ? g[j] : 0.f; o3[j] = w == 3 ? g[j] : 0.f;
-    }
+    for (int e = 0; e < V; ++e) win[e] = 0;
+    for (int i = 0; i < k; ++i)
+      for (int j = (i == 0 ? 1 : 0); j < k; ++j) {
+        Vec<V>::load(base + ((size_t)i * W + j) * ld_in, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (t[e] > m[e]) { m[e] = t[e]; win[e] = i * k + j; }
+      }
+    Vec<V>::load(dout + p * ld_dout + chunk * V, g);
     __nv_bfloat16* d = din + pix * ld_din + chunk * V;
-    Vec<V>::store(d, o0);
-    Vec<V>::store(d + ld_din, o1);
-    Vec<V>::store(d + (size_t)W * ld_din, o2);
-    Vec<V>::store(d + (size_t)(W + 1) * ld_din, o3);
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < k; ++j) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) t[e] = (win[e] == i * k + j) ? g[e] : 0.f;
+        Vec<V>::store(d + ((size_t)i * W + j) * ld_din, t);
+      }
   }
 }
 
@@ -412,30 +410,34 @@ int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t 
   return JVAE_OK;
 }
 
-int jvae_maxpool2_fwd(const void* in, int N, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream) {
-  JVAE_CHECK_ARG(in && out && N > 0 && H >= 2 && W >= 2 && C > 0 && ld_in >= C && ld_out >= C, "bad arguments");
+int jvae_maxpool_fwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, void* out, int ld_out, void* stream) {
+  JVAE_CHECK_ARG(in && out && N > 0 && C > 0 && ld_in >= C && ld_out >= C, "bad arguments");
+  JVAE_CHECK_ARG(k >= 1 && stride >= k && H >= k && W >= k, "window must fit and must not overlap (stride >= kernel)");
   const bool vec = vec_ok(C, {ld_in, ld_out}, {in, out});
   JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
-  const size_t Pout = (size_t)N * (H / 2) * (W / 2);
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  const size_t Pout = (size_t)N * Ho * Wo;
   const Geo g = make_geo(Pout, C, vec ? 8 : 1);
-  NORM_DISPATCH(vec, maxpool2_fwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
-                reinterpret_cast<__nv_bfloat16*>(out), ld_out, Pout, g.nchunk, g.ppb);
+  NORM_DISPATCH(vec, maxpool_fwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
+                reinterpret_cast<__nv_bfloat16*>(out), ld_out, Ho, Wo, k, stride, Pout, g.nchunk, g.ppb);
   return JVAE_OK;
 }
 
-int jvae_maxpool2_bwd(const void* in, int N, int H, int W, int C, int ld_in, const void* dout, int ld_dout, void* din, int ld_din,
-                      void* stream) {
-  JVAE_CHECK_ARG(in && dout && din && N > 0 && H >= 2 && W >= 2 && C > 0, "bad arguments");
+int jvae_maxpool_bwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, const void* dout, int ld_dout,
+                     void* din, int ld_din, void* stream) {
+  JVAE_CHECK_ARG(in && dout && din && N > 0 && C > 0, "bad arguments");
+  JVAE_CHECK_ARG(k >= 1 && stride >= k && H >= k && W >= k, "window must fit and must not overlap (stride >= kernel)");
   JVAE_CHECK_ARG(ld_in >= C && ld_dout >= C && ld_din >= C, "leading dimension < C");
   const bool vec = vec_ok(C, {ld_in, ld_dout, ld_din}, {in, dout, din});
   JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
-  if ((H & 1) || (W & 1))   // rows / columns outside every window get no gradient
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  if (stride > k || (Ho - 1) * stride + k != H || (Wo - 1) * stride + k != W)   // pixels outside every window: no gradient
     JVAE_CUDA(cudaMemsetAsync(din, 0, (size_t)N * H * W * ld_din * 2, (cudaStream_t)stream));
-  const size_t Pout = (size_t)N * (H / 2) * (W / 2);
+  const size_t Pout = (size_t)N * Ho * Wo;
   const Geo g = make_geo(Pout, C, vec ? 8 : 1);
-  NORM_DISPATCH(vec, maxpool2_bwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
-                reinterpret_cast<const __nv_bfloat16*>(dout), ld_dout, reinterpret_cast<__nv_bfloat16*>(din), ld_din, Pout,
-                g.nchunk, g.ppb);
+  NORM_DISPATCH(vec, maxpool_bwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), H, W, ld_in,
+                reinterpret_cast<const __nv_bfloat16*>(dout), ld_dout, reinterpret_cast<__nv_bfloat16*>(din), ld_din, Ho, Wo, k,
+                stride, Pout, g.nchunk, g.ppb);
   return JVAE_OK;
 }
 

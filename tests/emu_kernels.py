@@ -186,17 +186,17 @@ class EmuKernels:
             dbias += g.sum(0)
 
     @classmethod
-    def maxpool2_fwd(cls, x, N, H, W, C, ld_in, out, ld_out):
+    def maxpool_fwd(cls, x, N, H, W, C, ld_in, k, stride, out, ld_out):
         cls.launches += 1
-        v = x.float()[..., :C].permute(0, 3, 1, 2)
-        out[..., :C] = torch.nn.functional.max_pool2d(v, 2).permute(0, 2, 3, 1).to(EmuKernels.store)
+        v = torch.nan_to_num(x.float()[..., :C]).permute(0, 3, 1, 2)
+        out[..., :C] = torch.nn.functional.max_pool2d(v, k, stride).permute(0, 2, 3, 1).to(EmuKernels.store)
 
     @classmethod
-    def maxpool2_bwd(cls, x, N, H, W, C, ld_in, dout, ld_dout, din, ld_din):
+    def maxpool_bwd(cls, x, N, H, W, C, ld_in, k, stride, dout, ld_dout, din, ld_din):
         cls.launches += 1
         with torch.enable_grad():
             v = torch.nan_to_num(x.float()[..., :C]).permute(0, 3, 1, 2).clone().requires_grad_(True)
-            o = torch.nn.functional.max_pool2d(v, 2)
+            o = torch.nn.functional.max_pool2d(v, k, stride)
             o.backward(torch.nan_to_num(dout.float()[..., :C]).permute(0, 3, 1, 2))
         din[..., :C] = v.grad.permute(0, 2, 3, 1).to(EmuKernels.store)
 

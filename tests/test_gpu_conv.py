@@ -43,7 +43,8 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
         elif hasattr(m, 'weight'):
             m.weight.data = m.weight.data.to(torch.bfloat16).float()
     ref = copy.deepcopy(seq)
-    seq.train(), ref.train()
+    lib = copy.deepcopy(seq)          # the same layers through cuDNN in bf16: the noise floor of bf16 activations
+    seq.train(), ref.train(), lib.train()
     x = torch.randn(N, *shape, device=DEV).to(torch.bfloat16).float()
     xr = x.clone().requires_grad_(True)
     want = ref(xr)
@@ -56,18 +57,31 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
     assert _rel(got, want) < 2e-2, _rel(got, want)
     go = torch.randn_like(want)
     want.backward(go)
+    with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
+        lo = lib(x.contiguous(memory_format=torch.channels_last))
+    lo.backward(go.to(lo.dtype))
     g = go.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if where == 'output' else go
     got.backward(g)
     gmax = max(float(p.grad.norm()) for p in ref.parameters())
-    worst = 0.0
-    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+    report = []
+    for (k, p), (_, q), (_, l) in zip(seq.named_parameters(), ref.named_parameters(), lib.named_parameters()):
         assert p.grad is not None, k
         assert torch.isfinite(p.grad).all(), k
         err = float((p.grad.double() - q.grad.double()).norm())
-        assert err <= 0.12 * float(q.grad.norm()) + 0.01 * gmax, (k, err, float(q.grad.norm()))
-        worst = max(worst, err / max(float(q.grad.norm()), 0.01 * gmax))
+        err_lib = float((l.grad.double() - q.grad.double()).norm())
+        report.append((k, round(err, 4), round(err_lib, 4), round(float(q.grad.norm()), 4)))
+    print('grad errors (name, native, cudnn-bf16, |ref|):', report)
+    for k, err, err_lib, nr in report:
+        # within 12 % of the fp32 gradient, or no worse than twice what cuDNN's bf16 path does on the same layers
+        # (BatchNorm over few pixels and max-pool routing amplify bf16 activation rounding)
+        assert err <= max(0.12 * nr + 0.01 * gmax, 2.0 * err_lib), (k, err, err_lib, nr)
     if where == 'output':
-        assert _rel(xin.grad, xr.grad) < 0.12
+        xl = x.clone().requires_grad_(True)
+        lib2 = copy.deepcopy(ref).train()
+        with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
+            lo2 = lib2(xl)
+        lo2.backward(go.to(lo2.dtype))
+        assert _rel(xin.grad, xr.grad) < max(0.12, 2.0 * _rel(xl.grad, xr.grad)), (_rel(xin.grad, xr.grad), _rel(xl.grad, xr.grad))
     for m, r in zip(seq, ref):
         if isinstance(m, torch.nn.BatchNorm2d):
             assert float((m.running_mean - r.running_mean).abs().max()) < 2e-2 * max(1.0, float(r.running_mean.abs().max()))
@@ -121,18 +135,20 @@ def test_pool_upsample_act_kernels(pkg, C):
     ld = (C + 7) // 8 * 8
     x = torch.zeros(N, H, W, ld, dtype=torch.bfloat16, device=DEV)
     x[..., :C] = torch.randn(N, H, W, C, device=DEV).clamp_min(0)       # relu-like: exact ties at zero
-    out = torch.zeros(N, H // 2, W // 2, ld, dtype=torch.bfloat16, device=DEV)
-    nat.maxpool2_fwd(x, N, H, W, C, ld, out, ld)
-    xr = x[..., :C].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    want = torch.nn.functional.max_pool2d(xr, 2)
-    assert torch.equal(out[..., :C].float().permute(0, 3, 1, 2), want)
-    go = torch.randn_like(want).to(torch.bfloat16)
-    want.backward(go.float())
-    gob = torch.zeros(N, H // 2, W // 2, ld, dtype=torch.bfloat16, device=DEV)
-    gob[..., :C] = go.permute(0, 2, 3, 1)
-    din = torch.zeros_like(x)
-    nat.maxpool2_bwd(x, N, H, W, C, ld, gob, ld, din, ld)
-    assert torch.equal(din[..., :C].float().permute(0, 3, 1, 2), xr.grad)
+    for k, s in ((2, 2), (3, 3), (2, 3), (5, 5)):
+        Ho, Wo = (H - k) // s + 1, (W - k) // s + 1
+        out = torch.zeros(N, Ho, Wo, ld, dtype=torch.bfloat16, device=DEV)
+        nat.maxpool_fwd(x, N, H, W, C, ld, k, s, out, ld)
+        xr = x[..., :C].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        want = torch.nn.functional.max_pool2d(xr, k, s)
+        assert torch.equal(out[..., :C].float().permute(0, 3, 1, 2), want)
+        go = torch.randn_like(want).to(torch.bfloat16)
+        want.backward(go.float())
+        gob = torch.zeros(N, Ho, Wo, ld, dtype=torch.bfloat16, device=DEV)
+        gob[..., :C] = go.permute(0, 2, 3, 1)
+        din = torch.full_like(x, 7.0)
+        nat.maxpool_bwd(x, N, H, W, C, ld, k, s, gob, ld, din, ld)
+        assert torch.equal(din[..., :C].float().permute(0, 3, 1, 2), xr.grad), (k, s)
     up = torch.zeros(N, 2 * H, 2 * W, ld, dtype=torch.bfloat16, device=DEV)
     nat.upsample2(x, ld, up, ld, N, H, W, C, False)
     assert torch.equal(up[..., :C], x[..., :C].repeat_interleave(2, 1).repeat_interleave(2, 2))
