@@ -260,6 +260,8 @@ int jvae_selftest(int verbose);
 /* diagnostic: which shifted / strided start addresses K-major swizzled UMMA descriptors accept on this GPU (prints a
  * table; returns the number of baseline cases that failed) */
 int jvae_probe_descriptors(int verbose);
+/* diagnostic: measured cycles per tcgen05.mma for small N and for 1..8 independent accumulators (prints a table) */
+int jvae_probe_mma_rate(void);
 
 #ifdef __cplusplus
 }

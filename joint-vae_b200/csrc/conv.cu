@@ -13,6 +13,7 @@
 // of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 namespace jvae {
 
@@ -115,7 +116,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles_n;
@@ -138,7 +139,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       const uint32_t idesc = make_idesc_bf16(128, p.BN, false, false);
       const uint32_t swz = (p.Cblk == 64) ? SWZ_128B : (p.Cblk == 32 ? SWZ_64B : SWZ_32B);
       const uint32_t sbo = 8u * (uint32_t)p.Cblk * 2u;      // 8 rows of Cblk bf16
@@ -250,6 +251,300 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Halo-tile gather GEMM (input stride 1, one channel chunk): the A operand of EVERY filter tap is read out of ONE
+// TMA-loaded halo box of the NHWC input.  A box is an 8-pixel-wide strip, RT output rows (+ the taps' vertical extent)
+// of NBt consecutive images, stacked in shared memory as "slots" (rows of HWp = 8 + horizontal extent pixels).  An MMA
+// M-tile is 16 consecutive slots x 8 pixels; for tap (dy,dx) its K-major descriptor simply starts (dy*HWp + dx) pixel
+// rows further into the same box (8-row groups one slot = HWp pixel rows apart).  Shifted start addresses and arbitrary
+// group strides are legal for swizzled K-major descriptors with base_offset 0: measured by jvae_probe_descriptors
+// (profiles/r01_umma_descriptor_probe.txt).  Slots between two stacked images compute junk rows that are discarded;
+// in exchange the input is read from L2 ~1.7x instead of 25x (k = 5), and the layer's weights stay resident in shared
+// memory (or stream per tap when they do not fit, amortised over the MT M-tiles of the box).
+// ------------------------------------------------------------------------------------------------
+struct HaloParams {
+  int N, Hq, Wq;
+  int RT, NBt, HHs, HWp, MT;            // rows / images per box, slots per image, halo width (pixels), M-tiles per box
+  int strips_x, blocks_y, blocks_n, num_boxes, n_tiles_n;
+  int Cblk, ntaps, BN;
+  int dymin, dxmin;
+  short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
+  uint32_t tap_off16[CONV_MAX_TAPS];     // ((dy-dymin)*HWp + (dx-dxmin)) * row bytes / 16: descriptor start shift of the tap
+  int Ho, Wo, Cout, ldc, out_sy, out_sx, out_oy, out_ox, act;
+  const float* bias;
+  __nv_bfloat16* out;
+  float* stats;
+  int cout_pad;
+  uint32_t stage_bytes, box_bytes, w_tap_bytes, w_bytes, tmem_cols, acc_stride;
+  int stages, resident, wstages;
+};
+
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// All MMAs of one box: taps outer, (M-tile, k-step) fully unrolled.  Descriptors are (hi, lo) words; only the low word
+// (start address >> 4) moves: + tap_off16[t] per tap, + m_step16 per M-tile, + 2 per k-step.
+template <int KSTEPS, int MT>
+__device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, uint32_t a_hi, uint32_t a_lo0, uint32_t m_step16,
+                                             uint32_t b_hi, uint32_t b_lo_base, uint32_t w_tap16, uint32_t idesc,
+                                             uint64_t* wfull_bar, uint64_t* wempty_bar, uint32_t& ws, uint32_t& wph) {
+  uint32_t b_lo = b_lo_base;
+  for (int t = 0; t < p.ntaps; ++t) {
+    if (!p.resident) {
+      mbar_wait(&wfull_bar[ws], wph);
+      tc_fence_after();
+      b_lo = b_lo_base + ws * w_tap16;
+    }
+    const uint32_t a_lo = a_lo0 + p.tap_off16[t];
+    const uint32_t acc_first = t != 0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        umma_bf16(d0 + (uint32_t)(m * p.BN), desc64(a_hi, a_lo + (uint32_t)m * m_step16 + 2u * k), desc64(b_hi, b_lo + 2u * k), idesc,
+                  k == 0 ? acc_first : 1u);
+    if (p.resident) {
+      b_lo += w_tap16;
+    } else {
+      umma_commit(&wempty_bar[ws]);
+      if (++ws == (uint32_t)p.wstages) { ws = 0; wph ^= 1; }
+    }
+  }
+}
+
+// Epilogue of one M-tile for NCH 16-column chunks (BN = 16 * NCH): bias, activation, bf16 store, and per-THREAD running
+// sums of y and y^2 in registers (reduced across the CTA once, at the end of the kernel).
+template <int NCH>
+__device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t t_addr, bool ok, __nv_bfloat16* orow, int ch0,
+                                                   const float* s_bias, float (&s1)[NCH * 16], float (&s2)[NCH * 16]) {
+  uint32_t r[NCH][16];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) tmem_ld_32x16(t_addr + (uint32_t)(c * 16), r[c]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (ch0 + c * 16 >= p.Cout) continue;      // warp-uniform
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float t = __uint_as_float(r[c][j]) + s_bias[c * 16 + j];
+      v[j] = ok ? t : 0.f;
+    }
+    if (p.stats) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s1[c * 16 + j] += v[j]; s2[c * 16 + j] = fmaf(v[j], v[j], s2[c * 16 + j]); }
+    }
+    if (ok) {
+      if (p.act == JVAE_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == JVAE_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      }
+      const int c0 = c * 16;
+      if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
+        uint4 o0, o1;
+        o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+        o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+        *reinterpret_cast<uint4*>(orow + c0) = o0;
+        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (ch0 + c0 + j < p.ldc) orow[c0 + j] = __float2bfloat16(ch0 + c0 + j < p.Cout ? v[j] : 0.f);
+      }
+    }
+  }
+}
+
+template <int NCH>
+__device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                   float* s_stats, const float* s_bias, int warp, int lane, int nt, int box0,
+                                                   int box_step) {
+  const int q = warp & 3;
+  const int mrow = q * 32 + lane;
+  const int ch0 = nt * p.BN;
+  float s1[NCH * 16], s2[NCH * 16];
+#pragma unroll
+  for (int j = 0; j < NCH * 16; ++j) s1[j] = s2[j] = 0.f;
+  uint32_t it = 0;
+  for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
+    const uint32_t acc = it & 1;
+    int mm = box;
+    const int sx = mm % p.strips_x; mm /= p.strips_x;
+    const int by = mm % p.blocks_y; mm /= p.blocks_y;
+    const int qx = sx * 8 + (mrow & 7);
+    mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+    tc_fence_after();
+    int slot = mrow >> 3;
+    for (int m = 0; m < p.MT; ++m, slot += 16) {
+      const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
+      const int qy = by * p.RT + yy, n = mm * p.NBt + nb;
+      const bool ok = (nb < p.NBt) && (yy < p.RT) && (qy < p.Hq) && (qx < p.Wq) && (n < p.N);
+      const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
+      __nv_bfloat16* orow = p.out + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + (size_t)ch0;
+      const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(m * p.BN) + ((uint32_t)(q * 32) << 16);
+      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, ch0, s_bias, s1, s2);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+  }
+  if (p.stats) {
+    // CTA-level reduction of the per-thread sums: warp butterfly (16 values at a time), then shared + global atomics
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float a[16], b[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { a[j] = s1[c * 16 + j]; b[j] = s2[c * 16 + j]; }
+      int chn;
+      const float t1 = warp_sum16(a, lane, &chn);
+      const float t2 = warp_sum16(b, lane, &chn);
+      if ((lane & 1) == 0 && ch0 + c * 16 + chn < p.Cout) {
+        atomicAdd(&s_stats[ch0 + c * 16 + chn], t1);
+        atomicAdd(&s_stats[p.cout_pad + ch0 + c * 16 + chn], t2);
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < 2 * p.cout_pad; i += 128) {
+      const int ch = i % p.cout_pad;
+      const float val = s_stats[i];
+      if (ch < p.Cout && val != 0.f) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem + (size_t)p.stages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wsm + p.w_bytes);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* wfull_bar = empty_bar + 4;      // [wstages] (resident: only [0])
+  uint64_t* wempty_bar = wfull_bar + 8;
+  uint64_t* tfull_bar = wempty_bar + 8;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);                // [2][cout_pad] when p.stats
+  float* s_bias = s_stats + (p.stats ? 2 * p.cout_pad : 0);                // [BN] bias of this CTA's channel tile (0 if none)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = (int)blockIdx.x % p.n_tiles_n;
+  for (int i = threadIdx.x; i < p.BN; i += CONV_THREADS) {
+    const int ch = nt * p.BN + i;
+    s_bias[i] = (p.bias && ch < p.Cout) ? p.bias[ch] : 0.f;
+  }
+  const int box0 = (int)blockIdx.x / p.n_tiles_n, box_step = (int)gridDim.x / p.n_tiles_n;
+  const uint32_t rb = (uint32_t)p.Cblk * 2u;
+
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
+      if (p.resident) {
+        mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
+        for (int t = 0; t < p.ntaps; ++t)
+          tma_load_2d(wsm + (size_t)t * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
+      }
+      auto load_box = [&](int box, uint32_t it) {
+        int m = box;
+        const int sx = m % p.strips_x; m /= p.strips_x;
+        const int by = m % p.blocks_y; m /= p.blocks_y;
+        const int s = it % p.stages;
+        mbar_wait(&empty_bar[s], ((it / p.stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], p.box_bytes);
+        tma_load_4d(smem + (size_t)s * p.stage_bytes, &tmap_in, &full_bar[s], 0, sx * 8 + p.dxmin, by * p.RT + p.dymin,
+                    m * p.NBt);
+      };
+      uint32_t it = 0, wit = 0;
+      if (box0 < p.num_boxes) load_box(box0, 0);
+      for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
+        if (box + box_step < p.num_boxes) load_box(box + box_step, it + 1);   // one box ahead of the weights
+        if (!p.resident) {
+          for (int t = 0; t < p.ntaps; ++t, ++wit) {
+            const int ws = wit % p.wstages;
+            mbar_wait(&wempty_bar[ws], ((wit / p.wstages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&wfull_bar[ws], p.w_tap_bytes);
+            tma_load_2d(wsm + (size_t)ws * p.w_tap_bytes, &tmap_w, &wfull_bar[ws], t * p.Cblk, nt * p.BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, false, false);
+      const uint32_t swz = (p.Cblk == 64) ? SWZ_128B : (p.Cblk == 32 ? SWZ_64B : SWZ_32B);
+      const uint32_t sbo_a = (uint32_t)p.HWp * rb, sbo_b = 8u * rb;
+      // descriptor words: lo = start >> 4 | LBO(16 B) << 16; hi = SBO >> 4 | version 1 << 14 | swizzle << 29
+      const uint32_t a_hi = ((sbo_a >> 4) & 0x3fffu) | (1u << 14) | (swz << 29);
+      const uint32_t b_hi = ((sbo_b >> 4) & 0x3fffu) | (1u << 14) | (swz << 29);
+      const uint32_t m_step16 = (16u * sbo_a) >> 4, w_tap16 = p.w_tap_bytes >> 4;
+      const int ksteps = p.Cblk >> 4;
+      if (p.resident) { mbar_wait(&wfull_bar[0], 0); tc_fence_after(); }
+      uint32_t it = 0, s = 0, sph = 0, ws = 0, wph = 0;
+      for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&full_bar[s], sph);
+        tc_fence_after();
+        const uint32_t a_lo0 = ((smem_u32(smem + (size_t)s * p.stage_bytes) >> 4) & 0x3fffu) | (1u << 16);
+        const uint32_t d0 = tmem_base + acc * p.acc_stride;
+        const uint32_t b_lo = ((smem_u32(wsm) >> 4) & 0x3fffu) | (1u << 16);
+#define HALO_BOX(KS, M) halo_mma_box<KS, M>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, w_tap16, idesc, wfull_bar, wempty_bar, ws, wph)
+#define HALO_BOX_M(KS)                                                                 \
+        switch (p.MT) {                                                                \
+          case 1: HALO_BOX(KS, 1); break;                                              \
+          case 2: HALO_BOX(KS, 2); break;                                              \
+          case 3: HALO_BOX(KS, 3); break;                                              \
+          case 4: HALO_BOX(KS, 4); break;                                              \
+          default: HALO_BOX(KS, 5); break;                                             \
+        }
+        if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
+#undef HALO_BOX_M
+#undef HALO_BOX
+        umma_commit(&empty_bar[s]);
+        umma_commit(&tfull_bar[acc]);
+        if (++s == (uint32_t)p.stages) { s = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    switch (p.BN >> 4) {
+      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
+      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
+      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
+      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight gradient: dW[tap][co][ci] = sum_q dY[q, co] * X[q*stride + d_tap, ci]
 // Both operands are NHWC tiles whose contiguous dimension (channels) is the M / N dimension of the GEMM and whose
 // rows (pixels) are the reduction: MN-major descriptors on the same TMA boxes the forward kernel uses.
@@ -301,7 +596,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const uint32_t x_bytes = 128u * (uint32_t)p.Cblk_x * 2u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int m = tile;
@@ -322,7 +617,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       // D[M = dY channels (64 rows), N = X channels] += dY^T[M x 128 px] * X[128 px x N]; both MN-major
       const uint32_t idesc = make_idesc_bf16(64, p.Cblk_x, true, true);
       const uint32_t swz_y = (p.Cblk_y == 64) ? SWZ_128B : (p.Cblk_y == 32 ? SWZ_64B : SWZ_32B);
@@ -402,6 +697,91 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
   return make_tmap_bf16(t, base, 4, dims, strides, box, es, Cblk * 2);
 }
 
+// plans and launches the halo kernel; returns 1 if the geometry is not covered (caller falls back to the tap-box kernel)
+static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int Hq, int Wq, void* out, int Ho, int Wo,
+                           int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
+                           float* stats, cudaStream_t stream) {
+  if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  int dymin = 1 << 20, dymax = -(1 << 20), dxmin = 1 << 20, dxmax = -(1 << 20);
+  for (int t = 0; t < ntaps; ++t) {
+    p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t];
+    dymin = min(dymin, (int)tap_dy[t]); dymax = max(dymax, (int)tap_dy[t]);
+    dxmin = min(dxmin, (int)tap_dx[t]); dxmax = max(dxmax, (int)tap_dx[t]);
+  }
+  const int ey = dymax - dymin, ex = dxmax - dxmin;
+  if (ey > 16 || ex > 16) return 1;
+  p.N = N; p.Hq = Hq; p.Wq = Wq; p.dymin = dymin; p.dxmin = dxmin;
+  p.Cblk = cblk_of(Cin); p.ntaps = ntaps; p.BN = Cout_pad; p.n_tiles_n = 1;
+  const uint32_t rb = (uint32_t)p.Cblk * 2u;
+  p.HWp = 8 + ex;
+  p.RT = Hq <= 32 ? Hq : 32;
+  p.HHs = p.RT + ey;
+  for (int t = 0; t < ntaps; ++t)
+    p.tap_off16[t] = ((uint32_t)((tap_dy[t] - dymin) * p.HWp + (tap_dx[t] - dxmin)) * rb) >> 4;
+  p.w_tap_bytes = (uint32_t)p.BN * rb;
+  const uint32_t budget = 200u * 1024u;
+  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 4u : 0u;
+  const uint32_t w_res = (uint32_t)ntaps * p.w_tap_bytes;
+  // best (NBt) for resident and streamed weights
+  double best_eff = 0.0;
+  for (int resident = 1; resident >= 0; --resident) {
+    const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
+    for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
+      const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
+      const uint32_t stage = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
+      if (pow2_ceil(2 * MT * p.BN) > 512) break;
+      if (2u * stage + wb + stats_bytes + 768u > budget) break;
+      if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
+      const double eff = (double)(nbt * p.RT) / (16.0 * MT) * (resident ? 1.0 : 0.97);
+      if (eff > best_eff + 0.02) {
+        best_eff = eff; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.resident = resident; p.w_bytes = wb;
+      }
+    }
+    if (best_eff > 0.0 && resident) break;               // resident weights fit: take them
+  }
+  if (best_eff <= 0.0) return 1;
+  p.wstages = p.resident ? 1 : 4;
+  p.box_bytes = (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
+  p.stages = (int)((budget - p.w_bytes - stats_bytes - 768u) / p.stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 2) return 1;
+  p.acc_stride = (uint32_t)(p.MT * p.BN);
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.MT * p.BN < 32 ? 32 : 2 * p.MT * p.BN);
+  p.strips_x = (Wq + 7) / 8; p.blocks_y = (Hq + p.RT - 1) / p.RT; p.blocks_n = (N + p.NBt - 1) / p.NBt;
+  p.num_boxes = p.strips_x * p.blocks_y * p.blocks_n;
+  p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
+  p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
+  p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
+  CUtensorMap tin, tw;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)ld_in * 2, (uint64_t)W * ld_in * 2, (uint64_t)H * W * ld_in * 2};
+    uint32_t box[4] = {(uint32_t)p.Cblk, (uint32_t)p.HWp, (uint32_t)p.HHs, (uint32_t)p.NBt};
+    int rc = make_tmap_bf16(&tin, in, 4, dims, strides, box, nullptr, p.Cblk * 2);
+    if (rc) return rc;
+    const int Ktot = ntaps * p.Cblk;
+    uint64_t wd[2] = {(uint64_t)Ktot, (uint64_t)Cout_pad};
+    uint64_t ws[1] = {(uint64_t)ldw * 2};
+    uint32_t wbox[2] = {(uint32_t)p.Cblk, (uint32_t)p.BN};
+    if (ldw < Ktot) { set_error("jvae_conv_gather_gemm: weight matrix row shorter than taps*Cblk"); return JVAE_ERR_INVALID; }
+    rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    JVAE_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
+  conv_halo_kernel<<<grid, CONV_THREADS, smem, stream>>>(tin, tw, p);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
 }  // namespace jvae
 
 using namespace jvae;
@@ -420,6 +800,12 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
   JVAE_CHECK_ARG(!stats || Cout_pad <= 2048, "statistics epilogue supports up to 2048 channels");
   JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
   JVAE_CHECK_ARG((((uintptr_t)in | (uintptr_t)wmat | (uintptr_t)out) & 15) == 0, "16-byte alignment");
+  static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
+  if (in_stride == 1 && !force_v1) {
+    const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, Hq, Wq, out, Ho, Wo,
+                                   Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = geometry not covered, use the tap-box kernel
+  }
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.Hq = Hq; p.Wq = Wq;
@@ -723,6 +1109,11 @@ int conv_selftest(int verbose) {
       {3, 8, 8, 64, 64, 3, 1, 1, 2, 0},     // sub-pixel phase store (output stride 2)
       {70, 28, 28, 8, 24, 3, 1, 1, 1, 0},   // ragged W, many tiles
       {2, 1, 1, 64, 64, 1, 0, 1, 1, 0},     // 1x1 spatial
+      {7, 8, 8, 64, 64, 5, 2, 1, 1, 0},     // halo kernel: streamed weights, 3 stacked images per box, ragged batch
+      {5, 16, 16, 64, 32, 5, 2, 1, 1, 0},   // halo kernel: resident weights, one image per box
+      {3, 32, 32, 32, 32, 5, 2, 1, 1, 0},   // halo kernel: two M-tiles per box
+      {2, 40, 40, 8, 16, 3, 1, 1, 1, 0},    // halo kernel: two row blocks per image
+      {9, 8, 8, 64, 64, 3, 1, 1, 2, 0},     // halo kernel: sub-pixel phase store, stacked images
   };
   int fails = 0;
   for (const auto& c : cases) {

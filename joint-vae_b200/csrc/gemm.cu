@@ -74,7 +74,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % S::STAGES;
         const uint32_t ph = (kb / S::STAGES) & 1;
@@ -99,7 +99,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % S::STAGES;

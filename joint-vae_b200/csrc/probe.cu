@@ -124,3 +124,73 @@ int probe_descriptors(int verbose) {
 }  // namespace jvae
 
 extern "C" int jvae_probe_descriptors(int verbose) { return jvae::probe_descriptors(verbose); }
+
+// ------------------------------------------------------------------------------------------------
+// MMA pacing probe: cycles per tcgen05.mma (M=128, K=16, bf16) for N in {16,32,64,128,256}, issued back to back into
+// ONE accumulator versus round-robin over several accumulators, operands in shared memory (contents irrelevant).
+namespace jvae {
+
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(int N, int nacc, int iters, int cblk, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0 && elect_one()) {
+    const uint32_t rb = (uint32_t)cblk * 2u;
+    const uint32_t swz = (cblk == 64) ? SWZ_128B : (cblk == 32 ? SWZ_64B : SWZ_32B);
+    const uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint64_t a_desc = make_smem_desc(smem_u32(smem), 16, 8 * rb, swz);
+    const uint64_t b_desc = make_smem_desc(smem_u32(smem) + 16384, 16, 8 * rb, swz);
+    const long long t0 = clock64();
+    const uint32_t mask = (uint32_t)nacc - 1u;      // nacc is a power of two
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t a = (uint32_t)i & mask;
+      umma_bf16(tmem + a * (uint32_t)N, a_desc + (uint64_t)(2 * (i & 1)), b_desc + (uint64_t)(2 * (i & 1)), idesc, 1);
+    }
+    umma_commit(&bar);
+    const long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+int probe_mma_rate() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(probe_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int iters = 2048;
+  for (int cblk : {64, 32}) {
+    for (int N : {16, 32, 64, 128, 256}) {
+      for (int nacc : {1, 2, 4, 8}) {
+        if (nacc * N > 512) continue;
+        probe_mma_rate_kernel<<<1, 128, 64 * 1024>>>(N, nacc, iters, cblk, d);
+        probe_mma_rate_kernel<<<1, 128, 64 * 1024>>>(N, nacc, iters, cblk, d);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("[probe] mma rate: CUDA error\n"); return -1; }
+        long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("[probe] mma M=128 N=%3d K=16 rows=%dB accumulators=%d: issue %.1f clk/mma, complete %.1f clk/mma (ideal %d)\n", N,
+               cblk * 2, nacc, (double)h[0] / iters, (double)h[1] / iters, 128 * N / 256);
+      }
+    }
+  }
+  cudaFree(d);
+  return 0;
+}
+}  // namespace jvae
+
+extern "C" int jvae_probe_mma_rate(void) { return jvae::probe_mma_rate(); }
