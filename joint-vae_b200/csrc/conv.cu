@@ -13,6 +13,7 @@
 // of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
 #include <vector>
+#include <algorithm>
 #include <stdlib.h>
 
 namespace jvae {
@@ -674,6 +675,145 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   if (warp == 1) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo-tile weight gradient (input stride 1):  dW[t][a][b] += sum_px G[px, a] * X[px + d_t, b]
+// G = grid tensor (dY for a Conv2d, x for a ConvTranspose2d), X = gathered tensor.  K of the MMA = pixels; both
+// operands are MN-major views of NHWC boxes.  The X box is the same stacked halo box the forward kernel uses; up to
+// 128 / Cblk_x horizontally adjacent taps are ONE MMA: they are stacked along M through the descriptor's leading byte
+// offset (LBO = one pixel row).  D[(tap j, X channel)][G channel] accumulates in TMEM over every box the CTA owns;
+// one epilogue at the end adds it to dW with fp32 atomics.  Junk slots between stacked images contribute nothing
+// because the G box is zero there (rows beyond the image are TMA OOB fill); stage slack is zeroed once.
+// ------------------------------------------------------------------------------------------------
+constexpr int WH_MAX_GROUPS = 64;
+struct WHaloParams {
+  int N, Hq, Wq;
+  int NBt, HHs, HWp, MT, strips_x, num_boxes;
+  int Cblk_g, Cblk_x, ncx, Cg, Cx;          // blockIdx.z = (G channel block) * ncx + (X channel block)
+  int ngroups, groups_per_cta;              // blockIdx.y selects a slice of the tap groups
+  int dymin, dxmin;
+  uint32_t grp_off16[WH_MAX_GROUPS];        // descriptor start shift of the group's first tap (16-byte units)
+  unsigned char grp_ntap[WH_MAX_GROUPS];    // taps stacked in the group
+  short grp_tap[WH_MAX_GROUPS][8];          // tap index (into dW) of each stacked tap
+  float* dw;
+  int dw_ld_tap, dw_ld_co;
+  uint32_t x_stage_bytes, stage_bytes, x_box_bytes, g_box_bytes, tmem_cols;
+  int stages;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                       const __grid_constant__ WHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* done_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g_lo = (int)blockIdx.y * p.groups_per_cta;
+  const int ng = min(p.groups_per_cta, p.ngroups - g_lo);
+  const int cg0 = ((int)blockIdx.z / p.ncx) * p.Cblk_g, cx0 = ((int)blockIdx.z % p.ncx) * p.Cblk_x;
+  const uint32_t rbx = (uint32_t)p.Cblk_x * 2u, rbg = (uint32_t)p.Cblk_g * 2u;
+
+  // zero every stage once: slots past the TMA boxes stay zero for the whole kernel
+  for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * p.stage_bytes / 16u; i += CONV_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_g);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < 8; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc_dyn(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t s = 0, ph = 0;
+      for (int box = blockIdx.x; box < p.num_boxes; box += gridDim.x) {
+        const int sx = box % p.strips_x, nb = box / p.strips_x;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], p.x_box_bytes + p.g_box_bytes);
+        tma_load_4d(st, &tmap_x, &full_bar[s], cx0, sx * 8 + p.dxmin, p.dymin, nb * p.NBt);
+        tma_load_4d(st + p.x_stage_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t swx = (p.Cblk_x == 64) ? SWZ_128B : (p.Cblk_x == 32 ? SWZ_64B : SWZ_32B);
+      const uint32_t swg = (p.Cblk_g == 64) ? SWZ_128B : (p.Cblk_g == 32 ? SWZ_64B : SWZ_32B);
+      // MN-major descriptors: LBO = next M block (= next stacked tap = one pixel row), SBO = next 8-pixel K group (= next slot)
+      const uint32_t a_hi = (((uint32_t)p.HWp * rbx >> 4) & 0x3fffu) | (1u << 14) | (swx << 29);
+      const uint32_t b_hi = (((8u * rbg) >> 4) & 0x3fffu) | (1u << 14) | (swg << 29);
+      const uint32_t a_lbo = ((rbx >> 4) & 0x3fffu) << 16, b_lbo = (((8u * rbg) >> 4) & 0x3fffu) << 16;
+      const uint32_t ak16 = (2u * (uint32_t)p.HWp * rbx) >> 4, bk16 = (16u * rbg) >> 4;   // one MMA = 16 pixels = 2 slots
+      const uint32_t am16 = (16u * (uint32_t)p.HWp * rbx) >> 4, bm16 = (128u * rbg) >> 4;  // one M-tile = 16 slots
+      const uint32_t idesc128 = make_idesc_bf16(128, p.Cblk_g, true, true), idesc64 = make_idesc_bf16(64, p.Cblk_g, true, true);
+      uint32_t s = 0, ph = 0, first = 0;
+      for (int box = blockIdx.x; box < p.num_boxes; box += gridDim.x) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sx_ = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint32_t a_lo0 = ((sx_ >> 4) & 0x3fffu) | a_lbo;
+        const uint32_t b_lo0 = (((sx_ + p.x_stage_bytes) >> 4) & 0x3fffu) | b_lbo;
+        for (int m = 0; m < p.MT; ++m) {
+          const uint32_t b_lo = b_lo0 + (uint32_t)m * bm16;
+          for (int g = 0; g < ng; ++g) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)m * am16 + p.grp_off16[g_lo + g];
+            const uint32_t idesc = ((int)p.grp_ntap[g_lo + g] * p.Cblk_x > 64) ? idesc128 : idesc64;
+            const uint32_t d = tmem_base + (uint32_t)(g * p.Cblk_g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(d, desc64(a_hi, a_lo + (uint32_t)k * ak16), desc64(b_hi, b_lo + (uint32_t)k * bk16), idesc,
+                        k == 0 ? first : 1u);
+          }
+          first = 1;
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const bool has_work = (int)blockIdx.x < p.num_boxes;
+    const int Ng = min(p.Cblk_g, p.Cg - cg0), Nx = min(p.Cblk_x, p.Cx - cx0);
+    for (int g = 0; g < ng && has_work; ++g) {
+      const int ntap = p.grp_ntap[g_lo + g];
+      const bool m128 = ntap * p.Cblk_x > 64;
+      // accumulator row of this thread: M = 128 -> lane quarter q holds rows 32q..32q+31; M = 64 -> rows 16q..16q+15
+      const int row = m128 ? q * 32 + lane : q * 16 + lane;
+      const bool row_ok = m128 || lane < 16;
+      const int j = row / p.Cblk_x, cx = row - j * p.Cblk_x;
+      const bool live = row_ok && j < ntap && cx < Nx;
+      const int t = live ? p.grp_tap[g_lo + g][j] : 0;
+      for (int c0 = 0; c0 < p.Cblk_g; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cblk_g + c0), r);
+        tmem_ld_wait();
+        if (live) {
+          float* o = p.dw + (size_t)t * p.dw_ld_tap + (size_t)(cg0 + c0) * p.dw_ld_co + cx0 + cx;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < Ng) atomicAdd(o + (size_t)i * p.dw_ld_co, __uint_as_float(r[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, p.tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------------ host helpers
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
@@ -782,6 +922,103 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   return JVAE_OK;
 }
 
+// plans and launches the halo weight-gradient kernel; returns 1 when the geometry is not covered
+static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
+                                 int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, float* dw, int dw_ld_tap,
+                                 int dw_ld_co, cudaStream_t stream) {
+  if (Hq > 32 || Wq < 6) return 1;
+  WHaloParams p;
+  memset(&p, 0, sizeof(p));
+  int dymin = 1 << 20, dymax = -(1 << 20), dxmin = 1 << 20, dxmax = -(1 << 20);
+  for (int t = 0; t < ntaps; ++t) {
+    dymin = min(dymin, (int)tap_dy[t]); dymax = max(dymax, (int)tap_dy[t]);
+    dxmin = min(dxmin, (int)tap_dx[t]); dxmax = max(dxmax, (int)tap_dx[t]);
+  }
+  const int ey = dymax - dymin, ex = dxmax - dxmin;
+  if (ey > 16 || ex > 16) return 1;
+  p.N = N; p.Hq = Hq; p.Wq = Wq; p.dymin = dymin; p.dxmin = dxmin;
+  p.Cg = Cg; p.Cx = Cx;
+  p.Cblk_g = cblk_of(Cg > 64 ? 64 : Cg); p.Cblk_x = cblk_of(Cx > 64 ? 64 : Cx);
+  const int ncg = (Cg + p.Cblk_g - 1) / p.Cblk_g;
+  p.ncx = (Cx + p.Cblk_x - 1) / p.Cblk_x;
+  const uint32_t rbx = (uint32_t)p.Cblk_x * 2u, rbg = (uint32_t)p.Cblk_g * 2u;
+  p.HWp = 8 + ex; p.HHs = Hq + ey;
+  // tap groups: runs of horizontally adjacent taps with the same dy, at most 128 / Cblk_x per group
+  const int tpm = 128 / p.Cblk_x;
+  std::vector<int> order(ntaps);
+  for (int t = 0; t < ntaps; ++t) order[t] = t;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    return tap_dy[a] != tap_dy[b] ? tap_dy[a] < tap_dy[b] : tap_dx[a] < tap_dx[b];
+  });
+  int ngr = 0;
+  for (int i = 0; i < ntaps;) {
+    if (ngr >= WH_MAX_GROUPS) return 1;
+    int n = 1;
+    while (i + n < ntaps && n < tpm && n < 8 && tap_dy[order[i + n]] == tap_dy[order[i]] &&
+           tap_dx[order[i + n]] == tap_dx[order[i]] + n)
+      ++n;
+    p.grp_ntap[ngr] = (unsigned char)n;
+    p.grp_off16[ngr] = ((uint32_t)((tap_dy[order[i]] - dymin) * p.HWp + (tap_dx[order[i]] - dxmin)) * rbx) >> 4;
+    for (int j = 0; j < n; ++j) p.grp_tap[ngr][j] = (short)order[i + j];
+    ++ngr;
+    i += n;
+  }
+  p.ngroups = ngr;
+  p.groups_per_cta = 512 / p.Cblk_g;
+  if (p.groups_per_cta > ngr) p.groups_per_cta = ngr;
+  const int ysplit = (ngr + p.groups_per_cta - 1) / p.groups_per_cta;
+  p.groups_per_cta = (ngr + ysplit - 1) / ysplit;               // balance the slices
+  p.tmem_cols = (uint32_t)pow2_ceil(p.groups_per_cta * p.Cblk_g < 32 ? 32 : p.groups_per_cta * p.Cblk_g);
+  // images per box: best slot efficiency within the shared-memory budget
+  const uint32_t budget = 200u * 1024u;
+  double best = 0.0;
+  for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
+    const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
+    const uint32_t xs = ((uint32_t)(16 * MT + ey + 1) * p.HWp * rbx + 1023u) & ~1023u;     // +1 slot: stacked-tap overrun
+    const uint32_t gs = ((uint32_t)(16 * MT > S ? 16 * MT : S) * 8u * rbg + 1023u) & ~1023u;
+    if (2u * (xs + gs) + 1024u > budget) break;
+    if (nbt * p.HHs > 256) break;
+    const double eff = (double)(nbt * Hq) / (16.0 * MT);
+    if (eff > best + 0.02) { best = eff; p.NBt = nbt; p.MT = MT; p.x_stage_bytes = xs; p.stage_bytes = xs + gs; }
+  }
+  if (best <= 0.0) return 1;
+  p.x_box_bytes = (uint32_t)(p.NBt * p.HHs) * p.HWp * rbx;
+  p.g_box_bytes = (uint32_t)(p.NBt * p.HHs) * 8u * rbg;
+  p.stages = (int)((budget - 1024u) / p.stage_bytes);
+  if (p.stages > 6) p.stages = 6;
+  if (p.stages < 2) return 1;
+  p.strips_x = (Wq + 7) / 8;
+  p.num_boxes = p.strips_x * ((N + p.NBt - 1) / p.NBt);
+  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co;
+  CUtensorMap tg, tx;
+  {
+    uint64_t dg[4] = {(uint64_t)Cg, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)N};
+    uint64_t sg[3] = {(uint64_t)ld_g * 2, (uint64_t)Wq * ld_g * 2, (uint64_t)Hq * Wq * ld_g * 2};
+    uint32_t bg[4] = {(uint32_t)p.Cblk_g, 8u, (uint32_t)p.HHs, (uint32_t)p.NBt};
+    int rc = make_tmap_bf16(&tg, g, 4, dg, sg, bg, nullptr, p.Cblk_g * 2);
+    if (rc) return rc;
+    uint64_t dx[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t sx[3] = {(uint64_t)ld_x * 2, (uint64_t)W * ld_x * 2, (uint64_t)H * W * ld_x * 2};
+    uint32_t bx[4] = {(uint32_t)p.Cblk_x, (uint32_t)p.HWp, (uint32_t)p.HHs, (uint32_t)p.NBt};
+    rc = make_tmap_bf16(&tx, x, 4, dx, sx, bx, nullptr, p.Cblk_x * 2);
+    if (rc) return rc;
+  }
+  const int nz = ncg * p.ncx;
+  if (nz > 65535) return 1;
+  int gx = (sm_count() + ysplit * nz - 1) / (ysplit * nz);
+  if (gx < 1) gx = 1;
+  if (gx > p.num_boxes) gx = p.num_boxes;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    JVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  conv_wgrad_halo_kernel<<<dim3(gx, ysplit, nz), CONV_THREADS, smem, stream>>>(tg, tx, p);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
 }  // namespace jvae
 
 using namespace jvae;
@@ -861,6 +1098,12 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
   JVAE_CHECK_ARG((ld_dy % 8) == 0 && (ld_x % 8) == 0, "channel strides must be multiples of 8");
   JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
+  static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
+  if (in_stride == 1 && !force_v1) {
+    const int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, dw, dw_ld_tap,
+                                         dw_ld_co, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.Hq = Hq; p.Wq = Wq;
