@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 1
+#define JVAE_ABI_VERSION 2
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -71,11 +71,19 @@ typedef struct jvae_elbo_cfg {
   float   var_w;            /* kl_var_weighting, priors.py:323 */
   float   tau;              /* tilted / uniform priors */
   float   alpha;            /* uniform prior: log rho inside [-tau,tau], priors.py:423-424 */
+  int32_t prior_stats_ready;/* 1: jvae_elbo_prior_stats already ran on this workspace for the current prior parameters */
 } jvae_elbo_cfg;
 
 /* bytes of scratch the ELBO entry points need for `cfg`.  The first 4*B bytes (arrival counters) must be ZERO before
  * the first use; every launch leaves them zero again, so one workspace can be reused without clearing. */
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
+
+/* Prior statistics (mean of the class means, its variance, log det Sigma_c: cvae.py:747-754, priors.py:173-186) into the
+ * workspace.  They depend on the prior parameters only; calling this early (e.g. before the network forward) and setting
+ * cfg.prior_stats_ready = 1 keeps the tiny prologue launch off the loss step.  With prior_stats_ready = 0 the forward
+ * entry points run it themselves. */
+int jvae_elbo_prior_stats(const jvae_elbo_cfg* cfg, const float* means, const float* inv_trans, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Train forward (y given).  Replaces cvae.py:626-902 + priors.py:252-326 + losses.py:8-27,73-86.
  *   x (B,D) f32; x_reco (L+1,B,D) [slab 0 is not read]; mu, log_var (B,K) f32;
@@ -83,8 +91,8 @@ size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
  *   sigma: 1 f32 on the device = the raw Sigma parameter (log sigma if sigma_is_log; sdim == 1), it is a
  *   learned parameter so it is never read back to the host.
  *   outputs, each (B) f32 (NULL = not wanted): kl zdist var_kl wmse cross_x cross_y total dzdist.
- *   finite_flag: 1 int32, non-zero after the call unless some total is NaN/Inf or a label is out of range, then 0
- *   (replaces the per-parameter isnan scan of cvae.py:2454-2457). */
+ *   finite_flag: 1 int32 the CALLER initialises to non-zero; the kernel clears it if some total is NaN/Inf or a label is
+ *   out of range (replaces the per-parameter isnan scan of cvae.py:2454-2457). */
 int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco,
                         const float* mu, const float* log_var, const void* logits, const int64_t* y,
                         const float* means, const float* inv_trans, const float* sigma,

@@ -29,7 +29,8 @@ class ElboCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ('B', 'L', 'K', 'C', 'D', 'xreco_dtype', 'logits_dtype', 'var_dim', 'prior_kind', 'conditional',
                  'has_xreco', 'has_logits', 'sigma_is_log', 'sigma_is_rmse')] + \
-               [(n, ctypes.c_float) for n in ('beta', 'gamma_w', 'var_w', 'tau', 'alpha')]
+               [(n, ctypes.c_float) for n in ('beta', 'gamma_w', 'var_w', 'tau', 'alpha')] + \
+               [('prior_stats_ready', ctypes.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -87,7 +88,8 @@ def lib():
     L.jvae_maxpool_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
-    if L.jvae_abi_version() != 1:
+    L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
+    if L.jvae_abi_version() != 2:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -179,8 +181,8 @@ def workspace(cfg, device):
 
 
 def make_cfg(*, B, L, K, C, D, x_reco, logits, var_dim, prior_kind, conditional, sigma_is_log, sigma_is_rmse,
-             beta, gamma_w, var_w, tau=0.0, alpha=0.0):
-    return ElboCfg(B=B, L=L, K=K, C=C, D=D, xreco_dtype=dtype_code(x_reco), logits_dtype=dtype_code(logits),
+             beta, gamma_w, var_w, tau=0.0, alpha=0.0, prior_stats_ready=False):
+    return ElboCfg(prior_stats_ready=int(bool(prior_stats_ready)), B=B, L=L, K=K, C=C, D=D, xreco_dtype=dtype_code(x_reco), logits_dtype=dtype_code(logits),
                    var_dim=VAR_DIM[var_dim], prior_kind=PRIOR_KIND[prior_kind], conditional=int(bool(conditional)),
                    has_xreco=int(x_reco is not None), has_logits=int(logits is not None),
                    sigma_is_log=int(bool(sigma_is_log)), sigma_is_rmse=int(bool(sigma_is_rmse)),
@@ -188,12 +190,18 @@ def make_cfg(*, B, L, K, C, D, x_reco, logits, var_dim, prior_kind, conditional,
                    alpha=float(alpha or 0.0))
 
 
+def elbo_prior_stats(cfg, means, inv_trans):
+    """include/jvae_b200.h: jvae_elbo_prior_stats (run early; then pass prior_stats_ready=True to make_cfg)"""
+    ws, n = workspace(cfg, means.device)
+    check(lib().jvae_elbo_prior_stats(ctypes.byref(cfg), ptr(means), ptr(inv_trans), ptr(ws), n, stream()))
+
+
 def elbo_train_fwd(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma):
     """-> dict of (B,) f32 tensors + 'finite' int32 flag tensor.  include/jvae_b200.h: jvae_elbo_train_fwd"""
     dev = mu.device
     B = cfg.B
     out = torch.empty((8, B), dtype=torch.float32, device=dev)
-    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    flag = torch.ones(1, dtype=torch.int32, device=dev)       # the kernel clears it on a non-finite total
     ws, n = workspace(cfg, dev)
     with _timed('elbo_train_fwd'):
         check(lib().jvae_elbo_train_fwd(ctypes.byref(cfg), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var), ptr(logits),

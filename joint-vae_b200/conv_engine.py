@@ -55,10 +55,17 @@ class NativeKernels:
 
     @staticmethod
     def to_nhwc(x, c_pad):
-        return nat.nchw_to_nhwc_bf16(x.float().contiguous(), c_pad)
+        n, c, h, w = x.shape
+        x = x.float().contiguous()
+        if h * w == 1 and c_pad == c:          # a (N, C) matrix: the layouts coincide, plain cast
+            return nat.cast_f32_bf16(x).view(n, 1, 1, c)
+        return nat.nchw_to_nhwc_bf16(x, c_pad)
 
     @staticmethod
     def to_nchw(t, C):
+        n, h, w, ld = t.shape
+        if h * w == 1 and ld == C:
+            return nat.cast_bf16_f32(t).view(n, C, 1, 1)
         return nat.nhwc_bf16_to_nchw(t, C)
 
     @staticmethod

@@ -50,10 +50,11 @@ struct ElboArgs {
   float* ws_mse;            // (L,B) sum_d (x_reco - x)^2
   float* dict_mean;         // (K)
   float* logdet;            // (Cp)
+  float* ws_lat;            // (B,4): kl, cross_y, bad-label flag of the latent CTAs (train forward)
 };
 
 struct WsLayout {
-  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, total;
+  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, total;
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static WsLayout ws_layout(int B, int L, int K, int Cp) {
@@ -64,7 +65,8 @@ static WsLayout ws_layout(int B, int L, int K, int Cp) {
   w.mse = w.dnv + align256((size_t)((K + 31) / 32) * 4);
   w.dict_mean = w.mse + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.logdet = w.dict_mean + align256((size_t)K * 4);
-  w.total = w.logdet + align256((size_t)Cp * 4);
+  w.lat = w.logdet + align256((size_t)Cp * 4);
+  w.total = w.lat + align256((size_t)B * 16);
   return w;
 }
 
@@ -200,7 +202,7 @@ __device__ __forceinline__ void mse_partial(const ElboArgs& a, int b, int l0, in
 // Runs the streaming part for CTA (b, g) and elects the last CTA of sample b.  Returns true in every
 // thread of the elected CTA, after which ws_mse[(l-1)*B + b] is complete for all l.
 template <bool XR_BF16, int LG>
-__device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g, float* red) {
+__device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g, float* red, int extra = 0) {
   __shared__ int s_last;
   __shared__ float s_part[ELBO_THREADS / 32][LG];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -222,7 +224,7 @@ __device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g
       a.ws_mse[(size_t)(l0 - 1 + threadIdx.x) * a.B + b] = s;
     }
   }
-  if (a.G == 1) {
+  if (a.G + extra == 1) {
     __syncthreads();
     return true;
   }
@@ -231,7 +233,7 @@ __device__ __forceinline__ bool stream_and_elect(const ElboArgs& a, int b, int g
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int old = atomicAdd(&a.counters[b], 1u);
-    s_last = (old == (unsigned int)(a.G - 1));
+    s_last = (old == (unsigned int)(a.G + extra - 1));
     if (s_last) a.counters[b] = 0;   // self-cleaning: the workspace is ready for the next launch
   }
   __syncthreads();
@@ -312,31 +314,38 @@ __device__ __forceinline__ void kl_finish(const ElboArgs& a, float dist, float t
 // ================================================================================================
 // TRAIN FORWARD
 // ================================================================================================
-template <bool XR_BF16, int LG>
-__global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a) {
-  __shared__ float red[32];
-  __shared__ float s_ce[ELBO_THREADS / 32];
-  const int b = blockIdx.x % a.B, g = blockIdx.x / a.B;   // b fastest: neighbouring CTAs stream neighbouring rows
-  if (!stream_and_elect<XR_BF16, LG>(a, b, g, red)) return;
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int K = a.K, C = a.C;
-  long long yb = a.y[b];
-  bool bad_label = (yb < 0 || yb >= C);
-  if (bad_label) yb = 0;
-  const int c = a.conditional ? (int)yb : 0;
-
-  // ---- reconstruction term (cvae.py:649-672, 773-789)
+// The latent part of a sample (KL to the prior of its class, classifier cross-entropy) does not depend on the
+// reconstruction stream, so it runs on its own CTAs (the first ceil(B/4) blocks, one warp per sample) while the other
+// CTAs stream x_reco.  Every CTA that finishes a sample's work counts one arrival; the last one (G streaming CTAs + the
+// latent warp) combines the two halves: a few scalar operations, so the kernel has no serial latent tail.
+__device__ __forceinline__ void train_finalize(const ElboArgs& a, int b) {
   float wmse = 0.f, cross_x = 0.f;
   if (a.has_xreco) {
     float log_sigma, scale;
     sigma_terms(a, b, &wmse, &log_sigma, &scale);
     cross_x = 0.5f * (float)a.D * (2.f * log_sigma + wmse + LOG2PI_F);
   }
+  const float kl = __ldcg(&a.ws_lat[4 * b]), cross_y = __ldcg(&a.ws_lat[4 * b + 1]);
+  const bool bad_label = __ldcg(&a.ws_lat[4 * b + 2]) != 0.f;
+  float total = a.beta * kl;
+  if (a.has_xreco) total += cross_x;
+  if (a.has_logits && a.gamma_w != 0.f) total += a.gamma_w * cross_y;
+  if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
+  if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
+  if (a.total) a.total[b] = total;
+  if (a.finite_flag && (bad_label || !isfinite(total))) atomicExch(a.finite_flag, 0);
+}
+
+__device__ __forceinline__ void train_latent_warp(const ElboArgs& a, int b, int lane) {
+  const int K = a.K, C = a.C;
+  long long yb = a.y[b];
+  const bool bad_label = (yb < 0 || yb >= C);
+  if (bad_label) yb = 0;
+  const int c = a.conditional ? (int)yb : 0;
   // ---- KL to the prior of class y_b (priors.py:252-326)
   float dist = 0.f, tr = 0.f, aux = 0.f, slv = 0.f, dzd = 0.f;
   const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
-  for (int k = tid; k < K; k += ELBO_THREADS) {
+  for (int k = lane; k < K; k += 32) {
     const float mu = a.mu[(size_t)b * K + k], lv = a.lv[(size_t)b * K + k];
     const float m = a.means[(size_t)c * K + k];
     const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
@@ -347,19 +356,13 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a
       dzd = fmaf(dd, dd, dzd);
     }
   }
-  dist = block_sum(dist, red);
-  tr = block_sum(tr, red);
-  aux = block_sum(aux, red);
-  slv = block_sum(slv, red);
-  dzd = block_sum(dzd, red);
+  dist = warp_sum(dist); tr = warp_sum(tr); aux = warp_sum(aux); slv = warp_sum(slv); dzd = warp_sum(dzd);
   float kl, var_kl;
   kl_finish(a, dist, tr, aux, slv, a.logdet[c], &kl, &var_kl);
-
   // ---- cross entropy of the classifier over all L+1 draws (losses.py:73-86)
   float cross_y = 0.f;
   if (a.has_logits) {
-    float part = 0.f;
-    for (int r = wid; r <= a.L; r += ELBO_THREADS / 32) {
+    for (int r = 0; r <= a.L; ++r) {
       const size_t base = ((size_t)r * a.B + b) * C;
       float mx = -CUDART_INF_F;
       for (int j = lane; j < C; j += 32) mx = fmaxf(mx, load_logit(a.logits, base + j, a.lg_bf16));
@@ -367,33 +370,45 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a
       float se = 0.f;
       for (int j = lane; j < C; j += 32) se += expf(load_logit(a.logits, base + j, a.lg_bf16) - mx);
       se = warp_sum(se);
-      part += logf(se) + mx - load_logit(a.logits, base + (size_t)yb, a.lg_bf16);
+      cross_y += logf(se) + mx - load_logit(a.logits, base + (size_t)yb, a.lg_bf16);
     }
-    __syncthreads();
-    if (lane == 0) s_ce[wid] = part;
-    __syncthreads();
-    for (int i = 0; i < ELBO_THREADS / 32; ++i) cross_y += s_ce[i];
     cross_y /= (float)(a.L + 1);
   }
-
-  if (tid == 0) {
-    float total = a.beta * kl;
-    if (a.has_xreco) total += cross_x;
-    if (a.has_logits && a.gamma_w != 0.f) total += a.gamma_w * cross_y;
+  if (lane == 0) {
     if (a.kl) a.kl[b] = kl;
     if (a.zdist) a.zdist[b] = dist;
     if (a.var_kl) a.var_kl[b] = var_kl;
-    if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
-    if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
     if (a.cross_y && a.has_logits) a.cross_y[b] = cross_y;
-    if (a.total) a.total[b] = total;
     if (a.dzdist && a.conditional) {
       float dnv = 0.f;
-      for (int i = 0; i < a.nkb; ++i) dnv += __ldcg(&a.dict_norm_var[i]);
+      for (int i = 0; i < a.nkb; ++i) dnv += a.dict_norm_var[i];
       a.dzdist[b] = dzd + dnv;
     }
-    if (a.finite_flag && (bad_label || !isfinite(total))) atomicExch(a.finite_flag, 0);
+    a.ws_lat[4 * b] = kl; a.ws_lat[4 * b + 1] = cross_y; a.ws_lat[4 * b + 2] = bad_label ? 1.f : 0.f;
+    bool last = true;
+    if (a.has_xreco) {       // G streaming CTAs also arrive on this sample
+      __threadfence();
+      const unsigned int old = atomicAdd(&a.counters[b], 1u);
+      last = (old == (unsigned int)a.G);
+      if (last) { a.counters[b] = 0; __threadfence(); }
+    }
+    if (last) train_finalize(a, b);
   }
+}
+
+template <bool XR_BF16, int LG>
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a) {
+  __shared__ float red[32];
+  const int nlat = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
+  if ((int)blockIdx.x < nlat) {
+    const int b = (int)blockIdx.x * (ELBO_THREADS / 32) + (threadIdx.x >> 5);
+    if (b < a.B) train_latent_warp(a, b, threadIdx.x & 31);
+    return;
+  }
+  const int sid = (int)blockIdx.x - nlat;
+  const int b = sid % a.B, g = sid / a.B;   // b fastest: neighbouring CTAs stream neighbouring rows
+  if (!stream_and_elect<XR_BF16, LG>(a, b, g, red, 1)) return;
+  if (threadIdx.x == 0) train_finalize(a, b);
 }
 
 // ================================================================================================
@@ -922,6 +937,7 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.ws_mse = reinterpret_cast<float*>(p + w.mse);
   a.dict_mean = reinterpret_cast<float*>(p + w.dict_mean);
   a.logdet = reinterpret_cast<float*>(p + w.logdet);
+  a.ws_lat = reinterpret_cast<float*>(p + w.lat);
 }
 
 static int launch_prologue(const ElboArgs& a, cudaStream_t st) {
@@ -962,11 +978,12 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   a.kl = kl; a.zdist = zdist; a.var_kl = var_kl; a.wmse = wmse; a.cross_x = cross_x; a.cross_y = cross_y;
   a.total = total; a.dzdist = dzdist; a.finite_flag = finite_flag;
   cudaStream_t st = (cudaStream_t)stream;
-  // non-zero = all finite so far; the kernel clears it on the first non-finite total (no host memory involved)
-  if (finite_flag) JVAE_CUDA(cudaMemsetAsync(finite_flag, 0x01, sizeof(int32_t), st));
-  rc = launch_prologue(a, st);
-  if (rc) return rc;
-  const int grid = a.B * a.G;
+  if (!cfg->prior_stats_ready) {
+    rc = launch_prologue(a, st);
+    if (rc) return rc;
+  }
+  // latent CTAs (one warp per sample) first, then the streaming CTAs (none without a reconstruction term)
+  const int grid = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32) + (a.has_xreco ? a.B * a.G : 0);
 #define JVAE_ELBO_LAUNCH(kern, smem_)                                                              \
   do {                                                                                           \
     const int lg_ = elbo_lg();                                                                   \
@@ -985,6 +1002,18 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   JVAE_ELBO_LAUNCH(elbo_train_fwd_kernel, 0);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
+}
+
+int jvae_elbo_prior_stats(const jvae_elbo_cfg* cfg, const float* means, const float* inv_trans, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg, __func__);
+  if (rc) return rc;
+  JVAE_CHECK_ARG(means && inv_trans, "means and inv_trans are required");
+  JVAE_CHECK_ARG(workspace && workspace_bytes >= jvae_elbo_workspace_bytes(cfg), "workspace too small");
+  ElboArgs a;
+  fill_args(a, cfg, workspace);
+  a.means = means; a.inv_trans = inv_trans;
+  return launch_prologue(a, (cudaStream_t)stream);
 }
 
 int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x, const void* x_reco,
@@ -1012,6 +1041,7 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
   char dummy[4096];
   fill_args(a, cfg, dummy);
   a.counters = nullptr; a.dict_norm_var = nullptr; a.ws_mse = nullptr; a.dict_mean = nullptr; a.logdet = nullptr;
+  a.ws_lat = nullptr;
   a.g = g; a.x = x; a.xr = x_reco; a.mu = mu; a.lv = log_var; a.logits = logits; a.y = (const long long*)y;
   a.means = means; a.inv_trans = inv_trans; a.sigma = sigma; a.wmse_in = wmse;
   a.d_xr = d_x_reco; a.d_mu = d_mu; a.d_lv = d_log_var; a.d_logits = d_logits; a.d_means = d_means;
@@ -1054,8 +1084,10 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
     set_error("%s: (L+1)*K + 7*C floats = %zu bytes of shared memory exceed 200 KB", __func__, smem);
     return JVAE_ERR_UNSUPPORTED;
   }
-  rc = launch_prologue(a, st);
-  if (rc) return rc;
+  if (!cfg->prior_stats_ready) {
+    rc = launch_prologue(a, st);
+    if (rc) return rc;
+  }
   const int grid = a.B * a.G;
   if (smem > 48 * 1024) {
 #define JVAE_EVAL_ATTR(bf, lg) JVAE_CUDA(cudaFuncSetAttribute(elbo_eval_fwd_kernel<bf, lg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))

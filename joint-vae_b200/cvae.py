@@ -340,10 +340,21 @@ class ClassificationVariationalNetwork(nn.Module):
                 cross_y_weight = False
         B = x.shape[0]
         L = self.latent_sampling
+        # prior statistics (dictionary mean / variance, log-dets) depend on the prior parameters only: launch them
+        # before the network so the loss step itself is one kernel (include/jvae_b200.h: jvae_elbo_prior_stats)
+        prior0 = self.encoder.prior
+        means0, inv_trans0 = prior0.mean, prior0.inv_trans
+        pcfg = nat.make_cfg(B=B, L=L, K=self.latent_dim, C=self.num_labels, D=0, x_reco=None, logits=None,
+                            var_dim=prior0.var_dim, prior_kind=prior0.distribution, conditional=prior0.conditional,
+                            sigma_is_log=False, sigma_is_rmse=False, beta=1.0, gamma_w=0.0, var_w=1.0)
+        prior_ready = False
+        if prior0.var_dim != 'full':
+            nat.elbo_prior_stats(pcfg, means0.detach(), inv_trans0.detach())
+            prior_ready = True
         o = self.forward(x, y=y if self.y_is_coded else None, sampling_epsilon_norm_out=True, sigma_out=True, **kw)
         x_reco, y_est, mu, log_var, z, eps_norm, _ = o
         prior = self.encoder.prior
-        means, inv_trans = prior.mean, prior.inv_trans
+        means, inv_trans = means0, inv_trans0
         beta = self.beta if with_beta else 1.
 
         xr_k = x_k = None
@@ -359,6 +370,7 @@ class ClassificationVariationalNetwork(nn.Module):
         logits_k = y_est.float().contiguous() if self.y_is_decoded else None
         gw = float(cross_y_weight) if cross_y_weight else 0.0
         cfg = self._elbo_cfg(B, L, xr_k, logits_k, beta, gw, kl_var_weighting)
+        cfg.prior_stats_ready = int(prior_ready)
         sig = self.sigma if self.x_is_generated else None
         batch_losses = {}
         self._fused = None
