@@ -40,6 +40,8 @@ for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (20
     sig = torch.zeros(1, device=dev)
     cfg = nat.make_cfg(B=B, L=L, K=K, C=C, D=D, x_reco=xr, logits=None, var_dim='scalar', prior_kind='gaussian',
                        conditional=True, sigma_is_log=True, sigma_is_rmse=False, beta=1.0, gamma_w=0.0, var_w=1.0)
+    nat.elbo_prior_stats(cfg, means, T)
+    cfg.prior_stats_ready = 1          # time the loss kernel alone (the prologue runs before the network in the model)
     out = nat.elbo_train_fwd(cfg, x, xr, mu, lv, None, y, means, T, sig)
     gvec = torch.full((B,), 1.0 / B, device=dev)
     bytes_fwd = B * (D * 4 + L * D * 2 + 2 * K * 4 + 8 + 32)
