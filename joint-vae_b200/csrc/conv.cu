@@ -267,9 +267,12 @@ struct HaloParams {
   int RT, NBt, HHs, HWp, MT;            // rows / images per box, slots per image, halo width (pixels), M-tiles per box
   int strips_x, blocks_y, blocks_n, num_boxes, n_tiles_n;
   int Cblk, ntaps, BN;
-  int dymin, dxmin;
+  int dymin, dxmin;                      // smallest tap offset in PLANE coordinates (e = (d - r) / in_stride)
+  int in_stride, nplanes;                // input stride s: the input is read as up to s*s parity planes P_r[j] = in[s*j + r]
+  short plane_ry[4], plane_rx[4];
+  uint32_t plane_bytes;                  // bytes of one plane's box region inside a stage
   short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
-  uint32_t tap_off16[CONV_MAX_TAPS];     // ((dy-dymin)*HWp + (dx-dxmin)) * row bytes / 16: descriptor start shift of the tap
+  uint32_t tap_off16[CONV_MAX_TAPS];     // (plane * plane_bytes + ((ey-eymin)*HWp + (ex-exmin)) * row bytes) / 16
   int Ho, Wo, Cout, ldc, out_sy, out_sx, out_oy, out_ox, act;
   const float* bias;
   __nv_bfloat16* out;
@@ -476,8 +479,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         const int s = it % p.stages;
         mbar_wait(&empty_bar[s], ((it / p.stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], p.box_bytes);
-        tma_load_4d(smem + (size_t)s * p.stage_bytes, &tmap_in, &full_bar[s], 0, sx * 8 + p.dxmin, by * p.RT + p.dymin,
-                    m * p.NBt);
+        for (int pl = 0; pl < p.nplanes; ++pl)
+          tma_load_4d(smem + (size_t)s * p.stage_bytes + (size_t)pl * p.plane_bytes, &tmap_in, &full_bar[s], 0,
+                      p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl], p.in_stride * (by * p.RT + p.dymin) + p.plane_ry[pl],
+                      m * p.NBt);
       };
       uint32_t it = 0, wit = 0;
       if (box0 < p.num_boxes) load_box(box0, 0);
@@ -690,7 +695,10 @@ struct WHaloParams {
   int NBt, HHs, HWp, MT, strips_x, num_boxes;
   int Cblk_g, Cblk_x, ncx, Cg, Cx;          // blockIdx.z = (G channel block) * ncx + (X channel block)
   int ngroups, groups_per_cta;              // blockIdx.y selects a slice of the tap groups
-  int dymin, dxmin;
+  int dymin, dxmin;                         // smallest tap offset in plane coordinates
+  int in_stride, nplanes;                   // gathered tensor read as parity planes X_r[j] = X[s*j + r]
+  short plane_ry[4], plane_rx[4];
+  uint32_t plane_bytes;
   uint32_t grp_off16[WH_MAX_GROUPS];        // descriptor start shift of the group's first tap (16-byte units)
   unsigned char grp_ntap[WH_MAX_GROUPS];    // taps stacked in the group
   short grp_tap[WH_MAX_GROUPS][8];          // tap index (into dW) of each stacked tap
@@ -740,7 +748,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], p.x_box_bytes + p.g_box_bytes);
-        tma_load_4d(st, &tmap_x, &full_bar[s], cx0, sx * 8 + p.dxmin, p.dymin, nb * p.NBt);
+        for (int pl = 0; pl < p.nplanes; ++pl)
+          tma_load_4d(st + (size_t)pl * p.plane_bytes, &tmap_x, &full_bar[s], cx0, p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl],
+                      p.in_stride * p.dymin + p.plane_ry[pl], nb * p.NBt);
         tma_load_4d(st + p.x_stage_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
         if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
       }
@@ -839,17 +849,28 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
 
 // plans and launches the halo kernel; returns 1 if the geometry is not covered (caller falls back to the tap-box kernel)
 static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
-                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int Hq, int Wq, void* out, int Ho, int Wo,
-                           int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
-                           float* stats, cudaStream_t stream) {
+                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
+                           int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
+                           const float* bias, int act, float* stats, cudaStream_t stream) {
   if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
   HaloParams p;
   memset(&p, 0, sizeof(p));
+  // tap offset d = s * e + r: parity plane r, offset e inside the plane (floor division for negative d)
+  const int st = in_stride;
+  int tey[CONV_MAX_TAPS], tex[CONV_MAX_TAPS], tpl[CONV_MAX_TAPS];
   int dymin = 1 << 20, dymax = -(1 << 20), dxmin = 1 << 20, dxmax = -(1 << 20);
+  p.in_stride = st; p.nplanes = 0;
   for (int t = 0; t < ntaps; ++t) {
     p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t];
-    dymin = min(dymin, (int)tap_dy[t]); dymax = max(dymax, (int)tap_dy[t]);
-    dxmin = min(dxmin, (int)tap_dx[t]); dxmax = max(dxmax, (int)tap_dx[t]);
+    const int ry = ((tap_dy[t] % st) + st) % st, rx = ((tap_dx[t] % st) + st) % st;
+    tey[t] = (tap_dy[t] - ry) / st; tex[t] = (tap_dx[t] - rx) / st;
+    int pl = -1;
+    for (int i = 0; i < p.nplanes; ++i)
+      if (p.plane_ry[i] == ry && p.plane_rx[i] == rx) pl = i;
+    if (pl < 0) { pl = p.nplanes++; p.plane_ry[pl] = (short)ry; p.plane_rx[pl] = (short)rx; }
+    tpl[t] = pl;
+    dymin = min(dymin, tey[t]); dymax = max(dymax, tey[t]);
+    dxmin = min(dxmin, tex[t]); dxmax = max(dxmax, tex[t]);
   }
   const int ey = dymax - dymin, ex = dxmax - dxmin;
   if (ey > 16 || ex > 16) return 1;
@@ -859,8 +880,6 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.HWp = 8 + ex;
   p.RT = Hq <= 32 ? Hq : 32;
   p.HHs = p.RT + ey;
-  for (int t = 0; t < ntaps; ++t)
-    p.tap_off16[t] = ((uint32_t)((tap_dy[t] - dymin) * p.HWp + (tap_dx[t] - dxmin)) * rb) >> 4;
   p.w_tap_bytes = (uint32_t)p.BN * rb;
   const uint32_t budget = 200u * 1024u;
   const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 4u : 0u;
@@ -871,20 +890,25 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
     for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
       const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
-      const uint32_t stage = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
+      const uint32_t plane = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
+      const uint32_t stage = plane * (uint32_t)p.nplanes;
       if (pow2_ceil(2 * MT * p.BN) > 512) break;
       if (2u * stage + wb + stats_bytes + 768u > budget) break;
       if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
       const double eff = (double)(nbt * p.RT) / (16.0 * MT) * (resident ? 1.0 : 0.97);
       if (eff > best_eff + 0.02) {
-        best_eff = eff; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.resident = resident; p.w_bytes = wb;
+        best_eff = eff; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
+        p.w_bytes = wb;
       }
     }
     if (best_eff > 0.0 && resident) break;               // resident weights fit: take them
   }
   if (best_eff <= 0.0) return 1;
   p.wstages = p.resident ? 1 : 4;
-  p.box_bytes = (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
+  if ((size_t)p.stage_bytes + (size_t)p.HWp * rb * 16 >= (1u << 18)) return 1;        // descriptor start field is 14 bits of 16 B
+  for (int t = 0; t < ntaps; ++t)
+    p.tap_off16[t] = ((uint32_t)tpl[t] * p.plane_bytes + (uint32_t)((tey[t] - dymin) * p.HWp + (tex[t] - dxmin)) * rb) >> 4;
+  p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
   p.stages = (int)((budget - p.w_bytes - stats_bytes - 768u) / p.stage_bytes);
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
@@ -899,8 +923,10 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)ld_in * 2, (uint64_t)W * ld_in * 2, (uint64_t)H * W * ld_in * 2};
-    uint32_t box[4] = {(uint32_t)p.Cblk, (uint32_t)p.HWp, (uint32_t)p.HHs, (uint32_t)p.NBt};
-    int rc = make_tmap_bf16(&tin, in, 4, dims, strides, box, nullptr, p.Cblk * 2);
+    uint32_t box[4] = {(uint32_t)p.Cblk, (uint32_t)(p.HWp * st), (uint32_t)(p.HHs * st), (uint32_t)p.NBt};
+    uint32_t es[4] = {1u, (uint32_t)st, (uint32_t)st, 1u};
+    if (box[1] > 256 || box[2] > 256) return 1;
+    int rc = make_tmap_bf16(&tin, in, 4, dims, strides, box, es, p.Cblk * 2);
     if (rc) return rc;
     const int Ktot = ntaps * p.Cblk;
     uint64_t wd[2] = {(uint64_t)Ktot, (uint64_t)Cout_pad};
@@ -924,15 +950,25 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
 
 // plans and launches the halo weight-gradient kernel; returns 1 when the geometry is not covered
 static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
-                                 int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, float* dw, int dw_ld_tap,
-                                 int dw_ld_co, cudaStream_t stream) {
+                                 int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw,
+                                 int dw_ld_tap, int dw_ld_co, cudaStream_t stream) {
   if (Hq > 32 || Wq < 6) return 1;
   WHaloParams p;
   memset(&p, 0, sizeof(p));
+  const int st = in_stride;
+  std::vector<int> tey(ntaps), tex(ntaps), tpl(ntaps);
   int dymin = 1 << 20, dymax = -(1 << 20), dxmin = 1 << 20, dxmax = -(1 << 20);
+  p.in_stride = st; p.nplanes = 0;
   for (int t = 0; t < ntaps; ++t) {
-    dymin = min(dymin, (int)tap_dy[t]); dymax = max(dymax, (int)tap_dy[t]);
-    dxmin = min(dxmin, (int)tap_dx[t]); dxmax = max(dxmax, (int)tap_dx[t]);
+    const int ry = ((tap_dy[t] % st) + st) % st, rx = ((tap_dx[t] % st) + st) % st;
+    tey[t] = (tap_dy[t] - ry) / st; tex[t] = (tap_dx[t] - rx) / st;
+    int pl = -1;
+    for (int i = 0; i < p.nplanes; ++i)
+      if (p.plane_ry[i] == ry && p.plane_rx[i] == rx) pl = i;
+    if (pl < 0) { pl = p.nplanes++; p.plane_ry[pl] = (short)ry; p.plane_rx[pl] = (short)rx; }
+    tpl[t] = pl;
+    dymin = min(dymin, tey[t]); dymax = max(dymax, tey[t]);
+    dxmin = min(dxmin, tex[t]); dxmax = max(dxmax, tex[t]);
   }
   const int ey = dymax - dymin, ex = dxmax - dxmin;
   if (ey > 16 || ex > 16) return 1;
@@ -947,18 +983,21 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   const int tpm = 128 / p.Cblk_x;
   std::vector<int> order(ntaps);
   for (int t = 0; t < ntaps; ++t) order[t] = t;
+  // groups = runs of taps adjacent in x INSIDE one parity plane and one plane row
   std::sort(order.begin(), order.end(), [&](int a, int b) {
-    return tap_dy[a] != tap_dy[b] ? tap_dy[a] < tap_dy[b] : tap_dx[a] < tap_dx[b];
+    if (tpl[a] != tpl[b]) return tpl[a] < tpl[b];
+    return tey[a] != tey[b] ? tey[a] < tey[b] : tex[a] < tex[b];
   });
   int ngr = 0;
+  std::vector<int> grp_first;
   for (int i = 0; i < ntaps;) {
     if (ngr >= WH_MAX_GROUPS) return 1;
     int n = 1;
-    while (i + n < ntaps && n < tpm && n < 8 && tap_dy[order[i + n]] == tap_dy[order[i]] &&
-           tap_dx[order[i + n]] == tap_dx[order[i]] + n)
+    while (i + n < ntaps && n < tpm && n < 8 && tpl[order[i + n]] == tpl[order[i]] && tey[order[i + n]] == tey[order[i]] &&
+           tex[order[i + n]] == tex[order[i]] + n)
       ++n;
     p.grp_ntap[ngr] = (unsigned char)n;
-    p.grp_off16[ngr] = ((uint32_t)((tap_dy[order[i]] - dymin) * p.HWp + (tap_dx[order[i]] - dxmin)) * rbx) >> 4;
+    grp_first.push_back(order[i]);
     for (int j = 0; j < n; ++j) p.grp_tap[ngr][j] = (short)order[i + j];
     ++ngr;
     i += n;
@@ -974,15 +1013,23 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   double best = 0.0;
   for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
     const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
-    const uint32_t xs = ((uint32_t)(16 * MT + ey + 1) * p.HWp * rbx + 1023u) & ~1023u;     // +1 slot: stacked-tap overrun
+    const uint32_t plane = ((uint32_t)(16 * MT + ey + 1) * p.HWp * rbx + 1023u) & ~1023u;   // +1 slot: stacked-tap overrun
+    const uint32_t xs = plane * (uint32_t)p.nplanes;
     const uint32_t gs = ((uint32_t)(16 * MT > S ? 16 * MT : S) * 8u * rbg + 1023u) & ~1023u;
     if (2u * (xs + gs) + 1024u > budget) break;
     if (nbt * p.HHs > 256) break;
     const double eff = (double)(nbt * Hq) / (16.0 * MT);
-    if (eff > best + 0.02) { best = eff; p.NBt = nbt; p.MT = MT; p.x_stage_bytes = xs; p.stage_bytes = xs + gs; }
+    if (eff > best + 0.02) {
+      best = eff; p.NBt = nbt; p.MT = MT; p.x_stage_bytes = xs; p.stage_bytes = xs + gs; p.plane_bytes = plane;
+    }
   }
   if (best <= 0.0) return 1;
-  p.x_box_bytes = (uint32_t)(p.NBt * p.HHs) * p.HWp * rbx;
+  if ((size_t)p.stage_bytes >= (1u << 18)) return 1;
+  for (int gi = 0; gi < ngr; ++gi) {
+    const int t0 = grp_first[gi];
+    p.grp_off16[gi] = ((uint32_t)tpl[t0] * p.plane_bytes + (uint32_t)((tey[t0] - dymin) * p.HWp + (tex[t0] - dxmin)) * rbx) >> 4;
+  }
+  p.x_box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rbx;
   p.g_box_bytes = (uint32_t)(p.NBt * p.HHs) * 8u * rbg;
   p.stages = (int)((budget - 1024u) / p.stage_bytes);
   if (p.stages > 6) p.stages = 6;
@@ -999,8 +1046,10 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
     if (rc) return rc;
     uint64_t dx[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t sx[3] = {(uint64_t)ld_x * 2, (uint64_t)W * ld_x * 2, (uint64_t)H * W * ld_x * 2};
-    uint32_t bx[4] = {(uint32_t)p.Cblk_x, (uint32_t)p.HWp, (uint32_t)p.HHs, (uint32_t)p.NBt};
-    rc = make_tmap_bf16(&tx, x, 4, dx, sx, bx, nullptr, p.Cblk_x * 2);
+    uint32_t bx[4] = {(uint32_t)p.Cblk_x, (uint32_t)(p.HWp * st), (uint32_t)(p.HHs * st), (uint32_t)p.NBt};
+    uint32_t esx[4] = {1u, (uint32_t)st, (uint32_t)st, 1u};
+    if (bx[1] > 256 || bx[2] > 256) return 1;
+    rc = make_tmap_bf16(&tx, x, 4, dx, sx, bx, esx, p.Cblk_x * 2);
     if (rc) return rc;
   }
   const int nz = ncg * p.ncx;
@@ -1038,9 +1087,9 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
   JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
   JVAE_CHECK_ARG((((uintptr_t)in | (uintptr_t)wmat | (uintptr_t)out) & 15) == 0, "16-byte alignment");
   static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
-  if (in_stride == 1 && !force_v1) {
-    const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, Hq, Wq, out, Ho, Wo,
-                                   Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, (cudaStream_t)stream);
+  if (!force_v1) {
+    const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out,
+                                   Ho, Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = geometry not covered, use the tap-box kernel
   }
   ConvParams p;
@@ -1099,9 +1148,9 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   JVAE_CHECK_ARG((ld_dy % 8) == 0 && (ld_x % 8) == 0, "channel strides must be multiples of 8");
   JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
   static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
-  if (in_stride == 1 && !force_v1) {
-    const int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, dw, dw_ld_tap,
-                                         dw_ld_co, (cudaStream_t)stream);
+  if (!force_v1) {
+    const int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, in_stride, dw,
+                                         dw_ld_tap, dw_ld_co, (cudaStream_t)stream);
     if (rc <= 0) return rc;
   }
   WgradParams p;
