@@ -81,11 +81,24 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_stats_kernel(const __nv_b
   float acc[2][V];
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[0][j] = acc[1][j] = 0.f;
-  for (size_t p = (size_t)blockIdx.x * ppb + pl; p < P; p += (size_t)gridDim.x * ppb) {
-    float v[V];
-    Vec<V>::load(y + p * ld + chunk * V, v);
+  constexpr int U = 4;
+  const size_t step = (size_t)gridDim.x * ppb;
+  for (size_t p0 = (size_t)blockIdx.x * ppb + pl; p0 < P; p0 += U * step) {
+    float v[U][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      if (p < P) {
+        Vec<V>::load(y + p * ld + chunk * V, v[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) { acc[0][j] += v[u][j]; acc[1][j] += v[u][j] * v[u][j]; }
   }
   block_channel_reduce<V, 2>(acc, chunk, C, s_acc, stats);
 }
@@ -148,7 +161,7 @@ struct BnBwd {
 };
 
 template <int V>
-__global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_reduce_kernel(const BnBwd a) {
+__global__ void __launch_bounds__(NORM_MAX_THREADS, 2) bn_bwd_reduce_kernel(const BnBwd a) {
   extern __shared__ float s_acc[];
   const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
   float mean[V], rstd[V], scale[V], shift[V], acc[2][V];
@@ -160,16 +173,29 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_reduce_kernel(const B
     scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
     acc[0][j] = acc[1][j] = 0.f;
   }
-  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
-    float g[V], y[V];
-    Vec<V>::load(a.da + p * a.ld_da + chunk * V, g);
-    Vec<V>::load(a.y + p * a.ld_y + chunk * V, y);
+  constexpr int U = 4;
+  const size_t step = (size_t)gridDim.x * a.ppb;
+  for (size_t p0 = (size_t)blockIdx.x * a.ppb + pl; p0 < a.P; p0 += U * step) {
+    float g[U][V], y[U][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
-      acc[0][j] += gz;
-      acc[1][j] += gz * (y[j] - mean[j]) * rstd[j];
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      if (p < a.P) {
+        Vec<V>::load(a.da + p * a.ld_da + chunk * V, g[u]);
+        Vec<V>::load(a.y + p * a.ld_y + chunk * V, y[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { g[u][j] = 0.f; y[u][j] = 0.f; }
+      }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float gz = g[u][j] * act_grad_z(fmaf(y[u][j], scale[j], shift[j]), a.act);
+        acc[0][j] += gz;
+        acc[1][j] += gz * (y[u][j] - mean[j]) * rstd[j];
+      }
   }
   block_channel_reduce<V, 2>(acc, chunk, a.C, s_acc, a.sums);
 }
