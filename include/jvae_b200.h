@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 2
+#define JVAE_ABI_VERSION 4
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -201,15 +201,34 @@ int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const 
  *   stats (2,Cout) f32 or NULL: += per-channel sum and sum of squares of the pre-activation over the positions this
  *   call writes, taken from the fp32 accumulators (BatchNorm2d batch statistics, conv.py:216-217).
  * jvae_conv_wgrad: dw[t][co][ci] += sum_q dy[n,qy,qx,co] * x[n, qy*in_stride + tap_dy[t], qx*in_stride + tap_dx[t], ci]
- *   (fp32, atomically accumulated: zero dw first); dw strides in elements.
+ *   (fp32, atomically accumulated into dw: the caller zeroes it, or passes the live .grad buffer to accumulate into);
+ *   element (t, co, ci) lives at dw[t*dw_ld_tap + co*dw_ld_co + ci*dw_ld_ci], so the torch (Cout,Cin,kh,kw) layout is
+ *   (1, Cin*kh*kw, kh*kw).
  * ------------------------------------------------------------------------------------------ */
 int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                           const float* bias, int act, float* stats, void* stream);
+/* Data-gradient launches can fold the reduction pass of the PREVIOUS layer's BatchNorm backward into their epilogue: the
+ * output of the launch is dL/da of that layer (a = act(BN(y))), `bn` describes its BatchNorm, and `stats` (2,Cout)
+ * receives += sum g*act'(z) and sum g*act'(z)*xhat (what jvae_bn_bwd's first kernel computes; zero it first).
+ * *bn_fused (host int) is set to 1 when the kernel variant used supports the fusion, else 0: then call jvae_bn_bwd with
+ * skip_reduce = 0 as usual. */
+typedef struct jvae_bn_reduce {
+  const void* y;                /* previous layer's pre-BN output (P,C) bf16 at the pixels this launch writes */
+  int32_t ld_y;
+  const float* save_mean_rstd;  /* (2,C) from jvae_bn_apply_fwd */
+  const float* gamma;           /* (C) or NULL */
+  const float* beta;            /* (C) or NULL */
+  int32_t act;                  /* jvae_act of that layer */
+} jvae_bn_reduce;
+int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                             int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
+                             void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
+                             const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream);
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
-                    int dw_ld_co, void* stream);
+                    int dw_ld_co, int dw_ld_ci, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layers between the convolutions, NHWC bf16, P = N*H*W pixels (module/vae_layers/conv.py:189-227):
@@ -223,11 +242,11 @@ int jvae_bn_stats(const void* y, size_t P, int C, int ld, float* stats, void* st
 int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* stats, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches, int training,
                       int act, void* out, int ld_out, float* save_mean_rstd, void* stream);
-/* backward of act(BN_train(y)) given da = dL/d(out): dy (P,C) bf16, dgamma, dbeta (C) f32 (written, any may be NULL);
- * sums (2,C) f32 scratch */
+/* backward of act(BN_train(y)) given da = dL/d(out): dy (P,C) bf16, dgamma, dbeta (C) f32 (+=, any may be NULL);
+ * sums (2,C) f32 scratch; skip_reduce != 0: sums were already produced by jvae_conv_gather_gemm_bn */
 int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
                 const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
-                void* stream);
+                int skip_reduce, void* stream);
 /* dy = da * act'(.) expressed with the activation OUTPUT a_out (relu, sigmoid; act none: dy = da, dy may be NULL);
  * dbias (C) f32 += sum over pixels of dy (NULL = not wanted) */
 int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t P, int C, int act, void* dy, int ld_dy,

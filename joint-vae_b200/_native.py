@@ -33,6 +33,12 @@ class ElboCfg(ctypes.Structure):
                [('prior_stats_ready', ctypes.c_int32)]
 
 
+class BnReduce(ctypes.Structure):
+    """include/jvae_b200.h: jvae_bn_reduce"""
+    _fields_ = [('y', ctypes.c_void_p), ('ld_y', ctypes.c_int32), ('save_mean_rstd', ctypes.c_void_p),
+                ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p), ('act', ctypes.c_int32)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -78,18 +84,21 @@ def lib():
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
                                         c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int,
                                         P, P]
+    L.jvae_conv_gather_gemm_bn.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
+                                           c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                                           c_int, P, ctypes.POINTER(BnReduce), ctypes.POINTER(c_int), P]
     L.jvae_conv_wgrad.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, I16P, I16P,
-                                  c_int, P, c_int, c_int, P]
+                                  c_int, P, c_int, c_int, c_int, P]
     L.jvae_bn_stats.argtypes = [P, c_size_t, c_int, c_int, P, P]
     L.jvae_bn_apply_fwd.argtypes = [P, c_size_t, c_int, c_int, P, P, P, c_float, c_float, P, P, P, c_int, c_int, P, c_int,
                                     P, P]
-    L.jvae_bn_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, P, P, P, c_int, P, P, c_int, P, P, P]
+    L.jvae_bn_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, P, P, P, c_int, P, P, c_int, P, P, c_int, P]
     L.jvae_act_bwd.argtypes = [P, c_int, P, c_int, c_size_t, c_int, c_int, P, c_int, P, P]
     L.jvae_maxpool_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
-    if L.jvae_abi_version() != 2:
+    if L.jvae_abi_version() != 4:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -348,16 +357,29 @@ def taps_arg(taps):
 
 
 def conv_gather_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, taps, in_stride, Hq, Wq, out, Ho, Wo, Cout, ld_out,
-                     out_s=(1, 1), out_o=(0, 0), bias=None, act=0, stats=None):
-    """include/jvae_b200.h: jvae_conv_gather_gemm.  taps = (dy_array, dx_array) from taps_arg"""
-    check(lib().jvae_conv_gather_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]), taps[0],
-                                      taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s[0], out_s[1],
-                                      out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), stream()))
+                     out_s=(1, 1), out_o=(0, 0), bias=None, act=0, stats=None, bn=None):
+    """include/jvae_b200.h: jvae_conv_gather_gemm[_bn].  taps = (dy_array, dx_array) from taps_arg.
+    bn = dict(y, ld_y, save, gamma, beta, act): fold the previous layer's BatchNorm-backward reduction into this
+    data-gradient launch (sums go to `stats`); returns True when the launched kernel did it."""
+    if bn is None:
+        check(lib().jvae_conv_gather_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]),
+                                          taps[0], taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s[0],
+                                          out_s[1], out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), stream()))
+        return False
+    d = BnReduce(y=bn['y'].data_ptr(), ld_y=bn['ld_y'], save_mean_rstd=bn['save'].data_ptr(),
+                 gamma=bn['gamma'].data_ptr() if bn['gamma'] is not None else None,
+                 beta=bn['beta'].data_ptr() if bn['beta'] is not None else None, act=bn['act'])
+    fused = c_int(0)
+    check(lib().jvae_conv_gather_gemm_bn(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]),
+                                         taps[0], taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s[0],
+                                         out_s[1], out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), ctypes.byref(d),
+                                         ctypes.byref(fused), stream()))
+    return bool(fused.value)
 
 
-def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co):
+def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co, dw_ld_ci=1):
     check(lib().jvae_conv_wgrad(rawptr(dy), N, Hq, Wq, Cout, ld_dy, rawptr(x), H, W, Cin, ld_x, len(taps[0]), taps[0],
-                                taps[1], in_stride, rawptr(dw), dw_ld_tap, dw_ld_co, stream()))
+                                taps[1], in_stride, rawptr(dw), dw_ld_tap, dw_ld_co, dw_ld_ci, stream()))
 
 
 def bn_stats(y, P, C, ld, stats):
@@ -371,9 +393,9 @@ def bn_apply_fwd(y, P, C, ld_y, stats, gamma, beta, eps, momentum, running_mean,
                                   int(training), act, rawptr(out), ld_out, rawptr(save), stream()))
 
 
-def bn_bwd(da, ld_da, y, ld_y, P, C, save, gamma, beta, act, sums, dy, ld_dy, dgamma, dbeta):
+def bn_bwd(da, ld_da, y, ld_y, P, C, save, gamma, beta, act, sums, dy, ld_dy, dgamma, dbeta, skip_reduce=False):
     check(lib().jvae_bn_bwd(rawptr(da), ld_da, rawptr(y), ld_y, P, C, rawptr(save), rawptr(gamma), rawptr(beta), act,
-                            rawptr(sums), rawptr(dy), ld_dy, rawptr(dgamma), rawptr(dbeta), stream()))
+                            rawptr(sums), rawptr(dy), ld_dy, rawptr(dgamma), rawptr(dbeta), int(skip_reduce), stream()))
 
 
 def act_bwd(da, ld_da, a_out, ld_a, P, C, act, dy, ld_dy, dbias):

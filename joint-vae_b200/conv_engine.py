@@ -39,6 +39,13 @@ def cout_pad_of(c):
 
 _ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0}
 
+# Fold the BatchNorm-backward reduction of layer i-1 into the data-gradient kernel of layer i (jvae_conv_gather_gemm_bn).
+# Correct and covered by the GPU tests, but measured SLOWER on B200 at c2 (the epilogue's global reads of the saved pre-BN
+# tensor are latency-bound: +1.0 ms per fused launch against 0.37 ms saved), so it is opt-in until the operand is fed
+# through the TMA stage ring.
+import os as _os
+FUSE_BN_REDUCE = _os.environ.get('JVAE_FUSE_BN_REDUCE', '0') == '1'
+
 
 # ------------------------------------------------------------------------------------------------ kernel backend
 class NativeKernels:
@@ -69,17 +76,19 @@ class NativeKernels:
         return nat.nhwc_bf16_to_nchw(t, C)
 
     @staticmethod
-    def gather(x, Cin, wmat, cout_pad, taps, in_stride, Hq, Wq, out, Cout, out_s, out_o, bias, act, stats):
+    def gather(x, Cin, wmat, cout_pad, taps, in_stride, Hq, Wq, out, Cout, out_s, out_o, bias, act, stats, bn=None):
         N, H, W, ld_in = x.shape
         _, Ho, Wo, ld_out = out.shape
-        nat.conv_gather_gemm(x, N, H, W, Cin, ld_in, wmat, cout_pad, wmat.shape[1], taps, in_stride, Hq, Wq, out, Ho, Wo,
-                             Cout, ld_out, out_s, out_o, bias, act, stats)
+        return nat.conv_gather_gemm(x, N, H, W, Cin, ld_in, wmat, cout_pad, wmat.shape[1], taps, in_stride, Hq, Wq, out, Ho,
+                                    Wo, Cout, ld_out, out_s, out_o, bias, act, stats, bn=bn)
 
     @staticmethod
     def wgrad(g, Cg, x, Cx, taps, in_stride, dw):
+        """dw (Cg, Cx, T) fp32 (the torch weight layout with the kernel window flattened) += sum_px g x_shifted"""
         N, Hq, Wq, ld_g = g.shape
         _, H, W, ld_x = x.shape
-        nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, Cg * Cx, Cx)
+        T = len(taps[0])
+        nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, Cx * T, T)
 
     @staticmethod
     def gemm(mode, M, N, K, a, b, bias=None, act=0, out_bf16=None, out_f32=None):
@@ -137,6 +146,15 @@ def pack_gather_weights(G, idx, cin):
     return out.view(out.shape[0], T * nck * cb)
 
 
+def _live_grad(p, like):
+    """the Parameter's own dense fp32 .grad (the optimizer's flat gradient buffer, zeroed by zero_grad) when the native
+    kernels can accumulate into it directly; autograd then receives None for that parameter"""
+    if K is not NativeKernels or p is None or p.grad is None:
+        return None
+    g = p.grad
+    return g if (g.dtype == torch.float32 and g.is_contiguous() and g.device == like.device) else None
+
+
 # ------------------------------------------------------------------------------------------------ steps
 class ConvStep:
     """Conv2d | ConvTranspose2d [+ BatchNorm2d] [+ activation]"""
@@ -180,6 +198,7 @@ class ConvStep:
             self.dgrad_ops = deconv_form(k, p, s, H, W)
         self.wgrad_taps = [(i - p, j - p) for i in range(k) for j in range(k)]
         self._packed = None
+        self._packed_folded = None
         self._ctaps = {}
 
     def params(self):
@@ -194,15 +213,35 @@ class ConvStep:
             c = self._ctaps[key] = K.taps_arg(taps)
         return c
 
-    def _pack(self):
-        """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict)"""
+    def _pack(self, fold_bn=False):
+        """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict).
+        fold_bn (inference with running statistics): BatchNorm is folded into the weights and the bias, so the layer is
+        ONE kernel: W' = W * gamma * rstd, b' = (b - mean) * gamma * rstd + beta."""
         w = self.conv.weight
         key = (w._version, w.device, w.data_ptr())
-        if self._packed is not None and self._packed[0] == key:
-            return self._packed[1]
+        slot = '_packed'
+        if fold_bn:
+            bn = self.bn
+            key += tuple(t._version for t in (bn.running_mean, bn.running_var) if t is not None)
+            key += tuple(t._version for t in (bn.weight, bn.bias) if t is not None)
+            slot = '_packed_folded'
+        hit = getattr(self, slot, None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         wd = w.detach().float()
         kk = self.k * self.k
         d = {}
+        b0 = self.conv.bias.detach().float() if self.conv.bias is not None else None
+        if fold_bn:
+            scale = (bn.running_var.float() + bn.eps).rsqrt()
+            if bn.affine:
+                scale = scale * bn.weight.detach().float()
+            shift = -bn.running_mean.float() * scale
+            if bn.affine:
+                shift = shift + bn.bias.detach().float()
+            wd = wd * (scale.view(1, -1, 1, 1) if self.transposed else scale.view(-1, 1, 1, 1))
+            b0 = shift if b0 is None else b0 * scale + shift
+        d['b'] = b0
         if self.gemm1x1:
             # Bm[(y, x, co)][ci] = W[ci][co][y][x]
             d['bm'] = wd.permute(2, 3, 1, 0).reshape(kk * self.Co, self.Ci).to(torch.bfloat16).contiguous()
@@ -210,8 +249,7 @@ class ConvStep:
                 t = torch.zeros((kk * self.Co, r8(self.Ci)), dtype=torch.bfloat16, device=w.device)
                 t[:, :self.Ci] = d['bm']
                 d['bm'] = t[:, :self.Ci]
-            b = self.conv.bias
-            d['bias'] = b.detach().float().repeat(kk).contiguous() if b is not None else None
+            d['bias'] = b0.repeat(kk).contiguous() if b0 is not None else None
         else:
             if self.transposed:     # W (Ci, Co, k, k)
                 g_f = wd.permute(1, 2, 3, 0).reshape(self.Co, kk, self.Ci)
@@ -220,16 +258,19 @@ class ConvStep:
                 g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
                 g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
             d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
-            d['bwd'] = [pack_gather_weights(g_b, op['idx'], self.Co) for op in self.dgrad_ops]
-        self._packed = (key, d)
+            if not fold_bn:
+                d['bwd'] = [pack_gather_weights(g_b, op['idx'], self.Co) for op in self.dgrad_ops]
+        setattr(self, slot, (key, d))
         return d
 
     # ---- forward
     def forward(self, x, st, training):
         N = x.shape[0]
-        pk = self._pack()
         bn = self.bn
         bn_train = bn is not None and (training or not bn.track_running_stats)
+        if bn is not None and not bn_train and not torch.is_grad_enabled():
+            return self._forward_folded(x, st)
+        pk = self._pack()
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
         fused_act = self.act if bn is None else 0
         y = K.empty((N, self.Ho, self.Wo, self.ld_y), x)
@@ -260,8 +301,27 @@ class ConvStep:
         st['y'], st['save'], st['bn_train'] = y, save, bn_train
         return a
 
+    def _forward_folded(self, x, st):
+        """inference: conv + folded BatchNorm + activation in one kernel, no intermediate tensor"""
+        N = x.shape[0]
+        pk = self._pack(fold_bn=True)
+        a = K.empty((N, self.Ho, self.Wo, self.ld_a), x)
+        if self.gemm1x1:
+            kk = self.k * self.k
+            K.gemm(nat.GEMM_NT, N, kk * self.Co, self.Ci, x.view(N, x.shape[-1]), pk['bm'], bias=pk['bias'], act=self.act,
+                   out_bf16=a.view(N, kk * self.Co))
+        else:
+            for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
+                K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
+                         a, self.Co, op['out_s'], op['out_o'], pk['b'], self.act, None)
+        st['x'] = x
+        return a
+
     # ---- backward: da = dL/d(output) NHWC bf16 -> (dx or None, [param grads])
-    def backward(self, da, st, need_dx):
+    def backward(self, da, st, need_dx, prev_bn=None):
+        """prev_bn: dict describing the previous layer's train-mode BatchNorm (y, ld_y, save, gamma, beta, act, sums): its
+        backward reduction is folded into this layer's data-gradient kernel when the kernel supports it; prev_bn['done']
+        then tells that layer to skip its own reduction pass."""
         x = st['x']
         N = x.shape[0]
         P = N * self.Ho * self.Wo
@@ -272,17 +332,24 @@ class ConvStep:
                 raise NotImplementedError('backward through BatchNorm in eval mode')
             y = st['y']
             dy = K.empty(y.shape, x)
-            sums = K.empty((2, self.Co), x, torch.float32)
-            dg = K.empty((self.Co,), x, torch.float32) if bn.affine else None
-            db = K.empty((self.Co,), x, torch.float32) if bn.affine else None
+            pre = st.get('bn_sums')            # produced by the next layer's data-gradient kernel
+            sums = pre if pre is not None else K.empty((2, self.Co), x, torch.float32)
+            dg = db = lg = lb = None
+            if bn.affine:
+                lg, lb = _live_grad(bn.weight, x), _live_grad(bn.bias, x)
+                dg = lg if lg is not None else K.zeros((self.Co,), x)
+                db = lb if lb is not None else K.zeros((self.Co,), x)
             K.bn_bwd(da, da.shape[-1], y, self.ld_y, P, self.Co, st['save'], bn.weight.detach() if bn.affine else None,
-                     bn.bias.detach() if bn.affine else None, self.act, sums, dy, self.ld_y, dg, db)
-            grads['bn_w'], grads['bn_b'] = dg, db
+                     bn.bias.detach() if bn.affine else None, self.act, sums, dy, self.ld_y, dg, db,
+                     **({'skip_reduce': True} if pre is not None else {}))
+            grads['bn_w'], grads['bn_b'] = (None if lg is not None else dg), (None if lb is not None else db)
             # the bias of a convolution followed by train-mode BatchNorm has an exactly zero gradient
             # (BN subtracts the batch mean); the reference's autograd returns rounding noise here
-            grads['b'] = K.zeros((self.Co,), x) if self.conv.bias is not None else None
+            grads['b'] = K.zeros((self.Co,), x) if (self.conv.bias is not None and
+                                                     _live_grad(self.conv.bias, x) is None) else None
         else:
-            dbias = K.zeros((self.Co,), x) if self.conv.bias is not None else None
+            lbias = _live_grad(self.conv.bias, x)
+            dbias = lbias if lbias is not None else (K.zeros((self.Co,), x) if self.conv.bias is not None else None)
             if self.act == 0 and da.shape[-1] % 8 == 0:
                 dy = da
                 if dbias is not None:
@@ -292,7 +359,7 @@ class ConvStep:
                 dy = K.zeros((N, self.Ho, self.Wo, r8(self.Co)), x, torch.bfloat16) if r8(self.Co) != self.Co \
                     else K.empty((N, self.Ho, self.Wo, self.Co), x)
                 K.act_bwd(da, da.shape[-1], a, a.shape[-1], P, self.Co, self.act, dy, dy.shape[-1], dbias)
-            grads['b'] = dbias
+            grads['b'] = None if lbias is not None else dbias
         pk = self._pack()
         kk = self.k * self.k
         dx = None
@@ -313,19 +380,29 @@ class ConvStep:
                     dx = K.zeros(x.shape, x, torch.bfloat16)
                     dx.view(N, ldx)[:, :self.Ci] = tmp
         else:
-            if self.transposed:      # grid tensor = x, gathered tensor = dy   -> dw (T, Ci, Co)
-                dw = K.zeros((kk, self.Ci, self.Co), x)
-                K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw)
-                grads['w'] = dw.permute(1, 2, 0).reshape(self.Ci, self.Co, self.k, self.k)
-            else:                    # grid tensor = dy, gathered tensor = x   -> dw (T, Co, Ci)
-                dw = K.zeros((kk, self.Co, self.Ci), x)
-                K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw)
-                grads['w'] = dw.permute(1, 2, 0).reshape(self.Co, self.Ci, self.k, self.k)
+            # the kernel accumulates straight into the torch layout; when the Parameter already owns a dense fp32 .grad
+            # (the optimizer's flat gradient buffer, zeroed by zero_grad) it accumulates THERE and autograd gets None
+            w = self.conv.weight
+            live = _live_grad(w, x)
+            dw = live if live is not None else K.zeros(tuple(w.shape), x)
+            if self.transposed:      # grid tensor = x, gathered tensor = dy   -> W.grad (Ci, Co, k, k)
+                K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Ci, self.Co, kk))
+            else:                    # grid tensor = dy, gathered tensor = x   -> W.grad (Co, Ci, k, k)
+                K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Co, self.Ci, kk))
+            grads['w'] = None if live is not None else dw
             if need_dx:
                 dx = K.empty(x.shape, x)
+                fuse = FUSE_BN_REDUCE and prev_bn is not None and K is NativeKernels and \
+                    prev_bn['y'].shape[:3] == dx.shape[:3]
+                sums_prev = K.zeros((2, self.Ci), x) if fuse else None
+                done = fuse
                 for i, (op, wm) in enumerate(zip(self.dgrad_ops, pk['bwd'])):
-                    K.gather(dy, self.Co, wm, wm.shape[0], self._taps(('b', i), op['taps']), op['in_stride'], op['Hq'],
-                             op['Wq'], dx, self.Ci, op['out_s'], op['out_o'], None, 0, None)
+                    r = K.gather(dy, self.Co, wm, wm.shape[0], self._taps(('b', i), op['taps']), op['in_stride'], op['Hq'],
+                                 op['Wq'], dx, self.Ci, op['out_s'], op['out_o'], None, 0, sums_prev,
+                                 **({'bn': prev_bn} if fuse else {}))
+                    done = done and bool(r)
+                if fuse and done:
+                    prev_bn['sums'] = sums_prev
         out = [grads['w'], grads['b']]
         if bn is not None:
             out += [grads['bn_w'], grads['bn_b']]
@@ -479,7 +556,17 @@ class ConvStack:
         grads = []
         for idx in range(len(self.steps) - 1, -1, -1):
             s = self.steps[idx]
-            g, pg = s.backward(g, state[idx], need_dx or idx > 0)
+            kw = {}
+            prev = self.steps[idx - 1] if idx > 0 else None
+            if isinstance(s, ConvStep) and isinstance(prev, ConvStep) and prev.bn is not None and \
+                    state[idx - 1].get('bn_train') and not s.gemm1x1:
+                pb = prev.bn
+                kw['prev_bn'] = dict(y=state[idx - 1]['y'], ld_y=prev.ld_y, save=state[idx - 1]['save'],
+                                     gamma=pb.weight.detach() if pb.affine else None,
+                                     beta=pb.bias.detach() if pb.affine else None, act=prev.act)
+            g, pg = s.backward(g, state[idx], need_dx or idx > 0, **kw)
+            if 'prev_bn' in kw and kw['prev_bn'].get('sums') is not None:
+                state[idx - 1]['bn_sums'] = kw['prev_bn']['sums']
             grads = pg + grads
             if g is None:
                 break

@@ -278,6 +278,11 @@ struct HaloParams {
   __nv_bfloat16* out;
   float* stats;
   int cout_pad;
+  // fused BatchNorm-backward reduction (data-gradient launches): this launch's output is dL/da of the PREVIOUS layer,
+  // bn_y that layer's pre-BN output at the same pixels; stats then receives sum g*act'(z) and sum g*act'(z)*xhat
+  const __nv_bfloat16* bn_y;
+  const float* bn_save; const float* bn_gamma; const float* bn_beta;
+  int bn_ld, bn_act;
   uint32_t stage_bytes, box_bytes, w_tap_bytes, w_bytes, tmem_cols, acc_stride;
   int stages, resident, wstages;
 };
@@ -322,21 +327,66 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
 // sums of y and y^2 in registers (reduced across the CTA once, at the end of the kernel).
 template <int NCH>
 __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t t_addr, bool ok, __nv_bfloat16* orow, int ch0,
-                                                   const float* s_bias, float (&s1)[NCH * 16], float (&s2)[NCH * 16]) {
-  uint32_t r[NCH][16];
+                                                   const float* s_bias, const float* s_bn, const __nv_bfloat16* yrow,
+                                                   float (&s1)[NCH * 16], float (&s2)[NCH * 16]) {
+  // the BatchNorm-backward operand of every chunk is requested before the accumulator is read: one exposed global
+  // latency per tile instead of one per chunk
+  uint4 yq[NCH][2];
+  const bool bn_vec = p.bn_y && ok && (p.bn_ld & 7) == 0;
+  if (bn_vec) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) tmem_ld_32x16(t_addr + (uint32_t)(c * 16), r[c]);
-  tmem_ld_wait();
+    for (int c = 0; c < NCH; ++c) {
+      if (ch0 + c * 16 < p.Cout) {
+        yq[c][0] = ld_stream16(yrow + c * 16);
+        yq[c][1] = ld_stream16(yrow + c * 16 + 8);
+      }
+    }
+  }
+  // accumulator chunks: all at once for narrow tiles, two at a time for 48 / 64 channels (register budget)
+  constexpr int RG = NCH <= 2 ? NCH : 2;
+  uint32_t r[RG][16];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    if (c % RG == 0) {
+#pragma unroll
+      for (int cc = 0; cc < RG; ++cc)
+        if (c + cc < NCH) tmem_ld_32x16(t_addr + (uint32_t)((c + cc) * 16), r[cc]);
+      tmem_ld_wait();
+    }
     if (ch0 + c * 16 >= p.Cout) continue;      // warp-uniform
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float t = __uint_as_float(r[c][j]) + s_bias[c * 16 + j];
+      const float t = __uint_as_float(r[c % RG][j]) + s_bias[c * 16 + j];
       v[j] = ok ? t : 0.f;
     }
-    if (p.stats) {
+    if (p.bn_y) {
+      if (ok) {     // BatchNorm-backward sums of the previous layer: mask and xhat recomputed from its saved pre-BN output
+        float y[16];
+        if (bn_vec) {
+          const uint4 u0 = yq[c][0], u1 = yq[c][1];
+          y[0] = bf16_lo(u0.x); y[1] = bf16_hi(u0.x); y[2] = bf16_lo(u0.y); y[3] = bf16_hi(u0.y);
+          y[4] = bf16_lo(u0.z); y[5] = bf16_hi(u0.z); y[6] = bf16_lo(u0.w); y[7] = bf16_hi(u0.w);
+          y[8] = bf16_lo(u1.x); y[9] = bf16_hi(u1.x); y[10] = bf16_lo(u1.y); y[11] = bf16_hi(u1.y);
+          y[12] = bf16_lo(u1.z); y[13] = bf16_hi(u1.z); y[14] = bf16_lo(u1.w); y[15] = bf16_hi(u1.w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = (ch0 + c * 16 + j < p.Cout) ? __bfloat162float(yrow[c * 16 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int cc = c * 16 + j;
+          const float mean = s_bn[cc], rstd = s_bn[64 + cc], scale = s_bn[128 + cc], shift = s_bn[192 + cc];
+          const float z = fmaf(y[j], scale, shift);
+          float d = 1.f;
+          if (p.bn_act == JVAE_ACT_RELU) d = z > 0.f ? 1.f : 0.f;
+          else if (p.bn_act == JVAE_ACT_SIGMOID) { const float sg = 1.f / (1.f + __expf(-z)); d = sg * (1.f - sg); }
+          const float gz = v[j] * d;
+          s1[cc] += gz;
+          s2[cc] = fmaf(gz, (y[j] - mean) * rstd, s2[cc]);
+        }
+      }
+    } else if (p.stats) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) { s1[c * 16 + j] += v[j]; s2[c * 16 + j] = fmaf(v[j], v[j], s2[c * 16 + j]); }
     }
@@ -366,8 +416,8 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
 
 template <int NCH>
 __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                   float* s_stats, const float* s_bias, int warp, int lane, int nt, int box0,
-                                                   int box_step) {
+                                                   float* s_stats, const float* s_bias, const float* s_bn, int warp, int lane,
+                                                   int nt, int box0, int box_step) {
   const int q = warp & 3;
   const int mrow = q * 32 + lane;
   const int ch0 = nt * p.BN;
@@ -389,9 +439,11 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
       const int qy = by * p.RT + yy, n = mm * p.NBt + nb;
       const bool ok = (nb < p.NBt) && (yy < p.RT) && (qy < p.Hq) && (qx < p.Wq) && (n < p.N);
       const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
-      __nv_bfloat16* orow = p.out + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + (size_t)ch0;
+      const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+      __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
+      const __nv_bfloat16* yrow = p.bn_y ? p.bn_y + opix * p.bn_ld + (size_t)ch0 : nullptr;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(m * p.BN) + ((uint32_t)(q * 32) << 16);
-      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, ch0, s_bias, s1, s2);
+      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, ch0, s_bias, s_bn, yrow, s1, s2);
     }
     tc_fence_before();
     __syncwarp();
@@ -440,9 +492,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (int)blockIdx.x % p.n_tiles_n;
+  float* s_bn = s_bias + 64;                                               // [4][64]: mean, rstd, scale, shift (bn_y launches)
   for (int i = threadIdx.x; i < p.BN; i += CONV_THREADS) {
     const int ch = nt * p.BN + i;
     s_bias[i] = (p.bias && ch < p.Cout) ? p.bias[ch] : 0.f;
+    if (p.bn_y) {
+      const bool live = ch < p.Cout;
+      const float mean = live ? p.bn_save[ch] : 0.f, rstd = live ? p.bn_save[p.Cout + ch] : 0.f;
+      const float g = (live && p.bn_gamma) ? p.bn_gamma[ch] : 1.f, b = (live && p.bn_beta) ? p.bn_beta[ch] : 0.f;
+      s_bn[i] = mean; s_bn[64 + i] = rstd; s_bn[128 + i] = live ? g * rstd : 0.f; s_bn[192 + i] = live ? b - mean * g * rstd : 0.f;
+    }
   }
   const int box0 = (int)blockIdx.x / p.n_tiles_n, box_step = (int)gridDim.x / p.n_tiles_n;
   const uint32_t rb = (uint32_t)p.Cblk * 2u;
@@ -539,10 +598,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else {
     // ================= epilogue =================
     switch (p.BN >> 4) {
-      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
-      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
-      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
-      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, warp, lane, nt, box0, box_step); break;
+      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
+      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
+      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
+      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
     }
   }
   tc_fence_before();
@@ -563,7 +622,7 @@ struct WgradParams {
   int ntaps, tap0, taps_per_cta, in_stride;
   short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
   float* dw;                   // (ntaps_total, Cout, Cin) fp32, accumulated atomically
-  int dw_ld_tap, dw_ld_co;     // strides of dw in elements
+  int dw_ld_tap, dw_ld_co, dw_ld_cx;     // strides of dw in elements (tap, dY channel, X channel)
   uint32_t stage_bytes, a_bytes, tx_bytes, tmem_cols;
   int stages;
 };
@@ -667,10 +726,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         tmem_ld_wait();
         const int row = q * 16 + lane;     // valid for lane < 16
         if (lane < 16 && row < M_real) {
-          float* o = p.dw + (size_t)(tap_lo + t) * p.dw_ld_tap + (size_t)(cy0 + row) * p.dw_ld_co + cx0 + c0;
+          float* o = p.dw + (size_t)(tap_lo + t) * p.dw_ld_tap + (size_t)(cy0 + row) * p.dw_ld_co + (size_t)(cx0 + c0) * p.dw_ld_cx;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < N_real) atomicAdd(o + j, __uint_as_float(r[j]));
+            if (c0 + j < N_real) atomicAdd(o + (size_t)j * p.dw_ld_cx, __uint_as_float(r[j]));
         }
       }
     }
@@ -703,7 +762,7 @@ struct WHaloParams {
   unsigned char grp_ntap[WH_MAX_GROUPS];    // taps stacked in the group
   short grp_tap[WH_MAX_GROUPS][8];          // tap index (into dW) of each stacked tap
   float* dw;
-  int dw_ld_tap, dw_ld_co;
+  int dw_ld_tap, dw_ld_co, dw_ld_cx;
   uint32_t x_stage_bytes, stage_bytes, x_box_bytes, g_box_bytes, tmem_cols;
   int stages;
 };
@@ -811,7 +870,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cblk_g + c0), r);
         tmem_ld_wait();
         if (live) {
-          float* o = p.dw + (size_t)t * p.dw_ld_tap + (size_t)(cg0 + c0) * p.dw_ld_co + cx0 + cx;
+          float* o = p.dw + (size_t)t * p.dw_ld_tap + (size_t)(cg0 + c0) * p.dw_ld_co + (size_t)(cx0 + cx) * p.dw_ld_cx;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (c0 + i < Ng) atomicAdd(o + (size_t)i * p.dw_ld_co, __uint_as_float(r[i]));
@@ -851,7 +910,7 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
 static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                           const float* bias, int act, float* stats, cudaStream_t stream) {
+                           const float* bias, int act, float* stats, const jvae_bn_reduce* bn, cudaStream_t stream) {
   if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
   HaloParams p;
   memset(&p, 0, sizeof(p));
@@ -893,7 +952,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
       const uint32_t plane = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
       const uint32_t stage = plane * (uint32_t)p.nplanes;
       if (pow2_ceil(2 * MT * p.BN) > 512) break;
-      if (2u * stage + wb + stats_bytes + 768u > budget) break;
+      if (2u * stage + wb + stats_bytes + 1792u > budget) break;
       if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
       const double eff = (double)(nbt * p.RT) / (16.0 * MT) * (resident ? 1.0 : 0.97);
       if (eff > best_eff + 0.02) {
@@ -909,7 +968,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   for (int t = 0; t < ntaps; ++t)
     p.tap_off16[t] = ((uint32_t)tpl[t] * p.plane_bytes + (uint32_t)((tey[t] - dymin) * p.HWp + (tex[t] - dxmin)) * rb) >> 4;
   p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
-  p.stages = (int)((budget - p.w_bytes - stats_bytes - 768u) / p.stage_bytes);
+  p.stages = (int)((budget - p.w_bytes - stats_bytes - 1792u) / p.stage_bytes);
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
   p.acc_stride = (uint32_t)(p.MT * p.BN);
@@ -919,6 +978,10 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
+  if (bn) {
+    p.bn_y = reinterpret_cast<const __nv_bfloat16*>(bn->y); p.bn_ld = bn->ld_y; p.bn_save = bn->save_mean_rstd;
+    p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_act = bn->act;
+  }
   CUtensorMap tin, tw;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -936,7 +999,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes + 256 + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes + 256 + 1024 + 1024;
   static bool attr = false;
   if (!attr) {
     JVAE_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -951,7 +1014,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
 // plans and launches the halo weight-gradient kernel; returns 1 when the geometry is not covered
 static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
                                  int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw,
-                                 int dw_ld_tap, int dw_ld_co, cudaStream_t stream) {
+                                 int dw_ld_tap, int dw_ld_co, int dw_ld_cx, cudaStream_t stream) {
   if (Hq > 32 || Wq < 6) return 1;
   WHaloParams p;
   memset(&p, 0, sizeof(p));
@@ -1036,7 +1099,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   if (p.stages < 2) return 1;
   p.strips_x = (Wq + 7) / 8;
   p.num_boxes = p.strips_x * ((N + p.NBt - 1) / p.NBt);
-  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co;
+  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co; p.dw_ld_cx = dw_ld_cx;
   CUtensorMap tg, tx;
   {
     uint64_t dg[4] = {(uint64_t)Cg, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)N};
@@ -1078,7 +1141,17 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                           const float* bias, int act, float* stats, void* stream) {
+  return jvae_conv_gather_gemm_bn(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho,
+                                  Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, nullptr, nullptr, stream);
+}
+
+int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                             int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
+                             void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
+                             const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream) {
   JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
+  JVAE_CHECK_ARG(!bn || (bn->y && bn->save_mean_rstd && stats && bn->ld_y >= Cout), "bn reduce needs y, save_mean_rstd and the sums buffer");
+  if (bn_fused) *bn_fused = 0;
   JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
   JVAE_CHECK_ARG((ld_in % 8) == 0 && (ldw % 8) == 0, "input / weight channel strides must be multiples of 8");
   JVAE_CHECK_ARG(ld_out >= Cout, "ld_out < Cout");
@@ -1089,9 +1162,11 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
   static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
   if (!force_v1) {
     const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out,
-                                   Ho, Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, (cudaStream_t)stream);
+                                   Ho, Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, (cudaStream_t)stream);
+    if (rc == 0 && bn && bn_fused) *bn_fused = 1;
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = geometry not covered, use the tap-box kernel
   }
+  if (bn) stats = nullptr;       // the tap-box kernel has no fused BatchNorm-backward reduction: the caller runs jvae_bn_bwd
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.Hq = Hq; p.Wq = Wq;
@@ -1142,7 +1217,7 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
 
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
-                    int dw_ld_co, void* stream) {
+                    int dw_ld_co, int dw_ld_ci, void* stream) {
   JVAE_CHECK_ARG(dy && x && dw && tap_dy && tap_dx, "null pointer");
   JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
   JVAE_CHECK_ARG((ld_dy % 8) == 0 && (ld_x % 8) == 0, "channel strides must be multiples of 8");
@@ -1150,7 +1225,7 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
   if (!force_v1) {
     const int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, in_stride, dw,
-                                         dw_ld_tap, dw_ld_co, (cudaStream_t)stream);
+                                         dw_ld_tap, dw_ld_co, dw_ld_ci, (cudaStream_t)stream);
     if (rc <= 0) return rc;
   }
   WgradParams p;
@@ -1162,7 +1237,7 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   p.Cblk_y = cblk_of(Cout); p.Cblk_x = cblk_of(Cin);
   p.ntaps = ntaps; p.in_stride = in_stride;
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t]; }
-  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co;
+  p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co; p.dw_ld_cx = dw_ld_ci;
   p.a_bytes = 128u * 64u * 2u;     // the M=64 MMA reads 64 channel columns: reserve a full 64-wide slot for dY
   p.stage_bytes = p.a_bytes + 128u * (uint32_t)p.Cblk_x * 2u;
   p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
@@ -1367,7 +1442,7 @@ static int conv_case(const ConvCase& c, int verbose) {
     cudaMemset(dw, 0, dw_n * 4); cudaMemset(err, 0, 4);
     conv_fill_kernel<<<128, 256>>>(out, out_pix * ld_out, 5u, 0.5f);
     rc = jvae_conv_wgrad(out, c.N, Hq, Wq, c.Cout, ld_out, in, c.H, c.W, c.Cin, ld_in, ntaps, dy.data(), dx.data(), c.in_stride, dw,
-                         c.Cout * c.Cin, c.Cin, nullptr);
+                         c.Cout * c.Cin, c.Cin, 1, nullptr);
     h_err = -1.f;
     if (rc == 0) {
       wgrad_ref_kernel<<<(unsigned)((dw_n + 127) / 128), 128>>>(out, c.N, Hq, Wq, c.Cout, ld_out, in, c.H, c.W, c.Cin, ld_in, ntaps,

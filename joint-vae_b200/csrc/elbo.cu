@@ -402,7 +402,7 @@ __device__ __forceinline__ void train_latent_warp(const ElboArgs& a, int b, int 
 }
 
 template <bool XR_BF16, int LG>
-__global__ void __launch_bounds__(ELBO_THREADS) elbo_train_fwd_kernel(ElboArgs a) {
+__global__ void __launch_bounds__(ELBO_THREADS, LG <= 4 ? 12 : 8) elbo_train_fwd_kernel(ElboArgs a) {
   __shared__ float red[32];
   const int nlat = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
   if ((int)blockIdx.x < nlat) {

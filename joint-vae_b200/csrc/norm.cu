@@ -59,15 +59,31 @@ __device__ __forceinline__ float act_grad_z(float z, int act) {
   return 1.f;
 }
 
-// per-block reduction of per-thread channel partials: s_acc[(k * C) + channel] += v, then one global atomic per value
+// per-block reduction of per-thread channel partials: s_acc[(k * C) + channel] += v, then one global atomic per value.
+// When the chunk count divides the warp (power of two <= 16) the lanes that own the same chunk are folded with
+// shuffles first, so shared memory sees one atomic per chunk and warp instead of 32 / nchunk conflicting ones.
 template <int V, int NK>
 __device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][V], int chunk, int C, float* s_acc, float* gout) {
   for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
+  const int nchunk = C / V;
+  const bool fold = nchunk < 32 && (nchunk & (nchunk - 1)) == 0 && (blockDim.x & 31) == 0;
+  if (fold) {
 #pragma unroll
-  for (int k = 0; k < NK; ++k)
+    for (int k = 0; k < NK; ++k)
 #pragma unroll
-    for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], acc[k][j]);
+      for (int j = 0; j < V; ++j) {
+        float v = acc[k][j];
+        for (int off = nchunk; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        acc[k][j] = v;
+      }
+  }
+  if (!fold || (threadIdx.x & 31) < nchunk) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], acc[k][j]);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < NK * C; i += blockDim.x) atomicAdd(&gout[i], s_acc[i]);
 }
@@ -213,8 +229,8 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_apply_kernel(const Bn
     scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
     k1[j] = a.sums[c] * inv; k2[j] = a.sums[a.C + c] * inv;
     if (blockIdx.x == 0 && pl == 0) {
-      if (a.dbeta) a.dbeta[c] = a.sums[c];
-      if (a.dgamma) a.dgamma[c] = a.sums[a.C + c];
+      if (a.dbeta) a.dbeta[c] += a.sums[c];          // accumulated: the caller passes a zeroed buffer or the live .grad
+      if (a.dgamma) a.dgamma[c] += a.sums[a.C + c];
     }
   }
   for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
@@ -405,7 +421,7 @@ int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* sta
 
 int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
                 const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
-                void* stream) {
+                int skip_reduce, void* stream) {
   JVAE_CHECK_ARG(da && y && dy && sums && save_mean_rstd && P > 0 && C > 0, "bad arguments");
   JVAE_CHECK_ARG(ld_da >= C && ld_y >= C && ld_dy >= C, "leading dimension < C");
   const bool vec = vec_ok(C, {ld_da, ld_y, ld_dy}, {da, y, dy});
@@ -416,8 +432,10 @@ int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, in
   a.dy = reinterpret_cast<__nv_bfloat16*>(dy);
   a.P = P; a.C = C; a.ld_da = ld_da; a.ld_y = ld_y; a.ld_dy = ld_dy; a.nchunk = g.nchunk; a.ppb = g.ppb; a.act = act;
   a.save = save_mean_rstd; a.gamma = gamma; a.beta = beta; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
-  JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream));
-  NORM_DISPATCH(vec, bn_bwd_reduce_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream, a);
+  if (!skip_reduce) {
+    JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream));
+    NORM_DISPATCH(vec, bn_bwd_reduce_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream, a);
+  }
   NORM_DISPATCH(vec, bn_bwd_apply_kernel, g, 0, (cudaStream_t)stream, a);
   return JVAE_OK;
 }

@@ -93,9 +93,9 @@ class EmuKernels:
         N, Hq, Wq, _ = g.shape
         gf, xf = g.float()[..., :Cg], x.float()[..., :Cx]
         assert not torch.isnan(gf).any() and not torch.isnan(xf).any()
-        assert dw.shape == (len(taps[0]), Cg, Cx)
+        assert dw.shape == (Cg, Cx, len(taps[0]))
         for t in range(len(taps[0])):
-            dw[t] += torch.einsum('nhwa,nhwb->ab', gf, cls._shifted(xf, taps[0][t], taps[1][t], in_stride, Hq, Wq))
+            dw[:, :, t] += torch.einsum('nhwa,nhwb->ab', gf, cls._shifted(xf, taps[0][t], taps[1][t], in_stride, Hq, Wq))
 
     @classmethod
     def gemm(cls, mode, M, N, K, a, b, bias=None, act=0, out_bf16=None, out_f32=None):
@@ -168,9 +168,9 @@ class EmuKernels:
         s1, s2 = g.sum(0), (g * xh).sum(0)
         sums[0], sums[1] = s1, s2
         if dgamma is not None:
-            dgamma.copy_(s2)
+            dgamma += s2
         if dbeta is not None:
-            dbeta.copy_(s1)
+            dbeta += s1
         cls._flat(dy, P, ld_dy)[:, :C] = (scale * (g - s1 / P - xh * s2 / P)).to(EmuKernels.store)
 
     @classmethod
