@@ -40,9 +40,11 @@ def cout_pad_of(c):
 _ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0}
 
 # Fold the BatchNorm-backward reduction of layer i-1 into the data-gradient kernel of layer i (jvae_conv_gather_gemm_bn).
-# Correct and covered by the GPU tests, but measured SLOWER on B200 at c2 (the epilogue's global reads of the saved pre-BN
-# tensor are latency-bound: +1.0 ms per fused launch against 0.37 ms saved), so it is opt-in until the operand is fed
-# through the TMA stage ring.
+# Correct and covered by the GPU tests (run them with JVAE_FUSE_BN_REDUCE=1), but measured SLOWER on B200 at c2 even with the
+# saved pre-BN tile fed through its own TMA ring: +0.7 ms per fused 32-channel launch against 0.37 ms saved.  The N = 32
+# MMAs of these layers already saturate the shared-memory bandwidth (measured pacing), so every
+# extra shared-memory read in the epilogue slows the MMAs themselves.  Opt-in until the per-channel constants move to
+# registers / the constant bank.
 import os as _os
 FUSE_BN_REDUCE = _os.environ.get('JVAE_FUSE_BN_REDUCE', '0') == '1'
 

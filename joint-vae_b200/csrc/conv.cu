@@ -283,6 +283,8 @@ struct HaloParams {
   const __nv_bfloat16* bn_y;
   const float* bn_save; const float* bn_gamma; const float* bn_beta;
   int bn_ld, bn_act;
+  uint32_t y_stage_bytes, y_box_bytes;   // the bn_y tile of a box travels through its own TMA ring (ystages deep)
+  int ystages;
   uint32_t stage_bytes, box_bytes, w_tap_bytes, w_bytes, tmem_cols, acc_stride;
   int stages, resident, wstages;
 };
@@ -332,14 +334,12 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
   // the BatchNorm-backward operand of every chunk is requested before the accumulator is read: one exposed global
   // latency per tile instead of one per chunk
   uint4 yq[NCH][2];
-  const bool bn_vec = p.bn_y && ok && (p.bn_ld & 7) == 0;
+  const bool bn_vec = p.bn_y && ok;
   if (bn_vec) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      if (ch0 + c * 16 < p.Cout) {
-        yq[c][0] = ld_stream16(yrow + c * 16);
-        yq[c][1] = ld_stream16(yrow + c * 16 + 8);
-      }
+      yq[c][0] = *reinterpret_cast<const uint4*>(yrow + c * 16);
+      yq[c][1] = *reinterpret_cast<const uint4*>(yrow + c * 16 + 8);
     }
   }
   // accumulator chunks: all at once for narrow tiles, two at a time for 48 / 64 channels (register budget)
@@ -363,15 +363,12 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
     if (p.bn_y) {
       if (ok) {     // BatchNorm-backward sums of the previous layer: mask and xhat recomputed from its saved pre-BN output
         float y[16];
-        if (bn_vec) {
+        {
           const uint4 u0 = yq[c][0], u1 = yq[c][1];
           y[0] = bf16_lo(u0.x); y[1] = bf16_hi(u0.x); y[2] = bf16_lo(u0.y); y[3] = bf16_hi(u0.y);
           y[4] = bf16_lo(u0.z); y[5] = bf16_hi(u0.z); y[6] = bf16_lo(u0.w); y[7] = bf16_hi(u0.w);
           y[8] = bf16_lo(u1.x); y[9] = bf16_hi(u1.x); y[10] = bf16_lo(u1.y); y[11] = bf16_hi(u1.y);
           y[12] = bf16_lo(u1.z); y[13] = bf16_hi(u1.z); y[14] = bf16_lo(u1.w); y[15] = bf16_hi(u1.w);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = (ch0 + c * 16 + j < p.Cout) ? __bfloat162float(yrow[c * 16 + j]) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -416,8 +413,9 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
 
 template <int NCH>
 __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                   float* s_stats, const float* s_bias, const float* s_bn, int warp, int lane,
-                                                   int nt, int box0, int box_step) {
+                                                   float* s_stats, const float* s_bias, const float* s_bn, const uint8_t* ysm,
+                                                   uint64_t* yfull_bar, uint64_t* yempty_bar, int warp, int lane, int nt,
+                                                   int box0, int box_step) {
   const int q = warp & 3;
   const int mrow = q * 32 + lane;
   const int ch0 = nt * p.BN;
@@ -431,6 +429,8 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
     const int sx = mm % p.strips_x; mm /= p.strips_x;
     const int by = mm % p.blocks_y; mm /= p.blocks_y;
     const int qx = sx * 8 + (mrow & 7);
+    const int ys = it % (p.ystages > 0 ? p.ystages : 1);
+    if (p.bn_y) mbar_wait(&yfull_bar[ys], (it / p.ystages) & 1);
     mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
     tc_fence_after();
     int slot = mrow >> 3;
@@ -441,13 +441,18 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
       const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
       const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
       __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
-      const __nv_bfloat16* yrow = p.bn_y ? p.bn_y + opix * p.bn_ld + (size_t)ch0 : nullptr;
+      // row (128 m + mrow) of the y tile in shared memory: BN channels of the pixel this thread owns
+      const __nv_bfloat16* yrow = p.bn_y ? reinterpret_cast<const __nv_bfloat16*>(ysm + (size_t)ys * p.y_stage_bytes) +
+                                               (size_t)(m * 128 + mrow) * p.BN : nullptr;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(m * p.BN) + ((uint32_t)(q * 32) << 16);
       halo_epilogue_tile<NCH>(p, t_addr, ok, orow, ch0, s_bias, s_bn, yrow, s1, s2);
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    if (lane == 0) {
+      mbar_arrive(&tempty_bar[acc]);
+      if (p.bn_y) mbar_arrive(&yempty_bar[ys]);
+    }
   }
   if (p.stats) {
     // CTA-level reduction of the per-thread sums: warp butterfly (16 values at a time), then shared + global atomics
@@ -476,17 +481,20 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ HaloParams p) {
+                 const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + (size_t)p.stages * p.stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wsm + p.w_bytes);
+  uint8_t* ysm = wsm + p.w_bytes;                                           // [ystages][y_stage_bytes] (bn_y launches)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ysm + (size_t)p.ystages * p.y_stage_bytes);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* wfull_bar = empty_bar + 4;      // [wstages] (resident: only [0])
   uint64_t* wempty_bar = wfull_bar + 8;
   uint64_t* tfull_bar = wempty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* yfull_bar = tempty_bar + 2;     // [4]
+  uint64_t* yempty_bar = yfull_bar + 4;     // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty_bar + 4);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);                // [2][cout_pad] when p.stats
   float* s_bias = s_stats + (p.stats ? 2 * p.cout_pad : 0);                // [BN] bias of this CTA's channel tile (0 if none)
 
@@ -514,6 +522,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 4; ++a) { mbar_init(&yfull_bar[a], 1); mbar_init(&yempty_bar[a], 4); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -526,6 +535,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
+      if (p.bn_y) tma_prefetch_desc(&tmap_y);
       if (p.resident) {
         mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
         for (int t = 0; t < p.ntaps; ++t)
@@ -542,6 +552,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           tma_load_4d(smem + (size_t)s * p.stage_bytes + (size_t)pl * p.plane_bytes, &tmap_in, &full_bar[s], 0,
                       p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl], p.in_stride * (by * p.RT + p.dymin) + p.plane_ry[pl],
                       m * p.NBt);
+        if (p.bn_y) {       // the previous layer's pre-BN tile at the pixels this box writes (epilogue operand)
+          const int ys = it % p.ystages;
+          mbar_wait(&yempty_bar[ys], ((it / p.ystages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&yfull_bar[ys], p.y_box_bytes);
+          tma_load_4d(ysm + (size_t)ys * p.y_stage_bytes, &tmap_y, &yfull_bar[ys], nt * p.BN, sx * 8, by * p.RT, m * p.NBt);
+        }
       };
       uint32_t it = 0, wit = 0;
       if (box0 < p.num_boxes) load_box(box0, 0);
@@ -598,10 +614,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else {
     // ================= epilogue =================
     switch (p.BN >> 4) {
-      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
-      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
-      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
-      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, warp, lane, nt, box0, box_step); break;
+      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
+      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
+      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
+      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
     }
   }
   tc_fence_before();
@@ -910,8 +926,12 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
 static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                           const float* bias, int act, float* stats, const jvae_bn_reduce* bn, cudaStream_t stream) {
+                           const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused,
+                           cudaStream_t stream) {
   if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
+  if (bn && !(out_sy == 1 && out_sx == 1 && out_oy == 0 && out_ox == 0 && Ho == Hq && Wo == Wq)) {
+    bn = nullptr; stats = nullptr;                        // phase launches: the caller runs the separate reduction
+  }
   HaloParams p;
   memset(&p, 0, sizeof(p));
   // tap offset d = s * e + r: parity plane r, offset e inside the plane (floor division for negative d)
@@ -951,13 +971,14 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
       const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
       const uint32_t plane = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
       const uint32_t stage = plane * (uint32_t)p.nplanes;
+      const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
       if (pow2_ceil(2 * MT * p.BN) > 512) break;
-      if (2u * stage + wb + stats_bytes + 1792u > budget) break;
+      if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage > budget) break;
       if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
       const double eff = (double)(nbt * p.RT) / (16.0 * MT) * (resident ? 1.0 : 0.97);
       if (eff > best_eff + 0.02) {
         best_eff = eff; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
-        p.w_bytes = wb;
+        p.w_bytes = wb; p.y_stage_bytes = ystage;
       }
     }
     if (best_eff > 0.0 && resident) break;               // resident weights fit: take them
@@ -968,7 +989,9 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   for (int t = 0; t < ntaps; ++t)
     p.tap_off16[t] = ((uint32_t)tpl[t] * p.plane_bytes + (uint32_t)((tey[t] - dymin) * p.HWp + (tex[t] - dxmin)) * rb) >> 4;
   p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
-  p.stages = (int)((budget - p.w_bytes - stats_bytes - 1792u) / p.stage_bytes);
+  p.ystages = bn ? 3 : 0;
+  p.y_box_bytes = bn ? (uint32_t)(p.NBt * p.HHs) * 8u * (uint32_t)p.BN * 2u : 0u;
+  p.stages = (int)((budget - p.w_bytes - stats_bytes - 1792u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
   p.acc_stride = (uint32_t)(p.MT * p.BN);
@@ -978,11 +1001,18 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
+  CUtensorMap tin, tw, ty;
+  memset(&ty, 0, sizeof(ty));
   if (bn) {
     p.bn_y = reinterpret_cast<const __nv_bfloat16*>(bn->y); p.bn_ld = bn->ld_y; p.bn_save = bn->save_mean_rstd;
     p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_act = bn->act;
+    if ((bn->ld_y % 8) != 0) { set_error("jvae_conv_gather_gemm_bn: bn.ld_y must be a multiple of 8"); return JVAE_ERR_INVALID; }
+    uint64_t yd[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+    uint64_t ysd[3] = {(uint64_t)bn->ld_y * 2, (uint64_t)Wo * bn->ld_y * 2, (uint64_t)Ho * Wo * bn->ld_y * 2};
+    uint32_t ybox[4] = {(uint32_t)p.BN, 8u, (uint32_t)p.HHs, (uint32_t)p.NBt};
+    const int rcy = make_tmap_bf16(&ty, bn->y, 4, yd, ysd, ybox, nullptr, 0);
+    if (rcy) return rcy;
   }
-  CUtensorMap tin, tw;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)ld_in * 2, (uint64_t)W * ld_in * 2, (uint64_t)H * W * ld_in * 2};
@@ -999,15 +1029,17 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes + 256 + 1024 + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + (size_t)p.ystages * p.y_stage_bytes + 512 + stats_bytes +
+                      256 + 1024 + 1024;
   static bool attr = false;
   if (!attr) {
     JVAE_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
-  conv_halo_kernel<<<grid, CONV_THREADS, smem, stream>>>(tin, tw, p);
+  conv_halo_kernel<<<grid, CONV_THREADS, smem, stream>>>(tin, tw, ty, p);
   JVAE_LAUNCH_CHECK();
+  if (bn && bn_fused) *bn_fused = 1;
   return JVAE_OK;
 }
 
@@ -1162,8 +1194,8 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   static const bool force_v1 = getenv("JVAE_CONV_V1") != nullptr;
   if (!force_v1) {
     const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out,
-                                   Ho, Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, (cudaStream_t)stream);
-    if (rc == 0 && bn && bn_fused) *bn_fused = 1;
+                                   Ho, Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, bn_fused,
+                                   (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = geometry not covered, use the tap-box kernel
   }
   if (bn) stats = nullptr;       // the tap-box kernel has no fused BatchNorm-backward reduction: the caller runs jvae_bn_bwd
