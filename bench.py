@@ -218,6 +218,7 @@ def run_native(args, wl):
     ms_e2e = timed(step_e2e, args.steps)
 
     # ---- OOD scoring throughput (per-class evaluate + scores + predictions), device resident
+    n_methods = len(net.ood_methods)
     net.eval()
     with torch.no_grad():
         def score(i):
@@ -231,6 +232,30 @@ def run_native(args, wl):
         prof['elbo_eval_fwd'] = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
         nat.PROFILE = None
 
+    # ---- BASELINE configs[4]: OOD-scoring sweep over the class count (C = 10 / 100 / 1000, K = 256, L = 16), sample-sharded:
+    # every rank scores its own shard (no data-path collective); rate = samples of all ranks / max-over-ranks time
+    sweep = []
+    if args.sweep:
+        for C_ in (10, 100, 1000):
+            kw = make_ctor(wl)
+            kw.update(num_labels=C_, latent_dim=256)
+            torch.manual_seed(0)
+            m = pkg.ClassificationVariationalNetwork(**kw).to(dev)
+            m.eval()
+            xs_ = [torch.rand(B, *shape, device=dev) for _ in range(2)]
+            with torch.no_grad():
+                def sc(i, m=m, xs_=xs_):
+                    _, lg, ls, _ = m.evaluate(xs_[i % 2])
+                    m.batch_dist_measures(lg, ls, list(m.ood_methods))
+                    m.predict_after_evaluate(lg, ls, method=m.predict_methods[0])
+                for i in range(6):
+                    sc(i)
+                nat.PROFILE = {'elbo_eval_fwd': []}
+                ms_c = timed(sc, 5)
+                ev = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
+                nat.PROFILE = None
+            sweep.append({'C': C_, 'K': 256, 'L': wl['ctor']['test_latent_sampling'], 'samples_per_s': world * B * 5 / (ms_c * 1e-3),
+                          'eval_kernel_us': sum(ev) / max(1, len(ev)) * 1e3})
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -269,7 +294,8 @@ def run_native(args, wl):
         'gemm_roofline': {'bound': 'tensor', 'achieved': flops / 1e12, 'peak': tf, 'unit': 'TFLOP/s',
                           'frac': flops / 1e12 / tf, 'note': 'whole step: 3 x forward GEMM/conv FLOPs / step time'},
         'scoring': {'value': world * B * max(3, args.steps) / (ms_score * 1e-3), 'unit': 'samples/s',
-                    'methods': len(net.ood_methods)},
+                    'methods': n_methods},
+        'scoring_sweep': sweep,
     }
     if world == 1 and not args.no_cpu:
         v, dt, cores = cpu_reference_run(wl, 2, 1, args.cpu_batch)
@@ -292,6 +318,7 @@ def main():
     ap.add_argument('--conv', default='', choices=['', 'native', 'library'])
     ap.add_argument('--linear', default='', choices=['', 'native', 'library'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sweep', dest='sweep', action='store_false', help='skip the C = 10/100/1000 scoring sweep')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

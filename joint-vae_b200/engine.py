@@ -8,6 +8,7 @@ never selected silently: a 'native' op that cannot run raises.
 """
 import itertools
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -48,12 +49,13 @@ _wcache = {}
 
 
 def _weight_bf16(w):
+    """bf16 copy of a weight, cached per Parameter object (weak reference: a recycled id() never hits a stale entry)"""
     key = id(w)
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == w._version and hit[1].device == w.device:
+    if hit is not None and hit[2]() is w and hit[0] == (w._version, w.data_ptr()) and hit[1].device == w.device:
         return hit[1]
     wb = _bf16_ld8(w.detach())
-    _wcache[key] = (w._version, wb)
+    _wcache[key] = ((w._version, w.data_ptr()), wb, weakref.ref(w))
     return wb
 
 

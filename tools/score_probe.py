@@ -5,12 +5,12 @@ import bench
 import __graft_entry__ as g
 pkg = g.build()
 wl = bench.WORKLOADS['c2']
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+kw = bench.make_ctor(wl); kw.update(num_labels=C, latent_dim=K)
 torch.manual_seed(0)
-net = pkg.ClassificationVariationalNetwork(**bench.make_ctor(wl)).to('cuda:0')
+net = pkg.ClassificationVariationalNetwork(**kw).to('cuda:0')
 x = torch.rand(512, 3, 32, 32, device='cuda:0')
-y = torch.randint(0, 10, (512,), device='cuda:0')
-net.train()
-for i in range(2): net.train_step(x, y)
 net.eval()
 with torch.no_grad():
     for i in range(8):
@@ -23,4 +23,4 @@ with torch.no_grad():
         net.predict_after_evaluate(logits, losses, method=net.predict_methods[0])
         e1.record(); t2 = time.perf_counter()
         torch.cuda.synchronize(); t3 = time.perf_counter()
-        print(f'iter {i}: cpu evaluate {1e3*(t1-t0):.2f} ms, cpu scores {1e3*(t2-t1):.2f} ms, gpu span {e0.elapsed_time(e1):.2f} ms, wall {1e3*(t3-t0):.2f} ms', flush=True)
+        print(f'C={C} iter {i}: cpu evaluate {1e3*(t1-t0):.2f} ms, cpu scores {1e3*(t2-t1):.2f} ms, gpu span {e0.elapsed_time(e1):.2f} ms, wall {1e3*(t3-t0):.2f} ms', flush=True)
