@@ -753,6 +753,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
   float* s_lo = s_tot + max(C, Cp);     // (C) mean logits
   float* s_cy = s_lo + C;               // (C) cross_y per class
   float* s_li = s_cy + C;               // (warps, L) log importance weights of the class a warp works on
+  float* s_zn = s_li + (size_t)(ELBO_THREADS / 32) * L;   // (L+1) squared norms of mu and of the draws (fast path)
 
   for (int k = tid; k < K; k += ELBO_THREADS) {
     zs[k] = a.mu[(size_t)b * K + k];
@@ -821,8 +822,77 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
     __syncthreads();
   }
 
+  // ---- fast class loop (Gaussian prior, scalar variance, K <= 256: the default model).  ||T(z - m)||^2 is expanded as
+  // T^2 (||z||^2 - 2 z.m + ||m||^2): per class only the L+1 dot products z_l . m_c remain (class mean in registers, 8
+  // latent dims per lane, four rows reduced at a time), ||z_l||^2 and sum exp(log_var) are per-sample scalars.
+  const bool fast = a.var_dim == JVAE_VAR_SCALAR && a.prior_kind == JVAE_PRIOR_GAUSSIAN && K <= 256;
+  if (fast) {
+    for (int r = wid; r <= (do_iws ? L : 0); r += ELBO_THREADS / 32) {
+      float t = 0.f;
+      for (int k = lane; k < K; k += 32) { const float v = zs[(size_t)r * K + k]; t = fmaf(v, v, t); }
+      t = warp_sum(t);
+      if (lane == 0) s_zn[r] = t;
+    }
+    float sexp = 0.f;
+    for (int k = tid; k < K; k += ELBO_THREADS) sexp += expf(evar[k]);
+    sexp = block_sum(sexp, red);       // contains the __syncthreads that publishes s_zn
+    const int nrows = do_iws ? L + 1 : 1;
+    for (int c = wid; c < Cp; c += ELBO_THREADS / 32) {
+      const float Tc = a.inv_trans[c], T2 = Tc * Tc, logdet = a.logdet[c];
+      float mreg[8], mn = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        mreg[i] = (k < K) ? a.means[(size_t)c * K + k] : 0.f;
+        mn = fmaf(mreg[i], mreg[i], mn);
+      }
+      mn = warp_sum(mn);
+      float* li_w = s_li + (size_t)wid * L;
+      float kl = 0.f, var_kl = 0.f, dist = 0.f;
+      for (int r0 = 0; r0 < nrows; r0 += 4) {
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = min(lane + 32 * i, K - 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = fmaf(zs[(size_t)min(r0 + j, nrows - 1) * K + k], mreg[i], q[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = warp_sum(q[j]);
+        if (lane < 4 && r0 + lane < nrows) {
+          const int row = r0 + lane;
+          const float dot = lane == 0 ? q[0] : (lane == 1 ? q[1] : (lane == 2 ? q[2] : q[3]));
+          const float d = fmaxf(T2 * (s_zn[row] - 2.f * dot + mn), 0.f);
+          if (row == 0) {
+            dist = d;
+            kl_finish(a, d, T2 * sexp, 0.f, slv, logdet, &kl, &var_kl);
+          } else {
+            li_w[row - 1] = base_l[row - 1] - 0.5f * (float)K * LOG2PI_F - 0.5f * d - 0.5f * logdet;
+          }
+        }
+      }
+      float iws = 0.f;
+      if (do_iws) {
+        __syncwarp();
+        float mxl = -CUDART_INF_F;
+        for (int l = lane; l < L; l += 32) mxl = fmaxf(mxl, li_w[l]);
+        mxl = warp_max(mxl);
+        float se = 0.f;
+        for (int l = lane; l < L; l += 32) se += expf(li_w[l] - mxl);
+        se = warp_sum(se);
+        iws = se / (float)L + mxl;  // cvae.py:870: mean_l exp(.) + max, no log
+        __syncwarp();
+      }
+      if (lane == 0) {
+        s_kl[c] = kl;
+        s_zd[c] = dist;
+        s_vk[c] = var_kl;
+        s_iws[c] = iws;
+      }
+    }
+  }
   // ---- class loop: one warp per class, all L+1 rows of zs against mean_c
-  for (int c = wid; c < Cp; c += ELBO_THREADS / 32) {
+  for (int c = wid; c < (fast ? 0 : Cp); c += ELBO_THREADS / 32) {
     const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
     const float logdet = a.logdet[c];
     // KL terms on mu (row 0)
@@ -841,7 +911,49 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
     float iws = 0.f;
     if (do_iws) {
       float* li_w = s_li + (size_t)wid * L;
+      if (K <= 256 && a.prior_kind != JVAE_PRIOR_UNIFORM) {
+        // register-blocked path: the class mean / scale stay in registers (8 latent dims per lane) for all L draws,
+        // four draws are reduced at a time (independent shuffle chains)
+        float mreg[8], treg[8], vreg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = lane + 32 * i;
+          const bool valid = k < K;
+          mreg[i] = valid ? a.means[(size_t)c * K + k] : 0.f;
+          treg[i] = valid ? ((a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k]) : 0.f;
+          vreg[i] = valid ? 1.f : 0.f;
+        }
+        for (int l0 = 0; l0 < L; l0 += 4) {
+          float q[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = min(lane + 32 * i, K - 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int l = min(l0 + j, L - 1);
+              const float zv = zs[(size_t)(l + 1) * K + k];
+              const float w = treg[i] * (zv - mreg[i]);
+              q[j] = fmaf(w, w, q[j]);
+              nz[j] = fmaf(zv * vreg[i], zv, nz[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = warp_sum(q[j]);
+          if (a.prior_kind == JVAE_PRIOR_TILTED) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nz[j] = warp_sum(nz[j]);
+          }
+          if (lane < 4 && l0 + lane < L) {
+            const float qq = lane == 0 ? q[0] : (lane == 1 ? q[1] : (lane == 2 ? q[2] : q[3]));
+            const float nn = lane == 0 ? nz[0] : (lane == 1 ? nz[1] : (lane == 2 ? nz[2] : nz[3]));
+            float logp = -0.5f * (float)K * LOG2PI_F - 0.5f * qq - 0.5f * logdet;
+            if (a.prior_kind == JVAE_PRIOR_TILTED) logp -= sqrtf(nn);
+            li_w[l0 + lane] = base_l[l0 + lane] + logp;
+          }
+        }
+      } else
       for (int l = 0; l < L; ++l) {
+
         const float* zr = zs + (size_t)(l + 1) * K;
         float q = 0.f, nz = 0.f;
         for (int k = lane; k < K; k += 32) {
@@ -1246,7 +1358,7 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
   cudaStream_t st = (cudaStream_t)stream;
   const int Cmax = a.C > a.Cp ? a.C : a.Cp;
   const size_t smem = ((size_t)(a.L + 1) * a.K + a.K + a.L + 4 * (size_t)a.Cp + Cmax + 2 * (size_t)a.C +
-                       (size_t)(ELBO_THREADS / 32) * a.L) * sizeof(float);
+                       (size_t)(ELBO_THREADS / 32) * a.L + (size_t)(a.L + 1)) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("%s: (L+1)*K + 7*C floats = %zu bytes of shared memory exceed 200 KB", __func__, smem);
     return JVAE_ERR_UNSUPPORTED;
