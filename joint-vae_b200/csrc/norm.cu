@@ -35,14 +35,14 @@ template <> struct Vec<1> {
 struct Geo {
   int nchunk, ppb, threads, grid;
 };
-static Geo make_geo(size_t P, int C, int V) {
+static Geo make_geo(size_t P, int C, int V, int blocks_per_sm = 8) {
   Geo g;
   g.nchunk = C / V;
   g.ppb = NORM_MAX_THREADS / g.nchunk;
   if (g.ppb < 1) g.ppb = 1;
   g.threads = g.nchunk * g.ppb;
   size_t want = (P + g.ppb - 1) / g.ppb;
-  const size_t cap = (size_t)sm_count() * 8;
+  const size_t cap = (size_t)sm_count() * blocks_per_sm;
   g.grid = (int)(want < cap ? (want ? want : 1) : cap);
   return g;
 }
@@ -434,7 +434,8 @@ int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, in
   a.save = save_mean_rstd; a.gamma = gamma; a.beta = beta; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
   if (!skip_reduce) {
     JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream));
-    NORM_DISPATCH(vec, bn_bwd_reduce_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream, a);
+    const Geo gr = make_geo(P, C, vec ? 8 : 1, 2);     // one resident wave: the per-block reduction tail runs once
+    NORM_DISPATCH(vec, bn_bwd_reduce_kernel, gr, 2 * C * sizeof(float), (cudaStream_t)stream, a);
   }
   NORM_DISPATCH(vec, bn_bwd_apply_kernel, g, 0, (cudaStream_t)stream, a);
   return JVAE_OK;
