@@ -27,15 +27,27 @@ def _digest():
     files.append(os.path.join(HERE, '..', 'include', 'jvae_b200.h'))
     for f in files:
         with open(f, 'rb') as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())      # not the absolute path: the tree moves between machines
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
 def build(force=False, verbose=False):
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    """Compiles csrc/*.cu when the sources changed since the last build.  Safe to call from several processes at once
+    (one rank per GPU under torchrun): an exclusive file lock serialises them and the late comers find the fresh stamp."""
+    import fcntl
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    with open(os.path.join(HERE, 'build', '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
