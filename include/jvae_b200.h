@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 4
+#define JVAE_ABI_VERSION 5
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -75,7 +75,8 @@ typedef struct jvae_elbo_cfg {
 } jvae_elbo_cfg;
 
 /* bytes of scratch the ELBO entry points need for `cfg`.  The first 4*B bytes (arrival counters) must be ZERO before
- * the first use; every launch leaves them zero again, so one workspace can be reused without clearing. */
+ * the first use; every launch leaves them zero again, so one workspace can be reused without clearing AS LONG AS the
+ * layout (B, L, K, number of priors) stays the same: use one workspace per layout, or re-zero it when the layout changes. */
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg);
 
 /* Prior statistics (mean of the class means, its variance, log det Sigma_c: cvae.py:747-754, priors.py:173-186) into the
@@ -198,8 +199,9 @@ int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const 
  *   in  (N,H,W,ld_in) bf16, Cin real channels; wmat (Cout_pad, ldw) bf16 with row co = [tap][chunk][Cblk] where
  *   Cblk = 16/32/64 for Cin <= 16 / <= 32 / > 32 and chunk = ceil(Cin/Cblk) (zero padded); Cout_pad a multiple of 16
  *   (of 256 above 256); out (N,Ho,Wo,ld_out) bf16, channels >= Cout up to ld_out are written as zeros.
- *   stats (2,Cout) f32 or NULL: += per-channel sum and sum of squares of the pre-activation over the positions this
- *   call writes, taken from the fp32 accumulators (BatchNorm2d batch statistics, conv.py:216-217).
+ *   stats (2,Cout) f64 or NULL: += per-channel sum and sum of squares of the pre-activation over the positions this
+ *   call writes, taken from the fp32 accumulators (BatchNorm2d batch statistics, conv.py:216-217); fp64 so that the
+ *   arrival order of warps / CTAs does not change the result (run-to-run reproducible).
  * jvae_conv_wgrad: dw[t][co][ci] += sum_q dy[n,qy,qx,co] * x[n, qy*in_stride + tap_dy[t], qx*in_stride + tap_dx[t], ci]
  *   (fp32, atomically accumulated into dw: the caller zeroes it, or passes the live .grad buffer to accumulate into);
  *   element (t, co, ci) lives at dw[t*dw_ld_tap + co*dw_ld_co + ci*dw_ld_ci], so the torch (Cout,Cin,kh,kw) layout is
@@ -208,7 +210,7 @@ int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const 
 int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                          const float* bias, int act, float* stats, void* stream);
+                          const float* bias, int act, double* stats, void* stream);
 /* Data-gradient launches can fold the reduction pass of the PREVIOUS layer's BatchNorm backward into their epilogue: the
  * output of the launch is dL/da of that layer (a = act(BN(y))), `bn` describes its BatchNorm, and `stats` (2,Cout)
  * receives += sum g*act'(z) and sum g*act'(z)*xhat (what jvae_bn_bwd's first kernel computes; zero it first).
@@ -225,7 +227,7 @@ typedef struct jvae_bn_reduce {
 int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                              int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                              void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                             const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream);
+                             const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream);
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, int dw_ld_ci, void* stream);
@@ -235,17 +237,17 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
  * BatchNorm2d (torch semantics: biased variance to normalise, unbiased for running_var, momentum 0.1),
  * activation backward + bias gradient, MaxPool2d(2), UpsamplingNearest2d(2).
  * ------------------------------------------------------------------------------------------ */
-/* stats (2,C) += per-channel sum / sum of squares of y (P,C) with leading dimension ld (zero stats first) */
-int jvae_bn_stats(const void* y, size_t P, int C, int ld, float* stats, void* stream);
+/* stats (2,C) f64 += per-channel sum / sum of squares of y (P,C) with leading dimension ld (zero stats first) */
+int jvae_bn_stats(const void* y, size_t P, int C, int ld, double* stats, void* stream);
 /* out = act(gamma * (y - mean) * rstd + beta).  training != 0: mean / biased var from stats (sums over P), writes
  * save_mean_rstd (2,C), updates running_mean / running_var / num_batches (any may be NULL); training == 0: running stats */
-int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* stats, const float* gamma, const float* beta,
+int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const double* stats, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches, int training,
                       int act, void* out, int ld_out, float* save_mean_rstd, void* stream);
 /* backward of act(BN_train(y)) given da = dL/d(out): dy (P,C) bf16, dgamma, dbeta (C) f32 (+=, any may be NULL);
- * sums (2,C) f32 scratch; skip_reduce != 0: sums were already produced by jvae_conv_gather_gemm_bn */
+ * sums (2,C) f64 scratch; skip_reduce != 0: sums were already produced by jvae_conv_gather_gemm_bn */
 int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
-                const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
+                const float* gamma, const float* beta, int act, double* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
                 int skip_reduce, void* stream);
 /* dy = da * act'(.) expressed with the activation OUTPUT a_out (relu, sigmoid; act none: dy = da, dy may be NULL);
  * dbias (C) f32 += sum over pixels of dy (NULL = not wanted) */

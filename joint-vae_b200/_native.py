@@ -98,7 +98,7 @@ def lib():
     L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
-    if L.jvae_abi_version() != 4:
+    if L.jvae_abi_version() != 5:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -180,11 +180,16 @@ class _timed:
 
 
 def workspace(cfg, device):
+    """Scratch buffer of the ELBO entry points.  ONE buffer per workspace layout (the layout depends on B, L, K and the
+    number of priors): the kernels keep their arrival counters zero between launches only within a layout, so a buffer
+    is never shared between two layouts (train and eval steps of different L or batch size get their own)."""
     n = int(lib().jvae_elbo_workspace_bytes(ctypes.byref(cfg)))
-    key = (device, torch.cuda.current_stream().cuda_stream)
+    key = (device, torch.cuda.current_stream().cuda_stream, cfg.B, cfg.L, cfg.K, cfg.C if cfg.conditional else 1)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
-        ws = torch.zeros(max(n, 1 << 16), dtype=torch.uint8, device=device)    # counters start at zero
+        if len(_ws_cache) > 64:
+            _ws_cache.clear()
+        ws = torch.zeros(max(n, 1 << 12), dtype=torch.uint8, device=device)    # counters start at zero
         _ws_cache[key] = ws
     return ws, n
 

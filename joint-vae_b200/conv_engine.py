@@ -276,7 +276,7 @@ class ConvStep:
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
         fused_act = self.act if bn is None else 0
         y = K.empty((N, self.Ho, self.Wo, self.ld_y), x)
-        stats = K.zeros((2, self.Co), x) if bn_train else None
+        stats = K.zeros((2, self.Co), x, torch.float64) if bn_train else None
         if self.gemm1x1:
             kk = self.k * self.k
             a2 = x.view(N, x.shape[-1])
@@ -335,7 +335,7 @@ class ConvStep:
             y = st['y']
             dy = K.empty(y.shape, x)
             pre = st.get('bn_sums')            # produced by the next layer's data-gradient kernel
-            sums = pre if pre is not None else K.empty((2, self.Co), x, torch.float32)
+            sums = pre if pre is not None else K.empty((2, self.Co), x, torch.float64)
             dg = db = lg = lb = None
             if bn.affine:
                 lg, lb = _live_grad(bn.weight, x), _live_grad(bn.bias, x)
@@ -396,7 +396,7 @@ class ConvStep:
                 dx = K.empty(x.shape, x)
                 fuse = FUSE_BN_REDUCE and prev_bn is not None and K is NativeKernels and \
                     prev_bn['y'].shape[:3] == dx.shape[:3]
-                sums_prev = K.zeros((2, self.Ci), x) if fuse else None
+                sums_prev = K.zeros((2, self.Ci), x, torch.float64) if fuse else None
                 done = fuse
                 for i, (op, wm) in enumerate(zip(self.dgrad_ops, pk['bwd'])):
                     r = K.gather(dy, self.Co, wm, wm.shape[0], self._taps(('b', i), op['taps']), op['in_stride'], op['Hq'],
@@ -610,7 +610,13 @@ def run(mods, x, image_out=False):
     key = (tuple(id(m) for m in mods), tuple(x.shape[1:]), bool(image_out))
     stack = _stacks.get(key)
     if stack is None:
-        stack = _stacks[key] = ConvStack(list(mods), tuple(x.shape[1:]), image_out)
+        try:
+            stack = ConvStack(list(mods), tuple(x.shape[1:]), image_out)
+        except NotImplementedError as e:
+            stack = e                  # remembered: the engine routes this stack to the library path
+        _stacks[key] = stack
+    if isinstance(stack, NotImplementedError):
+        raise stack
     training = any(m.training for m in mods)
     params = [p for p in stack.parameters]
     live = [p if p is not None else torch.empty(0, device=x.device) for p in params]

@@ -37,7 +37,7 @@ struct ConvParams {
   int act;
   const float* bias;
   __nv_bfloat16* out;
-  float* stats;                // (2, Cout) per-channel sum / sum of squares of the pre-activation, += (or null)
+  double* stats;               // (2, Cout) per-channel sum / sum of squares of the pre-activation, += (or null)
   int cout_pad;                // padded channel count (size of the shared-memory statistics accumulators)
   uint32_t stage_bytes, a_bytes, tx_bytes, tmem_cols;
   int stages;
@@ -87,12 +87,12 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
   uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][cout_pad] when p.stats
+  double* s_stats = reinterpret_cast<double*>(tmem_slot + 4);   // [2][cout_pad] when p.stats (fp64: order-independent sums)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_per_tile = p.ntaps * p.nCk;
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -208,8 +208,8 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
           const float s1 = warp_sum16(v, lane, &chn);
           const float s2 = warp_sum16(sq, lane, &chn);
           if ((lane & 1) == 0 && ch0 + c0 + chn < p.Cout) {
-            atomicAdd(&s_stats[ch0 + c0 + chn], s1);
-            atomicAdd(&s_stats[p.cout_pad + ch0 + c0 + chn], s2);
+            atomicAdd(&s_stats[ch0 + c0 + chn], (double)s1);
+            atomicAdd(&s_stats[p.cout_pad + ch0 + c0 + chn], (double)s2);
           }
         }
         if (ok) {
@@ -241,8 +241,8 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
       const int t = threadIdx.x - 64;
       for (int i = t; i < 2 * p.cout_pad; i += 128) {
         const int ch = i % p.cout_pad;
-        const float val = s_stats[i];
-        if (ch < p.Cout && val != 0.f) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
+        const double val = s_stats[i];
+        if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
       }
     }
   }
@@ -276,7 +276,7 @@ struct HaloParams {
   int Ho, Wo, Cout, ldc, out_sy, out_sx, out_oy, out_ox, act;
   const float* bias;
   __nv_bfloat16* out;
-  float* stats;
+  double* stats;
   int cout_pad;
   // fused BatchNorm-backward reduction (data-gradient launches): this launch's output is dL/da of the PREVIOUS layer,
   // bn_y that layer's pre-BN output at the same pixels; stats then receives sum g*act'(z) and sum g*act'(z)*xhat
@@ -413,7 +413,7 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
 
 template <int NCH>
 __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                   float* s_stats, const float* s_bias, const float* s_bn, const uint8_t* ysm,
+                                                   double* s_stats, const float* s_bias, const float* s_bn, const uint8_t* ysm,
                                                    uint64_t* yfull_bar, uint64_t* yempty_bar, int warp, int lane, int nt,
                                                    int box0, int box_step) {
   const int q = warp & 3;
@@ -465,16 +465,16 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
       const float t1 = warp_sum16(a, lane, &chn);
       const float t2 = warp_sum16(b, lane, &chn);
       if ((lane & 1) == 0 && ch0 + c * 16 + chn < p.Cout) {
-        atomicAdd(&s_stats[ch0 + c * 16 + chn], t1);
-        atomicAdd(&s_stats[p.cout_pad + ch0 + c * 16 + chn], t2);
+        atomicAdd(&s_stats[ch0 + c * 16 + chn], (double)t1);
+        atomicAdd(&s_stats[p.cout_pad + ch0 + c * 16 + chn], (double)t2);
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int t = threadIdx.x - 64;
     for (int i = t; i < 2 * p.cout_pad; i += 128) {
       const int ch = i % p.cout_pad;
-      const float val = s_stats[i];
-      if (ch < p.Cout && val != 0.f) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
+      const double val = s_stats[i];
+      if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
     }
   }
 }
@@ -495,8 +495,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* yfull_bar = tempty_bar + 2;     // [4]
   uint64_t* yempty_bar = yfull_bar + 4;     // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty_bar + 4);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);                // [2][cout_pad] when p.stats
-  float* s_bias = s_stats + (p.stats ? 2 * p.cout_pad : 0);                // [BN] bias of this CTA's channel tile (0 if none)
+  double* s_stats = reinterpret_cast<double*>(tmem_slot + 4);              // [2][cout_pad] when p.stats (fp64 sums)
+  float* s_bias = reinterpret_cast<float*>(s_stats + (p.stats ? 2 * p.cout_pad : 0));   // [BN] bias of this CTA's channel tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (int)blockIdx.x % p.n_tiles_n;
@@ -515,7 +515,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const uint32_t rb = (uint32_t)p.Cblk * 2u;
 
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
@@ -926,7 +926,7 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
 static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                           const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused,
+                           const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused,
                            cudaStream_t stream) {
   if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
   if (bn && !(out_sy == 1 && out_sx == 1 && out_oy == 0 && out_ox == 0 && Ho == Hq && Wo == Wq)) {
@@ -961,7 +961,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.HHs = p.RT + ey;
   p.w_tap_bytes = (uint32_t)p.BN * rb;
   const uint32_t budget = 200u * 1024u;
-  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 4u : 0u;
+  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 8u : 0u;
   const uint32_t w_res = (uint32_t)ntaps * p.w_tap_bytes;
   // best (NBt) for resident and streamed weights
   double best_eff = 0.0;
@@ -1172,7 +1172,7 @@ extern "C" {
 int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                           int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                           void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                          const float* bias, int act, float* stats, void* stream) {
+                          const float* bias, int act, double* stats, void* stream) {
   return jvae_conv_gather_gemm_bn(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho,
                                   Wo, Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, nullptr, nullptr, stream);
 }
@@ -1180,7 +1180,7 @@ int jvae_conv_gather_gemm(const void* in, int N, int H, int W, int Cin, int ld_i
 int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                              int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                              void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
-                             const float* bias, int act, float* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream) {
+                             const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream) {
   JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
   JVAE_CHECK_ARG(!bn || (bn->y && bn->save_mean_rstd && stats && bn->ld_y >= Cout), "bn reduce needs y, save_mean_rstd and the sums buffer");
   if (bn_fused) *bn_fused = 0;
@@ -1214,7 +1214,7 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.stats = stats; p.cout_pad = Cout_pad;
-  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 4u : 0u;
+  const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 8u : 0u;
   p.a_bytes = 128u * p.Cblk * 2u;
   p.tx_bytes = p.a_bytes + (uint32_t)p.BN * p.Cblk * 2u;      // bytes the two TMA boxes deliver per stage
   p.stage_bytes = (p.tx_bytes + 1023u) & ~1023u;
@@ -1396,7 +1396,7 @@ __global__ void f32_cmp_kernel(const float* a, const float* b, size_t n, float* 
 }
 
 // per-channel sum / sum of squares of a dense (pixels, C) fp32 tensor restricted to the masked pixels; one thread per channel
-__global__ void stats_ref_kernel(const float* ref, int C, size_t pixels, const float* mask, float* out) {
+__global__ void stats_ref_kernel(const float* ref, int C, size_t pixels, const float* mask, const double* got, float* out, float* gotf) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
@@ -1406,6 +1406,7 @@ __global__ void stats_ref_kernel(const float* ref, int C, size_t pixels, const f
     s1 += v; s2 += v * v;
   }
   out[c] = (float)s1; out[C + c] = (float)s2;
+  gotf[c] = (float)got[c]; gotf[C + c] = (float)got[C + c];
 }
 
 struct ConvCase { int N, H, W, Cin, Cout, k, pad, in_stride, out_s, act; };
@@ -1425,10 +1426,10 @@ static int conv_case(const ConvCase& c, int verbose) {
   const int Cout_pad = c.Cout > 256 ? ((c.Cout + 255) / 256) * 256 : r16(c.Cout);
   const int ldw = ntaps * nCk * Cblk, ld_out = r8(c.Cout);
   const size_t in_n = (size_t)c.N * c.H * c.W * ld_in, w_n = (size_t)Cout_pad * ldw, out_pix = (size_t)c.N * Ho * Wo;
-  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *mask, *stats = nullptr, *stats_ref = nullptr; short *ddy, *ddx;
+  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *mask, *stats_ref = nullptr, *stats_f = nullptr; double* stats = nullptr; short *ddy, *ddx;
   if (c.act == 0) {
-    cudaMalloc(&stats, 2 * c.Cout * 4); cudaMalloc(&stats_ref, 2 * c.Cout * 4);
-    cudaMemset(stats, 0, 2 * c.Cout * 4);
+    cudaMalloc(&stats, 2 * c.Cout * 8); cudaMalloc(&stats_ref, 2 * c.Cout * 4); cudaMalloc(&stats_f, 2 * c.Cout * 4);
+    cudaMemset(stats, 0, 2 * c.Cout * 8);
   }
   cudaMalloc(&in, in_n * 2); cudaMalloc(&w, w_n * 2); cudaMalloc(&out, out_pix * ld_out * 2);
   cudaMalloc(&ref, out_pix * c.Cout * 4); cudaMalloc(&bias, c.Cout * 4); cudaMalloc(&err, 4); cudaMalloc(&mask, out_pix * 4);
@@ -1454,8 +1455,8 @@ static int conv_case(const ConvCase& c, int verbose) {
                                                              c.in_stride, Hq, Wq, ref, Ho, Wo, c.Cout, c.out_s, c.out_s, 0, 0, bias, c.act);
     conv_cmp_kernel<<<128, 256>>>(out, ld_out, ref, c.Cout, out_pix, mask, err);
     if (stats) {
-      stats_ref_kernel<<<(c.Cout + 63) / 64, 64>>>(ref, c.Cout, out_pix, mask, stats_ref);
-      f32_cmp_kernel<<<1, 256>>>(stats, stats_ref, 2 * (size_t)c.Cout, err);      // folded into the same error word
+      stats_ref_kernel<<<(c.Cout + 63) / 64, 64>>>(ref, c.Cout, out_pix, mask, stats, stats_ref, stats_f);
+      f32_cmp_kernel<<<1, 256>>>(stats_f, stats_ref, 2 * (size_t)c.Cout, err);      // folded into the same error word
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("[selftest] conv: CUDA error %s\n", cudaGetErrorString(e)); rc = -2; }
@@ -1490,7 +1491,7 @@ static int conv_case(const ConvCase& c, int verbose) {
     fails += ok2 ? 0 : 1;
     cudaFree(dw); cudaFree(dwr);
   }
-  if (stats) { cudaFree(stats); cudaFree(stats_ref); }
+  if (stats) { cudaFree(stats); cudaFree(stats_ref); cudaFree(stats_f); }
   cudaFree(in); cudaFree(w); cudaFree(out); cudaFree(ref); cudaFree(bias); cudaFree(err); cudaFree(mask); cudaFree(ddy); cudaFree(ddx);
   return fails;
 }

@@ -60,11 +60,13 @@ __device__ __forceinline__ float act_grad_z(float z, int act) {
 }
 
 // per-block reduction of per-thread channel partials: s_acc[(k * C) + channel] += v, then one global atomic per value.
+// Shared and global accumulators are fp64: the order in which warps / blocks arrive does not change the fp32 result,
+// so the statistics (and everything downstream) are reproducible run to run.
 // When the chunk count divides the warp (power of two <= 16) the lanes that own the same chunk are folded with
 // shuffles first, so shared memory sees one atomic per chunk and warp instead of 32 / nchunk conflicting ones.
 template <int V, int NK>
-__device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][V], int chunk, int C, float* s_acc, float* gout) {
-  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_acc[i] = 0.f;
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][V], int chunk, int C, double* s_acc, double* gout) {
+  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   const int nchunk = C / V;
   const bool fold = nchunk < 32 && (nchunk & (nchunk - 1)) == 0 && (blockDim.x & 31) == 0;
@@ -82,17 +84,30 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][V], int ch
 #pragma unroll
     for (int k = 0; k < NK; ++k)
 #pragma unroll
-      for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], acc[k][j]);
+      for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], (double)acc[k][j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NK * C; i += blockDim.x) atomicAdd(&gout[i], s_acc[i]);
 }
 
+// same, for a float destination (bias gradients accumulate straight into the fp32 .grad buffer)
+template <int V, int NK>
+__device__ __forceinline__ void block_channel_reduce_f32(float (&acc)[NK][V], int chunk, int C, double* s_acc, float* gout) {
+  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_acc[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + chunk * V + j], (double)acc[k][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NK * C; i += blockDim.x) atomicAdd(&gout[i], (float)s_acc[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ statistics
 template <int V>
 __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, size_t P, int C, int ld,
-                                                                    int nchunk, int ppb, float* stats) {
-  extern __shared__ float s_acc[];
+                                                                    int nchunk, int ppb, double* stats) {
+  extern __shared__ double s_acc[];
   const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
   float acc[2][V];
 #pragma unroll
@@ -123,7 +138,7 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_stats_kernel(const __nv_b
 struct BnFwd {
   const __nv_bfloat16* y; __nv_bfloat16* out;
   size_t P; int C, ld_y, ld_out, nchunk, ppb, act, training;
-  const float* stats; const float* gamma; const float* beta;
+  const double* stats; const float* gamma; const float* beta;
   float* running_mean; float* running_var; long long* num_batches; float* save;
   float eps, momentum;
 };
@@ -137,9 +152,10 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_apply_fwd_kernel(const Bn
     const int c = chunk * V + j;
     float mean, rstd;
     if (a.training) {
-      const float inv = 1.f / (float)a.P;
-      mean = a.stats[c] * inv;
-      const float var = fmaxf(a.stats[a.C + c] * inv - mean * mean, 0.f);
+      const double inv = 1.0 / (double)a.P;
+      const double mean_d = a.stats[c] * inv;
+      mean = (float)mean_d;
+      const float var = fmaxf((float)(a.stats[a.C + c] * inv - mean_d * mean_d), 0.f);
       rstd = rsqrtf(var + a.eps);
       if (blockIdx.x == 0 && pl == 0) {
         a.save[c] = mean; a.save[a.C + c] = rstd;
@@ -172,13 +188,13 @@ struct BnBwd {
   const __nv_bfloat16* da; const __nv_bfloat16* y; __nv_bfloat16* dy;
   size_t P; int C, ld_da, ld_y, ld_dy, nchunk, ppb, act;
   const float* save; const float* gamma; const float* beta;
-  float* sums;            // (2, C): sum g, sum g * xhat   (zeroed by the caller before the reduce kernel)
+  double* sums;           // (2, C): sum g, sum g * xhat   (zeroed by the caller before the reduce kernel)
   float* dgamma; float* dbeta;
 };
 
 template <int V>
 __global__ void __launch_bounds__(NORM_MAX_THREADS, 2) bn_bwd_reduce_kernel(const BnBwd a) {
-  extern __shared__ float s_acc[];
+  extern __shared__ double s_acc[];
   const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
   float mean[V], rstd[V], scale[V], shift[V], acc[2][V];
 #pragma unroll
@@ -227,10 +243,10 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_apply_kernel(const Bn
     mean[j] = a.save[c]; rstd[j] = a.save[a.C + c];
     const float g = a.gamma ? a.gamma[c] : 1.f, b = a.beta ? a.beta[c] : 0.f;
     scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
-    k1[j] = a.sums[c] * inv; k2[j] = a.sums[a.C + c] * inv;
+    k1[j] = (float)(a.sums[c] * (double)inv); k2[j] = (float)(a.sums[a.C + c] * (double)inv);
     if (blockIdx.x == 0 && pl == 0) {
-      if (a.dbeta) a.dbeta[c] += a.sums[c];          // accumulated: the caller passes a zeroed buffer or the live .grad
-      if (a.dgamma) a.dgamma[c] += a.sums[a.C + c];
+      if (a.dbeta) a.dbeta[c] += (float)a.sums[c];   // accumulated: the caller passes a zeroed buffer or the live .grad
+      if (a.dgamma) a.dgamma[c] += (float)a.sums[a.C + c];
     }
   }
   for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) act_bwd_kernel(const __nv_bf
                                                                    const __nv_bfloat16* __restrict__ aout, int ld_a, size_t P, int C,
                                                                    int nchunk, int ppb, int act, __nv_bfloat16* dy, int ld_dy,
                                                                    float* dbias) {
-  extern __shared__ float s_acc[];
+  extern __shared__ double s_acc[];
   const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
   float acc[1][V];
 #pragma unroll
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) act_bwd_kernel(const __nv_bf
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[0][j] += g[j];
   }
-  if (dbias) block_channel_reduce<V, 1>(acc, chunk, C, s_acc, dbias);
+  if (dbias) block_channel_reduce_f32<V, 1>(acc, chunk, C, s_acc, dbias);
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / up-sampling
@@ -392,17 +408,17 @@ using namespace jvae;
 
 extern "C" {
 
-int jvae_bn_stats(const void* y, size_t P, int C, int ld, float* stats, void* stream) {
+int jvae_bn_stats(const void* y, size_t P, int C, int ld, double* stats, void* stream) {
   JVAE_CHECK_ARG(y && stats && P > 0 && C > 0 && ld >= C, "bad arguments");
   const bool vec = vec_ok(C, {ld}, {y});
   JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
   const Geo g = make_geo(P, C, vec ? 8 : 1);
-  NORM_DISPATCH(vec, bn_stats_kernel, g, 2 * C * sizeof(float), (cudaStream_t)stream,
+  NORM_DISPATCH(vec, bn_stats_kernel, g, 2 * C * sizeof(double), (cudaStream_t)stream,
                 reinterpret_cast<const __nv_bfloat16*>(y), P, C, ld, g.nchunk, g.ppb, stats);
   return JVAE_OK;
 }
 
-int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* stats, const float* gamma, const float* beta,
+int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const double* stats, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, int64_t* num_batches, int training,
                       int act, void* out, int ld_out, float* save_mean_rstd, void* stream) {
   JVAE_CHECK_ARG(y && out && P > 0 && C > 0 && ld_y >= C && ld_out >= C, "bad arguments");
@@ -420,7 +436,7 @@ int jvae_bn_apply_fwd(const void* y, size_t P, int C, int ld_y, const float* sta
 }
 
 int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, int C, const float* save_mean_rstd,
-                const float* gamma, const float* beta, int act, float* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
+                const float* gamma, const float* beta, int act, double* sums, void* dy, int ld_dy, float* dgamma, float* dbeta,
                 int skip_reduce, void* stream) {
   JVAE_CHECK_ARG(da && y && dy && sums && save_mean_rstd && P > 0 && C > 0, "bad arguments");
   JVAE_CHECK_ARG(ld_da >= C && ld_y >= C && ld_dy >= C, "leading dimension < C");
@@ -433,9 +449,9 @@ int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, in
   a.P = P; a.C = C; a.ld_da = ld_da; a.ld_y = ld_y; a.ld_dy = ld_dy; a.nchunk = g.nchunk; a.ppb = g.ppb; a.act = act;
   a.save = save_mean_rstd; a.gamma = gamma; a.beta = beta; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
   if (!skip_reduce) {
-    JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), (cudaStream_t)stream));
+    JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), (cudaStream_t)stream));
     const Geo gr = make_geo(P, C, vec ? 8 : 1, 2);     // one resident wave: the per-block reduction tail runs once
-    NORM_DISPATCH(vec, bn_bwd_reduce_kernel, gr, 2 * C * sizeof(float), (cudaStream_t)stream, a);
+    NORM_DISPATCH(vec, bn_bwd_reduce_kernel, gr, 2 * C * sizeof(double), (cudaStream_t)stream, a);
   }
   NORM_DISPATCH(vec, bn_bwd_apply_kernel, g, 0, (cudaStream_t)stream, a);
   return JVAE_OK;
@@ -449,7 +465,7 @@ int jvae_act_bwd(const void* da, int ld_da, const void* a_out, int ld_a, size_t 
   const bool vec = vec_ok(C, {ld_da, a_out ? ld_a : 8, dy ? ld_dy : 8}, {da, a_out, dy});
   JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
   const Geo g = make_geo(P, C, vec ? 8 : 1);
-  NORM_DISPATCH(vec, act_bwd_kernel, g, C * sizeof(float), (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(da),
+  NORM_DISPATCH(vec, act_bwd_kernel, g, C * sizeof(double), (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(da),
                 ld_da, reinterpret_cast<const __nv_bfloat16*>(a_out), ld_a, P, C, g.nchunk, g.ppb, act,
                 reinterpret_cast<__nv_bfloat16*>(dy), ld_dy, dbias);
   return JVAE_OK;

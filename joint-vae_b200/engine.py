@@ -7,6 +7,7 @@ library setting exists only for layer families whose sm_100a kernel has not land
 never selected silently: a 'native' op that cannot run raises.
 """
 import itertools
+import logging
 import os
 import weakref
 
@@ -20,6 +21,7 @@ POLICY = {
     'conv': os.environ.get('JVAE_CONV', 'native'),
 }
 _rng_offset = itertools.count(1)
+_library_stacks = set()
 
 
 def _r8(n):
@@ -153,8 +155,12 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
             x = torch.nn.functional.leaky_relu(x, m.negative_slope)
         elif type(m) in _ACT_OF:
             x = m(x)
+        elif any(True for _ in m.parameters()):
+            # a parametrised module without a native kernel (e.g. torchvision's residual blocks): library path, bf16
+            with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
+                x = m(x)
         else:
-            x = m(x)     # Reshape and other shape-only modules
+            x = m(x)     # Reshape, pooling and other parameter-free modules
         i += 1
     if out_dtype is not None and x.dtype != out_dtype:
         x = x.to(out_dtype)
@@ -167,7 +173,16 @@ def run_conv_stack(mods, x, image_out=False):
     arm of bench.py --conv library and for layer types without a native kernel (never selected silently)."""
     if POLICY['conv'] == 'native':
         from . import conv_engine
-        return conv_engine.run(mods, x, image_out=image_out)
+        try:
+            return conv_engine.run(mods, x, image_out=image_out)
+        except NotImplementedError as e:
+            # a layer type without a native kernel (e.g. torchvision's overlapping MaxPool2d(3, 2, 1) in the resnet stem):
+            # this stack runs through the library path; said once per stack, never silently
+            key = tuple(id(m) for m in mods)
+            if key not in _library_stacks:
+                _library_stacks.add(key)
+                logging.warning('conv stack %s runs through the library (cuDNN) path: %s',
+                                [type(m).__name__ for m in mods], e)
     with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
         x = x.contiguous(memory_format=torch.channels_last)
         for m in mods:

@@ -184,7 +184,16 @@ class ResOrDenseNetFeatures(nn.Sequential):
     def __init__(self, model_name='resnet152', input_shape=(3, 32, 32), pretrained=True):
         from torchvision import models
         assert input_shape[0] == 3
-        model = getattr(models, model_name)(weights='DEFAULT' if pretrained else None)
+        try:
+            model = getattr(models, model_name)(weights='DEFAULT' if pretrained else None)
+        except Exception as e:      # no network / no cached weights: the reference would stop here
+            if not pretrained:
+                raise
+            import logging
+            logging.warning('pretrained weights of %s are not available (%s): random initialisation', model_name,
+                            type(e).__name__)
+            model = getattr(models, model_name)(weights=None)
+            pretrained = False
         modules = list(model.children())
         super().__init__(*modules[:-1])
         self.architecture = {'features': model_name}

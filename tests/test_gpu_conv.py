@@ -100,7 +100,7 @@ def test_batchnorm_kernels(pkg, C, ld):
     buf[:, :C] = y
     gamma = torch.rand(C, device=DEV) + 0.5
     beta = torch.randn(C, device=DEV) * 0.2
-    stats = torch.zeros(2, C, device=DEV)
+    stats = torch.zeros(2, C, device=DEV, dtype=torch.float64)
     nat.bn_stats(buf, P, C, ld, stats)
     yf = y.float()
     assert _rel(stats[0], yf.sum(0)) < 1e-4 and _rel(stats[1], (yf * yf).sum(0)) < 1e-4
@@ -120,7 +120,7 @@ def test_batchnorm_kernels(pkg, C, ld):
     dab[:, :C] = da
     want.backward(da.float())
     dy = torch.zeros(P, ld, dtype=torch.bfloat16, device=DEV)
-    sums = torch.empty(2, C, device=DEV)
+    sums = torch.empty(2, C, device=DEV, dtype=torch.float64)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     nat.bn_bwd(dab, ld, buf, ld, P, C, save, gamma, beta, 1, sums, dy, ld, dg, db)
     assert _rel(dy[:, :C], yr.grad) < 1e-2
