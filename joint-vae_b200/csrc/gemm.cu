@@ -19,6 +19,8 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
   int M, N, K, ldd, act, accumulate;
+  int stages;      // ring depth actually used (<= GemmSmem::STAGES): short reductions take less shared memory, so several
+                   // CTAs share an SM and their prologue / load / epilogue latencies overlap
   const float* bias;
   __nv_bfloat16* out_bf16;
   float* out_f32;
@@ -41,14 +43,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* accum_bar = empty_bar + S::STAGES;
+  const int STG = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STG * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STG;
+  uint64_t* accum_bar = empty_bar + STG;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,7 +61,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < S::STAGES; ++s) {
+    for (int s = 0; s < STG; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -76,8 +79,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ================= TMA producer =================
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
+        const int s = kb % STG;
+        const uint32_t ph = (kb / STG) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
@@ -102,8 +105,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
+        const int s = kb % STG;
+        const uint32_t ph = (kb / STG) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
@@ -254,7 +257,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_done = true;
   }
   dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN);
-  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  GemmParams q = p;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  q.stages = num_kb < S::STAGES ? (num_kb < 2 ? 2 : num_kb) : S::STAGES;
+  const size_t smem = (size_t)q.stages * S::STAGE_BYTES + 256 + 1024;
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, q);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }
