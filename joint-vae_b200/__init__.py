@@ -10,5 +10,6 @@ The directory name is not an importable identifier; load it with `__graft_entry_
 from . import _native, engine            # noqa: F401
 from . import cvae, distributed           # noqa: F401
 from .module import losses, priors, optimizers, vae_layers   # noqa: F401
+from . import utils                        # noqa: F401
 
 ClassificationVariationalNetwork = cvae.ClassificationVariationalNetwork

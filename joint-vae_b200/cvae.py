@@ -651,6 +651,34 @@ class ClassificationVariationalNetwork(nn.Module):
         y = torch.cat([b[1] for b in batches])
         return {m: float((preds[m] == y).float().mean()) for m in methods}
 
+    def ood_detection_rates(self, ind_batches, ood_batches, ood_methods='all', kept_tpr=None, update_self_ood=True,
+                            epoch='last', set_name='ood'):
+        """The arithmetic of cvae.py:1455-1911 for one OOD set: scores of the in-distribution and of the OOD batches
+        (per-class evaluate + batch_dist_measures, device resident, no per-batch host copies), then per method the ROC
+        table on the device (utils/roc_curves.py of this package: '-2s' -> around-mean, '-a-p-q' -> (p, q), else
+        one-sided).  Returns {method: {epochs, n, mean, std, auc, tpr, fpr, thresholds}} with the reference's keys
+        (cvae.py:1883-1890); fpr at TPR 95 % is `utils.roc_curves.fpr_at_tpr(r['fpr'], r['tpr'], 0.95)`."""
+        from .utils.roc_curves import roc_curve
+        methods = [m for m in self.ood_methods if not m.startswith('odin')] if ood_methods == 'all' else list(ood_methods)
+        kept_tpr = kept_tpr or [pc / 100 for pc in range(90, 100)]
+        ind, _ = self.score_batches(ind_batches, methods=methods, predict_methods=[])
+        ood, _ = self.score_batches(ood_batches, methods=methods, predict_methods=[])
+        epoch = self.trained if epoch == 'last' else epoch
+        results = {}
+        for m in methods:
+            two_sided = False
+            if m.endswith('-2s'):
+                two_sided = 'around-mean'
+            if '-a-' in m:
+                two_sided = tuple(int(_) for _ in m.split('-')[-2:])
+            auc, fpr, tpr, thr = roc_curve(ind[m], ood[m], *kept_tpr, two_sided=two_sided)
+            results[m] = {'epochs': epoch, 'n': int(ood[m].numel()), 'mean': float(ood[m].mean()),
+                          'std': float(ood[m].std()), 'auc': auc, 'tpr': kept_tpr, 'fpr': list(fpr),
+                          'thresholds': thr}      # the reference stores list(dict) = the two key names here
+        if update_self_ood:
+            self.ood_results.setdefault(epoch, {})[set_name] = results
+        return results
+
     # ------------------------------------------------------------------------------------------ persistence
     def save(self, dir_name):
         """state.pth / optimizer.pth / params.json / train_params.json as cvae.py:2650-2675"""

@@ -15,7 +15,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+    """model fixtures (tests/golden/make_golden.py); roc_cases.npz belongs to tests/test_roc_golden.py"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('roc_'))
 
 
 @pytest.fixture(scope='session')
