@@ -626,9 +626,11 @@ class ClassificationVariationalNetwork(nn.Module):
 
     # ------------------------------------------------------------------------------------------ scoring loops
     @torch.no_grad()
-    def score_batches(self, batches, methods=None, predict_methods=None):
+    def score_batches(self, batches, methods=None, predict_methods=None, recorder=None):
         """The per-batch body of accuracy() / ood_detection_rates() (cvae.py:1629-1687, 1788-1833): per-class evaluate,
-        OOD scores and predictions, accumulated on the device; nothing is pulled to the host per batch."""
+        OOD scores and predictions, accumulated on the device; nothing is pulled to the host per batch.
+        recorder: a utils.save_load.LossRecorder that receives every loss tensor of the batch, the logits transposed to
+        (C, N) and y_true when the batch carries labels (cvae.py:1332-1334, 1673-1675)."""
         methods = methods or [m for m in self.ood_methods if not m.startswith('odin')]
         predict_methods = predict_methods or self.predict_methods
         scores = {m: [] for m in methods}
@@ -637,6 +639,11 @@ class ClassificationVariationalNetwork(nn.Module):
         for b in batches:
             x = b[0] if isinstance(b, (tuple, list)) else b
             _, logits, losses, _ = self.evaluate(x)
+            if recorder is not None:
+                rec = dict(losses, logits=logits.T)
+                if isinstance(b, (tuple, list)) and len(b) > 1:
+                    rec['y_true'] = b[1]
+                recorder.append_batch(**rec)
             for m, v in self.batch_dist_measures(logits, losses, methods).items():
                 scores[m].append(v)
             for m in predict_methods:
