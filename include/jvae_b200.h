@@ -172,7 +172,8 @@ int jvae_sample_bwd(int B, int L, int K, const float* head, const float* log_var
  * ConvTranspose2d on a 1x1 input, conv-models.ini:25).  bf16 operands, fp32 accumulation in TMEM.
  *   D[M,N] = act( A[M,K] * W[N,K]^T + bias[N] )
  * ------------------------------------------------------------------------------------------ */
-enum jvae_act { JVAE_ACT_NONE = 0, JVAE_ACT_RELU = 1, JVAE_ACT_SIGMOID = 2 };
+enum jvae_act { JVAE_ACT_NONE = 0, JVAE_ACT_RELU = 1, JVAE_ACT_SIGMOID = 2, JVAE_ACT_LEAKY = 3 };   /* leaky: slope 0.01 (nn.LeakyReLU default, misc.py:27) */
+#define JVAE_LEAKY_SLOPE 0.01f
 enum jvae_gemm_mode {
   JVAE_GEMM_NT = 0,  /* D[M,N] = A[M,K] . B[N,K]^T   forward:  y = x W^T                       */
   JVAE_GEMM_NN = 1,  /* D[M,N] = A[M,K] . B[K,N]     dgrad:    dx = dy W                        */

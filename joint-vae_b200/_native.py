@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, 'libjvae_sm100.so')
 F32, BF16 = 0, 1
 VAR_DIM = {'scalar': 0, 'diag': 1, 'full': 2}
 PRIOR_KIND = {'gaussian': 0, 'tilted': 1, 'uniform': 2}
-ACT = {'none': 0, 'linear': 0, 'relu': 1, 'sigmoid': 2}
+ACT = {'none': 0, 'linear': 0, 'relu': 1, 'sigmoid': 2, 'leaky': 3}
+LEAKY_SLOPE = 0.01      # JVAE_LEAKY_SLOPE: nn.LeakyReLU() default, the only slope the reference builds (misc.py:27)
 NSCORES, NPRED = 16, 4
 SCORE_INDEX = {'elbo': 0, 'max': 0, 'sum': 1, 'mean': 2, 'iws': 3, 'soft': 4, 'softkl': 4, 'zdist': 5, 'kl': 6,
                'mse': 7, 'wmse': 8, 'logits': 9, 'baseline': 10, 'hyz': 11, 'std': 12, 'softiws': 13}

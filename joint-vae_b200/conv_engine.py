@@ -37,7 +37,7 @@ def cout_pad_of(c):
     return ((c + 255) // 256) * 256 if c > 256 else ((c + 15) // 16) * 16
 
 
-_ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0}
+_ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0, nn.LeakyReLU: 3}
 
 # Fold the BatchNorm-backward reduction of layer i-1 into the data-gradient kernel of layer i (jvae_conv_gather_gemm_bn).
 # Correct and covered by the GPU tests (run them with JVAE_FUSE_BN_REDUCE=1), but measured SLOWER on B200 at c2 even with the
@@ -492,9 +492,9 @@ class ConvStack:
                     j += 1
                 if j < n and type(mods[j]) in _ACT_CODE:
                     act = _ACT_CODE[type(mods[j])]
+                    if act == 3 and abs(mods[j].negative_slope - nat.LEAKY_SLOPE) > 1e-12:
+                        raise NotImplementedError('LeakyReLU with a slope other than 0.01 has no native kernel')
                     j += 1
-                elif j < n and isinstance(mods[j], (nn.LeakyReLU,)):
-                    raise NotImplementedError('LeakyReLU has no native kernel yet')
                 groups.append(('conv', m, bn, act))
                 i = j
             elif isinstance(m, nn.MaxPool2d):

@@ -219,6 +219,9 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
           } else if (p.act == JVAE_ACT_SIGMOID) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (ch0 + c0 + j < p.Cout) ? 1.f / (1.f + __expf(-v[j])) : 0.f;
+          } else if (p.act == JVAE_ACT_LEAKY) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
           }
           if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
             uint4 o0, o1;
@@ -378,6 +381,7 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
           float d = 1.f;
           if (p.bn_act == JVAE_ACT_RELU) d = z > 0.f ? 1.f : 0.f;
           else if (p.bn_act == JVAE_ACT_SIGMOID) { const float sg = 1.f / (1.f + __expf(-z)); d = sg * (1.f - sg); }
+          else if (p.bn_act == JVAE_ACT_LEAKY) d = z > 0.f ? 1.f : JVAE_LEAKY_SLOPE;
           const float gz = v[j] * d;
           s1[cc] += gz;
           s2[cc] = fmaf(gz, (y[j] - mean) * rstd, s2[cc]);
@@ -394,6 +398,9 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
       } else if (p.act == JVAE_ACT_SIGMOID) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      } else if (p.act == JVAE_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
       }
       const int c0 = c * 16;
       if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {

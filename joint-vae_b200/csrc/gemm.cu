@@ -39,6 +39,7 @@ struct GemmSmem {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == JVAE_ACT_RELU) return fmaxf(v, 0.f);
   if (act == JVAE_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (act == JVAE_ACT_LEAKY) return v > 0.f ? v : JVAE_LEAKY_SLOPE * v;
   return v;
 }
 

@@ -50,12 +50,14 @@ static Geo make_geo(size_t P, int C, int V, int blocks_per_sm = 8) {
 __device__ __forceinline__ float act_fwd(float z, int act) {
   if (act == JVAE_ACT_RELU) return fmaxf(z, 0.f);
   if (act == JVAE_ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
+  if (act == JVAE_ACT_LEAKY) return z > 0.f ? z : JVAE_LEAKY_SLOPE * z;
   return z;
 }
 // derivative of the activation expressed with the pre-activation z
 __device__ __forceinline__ float act_grad_z(float z, int act) {
   if (act == JVAE_ACT_RELU) return z > 0.f ? 1.f : 0.f;
   if (act == JVAE_ACT_SIGMOID) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
+  if (act == JVAE_ACT_LEAKY) return z > 0.f ? 1.f : JVAE_LEAKY_SLOPE;
   return 1.f;
 }
 
@@ -283,7 +285,9 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) act_bwd_kernel(const __nv_bf
       float o[V];
       Vec<V>::load(aout + p * ld_a + chunk * V, o);
 #pragma unroll
-      for (int j = 0; j < V; ++j) g[j] *= (act == JVAE_ACT_RELU) ? (o[j] > 0.f ? 1.f : 0.f) : o[j] * (1.f - o[j]);
+      for (int j = 0; j < V; ++j)
+        g[j] *= (act == JVAE_ACT_RELU) ? (o[j] > 0.f ? 1.f : 0.f)
+                : (act == JVAE_ACT_LEAKY) ? (o[j] > 0.f ? 1.f : JVAE_LEAKY_SLOPE) : o[j] * (1.f - o[j]);
     }
     if (dy) Vec<V>::store(dy + p * ld_dy + chunk * V, g);
 #pragma unroll

@@ -24,6 +24,7 @@ __global__ void ref_gemm_kernel(int M, int N, int K, const __nv_bfloat16* a, lon
   if (bias) acc += bias[n];
   if (act == JVAE_ACT_RELU) acc = fmaxf(acc, 0.f);
   else if (act == JVAE_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+  else if (act == JVAE_ACT_LEAKY) acc = acc > 0.f ? acc : JVAE_LEAKY_SLOPE * acc;
   out[(size_t)m * N + n] = acc;
 }
 
@@ -107,6 +108,7 @@ extern "C" int jvae_selftest(int verbose) {
     }
   fails += gemm_case(JVAE_GEMM_NT, 256, 256, 128, JVAE_ACT_RELU, true, verbose);
   fails += gemm_case(JVAE_GEMM_NT, 130, 72, 64, JVAE_ACT_SIGMOID, true, verbose);
+  fails += gemm_case(JVAE_GEMM_NT, 200, 48, 96, JVAE_ACT_LEAKY, true, verbose);
   fails += conv_selftest(verbose);
   if (verbose) printf("[selftest] %d failure(s)\n", fails);
   return fails;

@@ -77,7 +77,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.act = act
         ctx.has_bias = b is not None
         ctx.x_dtype = x.dtype
-        ctx.save_for_backward(xb, wb, out if act in ('relu', 'sigmoid') else None)
+        ctx.save_for_backward(xb, wb, out if act in ('relu', 'sigmoid', 'leaky') else None)
         return out
 
     @staticmethod
@@ -90,6 +90,8 @@ class _LinearFn(torch.autograd.Function):
         elif ctx.act == 'sigmoid':
             o = out.float()
             dy = dy.float() * o * (1 - o)
+        elif ctx.act == 'leaky':        # the output keeps the sign of the pre-activation
+            dy = torch.where(out > 0, dy, dy * nat.LEAKY_SLOPE)
         dzb = _bf16_ld8(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -116,10 +118,20 @@ def linear(x, w, b, act='linear', out_dtype=torch.bfloat16):
         y = torch.relu(y)
     elif act == 'sigmoid':
         y = torch.sigmoid(y)
+    elif act == 'leaky':
+        y = torch.nn.functional.leaky_relu(y, nat.LEAKY_SLOPE)
     return y.to(out_dtype)
 
 
-_ACT_OF = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Identity: 'linear'}
+_ACT_OF = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Identity: 'linear', nn.LeakyReLU: 'leaky'}
+
+
+def _act_name(m):
+    """name of the fused activation a module maps to, or None (LeakyReLU: only the default slope has a kernel)"""
+    name = _ACT_OF.get(type(m))
+    if name == 'leaky' and abs(m.negative_slope - nat.LEAKY_SLOPE) > 1e-12:
+        return None
+    return name
 _CONV_TYPES = (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d, nn.UpsamplingNearest2d)
 
 
@@ -138,21 +150,19 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
         last_linear = isinstance(m, nn.Linear) and not any(isinstance(k, nn.Linear) for k in mods[i + 1:])
         if isinstance(m, nn.Linear):
             act = 'linear'
-            if i + 1 < n and type(mods[i + 1]) in _ACT_OF:
-                act = _ACT_OF[type(mods[i + 1])]
+            if i + 1 < n and _act_name(mods[i + 1]) is not None:
+                act = _act_name(mods[i + 1])
                 i += 1
             dt = out_dtype if (last_linear and out_dtype is not None) else torch.bfloat16
             x = linear(x, m.weight, m.bias, act=act, out_dtype=dt)
         elif isinstance(m, _CONV_TYPES):
             j = i
-            while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF or isinstance(mods[j], nn.LeakyReLU)):
+            while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF):
                 j += 1
             x = run_conv_stack(mods[i:j], x, image_out=image_out and j == n)
             i = j - 1
         elif isinstance(m, nn.Dropout):
             x = torch.nn.functional.dropout(x, m.p, seq.training)
-        elif isinstance(m, nn.LeakyReLU):
-            x = torch.nn.functional.leaky_relu(x, m.negative_slope)
         elif type(m) in _ACT_OF:
             x = m(x)
         elif any(True for _ in m.parameters()):

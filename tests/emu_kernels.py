@@ -15,6 +15,8 @@ def _act(z, act):
         return z.clamp_min(0)
     if act == 2:
         return torch.sigmoid(z)
+    if act == 3:
+        return torch.where(z > 0, z, 0.01 * z)
     return z
 
 
@@ -164,6 +166,8 @@ class EmuKernels:
         elif act == 2:
             s = torch.sigmoid(z)
             g = g * s * (1 - s)
+        elif act == 3:
+            g = torch.where(z > 0, g, 0.01 * g)
         xh = (v - mean) * rstd
         s1, s2 = g.sum(0), (g * xh).sum(0)
         sums[0], sums[1] = s1, s2
@@ -179,7 +183,7 @@ class EmuKernels:
         g = cls._flat(da, P, ld_da)[:, :C].float()
         if act:
             o = cls._flat(a_out, P, ld_a)[:, :C].float()
-            g = g * ((o > 0).float() if act == 1 else o * (1 - o))
+            g = g * ((o > 0).float() if act == 1 else (torch.where(o > 0, 1.0, 0.01) if act == 3 else o * (1 - o)))
         if dy is not None:
             cls._flat(dy, P, ld_dy)[:, :C] = g.to(EmuKernels.store)
         if dbias is not None:

@@ -36,6 +36,11 @@ CASES = [
     ('output', '[x3+1]8-8:2++1-!2x3+1', (6, 3, 3), True, 'sigmoid'),
     ('output', '[!x3+1-U:2]U-!8-U-!3', (4, 2, 2), True, 'linear'),
     ('output', '[x4+1]8x4+1:2-!3x3+1', (6, 3, 3), False, 'linear'),  # even kernel, stride 2, no output padding
+    # activation = leaky (config.ini:113 of the reference), with and without BatchNorm
+    ('input/leaky', '[x5+2]8-8:2-16', (3, 8, 8), True, None),
+    ('input/leaky', '[x3-Mx2]8-M-24', (3, 12, 12), False, None),
+    ('output/leaky', '[x5+2]16x4+0-16:2++1-!3x5+2', (12, 1, 1), True, 'linear'),
+    ('output/leaky', '[x5+2]16x4+0-8:2++1-!3x5+2', (12, 1, 1), False, 'sigmoid'),
 ]
 
 
@@ -49,8 +54,9 @@ def test_stack_matches_torch(pkg, ce, monkeypatch, where, spec, shape, bn, out_a
     monkeypatch.setattr(EmuKernels, 'act_dtype', store)
     torch.manual_seed(0)
     build = pkg.module.vae_layers.build_de_conv_layers
+    where, _, act = where.partition('/')
     kw = dict(output_activation=out_act) if where == 'output' else {}
-    seq = build(shape, spec, batch_norm=bn, where=where, **kw)
+    seq = build(shape, spec, batch_norm=bn, where=where, activation=act or 'relu', **kw)
     for m in seq:
         if isinstance(m, torch.nn.BatchNorm2d):
             m.weight.data.uniform_(0.5, 1.5)
@@ -117,6 +123,6 @@ def test_phase_tables_cover_every_tap_once(pkg):
 
 
 def test_unsupported_layers_raise(pkg, ce):
-    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.LeakyReLU())
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.LeakyReLU(0.2))
     with pytest.raises(NotImplementedError):
         ce.run(list(seq), torch.randn(1, 3, 4, 4))

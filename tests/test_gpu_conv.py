@@ -27,6 +27,11 @@ CASES = [
     ('output', 'deconv32+', (32, 1, 1), 8, True, 'sigmoid'),
     ('output', 'ivgg', (16, 2, 2), 6, True, 'linear'),
     ('output', '[x4+1]8x4+1:2-!3x3+1', (6, 3, 3), 9, False, 'linear'),
+    # activation = leaky (config.ini:113 of the reference)
+    ('input/leaky', 'conv32', (3, 32, 32), 16, True, None),
+    ('input/leaky', 'conv32', (3, 32, 32), 8, False, None),
+    ('output/leaky', 'deconv32', (64, 1, 1), 16, True, 'linear'),
+    ('output/leaky', 'deconv32', (64, 1, 1), 8, False, 'sigmoid'),
 ]
 
 
@@ -34,8 +39,10 @@ CASES = [
 def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
     from jointvae_b200 import conv_engine as ce
     torch.manual_seed(0)
+    where, _, act = where.partition('/')
     kw = dict(output_activation=out_act) if where == 'output' else {}
-    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=bn, where=where, **kw).to(DEV)
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=bn, where=where, activation=act or 'relu',
+                                                     **kw).to(DEV)
     for m in seq:
         if isinstance(m, torch.nn.BatchNorm2d):
             m.weight.data.uniform_(0.5, 1.5)

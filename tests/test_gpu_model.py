@@ -131,3 +131,22 @@ def _eval(pkg, net, d, cfg, x, tol):
             net._fused = f
             assert (got == plain).all(), m
             assert (got == want).mean() >= 0.8, (m, got, want)
+
+
+@pytest.mark.parametrize('act', ['relu', 'leaky', 'sigmoid', 'linear'])
+def test_fused_linear_activations(pkg, act):
+    """Linear + activation pairs of the dense stacks (layers.py:284-298): forward and the three gradients vs torch fp32"""
+    torch.manual_seed(0)
+    M, K, N = 200, 96, 72
+    x = torch.randn(M, K, device='cuda').to(torch.bfloat16).float().requires_grad_(True)
+    w = (torch.randn(N, K, device='cuda') / K ** 0.5).to(torch.bfloat16).float().requires_grad_(True)
+    b = torch.randn(N, device='cuda').requires_grad_(True)
+    fn = {'relu': torch.relu, 'leaky': torch.nn.functional.leaky_relu, 'sigmoid': torch.sigmoid, 'linear': lambda t: t}[act]
+    want = fn(torch.nn.functional.linear(x, w, b))
+    go = torch.randn_like(want)
+    gw = torch.autograd.grad(want, (x, w, b), go)
+    got = pkg.engine.linear(x, w, b, act=act, out_dtype=torch.float32)
+    gg = torch.autograd.grad(got, (x, w, b), go)
+    assert float((got.detach() - want.detach()).norm() / want.detach().norm()) < 1e-2
+    for a, r in zip(gg, gw):
+        assert float((a - r).norm() / r.norm()) < 2e-2
