@@ -216,6 +216,18 @@ def run_native(args, wl):
     # ---- end-to-end timing through the public API with host buffers
     step_e2e(0)
     ms_e2e = timed(step_e2e, args.steps)
+    # ---- the same, fed by the uint8 input pipeline (utils/batch_loader.py): dataset in pinned HOST memory, per step one
+    # uint8 batch copy + gather / flip / random-crop / ToTensor kernel on a side stream, train step, loss read back
+    ms_loader = None
+    if len(shape) == 3:
+        from jointvae_b200.utils.batch_loader import DeviceBatchLoader
+        u8 = torch.randint(0, 256, ((args.steps + 2) * B, shape[1], shape[2], shape[0]), dtype=torch.uint8, generator=gen)
+        tg = torch.randint(0, C, (u8.shape[0],), generator=gen)
+        loader = DeviceBatchLoader(u8, tg, B, device=dev, data_augmentation=['flip', 'crop'], resident=False, seed=rank)
+        it = iter(loader)
+        step_loader = lambda i: float(net.train_step(*next(it))[0]['total'].mean().item())
+        step_loader(0)
+        ms_loader = timed(step_loader, args.steps)
 
     # ---- OOD scoring throughput (per-class evaluate + scores + predictions), device resident
     n_methods = len(net.ood_methods)
@@ -283,6 +295,9 @@ def run_native(args, wl):
         'clocks': clk,
         'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
+        'e2e_uint8_loader': None if ms_loader is None else {
+            'value': world * B * args.steps / (ms_loader * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B * D + B * 25,
+            'd2h_bytes_per_step': 4, 'note': 'uint8 dataset in pinned host memory, flip + crop + ToTensor on the device'},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'elbo_train_fwd_kernel (fused prior/ELBO forward)', 'bound': 'hbm', 'achieved': achieved,
                      'peak': hbm, 'unit': 'GB/s', 'frac': (achieved / hbm) if achieved else None,

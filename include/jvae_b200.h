@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 5
+#define JVAE_ABI_VERSION 6
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -271,6 +271,28 @@ int jvae_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
 /* NCHW f32 -> NHWC bf16 (optionally padding channels to c_pad with zeros) and back */
 int jvae_nchw_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
 int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input batches.  Replaces, for datasets held as uint8 (N, H, W, C) arrays (torchvision's
+ * CIFAR / SVHN / MNIST `.data`), the per-sample PIL transforms of utils/torch_load.py:405-426
+ * (RandomHorizontalFlip, RandomCrop(size, padding, padding_mode='edge'), Pad(2) / CenterCrop, ToTensor) and the
+ * DataLoader collate + x.to(device) of cvae.py:2245-2256, 2427: one gather of B samples by index, the augmentation as
+ * an index map, uint8 / 255 -> f32, written as the (B, C, out_H, out_W) NCHW batch `evaluate` takes.
+ * The random decisions (flip flags, crop offsets) are inputs, so the result is bit-identical to torchvision's for the
+ * same draws.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t H, W, C;                  /* source images: uint8 (n_src, H, W, C) */
+  int32_t out_H, out_W;             /* size of the produced images */
+  int32_t crop_pad;                 /* RandomCrop((H, W), padding=crop_pad, padding_mode='edge'); 0: no random crop */
+  int32_t flip_first;               /* 1: the flip precedes the crop in data_augmentation, 0: it follows it */
+  int32_t post_off_y, post_off_x;   /* output pixel (y, x) = augmented pixel (y + post_off_y, x + post_off_x), 0 outside the
+                                       image: Pad(p) is (-p, -p) with out = H + 2p; CenterCrop is (+round((H-out)/2), ..) */
+} jvae_batch_cfg;
+/* src: device (or pinned, device-mapped) uint8 images; index (B) int64 sample numbers < n_src; flip (B) uint8 or NULL;
+ * crop_ij (B, 2) int32 = RandomCrop's (i, j) in the padded image, or NULL; out (B, C, out_H, out_W) f32 */
+int jvae_batch_u8_to_f32(const jvae_batch_cfg* cfg, const void* src, long long n_src, const long long* index, int B,
+                         const unsigned char* flip, const int* crop_ij, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer (module/optimizers.py:79-81,120-121: clip_grad_norm_ then Adam with L2 weight decay)

@@ -40,6 +40,11 @@ class BnReduce(ctypes.Structure):
                 ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p), ('act', ctypes.c_int32)]
 
 
+class BatchCfg(ctypes.Structure):          # include/jvae_b200.h: jvae_batch_cfg
+    _fields_ = [(n, ctypes.c_int32) for n in ('H', 'W', 'C', 'out_H', 'out_W', 'crop_pad', 'flip_first', 'post_off_y',
+                                              'post_off_x')]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -99,7 +104,8 @@ def lib():
     L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
-    if L.jvae_abi_version() != 5:
+    L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
+    if L.jvae_abi_version() != 6:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -325,6 +331,13 @@ def nhwc_bf16_to_nchw(src, c=None):
     dst = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
     check(lib().jvae_nhwc_bf16_to_nchw(ptr(src), ptr(dst), n, c, h, w, c_pad, stream()))
     return dst
+
+
+def batch_u8_to_f32(cfg, src, index, flip, crop_ij, out):
+    """src uint8 (n, H, W, C) on the device; index (B) int64; flip (B) uint8 or None; crop_ij (B, 2) int32 or None"""
+    check(lib().jvae_batch_u8_to_f32(ctypes.byref(cfg), ptr(src), src.shape[0], ptr(index), index.numel(), ptr(flip),
+                                     ptr(crop_ij), ptr(out), stream()))
+    return out
 
 
 def grad_sqnorm(grad, out):

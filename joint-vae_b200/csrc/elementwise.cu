@@ -55,6 +55,38 @@ __global__ void __launch_bounds__(EW_THREADS) nhwc_to_nchw_kernel(const __nv_bfl
   }
 }
 
+// gather + augmentation + ToTensor of one batch (include/jvae_b200.h: jvae_batch_u8_to_f32).  One thread per output
+// element, x fastest: coalesced f32 stores; the uint8 source rows of an image (<= a few KB) stay in L1 / L2.
+struct BatchArgs {
+  const uint8_t* src; const long long* index; const unsigned char* flip; const int* crop_ij; float* out;
+  int B, H, W, C, oH, oW, crop_pad, flip_first, off_y, off_x;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) batch_u8_to_f32_kernel(const BatchArgs a) {
+  const size_t per_img = (size_t)a.C * a.oH * a.oW, total = per_img * a.B;
+  for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * EW_THREADS) {
+    const int b = (int)(i / per_img);
+    size_t r = i - (size_t)b * per_img;
+    const int c = (int)(r / ((size_t)a.oH * a.oW));
+    r -= (size_t)c * a.oH * a.oW;
+    const int oy = (int)(r / a.oW), ox = (int)(r - (size_t)oy * a.oW);
+    int y = oy + a.off_y, x = ox + a.off_x;          // position in the augmented (H, W) image
+    float v = 0.f;
+    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+      const bool fl = a.flip && a.flip[b];
+      if (fl && !a.flip_first) x = a.W - 1 - x;      // crop, then flip: the flip acts on the cropped image
+      if (a.crop_ij) {                               // padded(y + i, x + j) with edge replication
+        y = min(max(y + a.crop_ij[2 * b] - a.crop_pad, 0), a.H - 1);
+        x = min(max(x + a.crop_ij[2 * b + 1] - a.crop_pad, 0), a.W - 1);
+      }
+      if (fl && a.flip_first) x = a.W - 1 - x;       // flip, then crop: the crop reads the flipped image
+      const uint8_t u = a.src[(((size_t)a.index[b] * a.H + y) * a.W + x) * a.C + c];
+      v = __fdiv_rn((float)u, 255.f);                // ToTensor: byte tensor .div(255) in f32
+    }
+    a.out[i] = v;
+  }
+}
+
 static int ew_grid(size_t items) {
   const size_t want = (items + EW_THREADS - 1) / EW_THREADS;
   const size_t cap = (size_t)sm_count() * 8;
@@ -100,6 +132,21 @@ int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int
   JVAE_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c, "bad dims");
   nhwc_to_nchw_kernel<<<ew_grid((size_t)n * h * w), EW_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), dst, n, c, h * w, c_pad);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+int jvae_batch_u8_to_f32(const jvae_batch_cfg* cfg, const void* src, long long n_src, const long long* index, int B,
+                         const unsigned char* flip, const int* crop_ij, float* out, void* stream) {
+  JVAE_CHECK_ARG(cfg && src && index && out, "cfg, src, index and out are required");
+  JVAE_CHECK_ARG(B > 0 && n_src > 0, "empty batch or dataset");
+  JVAE_CHECK_ARG(cfg->H > 0 && cfg->W > 0 && cfg->C > 0 && cfg->out_H > 0 && cfg->out_W > 0, "bad image dims");
+  JVAE_CHECK_ARG(cfg->crop_pad >= 0 && (cfg->crop_pad > 0 || !crop_ij), "crop offsets given without RandomCrop padding");
+  BatchArgs a;
+  a.src = reinterpret_cast<const uint8_t*>(src); a.index = index; a.flip = flip; a.crop_ij = crop_ij; a.out = out;
+  a.B = B; a.H = cfg->H; a.W = cfg->W; a.C = cfg->C; a.oH = cfg->out_H; a.oW = cfg->out_W;
+  a.crop_pad = cfg->crop_pad; a.flip_first = cfg->flip_first; a.off_y = cfg->post_off_y; a.off_x = cfg->post_off_x;
+  batch_u8_to_f32_kernel<<<ew_grid((size_t)B * a.C * a.oH * a.oW), EW_THREADS, 0, (cudaStream_t)stream>>>(a);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }

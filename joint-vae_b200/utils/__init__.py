@@ -1,2 +1,2 @@
 """Counterparts of the reference's utils/ that sit next to the hot path."""
-from . import roc_curves, save_load      # noqa: F401
+from . import batch_loader, roc_curves, save_load      # noqa: F401

@@ -212,3 +212,26 @@ class EmuKernels:
             dst[..., :C] = s.repeat_interleave(2, 1).repeat_interleave(2, 2).to(EmuKernels.store)
         else:
             dst[..., :C] = s.view(N, H, 2, W, 2, C).sum((2, 4)).to(EmuKernels.store)
+
+
+def emu_batch_u8_to_f32(cfg, data, index, flip, crop_ij):
+    """TEST ONLY: the index map of jvae_batch_u8_to_f32 (include/jvae_b200.h) in torch, CPU.  data uint8 (n, H, W, C)."""
+    H, W, C, oH, oW = cfg.H, cfg.W, cfg.C, cfg.out_H, cfg.out_W
+    B = index.numel()
+    oy = torch.arange(oH).view(1, oH, 1).expand(B, oH, oW)
+    ox = torch.arange(oW).view(1, 1, oW).expand(B, oH, oW)
+    y, x = oy + cfg.post_off_y, ox + cfg.post_off_x
+    inside = (y >= 0) & (y < H) & (x >= 0) & (x < W)
+    fl = (flip.bool() if flip is not None else torch.zeros(B, dtype=torch.bool)).view(B, 1, 1)
+    if not cfg.flip_first:
+        x = torch.where(fl, W - 1 - x, x)
+    if crop_ij is not None:
+        y = (y + crop_ij[:, 0].view(B, 1, 1).long() - cfg.crop_pad).clamp(0, H - 1)
+        x = (x + crop_ij[:, 1].view(B, 1, 1).long() - cfg.crop_pad).clamp(0, W - 1)
+    if cfg.flip_first:
+        x = torch.where(fl, W - 1 - x, x)
+    y, x = y.clamp(0, H - 1), x.clamp(0, W - 1)
+    img = data[index.view(B, 1, 1).expand(B, oH, oW), y, x]              # (B, oH, oW, C) uint8
+    out = img.to(torch.float32).div(255)
+    out = torch.where(inside.unsqueeze(-1), out, torch.zeros(()))
+    return out.permute(0, 3, 1, 2).contiguous()
