@@ -191,7 +191,8 @@ def workspace(cfg, device):
     number of priors): the kernels keep their arrival counters zero between launches only within a layout, so a buffer
     is never shared between two layouts (train and eval steps of different L or batch size get their own)."""
     n = int(lib().jvae_elbo_workspace_bytes(ctypes.byref(cfg)))
-    key = (device, torch.cuda.current_stream().cuda_stream, cfg.B, cfg.L, cfg.K, cfg.C if cfg.conditional else 1)
+    key = (device, torch.cuda.current_stream().cuda_stream, cfg.B, cfg.L, cfg.K, cfg.C if cfg.conditional else 1,
+           cfg.var_dim == VAR_DIM['full'])
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
         if len(_ws_cache) > 64:
@@ -243,11 +244,12 @@ def elbo_train_bwd(cfg, g, x, x_reco, mu, log_var, logits, y, means, inv_trans, 
     d_means = torch.empty_like(means)
     d_it = torch.empty_like(inv_trans) if need_inv_trans else None
     d_sigma = torch.empty(1, dtype=torch.float32, device=dev) if x_reco is not None else None
+    ws, n = workspace(cfg, dev) if cfg.var_dim == VAR_DIM['full'] else (None, 0)
     with _timed('elbo_train_bwd'):
         check(lib().jvae_elbo_train_bwd(ctypes.byref(cfg), ptr(g), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),
                                         ptr(logits), ptr(y), ptr(means), ptr(inv_trans), ptr(sigma), ptr(wmse), ptr(d_xr),
-                                        ptr(d_mu), ptr(d_lv), ptr(d_logits), ptr(d_means), ptr(d_it), ptr(d_sigma), None, 0,
-                                        stream()))
+                                        ptr(d_mu), ptr(d_lv), ptr(d_logits), ptr(d_means), ptr(d_it), ptr(d_sigma),
+                                        ptr(ws), n, stream()))
     return d_xr, d_mu, d_lv, d_logits, d_means, d_it, d_sigma
 
 

@@ -51,16 +51,22 @@ struct ElboArgs {
   float* dict_mean;         // (K)
   float* logdet;            // (Cp)
   float* ws_lat;            // (B,4): kl, cross_y, bad-label flag of the latent CTAs (train forward)
+  // var_dim = full (inverse Cholesky T_c, priors.py:146): the main kernels run their diagonal code on
+  // tdiag = sqrt(diag(T^T T)) (exact for the trace term) and take the squared distances |T_c (v - m_c)|^2 from full_dist
+  const float* full_T;      // (Cp, K, K) lower-triangular
+  float* tdiag;             // (Cp, K)
+  float* full_dist;         // train: (B); eval: (L+1, Cp, B)
+  float* d_full_T;          // (Cp, K, K) gradient
   // TMA-staged train forward
   int tma_lg, tma_stages;
   unsigned int tma_stage_bytes;
 };
 
 struct WsLayout {
-  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, total;
+  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, tdiag, full_dist, total;
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static WsLayout ws_layout(int B, int L, int K, int Cp) {
+static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false) {
   WsLayout w;
   w.counters = 0;
   w.zero_bytes = (size_t)B * 4;
@@ -69,7 +75,9 @@ static WsLayout ws_layout(int B, int L, int K, int Cp) {
   w.dict_mean = w.mse + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.logdet = w.dict_mean + align256((size_t)K * 4);
   w.lat = w.logdet + align256((size_t)Cp * 4);
-  w.total = w.lat + align256((size_t)B * 16);
+  w.tdiag = w.lat + align256((size_t)B * 16);
+  w.full_dist = w.tdiag + (full ? align256((size_t)Cp * K * 4) : 0);
+  w.total = w.full_dist + (full ? align256((size_t)(L + 1) * Cp * B * 4) : 0);
   return w;
 }
 
@@ -122,6 +130,113 @@ __global__ void __launch_bounds__(256) prior_stats_kernel(ElboArgs a, int nkb) {
       v = -2.f * warp_sum(s);
     }
     if (lane == 0) a.logdet[c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// var_dim = full (priors.py:146, 205-212, 237-240): T_c lower-triangular inverse Cholesky factors
+// ------------------------------------------------------------------------------------------------
+// tdiag[c][k] = sqrt(sum_i T_c[i][k]^2): trace_prod_by_var is then the diagonal formula with T^2 = diag(T^T T)
+__global__ void __launch_bounds__(128) full_tdiag_kernel(const float* __restrict__ T, int K, float* __restrict__ tdiag) {
+  const int c = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float s = 0.f;
+    for (int i = k; i < K; ++i) { const float t = T[((size_t)c * K + i) * K + k]; s = fmaf(t, t, s); }
+    tdiag[(size_t)c * K + k] = sqrtf(s);
+  }
+}
+
+// out = |T_c (v_r - m_c)|^2 for 64 row vectors per CTA against class c = blockIdx.y.  T_c passes through shared memory in
+// tiles of 32 rows (padded: lane i walks row i without bank conflicts); lane i owns output row i of the product.
+// y != null (train): row r belongs to class y[r] only and out is (R); else (eval) out is (R / B, Cp, B).
+constexpr int FD_WARPS = 8, FD_RPW = 8;
+__global__ void __launch_bounds__(FD_WARPS * 32) full_dist_kernel(const float* __restrict__ T, const float* __restrict__ means,
+                                                                  const float* __restrict__ rows, const long long* __restrict__ y,
+                                                                  int R, int B, int K, int Cp, int C, float* __restrict__ out) {
+  extern __shared__ float s_T[];      // [32][K + 1]
+  const int c = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r_base = blockIdx.x * (FD_WARPS * FD_RPW) + w * FD_RPW;
+  float acc[FD_RPW];
+  bool mine[FD_RPW];
+#pragma unroll
+  for (int j = 0; j < FD_RPW; ++j) {
+    acc[j] = 0.f;
+    const int r = r_base + j;
+    mine[j] = r < R;
+    if (mine[j] && y) {
+      long long yr = y[r];
+      if (yr < 0 || yr >= C) yr = 0;
+      mine[j] = (Cp == 1) || (int)yr == c;
+    }
+  }
+  const float* m = means + (size_t)c * K;
+  for (int i0 = 0; i0 < K; i0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * K; idx += FD_WARPS * 32) {
+      const int ii = idx / K, k = idx - ii * K, gi = i0 + ii;
+      s_T[ii * (K + 1) + k] = (gi < K && k <= gi) ? T[((size_t)c * K + gi) * K + k] : 0.f;
+    }
+    __syncthreads();
+    const int kmax = min(K, i0 + 32);
+    const float* trow = s_T + lane * (K + 1);
+#pragma unroll
+    for (int j = 0; j < FD_RPW; ++j) {
+      if (!mine[j]) continue;      // warp-uniform
+      const float* v = rows + (size_t)(r_base + j) * K;
+      float sum = 0.f;
+      for (int k = 0; k < kmax; ++k) sum = fmaf(trow[k], v[k] - m[k], sum);
+      acc[j] = fmaf(sum, sum, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < FD_RPW; ++j) {
+    if (!mine[j]) continue;
+    const float d = warp_sum(acc[j]);
+    if (lane == 0) {
+      const int r = r_base + j;
+      if (y) out[r] = d;
+      else out[((size_t)(r / B) * Cp + c) * B + (r % B)] = d;
+    }
+  }
+}
+
+// gradients of beta * kl through the distance, the trace and log det of a full T (one CTA per sample):
+//   u = T d, d = mu - m:  d_mu += g beta T^T u;  d_m -= the same;  d_T[i][k] += g beta (u_i d_k + w T_ik exp(lv_k) - w [i = k] / T_kk)
+__global__ void __launch_bounds__(128) full_prior_bwd_kernel(ElboArgs a) {
+  extern __shared__ float s_fb[];      // d[K], u[K]
+  float* s_d = s_fb;
+  float* s_u = s_fb + a.K;
+  const int b = blockIdx.x, K = a.K, tid = threadIdx.x;
+  long long yb = a.y[b];
+  if (yb < 0 || yb >= a.C) yb = 0;
+  const int c = a.conditional ? (int)yb : 0;
+  const float coef = a.g[b] * a.beta;
+  const float* T = a.full_T + (size_t)c * K * K;
+  for (int k = tid; k < K; k += blockDim.x) s_d[k] = a.mu[(size_t)b * K + k] - a.means[(size_t)c * K + k];
+  __syncthreads();
+  for (int i = tid; i < K; i += blockDim.x) {
+    float sum = 0.f;
+    for (int k = 0; k <= i; ++k) sum = fmaf(T[(size_t)i * K + k], s_d[k], sum);
+    s_u[i] = sum;
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) {
+    float v = 0.f;
+    for (int i = k; i < K; ++i) v = fmaf(T[(size_t)i * K + k], s_u[i], v);
+    const float dmu = coef * v;
+    if (a.d_mu) a.d_mu[(size_t)b * K + k] += dmu;        // the main backward kernel wrote the other terms
+    if (a.d_means) atomicAdd(&a.d_means[(size_t)c * K + k], -dmu);
+  }
+  if (a.d_full_T) {
+    float* dT = a.d_full_T + (size_t)c * K * K;
+    for (int idx = tid; idx < K * K; idx += blockDim.x) {
+      const int i = idx / K, k = idx - i * K;
+      if (k > i) continue;
+      const float t = T[idx];
+      float val = s_u[i] * s_d[k] + a.var_w * t * expf(a.lv[(size_t)b * K + k]);
+      if (i == k) val -= a.var_w / t;
+      atomicAdd(&dT[idx], coef * val);
+    }
   }
 }
 
@@ -362,6 +477,7 @@ __device__ __forceinline__ void train_latent_warp(const ElboArgs& a, int b, int 
     }
   }
   dist = warp_sum(dist); tr = warp_sum(tr); aux = warp_sum(aux); slv = warp_sum(slv); dzd = warp_sum(dzd);
+  if (a.full_dist) dist = a.full_dist[b];
   float kl, var_kl;
   kl_finish(a, dist, tr, aux, slv, a.logdet[c], &kl, &var_kl);
   // ---- cross entropy of the classifier over all L+1 draws (losses.py:73-86)
@@ -667,12 +783,12 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
       dmu = gb * a.beta * tilt * t2 * (mu - m);
       dlv = 0.f;
     } else {
-      dmu = gb * a.beta * t2 * (mu - m);
+      dmu = a.full_T ? 0.f : gb * a.beta * t2 * (mu - m);      // full T: full_prior_bwd_kernel adds T^T T (mu - m)
       dlv = gb * a.beta * 0.5f * a.var_w * (t2 * expf(lv) - 1.f);
     }
     if (a.d_mu) a.d_mu[(size_t)b * K + k] = dmu;
     if (a.d_lv) a.d_lv[(size_t)b * K + k] = dlv;
-    if (a.d_means) atomicAdd(&a.d_means[(size_t)c * K + k], -dmu);
+    if (a.d_means && !a.full_T) atomicAdd(&a.d_means[(size_t)c * K + k], -dmu);
     if (a.d_inv_trans && a.var_dim == JVAE_VAR_DIAG && a.prior_kind == JVAE_PRIOR_GAUSSIAN) {
       // d/dT of 1/2 [ T^2 d^2 + w (exp(lv) T^2 - 2 log|T|) ]
       const float d = mu - m;
@@ -905,6 +1021,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
     dist = warp_sum(dist);
     tr = warp_sum(tr);
     aux = warp_sum(aux);
+    if (a.full_dist) dist = a.full_dist[(size_t)c * B + b];
     float kl, var_kl;
     kl_finish(a, dist, tr, aux, slv, logdet, &kl, &var_kl);
     // log p(z_l | c) for the L draws (priors.py:328-342, 381-383, 478-491) and the importance weights
@@ -944,7 +1061,8 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
             for (int j = 0; j < 4; ++j) nz[j] = warp_sum(nz[j]);
           }
           if (lane < 4 && l0 + lane < L) {
-            const float qq = lane == 0 ? q[0] : (lane == 1 ? q[1] : (lane == 2 ? q[2] : q[3]));
+            float qq = lane == 0 ? q[0] : (lane == 1 ? q[1] : (lane == 2 ? q[2] : q[3]));
+            if (a.full_dist) qq = a.full_dist[((size_t)(l0 + lane + 1) * Cp + c) * B + b];
             const float nn = lane == 0 ? nz[0] : (lane == 1 ? nz[1] : (lane == 2 ? nz[2] : nz[3]));
             float logp = -0.5f * (float)K * LOG2PI_F - 0.5f * qq - 0.5f * logdet;
             if (a.prior_kind == JVAE_PRIOR_TILTED) logp -= sqrtf(nn);
@@ -970,6 +1088,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
           }
         }
         q = warp_sum(q);
+        if (a.full_dist) q = a.full_dist[((size_t)(l + 1) * Cp + c) * B + b];
         float logp;
         if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
           logp = q;
@@ -1135,11 +1254,11 @@ static int check_cfg(const jvae_elbo_cfg* cfg, const char* fn) {
     set_error("%s: a reconstruction term needs D > 0 and L >= 1 (D=%d L=%d)", fn, cfg->D, cfg->L);
     return JVAE_ERR_INVALID;
   }
-  if (cfg->var_dim == JVAE_VAR_FULL) {
-    set_error("%s: var_dim='full' (inverse Cholesky) priors are not implemented in the fused kernel", fn);
+  if (cfg->var_dim == JVAE_VAR_FULL && cfg->K > 1024) {
+    set_error("%s: var_dim='full' supports K <= 1024 (K=%d)", fn, cfg->K);
     return JVAE_ERR_UNSUPPORTED;
   }
-  if (cfg->var_dim != JVAE_VAR_SCALAR && cfg->var_dim != JVAE_VAR_DIAG) {
+  if (cfg->var_dim != JVAE_VAR_SCALAR && cfg->var_dim != JVAE_VAR_DIAG && cfg->var_dim != JVAE_VAR_FULL) {
     set_error("%s: bad var_dim %d", fn, cfg->var_dim);
     return JVAE_ERR_INVALID;
   }
@@ -1177,8 +1296,13 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.has_xreco = cfg->has_xreco; a.has_logits = cfg->has_logits;
   a.sigma_is_log = cfg->sigma_is_log; a.sigma_is_rmse = cfg->sigma_is_rmse;
   a.beta = cfg->beta; a.gamma_w = cfg->gamma_w; a.var_w = cfg->var_w; a.tau = cfg->tau; a.alpha = cfg->alpha;
-  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp);
+  const bool full = cfg->var_dim == JVAE_VAR_FULL;
+  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp, full);
   char* p = reinterpret_cast<char*>(workspace);
+  if (full) {
+    a.tdiag = reinterpret_cast<float*>(p + w.tdiag);
+    a.full_dist = reinterpret_cast<float*>(p + w.full_dist);
+  }
   a.counters = reinterpret_cast<unsigned int*>(p + w.counters);
   a.dict_norm_var = reinterpret_cast<float*>(p + w.dnv);
   a.ws_mse = reinterpret_cast<float*>(p + w.mse);
@@ -1192,6 +1316,25 @@ static int launch_prologue(const ElboArgs& a, cudaStream_t st) {
   const int ncb = (a.Cp + 7) / 8;
   prior_stats_kernel<<<nkb + ncb, 256, 0, st>>>(a, nkb);
   JVAE_LAUNCH_CHECK();
+  if (a.var_dim == JVAE_VAR_FULL) {
+    full_tdiag_kernel<<<a.Cp, 128, 0, st>>>(a.inv_trans, a.K, a.tdiag);
+    JVAE_LAUNCH_CHECK();
+  }
+  return JVAE_OK;
+}
+
+// var_dim = full: squared distances of `rows` (R, K) to the class means under T_c, then the main kernels see a diagonal
+// prior (tdiag) plus the precomputed distances
+static int full_distances(ElboArgs& a, const float* rows, int R, const long long* y, cudaStream_t st) {
+  const size_t smem = (size_t)32 * (a.K + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    JVAE_CUDA(cudaFuncSetAttribute(full_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((R + FD_WARPS * FD_RPW - 1) / (FD_WARPS * FD_RPW), a.Cp);
+  full_dist_kernel<<<grid, FD_WARPS * 32, smem, st>>>(a.inv_trans, a.means, rows, y, R, a.B, a.K, a.Cp, a.C, a.full_dist);
+  JVAE_LAUNCH_CHECK();
+  a.full_T = a.inv_trans;
+  a.inv_trans = a.tdiag;
+  a.var_dim = JVAE_VAR_DIAG;
   return JVAE_OK;
 }
 
@@ -1203,7 +1346,7 @@ extern "C" {
 
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg) {
   if (!cfg) return 0;
-  return ws_layout(cfg->B, cfg->L, cfg->K, cfg->conditional ? cfg->C : 1).total;
+  return ws_layout(cfg->B, cfg->L, cfg->K, cfg->conditional ? cfg->C : 1, cfg->var_dim == JVAE_VAR_FULL).total;
 }
 
 int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco, const float* mu,
@@ -1227,6 +1370,10 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   cudaStream_t st = (cudaStream_t)stream;
   if (!cfg->prior_stats_ready) {
     rc = launch_prologue(a, st);
+    if (rc) return rc;
+  }
+  if (cfg->var_dim == JVAE_VAR_FULL) {
+    rc = full_distances(a, mu, a.B, a.y, st);
     if (rc) return rc;
   }
   // TMA-staged persistent variant (JVAE_ELBO_TMA=1): measured on B200 at c2 it takes 19.7 us against 17.9 us for the
@@ -1315,12 +1462,14 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
   JVAE_CHECK_ARG(!cfg->has_logits || logits, "logits is required when has_logits");
   JVAE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)x_reco & 15) == 0 && ((uintptr_t)d_x_reco & 15) == 0,
                  "x, x_reco and d_x_reco must be 16-byte aligned");
-  (void)workspace; (void)workspace_bytes;
+  const bool full = cfg->var_dim == JVAE_VAR_FULL;
+  JVAE_CHECK_ARG(!full || (workspace && workspace_bytes >= jvae_elbo_workspace_bytes(cfg)),
+                 "var_dim='full' needs the workspace in the backward pass");
   ElboArgs a;
   char dummy[4096];
-  fill_args(a, cfg, dummy);
+  fill_args(a, cfg, full ? workspace : dummy);
   a.counters = nullptr; a.dict_norm_var = nullptr; a.ws_mse = nullptr; a.dict_mean = nullptr; a.logdet = nullptr;
-  a.ws_lat = nullptr;
+  a.ws_lat = nullptr; a.full_dist = nullptr;
   a.g = g; a.x = x; a.xr = x_reco; a.mu = mu; a.lv = log_var; a.logits = logits; a.y = (const long long*)y;
   a.means = means; a.inv_trans = inv_trans; a.sigma = sigma; a.wmse_in = wmse;
   a.d_xr = d_x_reco; a.d_mu = d_mu; a.d_lv = d_log_var; a.d_logits = d_logits; a.d_means = d_means;
@@ -1329,10 +1478,21 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
   if (d_means) JVAE_CUDA(cudaMemsetAsync(d_means, 0, (size_t)a.Cp * a.K * 4, st));
   if (d_sigma) JVAE_CUDA(cudaMemsetAsync(d_sigma, 0, 4, st));
   if (d_inv_trans)
-    JVAE_CUDA(cudaMemsetAsync(d_inv_trans, 0, (size_t)a.Cp * (cfg->var_dim == JVAE_VAR_DIAG ? a.K : 1) * 4, st));
+    JVAE_CUDA(cudaMemsetAsync(d_inv_trans, 0,
+                              (size_t)a.Cp * (full ? (size_t)a.K * a.K : (cfg->var_dim == JVAE_VAR_DIAG ? a.K : 1)) * 4, st));
+  if (full) {      // the streaming kernel sees the diagonal view; the distance / T gradients come from full_prior_bwd_kernel
+    full_tdiag_kernel<<<a.Cp, 128, 0, st>>>(inv_trans, a.K, a.tdiag);
+    JVAE_LAUNCH_CHECK();
+    a.full_T = inv_trans; a.inv_trans = a.tdiag; a.var_dim = JVAE_VAR_DIAG;
+    a.d_full_T = d_inv_trans; a.d_inv_trans = nullptr;
+  }
   const int grid = a.B * a.G;
   JVAE_ELBO_LAUNCH(elbo_train_bwd_kernel, 0);
   JVAE_LAUNCH_CHECK();
+  if (full) {
+    full_prior_bwd_kernel<<<a.B, 128, 2 * (size_t)a.K * sizeof(float), st>>>(a);
+    JVAE_LAUNCH_CHECK();
+  }
   return JVAE_OK;
 }
 
@@ -1365,6 +1525,11 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
   }
   if (!cfg->prior_stats_ready) {
     rc = launch_prologue(a, st);
+    if (rc) return rc;
+  }
+  if (cfg->var_dim == JVAE_VAR_FULL) {
+    JVAE_CHECK_ARG(z, "z (L+1, B, K) is required for var_dim='full'");
+    rc = full_distances(a, z, (a.L + 1) * a.B, nullptr, st);
     if (rc) return rc;
   }
   const int grid = a.B * a.G;

@@ -347,10 +347,8 @@ class ClassificationVariationalNetwork(nn.Module):
         pcfg = nat.make_cfg(B=B, L=L, K=self.latent_dim, C=self.num_labels, D=0, x_reco=None, logits=None,
                             var_dim=prior0.var_dim, prior_kind=prior0.distribution, conditional=prior0.conditional,
                             sigma_is_log=False, sigma_is_rmse=False, beta=1.0, gamma_w=0.0, var_w=1.0)
-        prior_ready = False
-        if prior0.var_dim != 'full':
-            nat.elbo_prior_stats(pcfg, means0.detach(), inv_trans0.detach())
-            prior_ready = True
+        nat.elbo_prior_stats(pcfg, means0.detach().contiguous(), inv_trans0.detach().contiguous())
+        prior_ready = True
         o = self.forward(x, y=y if self.y_is_coded else None, sampling_epsilon_norm_out=True, sigma_out=True, **kw)
         x_reco, y_est, mu, log_var, z, eps_norm, _ = o
         prior = self.encoder.prior

@@ -256,12 +256,12 @@ class _ElboTrainFn(torch.autograd.Function):
                                       'total.mean()); detach the other loss terms')
         x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, wmse = ctx.saved_tensors
         cfg = ctx.cfg
-        need_it = ctx.needs_input_grad[7] and cfg.var_dim == nat.VAR_DIM['diag']
+        need_it = ctx.needs_input_grad[7] and cfg.var_dim in (nat.VAR_DIM['diag'], nat.VAR_DIM['full'])
         d_xr, d_mu, d_lv, d_lg, d_means, d_it, d_sigma = nat.elbo_train_bwd(
             cfg, g_total.contiguous(), x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, wmse,
             need_inv_trans=need_it)
         if ctx.needs_input_grad[7] and not need_it and inv_trans.requires_grad:
-            raise NotImplementedError('gradient of the prior variance is implemented for var_dim="diag" only')
+            raise NotImplementedError('a scalar prior variance is not a learned parameter (priors.py:79)')
         ng = ctx.needs_input_grad
         return (None, d_xr if ng[1] else None, d_mu if ng[2] else None, d_lv if ng[3] else None,
                 d_lg if ng[4] else None, None, d_means if ng[6] else None, d_it if ng[7] else None,

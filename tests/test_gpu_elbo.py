@@ -31,6 +31,9 @@ def rand_case(B, L, K, C, D, var_dim, kind, seed, conditional=True, gamma=0.0):
     means = f(Cp, K) * 1.5
     if var_dim == 'scalar':
         T = (1 + 0.3 * rng.random(Cp)).astype(np.float32)
+    elif var_dim == 'full':        # inverse Cholesky factors: the kernels must ignore the (non-zero) upper triangle
+        T = (0.2 * rng.standard_normal((Cp, K, K)) / np.sqrt(K)).astype(np.float32)
+        T[:, np.arange(K), np.arange(K)] = (1 + 0.3 * rng.random((Cp, K))).astype(np.float32) * rng.choice([-1, 1], (Cp, K))
     else:
         T = (1 + 0.3 * rng.random((Cp, K))).astype(np.float32)
     x = rng.random((B, D)).astype(np.float32)
@@ -64,6 +67,8 @@ CASES = [
     (12, 4, 32, 7, 192, 'scalar', 'tilted'),
     (12, 4, 32, 7, 192, 'scalar', 'uniform'),
     (4, 9, 256, 1000, 512, 'scalar', 'gaussian'),
+    (19, 3, 40, 7, 192, 'full', 'gaussian'),
+    (70, 2, 130, 3, 64, 'full', 'gaussian'),
 ]
 
 
@@ -91,8 +96,23 @@ def test_train_fwd_bwd(pkg, case, xr_dtype):
         return
     g = torch.full((B,), 1.0 / B, device=DEV)
     d_xr, d_mu, d_lv, d_lg, d_means, d_it, d_sigma = nat.elbo_train_bwd(
-        cfg, g, d['x'], d['xr'], d['mu'], d['lv'], d['logits'], d['y'], d['means'], d['T'], sig, out['wmse'])
-    if kind == 'gaussian':
+        cfg, g, d['x'], d['xr'], d['mu'], d['lv'], d['logits'], d['y'], d['means'], d['T'], sig, out['wmse'],
+        need_inv_trans=(var_dim != 'scalar'))
+    if var_dim == 'full':   # against torch autograd of priors.py:188-326 written out for the tril factors
+        mu, lv = d['mu'].clone().requires_grad_(), d['lv'].clone().requires_grad_()
+        means, Tp = d['means'].clone().requires_grad_(), d['T'].clone().requires_grad_()
+        T = Tp.tril()[d['y']]
+        dist = (T @ (mu - means[d['y']]).unsqueeze(-1)).squeeze(-1).pow(2).sum(-1)
+        tr = (lv.exp() * T.pow(2).sum(-2)).sum(-1)
+        logdet = -2 * T.diagonal(dim1=-2, dim2=-1).abs().log().sum(-1)
+        kl = 0.5 * (dist + var_w * (tr - lv.sum(-1) + logdet - K))
+        (beta * kl / B).sum().backward()
+        close(d_mu * B, (mu.grad * B).cpu().numpy(), what='d_mu full')
+        close(d_lv * B, (lv.grad * B).cpu().numpy(), what='d_lv full')
+        close(d_means, means.grad.cpu().numpy(), what='d_means full')
+        assert d_it.shape == d['T'].shape and float(d_it.triu(1).abs().max()) == 0.0
+        close(d_it, Tp.grad.cpu().numpy(), what='d_T full')
+    elif kind == 'gaussian':
         rb = on.elbo_train_backward(c['x'], xr_np, c['logits'], c['mu'], c['lv'], c['eps'], c['y'], c['prior'],
                                     sigma_value=float(np.log(sigma)), sigma_is_log=True, beta=beta, gamma_w=gamma_w,
                                     kl_var_weighting=var_w)
@@ -146,7 +166,7 @@ def test_eval_fwd(pkg, case, xr_dtype):
         close(r['scores'][:, nat.SCORE_INDEX[m]], dm[m], what='score ' + m, rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize('name', [n for n in golden_names() if 'full' not in n])
+@pytest.mark.parametrize('name', golden_names())
 def test_kernels_on_reference_network_outputs(pkg, name):
     """fused kernels fed with the REFERENCE's own network outputs (golden fixtures) reproduce the reference's
     per-class losses, logits and predictions"""

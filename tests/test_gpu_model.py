@@ -36,7 +36,7 @@ def build(pkg, d):
     return cfg, net.to(DEV)
 
 
-SUPPORTED = [n for n in golden_names() if 'full' not in n]
+SUPPORTED = golden_names()
 
 
 @pytest.mark.parametrize('linear', ['native', 'library'])
