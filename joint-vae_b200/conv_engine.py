@@ -215,7 +215,7 @@ class ConvStep:
             c = self._ctaps[key] = K.taps_arg(taps)
         return c
 
-    def _pack(self, fold_bn=False):
+    def _pack(self, fold_bn=False, want_bwd=None):
         """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict).
         fold_bn (inference with running statistics): BatchNorm is folded into the weights and the bias, so the layer is
         ONE kernel: W' = W * gamma * rstd, b' = (b - mean) * gamma * rstd + beta."""
@@ -228,7 +228,9 @@ class ConvStep:
             key += tuple(t._version for t in (bn.weight, bn.bias) if t is not None)
             slot = '_packed_folded'
         hit = getattr(self, slot, None)
-        if hit is not None and hit[0] == key:
+        if want_bwd is None:      # folded data-gradient weights are only needed for input gradients in eval mode (ODIN)
+            want_bwd = not fold_bn
+        if hit is not None and hit[0] == key and (not want_bwd or self.gemm1x1 or 'bwd' in hit[1]):
             return hit[1]
         wd = w.detach().float()
         kk = self.k * self.k
@@ -260,7 +262,7 @@ class ConvStep:
                 g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
                 g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
             d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
-            if not fold_bn:
+            if want_bwd:
                 d['bwd'] = [pack_gather_weights(g_b, op['idx'], self.Co) for op in self.dgrad_ops]
         setattr(self, slot, (key, d))
         return d
@@ -270,7 +272,7 @@ class ConvStep:
         N = x.shape[0]
         bn = self.bn
         bn_train = bn is not None and (training or not bn.track_running_stats)
-        if bn is not None and not bn_train and not torch.is_grad_enabled():
+        if bn is not None and not bn_train:
             return self._forward_folded(x, st)
         pk = self._pack()
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
@@ -316,7 +318,7 @@ class ConvStep:
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
                 K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
                          a, self.Co, op['out_s'], op['out_o'], pk['b'], self.act, None)
-        st['x'] = x
+        st['x'], st['a'], st['bn_train'], st['folded'] = x, a, False, True
         return a
 
     # ---- backward: da = dL/d(output) NHWC bf16 -> (dx or None, [param grads])
@@ -329,9 +331,18 @@ class ConvStep:
         P = N * self.Ho * self.Wo
         bn = self.bn
         grads = {}
-        if bn is not None:
-            if not st['bn_train']:
-                raise NotImplementedError('backward through BatchNorm in eval mode')
+        folded = bool(st.get('folded'))
+        if folded:
+            # eval-mode BatchNorm is a per-channel affine map folded into the weights: a = act(conv'(x)).  Only the input
+            # gradient is produced (what ODIN differentiates, cvae.py:1648-1656); the parameters get no gradient here.
+            a = st['a']
+            if self.act == 0 and da.shape[-1] % 8 == 0:
+                dy = da
+            else:
+                dy = K.zeros((N, self.Ho, self.Wo, r8(self.Co)), x, torch.bfloat16) if r8(self.Co) != self.Co \
+                    else K.empty((N, self.Ho, self.Wo, self.Co), x)
+                K.act_bwd(da, da.shape[-1], a, a.shape[-1], P, self.Co, self.act, dy, dy.shape[-1], None)
+        elif bn is not None:
             y = st['y']
             dy = K.empty(y.shape, x)
             pre = st.get('bn_sums')            # produced by the next layer's data-gradient kernel
@@ -362,15 +373,18 @@ class ConvStep:
                     else K.empty((N, self.Ho, self.Wo, self.Co), x)
                 K.act_bwd(da, da.shape[-1], a, a.shape[-1], P, self.Co, self.act, dy, dy.shape[-1], dbias)
             grads['b'] = None if lbias is not None else dbias
-        pk = self._pack()
+        pk = self._pack(fold_bn=folded, want_bwd=True)
         kk = self.k * self.k
         dx = None
+        if folded:
+            grads = {'w': None, 'b': None, 'bn_w': None, 'bn_b': None}
         if self.gemm1x1:
             dy2 = dy.view(N, kk * self.Co)
             x2 = x.view(N, x.shape[-1])
-            dbm = K.empty((kk * self.Co, self.Ci), x, torch.float32)
-            K.gemm(nat.GEMM_TN, kk * self.Co, self.Ci, N, dy2, x2, out_f32=dbm)
-            grads['w'] = dbm.view(self.k, self.k, self.Co, self.Ci).permute(3, 2, 0, 1).contiguous()
+            if not folded:
+                dbm = K.empty((kk * self.Co, self.Ci), x, torch.float32)
+                K.gemm(nat.GEMM_TN, kk * self.Co, self.Ci, N, dy2, x2, out_f32=dbm)
+                grads['w'] = dbm.view(self.k, self.k, self.Co, self.Ci).permute(3, 2, 0, 1).contiguous()
             if need_dx:
                 ldx = x.shape[-1]
                 if ldx == self.Ci:
@@ -385,13 +399,14 @@ class ConvStep:
             # the kernel accumulates straight into the torch layout; when the Parameter already owns a dense fp32 .grad
             # (the optimizer's flat gradient buffer, zeroed by zero_grad) it accumulates THERE and autograd gets None
             w = self.conv.weight
-            live = _live_grad(w, x)
-            dw = live if live is not None else K.zeros(tuple(w.shape), x)
-            if self.transposed:      # grid tensor = x, gathered tensor = dy   -> W.grad (Ci, Co, k, k)
-                K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Ci, self.Co, kk))
-            else:                    # grid tensor = dy, gathered tensor = x   -> W.grad (Co, Ci, k, k)
-                K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Co, self.Ci, kk))
-            grads['w'] = None if live is not None else dw
+            if not folded:
+                live = _live_grad(w, x)
+                dw = live if live is not None else K.zeros(tuple(w.shape), x)
+                if self.transposed:      # grid tensor = x, gathered tensor = dy   -> W.grad (Ci, Co, k, k)
+                    K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Ci, self.Co, kk))
+                else:                    # grid tensor = dy, gathered tensor = x   -> W.grad (Co, Ci, k, k)
+                    K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Co, self.Ci, kk))
+                grads['w'] = None if live is not None else dw
             if need_dx:
                 dx = K.empty(x.shape, x)
                 fuse = FUSE_BN_REDUCE and prev_bn is not None and K is NativeKernels and \

@@ -271,7 +271,8 @@ class ClassificationVariationalNetwork(nn.Module):
             x_features = t.reshape(*batch_shape, *self.encoder.input_shape)
         return self.forward_from_features(x_features, None if y is None else y.view(*batch_shape), x, **kw)
 
-    def forward_from_features(self, x_features, y, x, z_output=True, sampling_epsilon_norm_out=False, sigma_out=False):
+    def forward_from_features(self, x_features, y, x, z_output=True, sampling_epsilon_norm_out=False, sigma_out=False,
+                              decode=True):
         """cvae.py:455-521 -> (x_reco (L+1,..,*shape), y_out (L+1,..,C)[, mu, log_var, z][, |eps|^2][, sigma_coded])"""
         nf = len(self.encoder.input_shape)
         batch_size = x_features.shape[:-nf]
@@ -282,7 +283,7 @@ class ClassificationVariationalNetwork(nn.Module):
         L1 = self.latent_sampling + 1
         K = self.latent_dim
         z2 = z.reshape(-1, K)
-        if not self.is_vib:
+        if not self.is_vib and decode:
             u = engine.run_sequential(self.decoder, z2)
             xr = engine.run_sequential(self.imager, u.reshape(-1, *self.imager.input_shape), image_out=True)
         if self.classifier_type in ('linear', None):
@@ -290,7 +291,7 @@ class ClassificationVariationalNetwork(nn.Module):
         else:   # 'softmax': z.m^T + |m|^2/2 (cvae.py:499)
             m = self.encoder.prior.mean
             y_output = engine.linear(z2, m, m.pow(2).sum(-1) / 2, out_dtype=torch.float32).view(*z.shape[:-1], -1)
-        out = (x,) if self.is_vib else (xr.view(L1, *reco_shape),)
+        out = (x,) if self.is_vib else ((xr.view(L1, *reco_shape),) if decode else (None,))
         out += (y_output,)
         if z_output:
             out += (mu, log_var, z)
@@ -633,10 +634,13 @@ class ClassificationVariationalNetwork(nn.Module):
         predict_methods = predict_methods or self.predict_methods
         scores = {m: [] for m in methods}
         preds = {m: [] for m in predict_methods}
+        with_odin = any(m.startswith('odin') for m in methods)
         self.eval()
         for b in batches:
             x = b[0] if isinstance(b, (tuple, list)) else b
             _, logits, losses, _ = self.evaluate(x)
+            if with_odin:          # cvae.py:1646-1663: the whole temperature x eps grid, merged into the loss dictionary
+                losses = dict(losses, **self.odin_softmax(x))
             if recorder is not None:
                 rec = dict(losses, logits=logits.T)
                 if isinstance(b, (tuple, list)) and len(b) > 1:
@@ -647,6 +651,28 @@ class ClassificationVariationalNetwork(nn.Module):
             for m in predict_methods:
                 preds[m].append(self.predict_after_evaluate(logits, losses, method=m))
         return ({m: torch.cat(v) for m, v in scores.items() if v}, {m: torch.cat(v) for m, v in preds.items() if v})
+
+    def odin_softmax(self, x, temps=None, eps=None):
+        """ODIN scores of one batch, the inline loop of cvae.py:1627, 1646-1663 and 1798-1815: with x requiring a gradient,
+        for every temperature T the sum over the batch of max softmax(logits / T) (logits = mean over the L draws) is
+        back-propagated to x -- x.grad is NOT reset between temperatures, as in the reference -- and for every eps the
+        network is evaluated again at x + eps * sign(x.grad).  Returns {'odin-T-eps': (B,) max softmax}.  The input
+        gradient runs through the native data-gradient kernels (eval-mode BatchNorm folded into the weights); the
+        reconstruction, which the reference also computes here and discards, is skipped."""
+        temps = self.ODIN_TEMPS if temps is None else list(temps)
+        eps = self.ODIN_EPS if eps is None else list(eps)
+        x = x.detach().clone().requires_grad_(True)
+        out = {}
+        score = lambda logits, T: (logits[1:].float().mean(0) / T).softmax(-1).max(-1)[0]
+        with torch.no_grad():
+            for T in temps:
+                with torch.enable_grad():
+                    X = score(self.forward(x, z_output=False, decode=False)[1], T).sum()
+                X.backward()
+                dx = x.grad.sign()
+                for e in eps:
+                    out['odin-{:.0f}-{:.4f}'.format(T, e)] = score(self.forward(x + e * dx, z_output=False, decode=False)[1], T)
+        return out
 
     def accuracy(self, batches, method='all'):
         """cvae.py:1187-1453 reduced to its arithmetic: accuracy per predict method over (x, y) batches"""

@@ -15,8 +15,9 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """model fixtures (tests/golden/make_golden.py); roc_cases.npz belongs to tests/test_roc_golden.py"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('roc_'))
+    """model fixtures (tests/golden/make_golden.py); roc_cases.npz belongs to tests/test_roc_golden.py, odin_*.npz to
+    tests/test_gpu_odin.py, wim_*.npz to tests/test_gpu_wim.py"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('roc_', 'odin_', 'wim_')))
 
 
 @pytest.fixture(scope='session')

@@ -126,3 +126,46 @@ def test_unsupported_layers_raise(pkg, ce):
     seq = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.LeakyReLU(0.2))
     with pytest.raises(NotImplementedError):
         ce.run(list(seq), torch.randn(1, 3, 4, 4))
+
+
+@pytest.mark.parametrize('spec,shape,act', [('[x3-Mx2]8-M-16', (3, 8, 8), 'relu'), ('[x5+2]8-8:2-16', (3, 8, 8), 'leaky'),
+                                            ('[x3+1]8-8-M-16:2-16', (3, 16, 16), 'relu')])
+def test_input_gradient_in_eval_mode(pkg, ce, monkeypatch, spec, shape, act):
+    """ODIN (cvae.py:1648-1656) differentiates the eval-mode network w.r.t. its input: BatchNorm with running statistics
+    is folded into the weights, the backward produces the input gradient only."""
+    monkeypatch.setattr(EmuKernels, 'store', torch.float32)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', torch.float32)
+    torch.manual_seed(2)
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=True, where='input', activation=act)
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+    seq.eval()
+    # the torch reference runs the folded bf16 weights the kernels see (W' = W gamma rstd rounded to bf16, b' likewise in f32):
+    # otherwise a ReLU / max-pool decision flipped by the weight rounding dominates the comparison at this tiny size
+    ref = copy.deepcopy(seq)
+    mods = list(ref)
+    for i, m in enumerate(mods):
+        if isinstance(m, torch.nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.BatchNorm2d):
+            bn = mods[i + 1]
+            scale = (bn.running_var + bn.eps).rsqrt() * bn.weight.data
+            m.weight.data = (m.weight.data * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+            m.bias.data = (m.bias.data - bn.running_mean) * scale + bn.bias.data
+            bn.running_mean.zero_(); bn.running_var.fill_(1 - bn.eps); bn.weight.data.fill_(1); bn.bias.data.zero_()
+    x = torch.randn(3, *shape)
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    go = torch.randn_like(want)
+    want.backward(go)
+    xin = x.clone().requires_grad_(True)
+    got = ce.run(list(seq), xin)
+    assert _rel(got, want) < 2e-2
+    got.backward(go)
+    assert xin.grad is not None and _rel(xin.grad, xr.grad) < 3e-2, _rel(xin.grad, xr.grad)
+    # the running statistics are untouched
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            assert int(m.num_batches_tracked) == 0

@@ -55,7 +55,7 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
     x = torch.randn(N, *shape, device=DEV).to(torch.bfloat16).float()
     xr = x.clone().requires_grad_(True)
     want = ref(xr)
-    xin = x.clone().requires_grad_(where == 'output')
+    xin = x.clone().requires_grad_(True)      # 'input' stacks: the gradient w.r.t. the image (ODIN differentiates it)
     n0 = pkg._native.launch_count()
     got = ce.run(list(seq), xin, image_out=(where == 'output'))
     assert pkg._native.launch_count() > n0
@@ -82,7 +82,7 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
         # within 12 % of the fp32 gradient, or no worse than twice what cuDNN's bf16 path does on the same layers
         # (BatchNorm over few pixels and max-pool routing amplify bf16 activation rounding)
         assert err <= max(0.12 * nr + 0.01 * gmax, 2.0 * err_lib), (k, err, err_lib, nr)
-    if where == 'output':
+    if True:
         xl = x.clone().requires_grad_(True)
         lib2 = copy.deepcopy(ref).train()
         with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
@@ -172,3 +172,48 @@ def test_pool_upsample_act_kernels(pkg, C):
     wantd = da[:, :C].float() * (x.view(P, ld)[:, :C] > 0)
     assert _rel(dy[:, :C], wantd) < 1e-6 or float(wantd.norm()) == 0
     assert _rel(dbias, wantd.sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize('spec,shape,N,act', [('[x3-Mx2]8-M-16', (3, 8, 8), 6, 'relu'), ('[x5+2]8-8:2-16', (3, 8, 8), 6, 'leaky'),
+                                              ('[x3+1]8-8-M-16:2-16', (3, 16, 16), 6, 'relu'), ('vgg11', (3, 32, 32), 16, 'relu'),
+                                              ('conv32', (3, 32, 32), 32, 'relu')])
+def test_input_gradient_in_eval_mode(pkg, spec, shape, N, act):
+    """eval-mode stack (BatchNorm folded into the weights) differentiated w.r.t. its input, as ODIN does
+    (cvae.py:1648-1656), against torch fp32 running the same folded bf16 weights; cuDNN-bf16 gives the noise floor"""
+    from jointvae_b200 import conv_engine as ce
+    torch.manual_seed(2)
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=True, where='input', activation=act).to(DEV)
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+    seq.eval()
+    ref = copy.deepcopy(seq)
+    mods = list(ref)
+    for i, m in enumerate(mods):
+        if isinstance(m, torch.nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.BatchNorm2d):
+            bn = mods[i + 1]
+            scale = (bn.running_var + bn.eps).rsqrt() * bn.weight.data
+            m.weight.data = (m.weight.data * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+            m.bias.data = (m.bias.data - bn.running_mean) * scale + bn.bias.data
+            bn.running_mean.zero_(); bn.running_var.fill_(1 - bn.eps); bn.weight.data.fill_(1); bn.bias.data.zero_()
+    lib = copy.deepcopy(ref)
+    x = torch.randn(N, *shape, device=DEV).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    go = torch.randn_like(want)
+    want.backward(go)
+    xl = x.clone().requires_grad_(True)
+    with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
+        lo = lib(xl)
+    lo.backward(go.to(lo.dtype))
+    xin = x.clone().requires_grad_(True)
+    got = ce.run(list(seq), xin)
+    assert _rel(got, want) < 2e-2
+    got.backward(go)
+    e, e_lib = _rel(xin.grad, xr.grad), _rel(xl.grad, xr.grad)
+    print('input-gradient error: native', e, 'cudnn-bf16', e_lib)
+    assert e < max(0.05, 2.0 * e_lib), (e, e_lib)
+    assert all(int(m.num_batches_tracked) == 0 for m in seq if isinstance(m, torch.nn.BatchNorm2d))
