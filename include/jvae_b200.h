@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 6
+#define JVAE_ABI_VERSION 7
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -72,6 +72,12 @@ typedef struct jvae_elbo_cfg {
   float   tau;              /* tilted / uniform priors */
   float   alpha;            /* uniform prior: log rho inside [-tau,tau], priors.py:423-424 */
   int32_t prior_stats_ready;/* 1: jvae_elbo_prior_stats already ran on this workspace for the current prior parameters */
+  int32_t categorical;      /* 1: output_distribution='categorical' (losses.py:30-49, cvae.py:654-660, 683, 776): x_reco holds 256
+                               logits per pixel variable, cross_x = mean_l sum_d CE(logits, floor(255 x_d)),
+                               wmse = mean_l mean_d (argmax / 255 - x_d)^2 (not divided by sigma), log_iws = -CE */
+  int32_t cat_group;        /* logit v of variable d of row r = (l, b) sits at r*256*D + (d / cat_group)*256*cat_group +
+                               v*cat_group + d % cat_group: cat_group = channels for the conv imager's channels_last output
+                               (x in channels_last order), cat_group = D for the reference's (256, *input_shape) layout */
 } jvae_elbo_cfg;
 
 /* bytes of scratch the ELBO entry points need for `cfg`.  The first 4*B bytes (arrival counters) must be ZERO before

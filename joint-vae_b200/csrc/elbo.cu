@@ -53,6 +53,10 @@ struct ElboArgs {
   float* ws_lat;            // (B,4): kl, cross_y, bad-label flag of the latent CTAs (train forward)
   // var_dim = full (inverse Cholesky T_c, priors.py:146): the main kernels run their diagonal code on
   // tdiag = sqrt(diag(T^T T)) (exact for the trace term) and take the squared distances |T_c (v - m_c)|^2 from full_dist
+  // output_distribution = 'categorical' (losses.py:30-49, cvae.py:654-660, 776): 256 logits per pixel; the pre-pass
+  // fills ws_mse with sum_d (argmax / 255 - x)^2 and ws_ce with sum_d cross-entropy per (draw, sample)
+  int categorical, cat_group;
+  float* ws_ce;             // (L, B)
   const float* full_T;      // (Cp, K, K) lower-triangular
   float* tdiag;             // (Cp, K)
   float* full_dist;         // train: (B); eval: (L+1, Cp, B)
@@ -63,7 +67,7 @@ struct ElboArgs {
 };
 
 struct WsLayout {
-  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, tdiag, full_dist, total;
+  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, ce, tdiag, full_dist, total;
 };
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false) {
@@ -75,7 +79,8 @@ static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false) {
   w.dict_mean = w.mse + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.logdet = w.dict_mean + align256((size_t)K * 4);
   w.lat = w.logdet + align256((size_t)Cp * 4);
-  w.tdiag = w.lat + align256((size_t)B * 16);
+  w.ce = w.lat + align256((size_t)B * 16);
+  w.tdiag = w.ce + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.full_dist = w.tdiag + (full ? align256((size_t)Cp * K * 4) : 0);
   w.total = w.full_dist + (full ? align256((size_t)(L + 1) * Cp * B * 4) : 0);
   return w;
@@ -130,6 +135,87 @@ __global__ void __launch_bounds__(256) prior_stats_kernel(ElboArgs a, int nkb) {
       v = -2.f * warp_sum(s);
     }
     if (lane == 0) a.logdet[c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// output_distribution = 'categorical' (losses.py:30-49): 256 logits per pixel variable d, target floor(255 x_d).
+// Variable d of row r = (l, b) keeps its logits at  r * 256 D + (d / G) * 256 G + v * G + d % G  with G = cat_group:
+//   G = channels: the conv imager's channels_last output (channel index v * C + c), x in channels_last order;
+//   G = D: the reference's (256, *input_shape) layout, x in NCHW order.
+// One thread per variable, online soft-max over v; a CTA reduces its variables and adds once per (l, b).
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ float cat_load(const void* p, size_t i) {
+  return BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ int cat_target(float x) {      // (x * 255).long(), losses.py:43
+  const int t = (int)(__fmul_rn(x, 255.f));
+  return min(max(t, 0), 255);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) categorical_fwd_kernel(ElboArgs a) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;                 // (l - 1) * B + b over the L draws
+  const int b = row % a.B;
+  const int D = a.D, G = a.cat_group;
+  const size_t base = ((size_t)(row + a.B)) * 256 * (size_t)D;      // draw 0 (the mean) carries no loss
+  float ce = 0.f, se = 0.f;
+  for (int d = blockIdx.y * blockDim.x + threadIdx.x; d < D; d += gridDim.y * blockDim.x) {
+    const size_t off = base + (size_t)(d / G) * 256 * G + (d % G);
+    const float xv = a.x[(size_t)b * D + d];
+    const int tgt = cat_target(xv);
+    float m = -CUDART_INF_F, sum = 0.f, best = -CUDART_INF_F, tl = 0.f;
+    int arg = 0;
+    for (int v = 0; v < 256; ++v) {
+      const float val = cat_load<BF16>(a.xr, off + (size_t)v * G);
+      if (val > best) { best = val; arg = v; }          // first maximum, like torch.argmax
+      if (v == tgt) tl = val;
+      const float mn = fmaxf(m, val);
+      sum = sum * expf(m - mn) + expf(val - mn);
+      m = mn;
+    }
+    ce += m + logf(sum) - tl;
+    const float e = (float)arg / 255.f - xv;
+    se = fmaf(e, e, se);
+  }
+  ce = block_sum(ce, red);
+  se = block_sum(se, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.ws_ce[row], ce);
+    atomicAdd(&a.ws_mse[row], se);
+  }
+}
+
+// d logits = g_b / L (softmax - onehot) for the L draws, zero for draw 0
+template <bool BF16>
+__global__ void __launch_bounds__(256) categorical_bwd_kernel(ElboArgs a) {
+  const int row = blockIdx.x;                 // l * B + b over all L + 1 draws
+  const int b = row % a.B, l = row / a.B;
+  const int D = a.D, G = a.cat_group;
+  const size_t base = (size_t)row * 256 * (size_t)D;
+  const float coef = (l == 0) ? 0.f : a.g[b] / (float)a.L;
+  for (int d = blockIdx.y * blockDim.x + threadIdx.x; d < D; d += gridDim.y * blockDim.x) {
+    const size_t off = base + (size_t)(d / G) * 256 * G + (d % G);
+    float m = -CUDART_INF_F, sum = 0.f;
+    int tgt = -1;
+    if (l > 0) {
+      tgt = cat_target(a.x[(size_t)b * D + d]);
+      for (int v = 0; v < 256; ++v) {
+        const float val = cat_load<BF16>(a.xr, off + (size_t)v * G);
+        const float mn = fmaxf(m, val);
+        sum = sum * expf(m - mn) + expf(val - mn);
+        m = mn;
+      }
+    }
+    const float inv = (l > 0) ? 1.f / sum : 0.f;
+    for (int v = 0; v < 256; ++v) {
+      float gv = 0.f;
+      if (l > 0) gv = coef * (expf(cat_load<BF16>(a.xr, off + (size_t)v * G) - m) * inv - (v == tgt ? 1.f : 0.f));
+      if (BF16) reinterpret_cast<__nv_bfloat16*>(a.d_xr)[off + (size_t)v * G] = __float2bfloat16(gv);
+      else reinterpret_cast<float*>(a.d_xr)[off + (size_t)v * G] = gv;
+    }
   }
 }
 
@@ -371,7 +457,11 @@ __device__ __forceinline__ void sigma_terms(const ElboArgs& a, int b, float* wms
 #pragma unroll 8
   for (int l = 0; l < a.L; ++l) raw += __ldcg(&a.ws_mse[(size_t)l * a.B + b]);
   const float mse = raw / ((float)a.L * (float)a.D);
-  if (a.sigma_is_rmse) {
+  if (a.categorical) {      // cvae.py:657-660: mse_loss(argmax / 255, x), no division by sigma
+    *wmse = mse;
+    *log_sigma = 0.f;
+    *scale = 1.f / (float)a.D;
+  } else if (a.sigma_is_rmse) {
     *wmse = mse / mse;
     *log_sigma = 0.5f * logf(mse);
     *scale = 1.f / ((float)a.D * mse);
@@ -439,18 +529,24 @@ __device__ __forceinline__ void kl_finish(const ElboArgs& a, float dist, float t
 // latent warp) combines the two halves: a few scalar operations, so the kernel has no serial latent tail.
 __device__ __forceinline__ void train_finalize(const ElboArgs& a, int b) {
   float wmse = 0.f, cross_x = 0.f;
-  if (a.has_xreco) {
+  const bool has_x = a.has_xreco || a.categorical;
+  if (has_x) {
     float log_sigma, scale;
     sigma_terms(a, b, &wmse, &log_sigma, &scale);
     cross_x = 0.5f * (float)a.D * (2.f * log_sigma + wmse + LOG2PI_F);
+    if (a.categorical) {      // cvae.py:776: cross_x = mean_l sum_d CE
+      float ce = 0.f;
+      for (int l = 0; l < a.L; ++l) ce += __ldcg(&a.ws_ce[(size_t)l * a.B + b]);
+      cross_x = ce / (float)a.L;
+    }
   }
   const float kl = __ldcg(&a.ws_lat[4 * b]), cross_y = __ldcg(&a.ws_lat[4 * b + 1]);
   const bool bad_label = __ldcg(&a.ws_lat[4 * b + 2]) != 0.f;
   float total = a.beta * kl;
-  if (a.has_xreco) total += cross_x;
+  if (has_x) total += cross_x;
   if (a.has_logits && a.gamma_w != 0.f) total += a.gamma_w * cross_y;
-  if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
-  if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
+  if (a.wmse && has_x) a.wmse[b] = wmse;
+  if (a.cross_x && has_x) a.cross_x[b] = cross_x;
   if (a.total) a.total[b] = total;
   if (a.finite_flag && (bad_label || !isfinite(total))) atomicExch(a.finite_flag, 0);
 }
@@ -895,15 +991,22 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
   dzd = block_sum(dzd, red);
 
   float wmse = 0.f, cross_x = 0.f, log_sigma = 0.f, scale = 0.f;
-  const bool do_iws = a.has_xreco && a.z && a.eps_norm;
-  if (a.has_xreco) {
+  const bool has_x = a.has_xreco || a.categorical;
+  const bool do_iws = has_x && a.z && a.eps_norm;
+  if (has_x) {
     sigma_terms(a, b, &wmse, &log_sigma, &scale);
     cross_x = 0.5f * (float)a.D * (2.f * log_sigma + wmse + LOG2PI_F);
+    if (a.categorical) {
+      float ce = 0.f;
+      for (int l = 0; l < L; ++l) ce += __ldcg(&a.ws_ce[(size_t)l * B + b]);
+      cross_x = ce / (float)L;
+    }
     if (do_iws)
       for (int l = tid; l < L; l += ELBO_THREADS) {
         const float wl = __ldcg(&a.ws_mse[(size_t)l * B + b]) * scale;
         // cvae.py:676-683 and 837-850
         float v = -0.5f * (float)a.D * (wl + 2.f * log_sigma + LOG2PI_F);
+        if (a.categorical) v = -__ldcg(&a.ws_ce[(size_t)l * B + b]);      // cvae.py:683: log_iws = -CE
         v += 0.5f * (a.eps_norm[(size_t)l * B + b] + slv) + 0.5f * (float)K * LOG2PI_F;
         base_l[l] = v;
       }
@@ -1122,7 +1225,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
   const int nT = (Cp > 1) ? Cp : (add_cy ? C : 1);
   for (int j = tid; j < nT; j += ELBO_THREADS) {
     float t = a.beta * s_kl[(Cp > 1) ? j : 0];
-    if (a.has_xreco) t += cross_x;
+    if (has_x) t += cross_x;
     if (add_cy) t += a.gamma_w * s_cy[j];
     s_tot[j] = t;
   }
@@ -1144,8 +1247,8 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
       if (a.logits_out) a.logits_out[(size_t)b * C + j] = s_lo[j];
     }
   if (tid == 0) {
-    if (a.wmse && a.has_xreco) a.wmse[b] = wmse;
-    if (a.cross_x && a.has_xreco) a.cross_x[b] = cross_x;
+    if (a.wmse && has_x) a.wmse[b] = wmse;
+    if (a.cross_x && has_x) a.cross_x[b] = cross_x;
     if (a.dzdist && a.conditional) {
       float dnv = 0.f;
       for (int i = 0; i < a.nkb; ++i) dnv += __ldcg(&a.dict_norm_var[i]);
@@ -1254,6 +1357,11 @@ static int check_cfg(const jvae_elbo_cfg* cfg, const char* fn) {
     set_error("%s: a reconstruction term needs D > 0 and L >= 1 (D=%d L=%d)", fn, cfg->D, cfg->L);
     return JVAE_ERR_INVALID;
   }
+  if (cfg->categorical && (!cfg->has_xreco || cfg->cat_group <= 0 || cfg->D % cfg->cat_group != 0 || cfg->sigma_is_rmse)) {
+    set_error("%s: categorical output needs has_xreco, cat_group dividing D (D=%d cat_group=%d) and no rmse sigma", fn, cfg->D,
+              cfg->cat_group);
+    return JVAE_ERR_INVALID;
+  }
   if (cfg->var_dim == JVAE_VAR_FULL && cfg->K > 1024) {
     set_error("%s: var_dim='full' supports K <= 1024 (K=%d)", fn, cfg->K);
     return JVAE_ERR_UNSUPPORTED;
@@ -1294,6 +1402,8 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.lg_bf16 = cfg->logits_dtype == JVAE_BF16;
   a.var_dim = cfg->var_dim; a.prior_kind = cfg->prior_kind; a.conditional = cfg->conditional;
   a.has_xreco = cfg->has_xreco; a.has_logits = cfg->has_logits;
+  a.categorical = cfg->categorical ? 1 : 0; a.cat_group = cfg->cat_group;
+  if (a.categorical) { a.has_xreco = 0; a.G = 1; }      // the pre-pass replaces the (x_reco - x)^2 stream
   a.sigma_is_log = cfg->sigma_is_log; a.sigma_is_rmse = cfg->sigma_is_rmse;
   a.beta = cfg->beta; a.gamma_w = cfg->gamma_w; a.var_w = cfg->var_w; a.tau = cfg->tau; a.alpha = cfg->alpha;
   const bool full = cfg->var_dim == JVAE_VAR_FULL;
@@ -1309,6 +1419,20 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.dict_mean = reinterpret_cast<float*>(p + w.dict_mean);
   a.logdet = reinterpret_cast<float*>(p + w.logdet);
   a.ws_lat = reinterpret_cast<float*>(p + w.lat);
+  a.ws_ce = reinterpret_cast<float*>(p + w.ce);
+}
+
+// categorical output: cross-entropy / arg-max error sums per (draw, sample) into ws_ce / ws_mse
+static int categorical_prepass(const ElboArgs& a, cudaStream_t st) {
+  JVAE_CUDA(cudaMemsetAsync(a.ws_mse, 0, (size_t)a.L * a.B * 4, st));
+  JVAE_CUDA(cudaMemsetAsync(a.ws_ce, 0, (size_t)a.L * a.B * 4, st));
+  int chunks = (a.D + 255) / 256;
+  if (chunks > 8) chunks = 8;
+  dim3 grid(a.L * a.B, chunks);
+  if (a.xr_bf16) categorical_fwd_kernel<true><<<grid, 256, 0, st>>>(a);
+  else categorical_fwd_kernel<false><<<grid, 256, 0, st>>>(a);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
 }
 
 static int launch_prologue(const ElboArgs& a, cudaStream_t st) {
@@ -1374,6 +1498,10 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
   }
   if (cfg->var_dim == JVAE_VAR_FULL) {
     rc = full_distances(a, mu, a.B, a.y, st);
+    if (rc) return rc;
+  }
+  if (a.categorical) {
+    rc = categorical_prepass(a, st);
     if (rc) return rc;
   }
   // TMA-staged persistent variant (JVAE_ELBO_TMA=1): measured on B200 at c2 it takes 19.7 us against 17.9 us for the
@@ -1486,6 +1614,15 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
     a.full_T = inv_trans; a.inv_trans = a.tdiag; a.var_dim = JVAE_VAR_DIAG;
     a.d_full_T = d_inv_trans; a.d_inv_trans = nullptr;
   }
+  if (a.categorical) {
+    JVAE_CHECK_ARG(d_x_reco, "d_x_reco is required for the categorical output");
+    int chunks = (a.D + 255) / 256;
+    if (chunks > 8) chunks = 8;
+    dim3 cgrid((a.L + 1) * a.B, chunks);
+    if (a.xr_bf16) categorical_bwd_kernel<true><<<cgrid, 256, 0, st>>>(a);
+    else categorical_bwd_kernel<false><<<cgrid, 256, 0, st>>>(a);
+    JVAE_LAUNCH_CHECK();
+  }
   const int grid = a.B * a.G;
   JVAE_ELBO_LAUNCH(elbo_train_bwd_kernel, 0);
   JVAE_LAUNCH_CHECK();
@@ -1530,6 +1667,10 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
   if (cfg->var_dim == JVAE_VAR_FULL) {
     JVAE_CHECK_ARG(z, "z (L+1, B, K) is required for var_dim='full'");
     rc = full_distances(a, z, (a.L + 1) * a.B, nullptr, st);
+    if (rc) return rc;
+  }
+  if (a.categorical) {
+    rc = categorical_prepass(a, st);
     if (rc) return rc;
   }
   const int grid = a.B * a.G;

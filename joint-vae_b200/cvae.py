@@ -306,10 +306,15 @@ class ClassificationVariationalNetwork(nn.Module):
         prior = self.encoder.prior
         if self.sigma.coded or self.sigma.per_dim:
             raise NotImplementedError('coded / per-pixel sigma is not implemented by the fused ELBO kernel')
-        if self.output_distribution == 'categorical':
-            raise NotImplementedError('categorical (256-way) output is not implemented by the fused ELBO kernel')
         D = int(np.prod(self.input_shape)) if x_reco is not None else 0
-        return nat.make_cfg(B=B, L=L, K=self.latent_dim, C=self.num_labels, D=D, x_reco=x_reco, logits=logits,
+        cat = self.output_distribution == 'categorical' and x_reco is not None
+        cat_group = 0
+        if cat:
+            if self.sigma.is_rmse:
+                raise NotImplementedError('categorical output with sigma=rmse')
+            # 256 logits per pixel variable: channels_last conv output (channel = v * C + c) or the reference's (256, *shape)
+            cat_group = self.input_shape[0] if (x_reco.dim() == 4 and not x_reco.is_contiguous()) else D
+        return nat.make_cfg(categorical=cat, cat_group=cat_group, B=B, L=L, K=self.latent_dim, C=self.num_labels, D=D, x_reco=x_reco, logits=logits,
                             var_dim=prior.var_dim, prior_kind=prior.distribution, conditional=prior.conditional,
                             sigma_is_log=self.sigma.is_log, sigma_is_rmse=self.sigma.is_rmse, beta=beta, gamma_w=gamma_w,
                             var_w=var_w, tau=getattr(prior, 'tau', 0.0), alpha=getattr(prior, '_alpha', 0.0))
@@ -358,7 +363,10 @@ class ClassificationVariationalNetwork(nn.Module):
 
         xr_k = x_k = None
         if self.x_is_generated:
-            xr4 = x_reco.reshape(-1, *self.input_shape)
+            if self.output_distribution == 'categorical':      # (L+1, B, 256, C, H, W): 256 C channels per pixel
+                xr4 = x_reco.reshape(-1, 256 * self.input_shape[0], *self.input_shape[1:])
+            else:
+                xr4 = x_reco.reshape(-1, *self.input_shape)
             xr_k = self._dense(xr4)
             if xr_k.dim() == 4 and not xr_k.is_contiguous():      # channels_last reconstruction: same order for x
                 x_k = x.float().contiguous(memory_format=torch.channels_last)

@@ -159,7 +159,9 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
             j = i
             while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF):
                 j += 1
-            x = run_conv_stack(mods[i:j], x, image_out=image_out and j == n)
+            # a trailing Reshape (categorical imager: channels -> (256, C), conv.py:228-230) is a view of the channels_last image
+            tail_is_view = all(type(k).__name__ == 'Reshape' for k in mods[j:])
+            x = run_conv_stack(mods[i:j], x, image_out=image_out and (j == n or tail_is_view))
             i = j - 1
         elif isinstance(m, nn.Dropout):
             x = torch.nn.functional.dropout(x, m.p, seq.training)

@@ -164,6 +164,8 @@ def describe(seq):
             out.append(dict(t='identity'))
         elif isinstance(m, nn.LeakyReLU):
             out.append(dict(t='leaky'))
+        elif type(m).__name__ == 'Reshape':      # categorical imager: channels -> (256, C), conv.py:228-230
+            out.append(dict(t='reshape', shape=[int(v) for v in m.shape]))
         else:
             raise TypeError(str(m))
     return out
