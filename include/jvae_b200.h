@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 7
+#define JVAE_ABI_VERSION 8
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -78,6 +78,8 @@ typedef struct jvae_elbo_cfg {
   int32_t cat_group;        /* logit v of variable d of row r = (l, b) sits at r*256*D + (d / cat_group)*256*cat_group +
                                v*cat_group + d % cat_group: cat_group = channels for the conv imager's channels_last output
                                (x in channels_last order), cat_group = D for the reference's (256, *input_shape) layout */
+  int32_t sigma_per_sample; /* 1: sigma (and d_sigma) hold one value per sample (B): Sigma coded by the encoder's sigma head,
+                               layers.py:297-298, 398-399, cvae.py:631-634 (sdim = 1) */
 } jvae_elbo_cfg;
 
 /* bytes of scratch the ELBO entry points need for `cfg`.  The first 4*B bytes (arrival counters) must be ZERO before
@@ -111,7 +113,7 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
  * autograd over the same lines).  g (B) f32 (= 1/B for total.mean()).  wmse (B): saved forward output.
  *   d_x_reco (L+1,B,D) [slab 0 written as zeros]; d_mu, d_log_var (B,K) f32: DIRECT terms only
  *   (the path through z is added by jvae_sample_bwd); d_logits (L+1,B,C); d_means (C,K) f32;
- *   d_inv_trans like inv_trans (NULL unless var_dim is diag/full); d_sigma: 1 f32. */
+ *   d_inv_trans like inv_trans (NULL unless var_dim is diag/full); d_sigma: 1 f32 (B with sigma_per_sample). */
 int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x, const void* x_reco,
                         const float* mu, const float* log_var, const void* logits, const int64_t* y,
                         const float* means, const float* inv_trans, const float* sigma, const float* wmse,

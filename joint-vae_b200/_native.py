@@ -31,7 +31,7 @@ class ElboCfg(ctypes.Structure):
                 ('B', 'L', 'K', 'C', 'D', 'xreco_dtype', 'logits_dtype', 'var_dim', 'prior_kind', 'conditional',
                  'has_xreco', 'has_logits', 'sigma_is_log', 'sigma_is_rmse')] + \
                [(n, ctypes.c_float) for n in ('beta', 'gamma_w', 'var_w', 'tau', 'alpha')] + \
-               [('prior_stats_ready', ctypes.c_int32), ('categorical', ctypes.c_int32), ('cat_group', ctypes.c_int32)]
+               [(n, ctypes.c_int32) for n in ('prior_stats_ready', 'categorical', 'cat_group', 'sigma_per_sample')]
 
 
 class BnReduce(ctypes.Structure):
@@ -105,7 +105,7 @@ def lib():
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
     L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
-    if L.jvae_abi_version() != 7:
+    if L.jvae_abi_version() != 8:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -203,8 +203,9 @@ def workspace(cfg, device):
 
 
 def make_cfg(*, B, L, K, C, D, x_reco, logits, var_dim, prior_kind, conditional, sigma_is_log, sigma_is_rmse,
-             beta, gamma_w, var_w, tau=0.0, alpha=0.0, prior_stats_ready=False, categorical=False, cat_group=0):
-    return ElboCfg(categorical=int(bool(categorical)), cat_group=int(cat_group), prior_stats_ready=int(bool(prior_stats_ready)), B=B, L=L, K=K, C=C, D=D, xreco_dtype=dtype_code(x_reco), logits_dtype=dtype_code(logits),
+             beta, gamma_w, var_w, tau=0.0, alpha=0.0, prior_stats_ready=False, categorical=False, cat_group=0,
+             sigma_per_sample=False):
+    return ElboCfg(categorical=int(bool(categorical)), cat_group=int(cat_group), sigma_per_sample=int(bool(sigma_per_sample)), prior_stats_ready=int(bool(prior_stats_ready)), B=B, L=L, K=K, C=C, D=D, xreco_dtype=dtype_code(x_reco), logits_dtype=dtype_code(logits),
                    var_dim=VAR_DIM[var_dim], prior_kind=PRIOR_KIND[prior_kind], conditional=int(bool(conditional)),
                    has_xreco=int(x_reco is not None), has_logits=int(logits is not None),
                    sigma_is_log=int(bool(sigma_is_log)), sigma_is_rmse=int(bool(sigma_is_rmse)),
@@ -243,7 +244,7 @@ def elbo_train_bwd(cfg, g, x, x_reco, mu, log_var, logits, y, means, inv_trans, 
     d_logits = torch.empty_like(logits) if logits is not None else None
     d_means = torch.empty_like(means)
     d_it = torch.empty_like(inv_trans) if need_inv_trans else None
-    d_sigma = torch.empty(1, dtype=torch.float32, device=dev) if x_reco is not None else None
+    d_sigma = torch.empty(cfg.B if cfg.sigma_per_sample else 1, dtype=torch.float32, device=dev) if x_reco is not None else None
     ws, n = workspace(cfg, dev) if cfg.var_dim == VAR_DIM['full'] else (None, 0)
     with _timed('elbo_train_bwd'):
         check(lib().jvae_elbo_train_bwd(ctypes.byref(cfg), ptr(g), ptr(x), ptr(x_reco), ptr(mu), ptr(log_var),

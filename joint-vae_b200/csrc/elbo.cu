@@ -56,6 +56,7 @@ struct ElboArgs {
   // output_distribution = 'categorical' (losses.py:30-49, cvae.py:654-660, 776): 256 logits per pixel; the pre-pass
   // fills ws_mse with sum_d (argmax / 255 - x)^2 and ws_ce with sum_d cross-entropy per (draw, sample)
   int categorical, cat_group;
+  int sigma_stride;         // 0: one sigma for the batch; 1: sigma[b] (Sigma coded by the encoder, cvae.py:631-634)
   float* ws_ce;             // (L, B)
   const float* full_T;      // (Cp, K, K) lower-triangular
   float* tdiag;             // (Cp, K)
@@ -466,7 +467,7 @@ __device__ __forceinline__ void sigma_terms(const ElboArgs& a, int b, float* wms
     *log_sigma = 0.5f * logf(mse);
     *scale = 1.f / ((float)a.D * mse);
   } else {
-    const float s = *a.sigma;
+    const float s = a.sigma[(size_t)a.sigma_stride * b];
     const float sig = a.sigma_is_log ? expf(s) : s;
     *log_sigma = a.sigma_is_log ? s : logf(s);
     *wmse = mse / (sig * sig);
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
   const int D = a.D, K = a.K, C = a.C;
   float sig = 1.f;
   if (a.has_xreco) {
-    const float s = *a.sigma;
+    const float s = a.sigma[(size_t)a.sigma_stride * b];
     sig = a.sigma_is_log ? expf(s) : s;
   }
   // ---- d x_reco[l,b,:] = g_b (x_reco - x) / (L sigma^2), l >= 1; slab 0 gets zeros
@@ -854,7 +855,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
     // cross_x = D/2 (2 log sigma + wmse + log 2pi), wmse ~ sigma^-2
     float ds = gb * (float)D * (1.f - a.wmse_in[b]);
     if (!a.sigma_is_log) ds /= sig;
-    atomicAdd(a.d_sigma, ds);
+    atomicAdd(&a.d_sigma[(size_t)a.sigma_stride * b], ds);
   }
   const float Tc = (a.var_dim == JVAE_VAR_SCALAR) ? a.inv_trans[c] : 0.f;
   float tilt = 1.f;
@@ -1403,6 +1404,7 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.var_dim = cfg->var_dim; a.prior_kind = cfg->prior_kind; a.conditional = cfg->conditional;
   a.has_xreco = cfg->has_xreco; a.has_logits = cfg->has_logits;
   a.categorical = cfg->categorical ? 1 : 0; a.cat_group = cfg->cat_group;
+  a.sigma_stride = cfg->sigma_per_sample ? 1 : 0;
   if (a.categorical) { a.has_xreco = 0; a.G = 1; }      // the pre-pass replaces the (x_reco - x)^2 stream
   a.sigma_is_log = cfg->sigma_is_log; a.sigma_is_rmse = cfg->sigma_is_rmse;
   a.beta = cfg->beta; a.gamma_w = cfg->gamma_w; a.var_w = cfg->var_w; a.tau = cfg->tau; a.alpha = cfg->alpha;
@@ -1604,7 +1606,7 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
   a.d_inv_trans = d_inv_trans; a.d_sigma = d_sigma;
   cudaStream_t st = (cudaStream_t)stream;
   if (d_means) JVAE_CUDA(cudaMemsetAsync(d_means, 0, (size_t)a.Cp * a.K * 4, st));
-  if (d_sigma) JVAE_CUDA(cudaMemsetAsync(d_sigma, 0, 4, st));
+  if (d_sigma) JVAE_CUDA(cudaMemsetAsync(d_sigma, 0, (cfg->sigma_per_sample ? (size_t)a.B : 1) * 4, st));
   if (d_inv_trans)
     JVAE_CUDA(cudaMemsetAsync(d_inv_trans, 0,
                               (size_t)a.Cp * (full ? (size_t)a.K * a.K : (cfg->var_dim == JVAE_VAR_DIAG ? a.K : 1)) * 4, st));

@@ -304,8 +304,10 @@ class ClassificationVariationalNetwork(nn.Module):
     # ------------------------------------------------------------------------------------------ the ELBO step
     def _elbo_cfg(self, B, L, x_reco, logits, beta, gamma_w, var_w):
         prior = self.encoder.prior
-        if self.sigma.coded or self.sigma.per_dim:
-            raise NotImplementedError('coded / per-pixel sigma is not implemented by the fused ELBO kernel')
+        if self.sigma.per_dim:
+            # the reference adds the per-pixel log sigma (*input_shape) to the per-sample wmse (B,) (cvae.py:773-775): that only
+            # broadcasts when the batch happens to match the image width, so there is no contract to reproduce
+            raise NotImplementedError('per-pixel sigma (sdim != 1) is not supported')
         D = int(np.prod(self.input_shape)) if x_reco is not None else 0
         cat = self.output_distribution == 'categorical' and x_reco is not None
         cat_group = 0
@@ -314,7 +316,8 @@ class ClassificationVariationalNetwork(nn.Module):
                 raise NotImplementedError('categorical output with sigma=rmse')
             # 256 logits per pixel variable: channels_last conv output (channel = v * C + c) or the reference's (256, *shape)
             cat_group = self.input_shape[0] if (x_reco.dim() == 4 and not x_reco.is_contiguous()) else D
-        return nat.make_cfg(categorical=cat, cat_group=cat_group, B=B, L=L, K=self.latent_dim, C=self.num_labels, D=D, x_reco=x_reco, logits=logits,
+        return nat.make_cfg(categorical=cat, cat_group=cat_group, sigma_per_sample=bool(self.sigma.coded) and x_reco is not None,
+                            B=B, L=L, K=self.latent_dim, C=self.num_labels, D=D, x_reco=x_reco, logits=logits,
                             var_dim=prior.var_dim, prior_kind=prior.distribution, conditional=prior.conditional,
                             sigma_is_log=self.sigma.is_log, sigma_is_rmse=self.sigma.is_rmse, beta=beta, gamma_w=gamma_w,
                             var_w=var_w, tau=getattr(prior, 'tau', 0.0), alpha=getattr(prior, '_alpha', 0.0))
@@ -356,7 +359,7 @@ class ClassificationVariationalNetwork(nn.Module):
         nat.elbo_prior_stats(pcfg, means0.detach().contiguous(), inv_trans0.detach().contiguous())
         prior_ready = True
         o = self.forward(x, y=y if self.y_is_coded else None, sampling_epsilon_norm_out=True, sigma_out=True, **kw)
-        x_reco, y_est, mu, log_var, z, eps_norm, _ = o
+        x_reco, y_est, mu, log_var, z, eps_norm, sigma_coded = o
         prior = self.encoder.prior
         means, inv_trans = means0, inv_trans0
         beta = self.beta if with_beta else 1.
@@ -379,6 +382,10 @@ class ClassificationVariationalNetwork(nn.Module):
         cfg = self._elbo_cfg(B, L, xr_k, logits_k, beta, gw, kl_var_weighting)
         cfg.prior_stats_ready = int(prior_ready)
         sig = self.sigma if self.x_is_generated else None
+        sigma_seen = self.sigma.data       # the `sigma` measure is read before any update (cvae.py:624)
+        if self.x_is_generated and self.sigma.coded:       # cvae.py:631-634: one log sigma per sample from the encoder's head
+            sig = sigma_coded.reshape(-1).float().contiguous()
+            self.sigma.update(v=sigma_coded.detach().reshape(-1, *self.sigma.output_dim))
         batch_losses = {}
         self._fused = None
 
@@ -424,13 +431,14 @@ class ClassificationVariationalNetwork(nn.Module):
             batch_losses['cross_y'] = res['cross_y']
 
         logits_out = res['logits'] if res.get('logits') is not None else y_est[1:].mean(0)
-        measures = self._lazy_measures(x, batch_losses, batch, current_measures)
+        measures = self._lazy_measures(x, batch_losses, batch, current_measures, sigma_seen,
+                                       sig.detach() if (self.x_is_generated and self.sigma.coded) else None)
         out = (x_reco, logits_out, batch_losses, measures)
         if z_output:
             out += (mu, log_var, z)
         return out
 
-    def _lazy_measures(self, x, losses, batch, current):
+    def _lazy_measures(self, x, losses, batch, current, sigma_data=None, sigma_coded=None):
         names = ['sigma']
         if self.x_is_generated:
             names += ['xpow', 'mse', 'rmse', 'dB']
@@ -442,11 +450,13 @@ class ClassificationVariationalNetwork(nn.Module):
 
         def thunk():
             with torch.no_grad():
-                dev = [self.sigma.data.float().reshape(-1)[:1] if not self.sigma.is_log
-                       else self.sigma.data.float().reshape(-1)[:1].exp(),
+                sd = (self.sigma.data if sigma_data is None else sigma_data).float().reshape(-1)[:1]
+                dev = [sd if not self.sigma.is_log else sd.exp(),
                        losses['zdist'].mean().reshape(1), losses['var_kl'].mean().reshape(1)]
                 if self.x_is_generated:
                     s2 = 1.0 if self.sigma.is_rmse else dev[0] ** 2
+                    if sigma_coded is not None:       # per-sample sigma^2 (cvae.py:644-645, 674)
+                        s2 = (2 * sigma_coded).exp() if self.sigma.is_log else sigma_coded ** 2
                     dev += [x.float().pow(2).mean().reshape(1), (losses['wmse'] * s2).mean().reshape(1)]
                 if conditional:
                     m = self.encoder.prior.mean

@@ -49,6 +49,12 @@ def test_train_and_eval_match_reference(pkg, name, linear):
         pkg.engine.POLICY['linear'] = 'native'
 
 
+def test_sigma_coded_matches_reference(pkg):
+    """Sigma coded by the encoder's sigma head (train.py --sigma coded; cvae.py:631-634): per-sample log sigma in the
+    fused kernels, gradient back into the head (tests/golden/make_sigma_coded_golden.py)"""
+    _run(pkg, 'sig_mlp_cvae_coded')
+
+
 def _run(pkg, name):
     d = np.load(os.path.join(GOLDEN, name + '.npz'))
     cfg, net = build(pkg, d)
