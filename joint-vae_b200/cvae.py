@@ -339,6 +339,7 @@ class ClassificationVariationalNetwork(nn.Module):
         y_in_input = y is not None
         per_class = self.losses_might_be_computed_for_each_class and not y_in_input
         if self.y_is_coded and not y_in_input:
+            # the reference itself raises here (cvae.py:451 reshapes the C-replicated y to x's batch shape): no contract to mirror
             raise NotImplementedError('y_is_coded with per-class evaluation (x replicated C times, cvae.py:589-591)')
         if x.dim() != self.input_dim + 1:
             raise NotImplementedError('evaluate expects one batch dimension: x of shape (B, *input_shape)')
