@@ -192,7 +192,7 @@ def describe_model(model):
     return arch
 
 
-def run_case(cvae_mod, name, kw):
+def run_case(cvae_mod, name, kw, eval_part=True):
     CVNet = cvae_mod.ClassificationVariationalNetwork
     kw = json.loads(json.dumps(kw))  # deep copy; the reference mutates prior/sigma dicts
     ctor = dict(kw)
@@ -242,6 +242,11 @@ def run_case(cvae_mod, name, kw):
 
     # ---------------- eval / scoring step, cvae.py:1629-1677
     model.eval()
+    if not eval_part:
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, **out)
+        print(name, 'ok (train step only)', '%.1f KB' % (os.path.getsize(path) / 1024))
+        return
     with torch.no_grad():
         with injected_noise(eps_te):
             o = model.evaluate(x, z_output=True)

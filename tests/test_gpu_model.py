@@ -55,7 +55,13 @@ def test_sigma_coded_matches_reference(pkg):
     _run(pkg, 'sig_mlp_cvae_coded')
 
 
-def _run(pkg, name):
+def test_y_is_coded_train_step_matches_reference(pkg):
+    """y_is_coded=True: the one-hot label enters the encoder (layers.py:366-369); train step against the reference
+    (its label-free evaluation fails in the reference itself, tests/golden/make_ycoded_golden.py)"""
+    _run(pkg, 'ycoded_mlp_cvae', eval_part=False)
+
+
+def _run(pkg, name, eval_part=True):
     d = np.load(os.path.join(GOLDEN, name + '.npz'))
     cfg, net = build(pkg, d)
     x = torch.from_numpy(d['x']).to(DEV)
@@ -105,7 +111,8 @@ def _run(pkg, name):
         if k.startswith('train.measure.'):
             mk = k[len('train.measure.'):]
             assert abs(measures[mk] - float(d[k])) <= tol * max(1.0, abs(float(d[k]))), mk
-    _eval(pkg, net, d, cfg, x, tol)
+    if eval_part:
+        _eval(pkg, net, d, cfg, x, tol)
 
 
 def _eval(pkg, net, d, cfg, x, tol):
