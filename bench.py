@@ -28,6 +28,22 @@ WORKLOADS = {
                          optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
                batch=512, fwd_gflop_per_img=2.903,
                name='conv joint-VAE 3x32x32 vgg19+deconv32 BN K=128 L=16 C=10 B=512/GPU'),
+    # BASELINE.json configs[2]: CIFAR-100 shape, wider per-class contraction (parity-test case; optional bench workload)
+    'c3': dict(ctor=dict(input_shape=(3, 32, 32), num_labels=100, type='cvae', features='vgg19', upsampler='deconv32',
+                         encoder=[], decoder=[], classifier=[], batch_norm='both', latent_dim=256, latent_sampling=16,
+                         test_latent_sampling=16, gamma=0, beta=1.0, output_activation='linear',
+                         sigma={'value': 1.0, 'learned': True},
+                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
+               batch=512, fwd_gflop_per_img=2.921,
+               name='conv joint-VAE 3x32x32 vgg19+deconv32 BN K=256 L=16 C=100 B=512/GPU'),
+    # BASELINE.json configs[3]: ResNet-style, imagenet20-subset shape (parity-test case; optional bench workload)
+    'c4': dict(ctor=dict(input_shape=(3, 64, 64), num_labels=20, type='cvae', features='resnet18', upsampler='ivgg',
+                         encoder=[], decoder=[], classifier=[], batch_norm='both', latent_dim=256, latent_sampling=8,
+                         test_latent_sampling=8, gamma=0, beta=1.0, output_activation='linear',
+                         sigma={'value': 1.0, 'learned': True},
+                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
+               batch=128, fwd_gflop_per_img=None,
+               name='ResNet joint-VAE 3x64x64 resnet18+ivgg BN K=256 L=8 C=20 B=128/GPU'),
     # BASELINE.json configs[0]: the reference's CPU-runnable case
     'c1': dict(ctor=dict(input_shape=(1, 28, 28), num_labels=10, type='cvae', encoder=[512, 256], decoder=[256, 512],
                          classifier=[], latent_dim=16, latent_sampling=1, test_latent_sampling=1, gamma=0, beta=1.0,
@@ -284,7 +300,7 @@ def run_native(args, wl):
     achieved = bytes_fwd / t_fwd / 1e9 if t_fwd > 0 else None
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
-    flops = 3 * wl['fwd_gflop_per_img'] * 1e9 * B * args.steps / (ms * 1e-3)
+    flops = 3 * (wl['fwd_gflop_per_img'] or 0.0) * 1e9 * B * args.steps / (ms * 1e-3)
     line = {
         'metric': 'train_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -308,8 +324,9 @@ def run_native(args, wl):
                      'us_per_launch': t_fwd * 1e6,
                      'bwd_us_per_launch': sum(prof['elbo_train_bwd']) / max(1, len(prof['elbo_train_bwd'])) * 1e3,
                      'eval_us_per_launch': sum(prof['elbo_eval_fwd']) / max(1, len(prof['elbo_eval_fwd'])) * 1e3},
-        'gemm_roofline': {'bound': 'tensor', 'achieved': flops / 1e12, 'peak': tf, 'unit': 'TFLOP/s',
-                          'frac': flops / 1e12 / tf, 'note': 'whole step: 3 x forward GEMM/conv FLOPs / step time'},
+        'gemm_roofline': None if not wl['fwd_gflop_per_img'] else {
+            'bound': 'tensor', 'achieved': flops / 1e12, 'peak': tf, 'unit': 'TFLOP/s', 'frac': flops / 1e12 / tf,
+            'note': 'whole step: 3 x forward GEMM/conv FLOPs / step time'},
         'scoring': {'value': world * B * max(3, args.steps) / (ms_score * 1e-3), 'unit': 'samples/s',
                     'methods': n_methods},
         'scoring_sweep': sweep,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 8
+#define JVAE_ABI_VERSION 9
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -267,6 +267,23 @@ int jvae_maxpool_fwd(const void* in, int N, int H, int W, int C, int ld_in, int 
 /* gradient to the first maximum of each window (torch tie rule); `in` is the pooling input */
 int jvae_maxpool_bwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, const void* dout, int ld_dout,
                      void* din, int ld_din, void* stream);
+/* Padded / overlapping max pooling (kernel k, stride, padding pad <= k/2, floor mode; padded positions never win): the
+ * stem MaxPool2d(3, 2, 1) of torchvision's ResNets (conv.py:247-272 of the reference wraps them).  out is
+ * (N, (H+2pad-k)/stride+1, (W+2pad-k)/stride+1, C); backward gives every input pixel the gradients of the windows whose FIRST
+ * maximum (row-major scan, torch's tie rule) it is -- gather form, no atomics. */
+int jvae_maxpool_pad_fwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, int pad, void* out,
+                         int ld_out, void* stream);
+int jvae_maxpool_pad_bwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, int pad, const void* dout,
+                         int ld_dout, void* din, int ld_din, void* stream);
+/* k x k average pooling with stride k (k = H = W is AdaptiveAvgPool2d(1), the last layer of the ResNet features; 'A' tokens of
+ * the conv spec language): backward == 0: dst (N,H/k,W/k,C) = window means of src (N,H,W,C); backward != 0: dst (N,H,W,C) =
+ * src (N,H/k,W/k,C) / k^2 spread over the windows */
+int jvae_avgpool(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int k, int backward,
+                 void* stream);
+/* out = act(a + b) over P pixels x C channels: the join of a residual block (out += identity; relu); act = NONE adds two
+ * gradient branches */
+int jvae_add_act(const void* a, int ld_a, const void* b, int ld_b, size_t P, int C, int act, void* out, int ld_out,
+                 void* stream);
 /* backward == 0: dst (N,2H,2W,C) = nearest up-sampling of src (N,H,W,C); backward != 0: dst (N,H,W,C) = 2x2 block sums of src */
 int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int backward, void* stream);
 

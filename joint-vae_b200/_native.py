@@ -103,9 +103,13 @@ def lib():
     L.jvae_maxpool_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_maxpool_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_upsample2.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]
+    L.jvae_maxpool_pad_fwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
+    L.jvae_maxpool_pad_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
+    L.jvae_avgpool.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]
+    L.jvae_add_act.argtypes = [P, c_int, P, c_int, c_size_t, c_int, c_int, P, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
     L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
-    if L.jvae_abi_version() != 8:
+    if L.jvae_abi_version() != 9:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -435,6 +439,23 @@ def maxpool_bwd(inp, N, H, W, C, ld_in, k, stride, dout, ld_dout, din, ld_din):
 
 def upsample2(src, ld_src, dst, ld_dst, N, H, W, C, backward=False):
     check(lib().jvae_upsample2(rawptr(src), ld_src, rawptr(dst), ld_dst, N, H, W, C, int(backward), stream()))
+
+
+def maxpool_pad_fwd(inp, N, H, W, C, ld_in, k, stride, pad, out, ld_out):
+    check(lib().jvae_maxpool_pad_fwd(rawptr(inp), N, H, W, C, ld_in, k, stride, pad, rawptr(out), ld_out, stream()))
+
+
+def maxpool_pad_bwd(inp, N, H, W, C, ld_in, k, stride, pad, dout, ld_dout, din, ld_din):
+    check(lib().jvae_maxpool_pad_bwd(rawptr(inp), N, H, W, C, ld_in, k, stride, pad, rawptr(dout), ld_dout, rawptr(din),
+                                     ld_din, stream()))
+
+
+def avgpool(src, ld_src, dst, ld_dst, N, H, W, C, k, backward=False):
+    check(lib().jvae_avgpool(rawptr(src), ld_src, rawptr(dst), ld_dst, N, H, W, C, k, int(backward), stream()))
+
+
+def add_act(a, ld_a, b, ld_b, P, C, act, out, ld_out):
+    check(lib().jvae_add_act(rawptr(a), ld_a, rawptr(b), ld_b, P, C, act, rawptr(out), ld_out, stream()))
 
 
 def selftest(verbose=1):

@@ -104,6 +104,10 @@ class NativeKernels:
     maxpool_fwd = staticmethod(nat.maxpool_fwd)
     maxpool_bwd = staticmethod(nat.maxpool_bwd)
     upsample2 = staticmethod(nat.upsample2)
+    maxpool_pad_fwd = staticmethod(nat.maxpool_pad_fwd)
+    maxpool_pad_bwd = staticmethod(nat.maxpool_pad_bwd)
+    avgpool = staticmethod(nat.avgpool)
+    add_act = staticmethod(nat.add_act)
     taps_arg = staticmethod(nat.taps_arg)
 
 
@@ -117,7 +121,7 @@ def conv_form(k, p, s, Hq, Wq):
     return [dict(taps=taps, idx=list(range(k * k)), in_stride=s, Hq=Hq, Wq=Wq, out_s=(1, 1), out_o=(0, 0))]
 
 
-def deconv_form(k, p, s, Ho, Wo):
+def deconv_form(k, p, s, Ho, Wo, allow_empty=False):
     """out[o] = sum over (i, j) with (o + p - i) divisible by s of in[(o + p - (i,j)) / s] * G[:, ij, :]
     (ConvTranspose2d forward, Conv2d data gradient): one stride-1 gather per sub-pixel phase, no zero insertion."""
     ops = []
@@ -129,6 +133,8 @@ def deconv_form(k, p, s, Ho, Wo):
             if Hq <= 0 or Wq <= 0:
                 continue
             if not rows or not cols:
+                if allow_empty:      # data gradient of a kernel smaller than its stride (conv1x1 stride 2 shortcuts): this
+                    continue         # sub-pixel phase receives nothing; the caller zero-fills the gradient tensor
                 raise NotImplementedError('transposed convolution with kernel smaller than its stride')
             taps = [((fy + p - i) // s, (fx + p - j) // s) for i in rows for j in cols]
             ops.append(dict(taps=taps, idx=[i * k + j for i in rows for j in cols], in_stride=1, Hq=Hq, Wq=Wq,
@@ -197,7 +203,9 @@ class ConvStep:
             self.dgrad_ops = conv_form(k, p, s, H, W)
         else:
             self.fwd_ops = conv_form(k, p, s, self.Ho, self.Wo)
-            self.dgrad_ops = deconv_form(k, p, s, H, W)
+            self.dgrad_ops = deconv_form(k, p, s, H, W, allow_empty=True)
+        # phases of the data gradient that no tap reaches (kernel < stride) stay zero
+        self.dgrad_sparse = (not self.gemm1x1) and (not self.transposed) and len(self.dgrad_ops) < min(s, H) * min(s, W)
         self.wgrad_taps = [(i - p, j - p) for i in range(k) for j in range(k)]
         self._packed = None
         self._packed_folded = None
@@ -408,7 +416,7 @@ class ConvStep:
                     K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Co, self.Ci, kk))
                 grads['w'] = None if live is not None else dw
             if need_dx:
-                dx = K.empty(x.shape, x)
+                dx = K.zeros(x.shape, x, torch.bfloat16) if self.dgrad_sparse else K.empty(x.shape, x)
                 fuse = FUSE_BN_REDUCE and prev_bn is not None and K is NativeKernels and \
                     prev_bn['y'].shape[:3] == dx.shape[:3]
                 sums_prev = K.zeros((2, self.Ci), x, torch.float64) if fuse else None
@@ -433,11 +441,12 @@ class PoolStep:
         ks = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
         stv = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
         pad = mod.padding if isinstance(mod.padding, int) else mod.padding[0]
-        if pad != 0 or stv < ks or mod.ceil_mode or mod.dilation not in (1, (1, 1)):
-            raise NotImplementedError('only non-overlapping, unpadded MaxPool2d has a native kernel')
-        self.k, self.s = ks, stv
+        if mod.ceil_mode or mod.dilation not in (1, (1, 1)) or 2 * pad > ks:
+            raise NotImplementedError('MaxPool2d with ceil_mode / dilation has no native kernel')
+        self.k, self.s, self.p = ks, stv, pad
+        self.general = pad != 0 or stv < ks        # padded / overlapping windows (ResNet stem MaxPool2d(3, 2, 1))
         self.C, self.H, self.W = in_shape
-        self.Ho, self.Wo = (self.H - ks) // stv + 1, (self.W - ks) // stv + 1
+        self.Ho, self.Wo = (self.H + 2 * pad - ks) // stv + 1, (self.W + 2 * pad - ks) // stv + 1
         self.out_shape = (self.C, self.Ho, self.Wo)
 
     def params(self):
@@ -446,7 +455,10 @@ class PoolStep:
     def forward(self, x, st, training):
         N, _, _, ld = x.shape
         out = K.empty((N, self.Ho, self.Wo, ld), x)
-        K.maxpool_fwd(x, N, self.H, self.W, ld, ld, self.k, self.s, out, ld)      # padded channels are pooled as well
+        if self.general:
+            K.maxpool_pad_fwd(x, N, self.H, self.W, ld, ld, self.k, self.s, self.p, out, ld)
+        else:
+            K.maxpool_fwd(x, N, self.H, self.W, ld, ld, self.k, self.s, out, ld)      # padded channels are pooled as well
         st['x'] = x
         return out
 
@@ -456,8 +468,123 @@ class PoolStep:
         x = st['x']
         N, _, _, ld = x.shape
         dx = K.empty(x.shape, x)
-        K.maxpool_bwd(x, N, self.H, self.W, ld, ld, self.k, self.s, da, da.shape[-1], dx, ld)
+        if self.general:
+            K.maxpool_pad_bwd(x, N, self.H, self.W, ld, ld, self.k, self.s, self.p, da, da.shape[-1], dx, ld)
+        else:
+            K.maxpool_bwd(x, N, self.H, self.W, ld, ld, self.k, self.s, da, da.shape[-1], dx, ld)
         return dx, []
+
+
+class AvgStep:
+    """AvgPool2d(k) with stride k, or AdaptiveAvgPool2d(1) (k = H = W: the last layer of torchvision's ResNet features)"""
+
+    def __init__(self, mod, in_shape):
+        self.C, self.H, self.W = in_shape
+        if isinstance(mod, nn.AdaptiveAvgPool2d):
+            o = mod.output_size if isinstance(mod.output_size, (tuple, list)) else (mod.output_size, mod.output_size)
+            if tuple(o) != (1, 1) or self.H != self.W:
+                raise NotImplementedError('AdaptiveAvgPool2d other than (1, 1) on a square map has no native kernel')
+            k = self.H
+        else:
+            k = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
+            stv = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
+            pad = mod.padding if isinstance(mod.padding, int) else mod.padding[0]
+            if stv != k or pad != 0 or self.H % k or self.W % k or mod.ceil_mode:
+                raise NotImplementedError('AvgPool2d must tile the map (stride = kernel, no padding)')
+        self.k = k
+        self.out_shape = (self.C, self.H // k, self.W // k)
+
+    def params(self):
+        return []
+
+    def forward(self, x, st, training):
+        N, _, _, ld = x.shape
+        out = K.empty((N, self.H // self.k, self.W // self.k, ld), x)
+        K.avgpool(x, ld, out, ld, N, self.H, self.W, ld, self.k, False)
+        st['ld'] = ld
+        return out
+
+    def backward(self, da, st, need_dx):
+        if not need_dx:
+            return None, []
+        N, ld = da.shape[0], st['ld']
+        dx = K.empty((N, self.H, self.W, ld), da)
+        K.avgpool(da, da.shape[-1], dx, ld, N, self.H, self.W, ld, self.k, True)
+        return dx, []
+
+
+def is_residual_block(m):
+    """torchvision.models.resnet.BasicBlock / Bottleneck (duck-typed: the package need not be imported here)"""
+    return type(m).__name__ in ('BasicBlock', 'Bottleneck') and hasattr(m, 'conv1') and hasattr(m, 'downsample')
+
+
+class ResidualStep:
+    """out = relu(F(x) + shortcut(x)) with F = conv-bn-relu ... conv-bn (BasicBlock: 2 convs, Bottleneck: 3) and shortcut =
+    identity or downsample = conv1x1-bn (torchvision/models/resnet.py; the reference wraps these models, conv.py:247-272)"""
+
+    def __init__(self, block, in_shape):
+        names = [n for n in ('conv1', 'conv2', 'conv3') if hasattr(block, n)]
+        self.chain, shape = [], tuple(in_shape)
+        for i, n in enumerate(names):
+            conv, bn = getattr(block, n), getattr(block, 'bn' + n[-1])
+            stp = ConvStep(conv, bn, 1 if i < len(names) - 1 else 0, shape, final_dense=False)
+            self.chain.append(stp)
+            shape = stp.out_shape
+        self.ds = None
+        if block.downsample is not None:
+            ds = list(block.downsample)
+            if len(ds) != 2 or not isinstance(ds[0], nn.Conv2d) or not isinstance(ds[1], nn.BatchNorm2d):
+                raise NotImplementedError('residual shortcut other than conv1x1 + BatchNorm')
+            self.ds = ConvStep(ds[0], ds[1], 0, tuple(in_shape), final_dense=False)
+            if self.ds.out_shape != shape:
+                raise NotImplementedError('shortcut / residual shape mismatch')
+        elif tuple(in_shape) != shape:
+            raise NotImplementedError('identity shortcut with a shape change')
+        self.out_shape = shape
+
+    def params(self):
+        ps = [p for s in self.chain for p in s.params()]
+        if self.ds is not None:
+            ps += self.ds.params()
+        return ps
+
+    def forward(self, x, st, training):
+        sts, t = [], x
+        for s in self.chain:
+            si = {}
+            t = s.forward(t, si, training)
+            sts.append(si)
+        st_ds, idn = None, x
+        if self.ds is not None:
+            st_ds = {}
+            idn = self.ds.forward(x, st_ds, training)
+        N, Ho, Wo, ld = t.shape
+        out = K.empty(t.shape, x)
+        K.add_act(t, ld, idn, idn.shape[-1], N * Ho * Wo, ld, 1, out, ld)
+        st['chain'], st['ds'], st['out'] = sts, st_ds, out
+        return out
+
+    def backward(self, da, st, need_dx):
+        out = st['out']
+        N, Ho, Wo, ld = out.shape
+        P = N * Ho * Wo
+        g = K.empty(out.shape, out)
+        K.act_bwd(da, da.shape[-1], out, ld, P, ld, 1, g, ld, None)        # through the final ReLU: both branches see g
+        grads, gi = [], g
+        for idx in range(len(self.chain) - 1, -1, -1):
+            gi, pg = self.chain[idx].backward(gi, st['chain'][idx], need_dx or idx > 0)
+            grads = pg + grads
+        dx = None
+        if self.ds is not None:
+            d2, pg = self.ds.backward(g, st['ds'], need_dx)
+            grads = grads + pg
+        else:
+            d2 = g
+        if need_dx:
+            dx = K.empty(gi.shape, gi)
+            Nn, H, W, ldx = gi.shape
+            K.add_act(gi, ldx, d2, d2.shape[-1], Nn * H * W, ldx, 0, dx, ldx)
+        return dx, grads
 
 
 class UpStep:
@@ -495,6 +622,13 @@ class ConvStack:
         self.in_shape = tuple(in_shape)
         self.image_out = image_out
         steps, shape = [], tuple(in_shape)
+        flat = []
+        for m in mods:          # torchvision's layer1..4 are Sequentials of residual blocks
+            if isinstance(m, nn.Sequential) and all(is_residual_block(b) for b in m):
+                flat += list(m)
+            else:
+                flat.append(m)
+        mods = flat
         i, n = 0, len(mods)
         groups = []
         while i < n:
@@ -515,11 +649,14 @@ class ConvStack:
             elif isinstance(m, nn.MaxPool2d):
                 groups.append(('pool', m))
                 i += 1
-            elif isinstance(m, nn.AvgPool2d):
-                ks = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
-                if ks != 1:
-                    raise NotImplementedError('AvgPool2d with kernel > 1 has no native kernel yet')
+            elif isinstance(m, nn.AvgPool2d) and (m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]) == 1:
                 i += 1      # AvgPool2d(1) is the identity (the vgg specs end with it)
+            elif isinstance(m, (nn.AvgPool2d, nn.AdaptiveAvgPool2d)):
+                groups.append(('avg', m))
+                i += 1
+            elif is_residual_block(m):
+                groups.append(('res', m))
+                i += 1
             elif isinstance(m, nn.UpsamplingNearest2d):
                 groups.append(('up', m))
                 i += 1
@@ -533,6 +670,10 @@ class ConvStack:
                 stp = ConvStep(g[1], g[2], g[3], shape, final_dense=last and image_out)
             elif g[0] == 'pool':
                 stp = PoolStep(g[1], shape)
+            elif g[0] == 'avg':
+                stp = AvgStep(g[1], shape)
+            elif g[0] == 'res':
+                stp = ResidualStep(g[1], shape)
             else:
                 stp = UpStep(g[1], shape)
             steps.append(stp)

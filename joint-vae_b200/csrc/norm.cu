@@ -392,6 +392,135 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) upsample2_kernel(const __nv_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ padded / overlapping max pooling
+// kernel k, stride s, padding p (padded positions never win), floor mode: torchvision's ResNet stem MaxPool2d(3, 2, 1)
+struct PoolGeo { int H, W, Ho, Wo, k, s, p; };
+
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool_pad_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
+                                                                           __nv_bfloat16* __restrict__ out, int ld_out, PoolGeo q,
+                                                                           size_t Pout, int nchunk, int ppb) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  for (size_t pp = (size_t)blockIdx.x * ppb + pl; pp < Pout; pp += (size_t)gridDim.x * ppb) {
+    const int ox = (int)(pp % q.Wo), oy = (int)((pp / q.Wo) % q.Ho);
+    const size_t n = pp / ((size_t)q.Wo * q.Ho);
+    float m[V], t[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = -__int_as_float(0x7f800000);
+    for (int i = 0; i < q.k; ++i) {
+      const int iy = oy * q.s - q.p + i;
+      if (iy < 0 || iy >= q.H) continue;
+      for (int j = 0; j < q.k; ++j) {
+        const int ix = ox * q.s - q.p + j;
+        if (ix < 0 || ix >= q.W) continue;
+        Vec<V>::load(in + ((n * q.H + iy) * q.W + ix) * ld_in + chunk * V, t);
+#pragma unroll
+        for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], t[e]);
+      }
+    }
+    Vec<V>::store(out + pp * ld_out + chunk * V, m);
+  }
+}
+
+// one thread per INPUT pixel: it collects the gradient of every window that contains it and whose first maximum (row-major
+// scan, torch's tie rule) it is; no atomics, every input pixel is written once
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) maxpool_pad_bwd_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
+                                                                           const __nv_bfloat16* __restrict__ dout, int ld_dout,
+                                                                           __nv_bfloat16* __restrict__ din, int ld_din, PoolGeo q,
+                                                                           size_t Pin, int nchunk, int ppb) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  for (size_t pp = (size_t)blockIdx.x * ppb + pl; pp < Pin; pp += (size_t)gridDim.x * ppb) {
+    const int ix = (int)(pp % q.W), iy = (int)((pp / q.W) % q.H);
+    const size_t n = pp / ((size_t)q.W * q.H);
+    float acc[V], me[V], t[V], g[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    Vec<V>::load(in + pp * ld_in + chunk * V, me);
+    // windows oy with oy*s - p <= iy <= oy*s - p + k - 1
+    int oy0 = iy + q.p - q.k + 1;
+    oy0 = oy0 <= 0 ? 0 : (oy0 + q.s - 1) / q.s;
+    int ox0 = ix + q.p - q.k + 1;
+    ox0 = ox0 <= 0 ? 0 : (ox0 + q.s - 1) / q.s;
+    const int oy1 = min((iy + q.p) / q.s, q.Ho - 1), ox1 = min((ix + q.p) / q.s, q.Wo - 1);
+    for (int oy = oy0; oy <= oy1; ++oy)
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        // this pixel wins the window iff no EARLIER position is >= it and no LATER position is > it
+        bool win[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) win[e] = true;
+        for (int i = 0; i < q.k; ++i) {
+          const int yy = oy * q.s - q.p + i;
+          if (yy < 0 || yy >= q.H) continue;
+          for (int j = 0; j < q.k; ++j) {
+            const int xx = ox * q.s - q.p + j;
+            if (xx < 0 || xx >= q.W || (yy == iy && xx == ix)) continue;
+            Vec<V>::load(in + ((n * q.H + yy) * q.W + xx) * ld_in + chunk * V, t);
+            const bool earlier = yy < iy || (yy == iy && xx < ix);
+#pragma unroll
+            for (int e = 0; e < V; ++e) win[e] = win[e] && (earlier ? t[e] < me[e] : t[e] <= me[e]);
+          }
+        }
+        Vec<V>::load(dout + ((n * q.Ho + oy) * q.Wo + ox) * ld_dout + chunk * V, g);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += win[e] ? g[e] : 0.f;
+      }
+    Vec<V>::store(din + pp * ld_din + chunk * V, acc);
+  }
+}
+
+// k x k average pooling with stride k (k = H = W: AdaptiveAvgPool2d(1)); backward spreads dout / k^2 over the window
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) avgpool_kernel(const __nv_bfloat16* __restrict__ src, int ld_src,
+                                                                   __nv_bfloat16* __restrict__ dst, int ld_dst, int H, int W, int k,
+                                                                   size_t Psmall, int nchunk, int ppb, int backward) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  const int Ho = H / k, Wo = W / k;
+  const float inv = 1.f / (float)(k * k);
+  for (size_t pp = (size_t)blockIdx.x * ppb + pl; pp < Psmall; pp += (size_t)gridDim.x * ppb) {
+    const int ox = (int)(pp % Wo), oy = (int)((pp / Wo) % Ho);
+    const size_t n = pp / ((size_t)Wo * Ho);
+    const size_t big = (n * H + (size_t)oy * k) * W + (size_t)ox * k;
+    float v[V], t[V];
+    if (!backward) {      // src = large, dst = small
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = 0.f;
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {
+          Vec<V>::load(src + (big + (size_t)i * W + j) * ld_src + chunk * V, t);
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[e] += t[e];
+        }
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] *= inv;
+      Vec<V>::store(dst + pp * ld_dst + chunk * V, v);
+    } else {              // src = small gradient, dst = large gradient
+      Vec<V>::load(src + pp * ld_src + chunk * V, v);
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] *= inv;
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) Vec<V>::store(dst + (big + (size_t)i * W + j) * ld_dst + chunk * V, v);
+    }
+  }
+}
+
+// out = act(a + b): the join of a residual block (torchvision BasicBlock / Bottleneck: out += identity; relu)
+template <int V>
+__global__ void __launch_bounds__(NORM_MAX_THREADS) add_act_kernel(const __nv_bfloat16* __restrict__ a, int ld_a,
+                                                                   const __nv_bfloat16* __restrict__ b, int ld_b,
+                                                                   __nv_bfloat16* __restrict__ out, int ld_out, size_t P, int act,
+                                                                   int nchunk, int ppb) {
+  const int chunk = threadIdx.x % nchunk, pl = threadIdx.x / nchunk;
+  for (size_t pp = (size_t)blockIdx.x * ppb + pl; pp < P; pp += (size_t)gridDim.x * ppb) {
+    float u[V], v[V];
+    Vec<V>::load(a + pp * ld_a + chunk * V, u);
+    Vec<V>::load(b + pp * ld_b + chunk * V, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) u[e] = act_fwd(u[e] + v[e], act);
+    Vec<V>::store(out + pp * ld_out + chunk * V, u);
+  }
+}
+
 static bool vec_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void*> ptrs) {
   if (C % 8) return false;
   for (int l : lds) if (l % 8) return false;
@@ -514,6 +643,60 @@ int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, in
   const Geo g = make_geo(Pin, C, vec ? 8 : 1);
   NORM_DISPATCH(vec, upsample2_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
                 reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, H, W, Pin, g.nchunk, g.ppb, backward);
+  return JVAE_OK;
+}
+
+int jvae_maxpool_pad_fwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, int pad, void* out,
+                         int ld_out, void* stream) {
+  JVAE_CHECK_ARG(in && out && N > 0 && C > 0 && ld_in >= C && ld_out >= C, "bad arguments");
+  JVAE_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k && H + 2 * pad >= k && W + 2 * pad >= k, "bad window");
+  const bool vec = vec_ok(C, {ld_in, ld_out}, {in, out});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  PoolGeo q{H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad};
+  const size_t Pout = (size_t)N * q.Ho * q.Wo;
+  const Geo g = make_geo(Pout, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, maxpool_pad_fwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), ld_in,
+                reinterpret_cast<__nv_bfloat16*>(out), ld_out, q, Pout, g.nchunk, g.ppb);
+  return JVAE_OK;
+}
+
+int jvae_maxpool_pad_bwd(const void* in, int N, int H, int W, int C, int ld_in, int k, int stride, int pad, const void* dout,
+                         int ld_dout, void* din, int ld_din, void* stream) {
+  JVAE_CHECK_ARG(in && dout && din && N > 0 && C > 0, "bad arguments");
+  JVAE_CHECK_ARG(ld_in >= C && ld_dout >= C && ld_din >= C, "leading dimension < C");
+  JVAE_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k && H + 2 * pad >= k && W + 2 * pad >= k, "bad window");
+  const bool vec = vec_ok(C, {ld_in, ld_dout, ld_din}, {in, dout, din});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  PoolGeo q{H, W, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1, k, stride, pad};
+  const size_t Pin = (size_t)N * H * W;
+  const Geo g = make_geo(Pin, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, maxpool_pad_bwd_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(in), ld_in,
+                reinterpret_cast<const __nv_bfloat16*>(dout), ld_dout, reinterpret_cast<__nv_bfloat16*>(din), ld_din, q, Pin,
+                g.nchunk, g.ppb);
+  return JVAE_OK;
+}
+
+int jvae_avgpool(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int k, int backward,
+                 void* stream) {
+  JVAE_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && ld_src >= C && ld_dst >= C, "bad arguments");
+  JVAE_CHECK_ARG(k >= 1 && H % k == 0 && W % k == 0, "the window must tile the image (stride = kernel)");
+  const bool vec = vec_ok(C, {ld_src, ld_dst}, {src, dst});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const size_t Ps = (size_t)N * (H / k) * (W / k);
+  const Geo g = make_geo(Ps, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, avgpool_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
+                reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, H, W, k, Ps, g.nchunk, g.ppb, backward);
+  return JVAE_OK;
+}
+
+int jvae_add_act(const void* a, int ld_a, const void* b, int ld_b, size_t P, int C, int act, void* out, int ld_out, void* stream) {
+  JVAE_CHECK_ARG(a && b && out && P > 0 && C > 0 && ld_a >= C && ld_b >= C && ld_out >= C, "bad arguments");
+  const bool vec = vec_ok(C, {ld_a, ld_b, ld_out}, {a, b, out});
+  JVAE_CHECK_ARG(vec ? C <= 8 * NORM_MAX_THREADS : C <= NORM_MAX_THREADS, "too many channels for this layout");
+  const Geo g = make_geo(P, C, vec ? 8 : 1);
+  NORM_DISPATCH(vec, add_act_kernel, g, 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(a), ld_a,
+                reinterpret_cast<const __nv_bfloat16*>(b), ld_b, reinterpret_cast<__nv_bfloat16*>(out), ld_out, P, act,
+                g.nchunk, g.ppb);
   return JVAE_OK;
 }
 

@@ -132,7 +132,15 @@ def _act_name(m):
     if name == 'leaky' and abs(m.negative_slope - nat.LEAKY_SLOPE) > 1e-12:
         return None
     return name
-_CONV_TYPES = (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d, nn.UpsamplingNearest2d)
+_CONV_TYPES = (nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.MaxPool2d, nn.AvgPool2d, nn.AdaptiveAvgPool2d,
+               nn.UpsamplingNearest2d)
+
+
+def _is_conv_type(m):
+    """layers the native conv engine executes, including torchvision's residual blocks and Sequentials of them"""
+    from .conv_engine import is_residual_block
+    return isinstance(m, _CONV_TYPES) or is_residual_block(m) or \
+        (isinstance(m, nn.Sequential) and len(m) > 0 and all(is_residual_block(b) for b in m))
 
 
 def run_sequential(seq, x, out_dtype=None, image_out=False):
@@ -155,9 +163,9 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
                 i += 1
             dt = out_dtype if (last_linear and out_dtype is not None) else torch.bfloat16
             x = linear(x, m.weight, m.bias, act=act, out_dtype=dt)
-        elif isinstance(m, _CONV_TYPES):
+        elif _is_conv_type(m):
             j = i
-            while j < n and (isinstance(mods[j], _CONV_TYPES) or type(mods[j]) in _ACT_OF):
+            while j < n and (_is_conv_type(mods[j]) or type(mods[j]) in _ACT_OF):
                 j += 1
             # a trailing Reshape (categorical imager: channels -> (256, C), conv.py:228-230) is a view of the channels_last image
             tail_is_view = all(type(k).__name__ == 'Reshape' for k in mods[j:])

@@ -91,6 +91,8 @@ class DeviceBatchLoader:
         self._resident = (self.data.numel() <= max_resident_bytes) if resident is None else bool(resident)
         self._dev_data = self._dev_targets = None
         self._side = None
+        self._ring, self._ring_pos = [], 0      # pinned host buffers, reused round-robin (pinning a fresh buffer per batch
+        #                                         costs a cudaHostAlloc, milliseconds)
 
     # ------------------------------------------------------------------ host side: which samples, which decisions
     def __len__(self):
@@ -160,12 +162,28 @@ class DeviceBatchLoader:
             self._side = torch.cuda.Stream(self.device)
             self._side.wait_stream(torch.cuda.current_stream(self.device))      # the resident copy was enqueued there
 
+    def _host_slot(self):
+        """one of 3 pinned (control block, staging) pairs; waits for the copies that last read it"""
+        if not self._ring:
+            bs = self.batch_size
+            for _ in range(3):
+                slot = {'ctrl': torch.empty(25 * bs, dtype=torch.uint8, pin_memory=True), 'stage': None, 'busy': None}
+                if not self._resident:
+                    slot['stage'] = torch.empty((bs,) + tuple(self.data.shape[1:]), dtype=torch.uint8, pin_memory=True)
+                self._ring.append(slot)
+        slot = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+        if slot['busy'] is not None:
+            slot['busy'].synchronize()
+        return slot
+
     def _produce(self, idx, flip, crop):
         """enqueue one batch on the side stream; returns (x, y, event, host buffers kept alive until consumed)"""
         nb = idx.numel()
         C, oH, oW = self.out_shape
         # one pinned control block per batch: [index int64 nb][targets int64 nb][crop int32 2 nb][flip uint8 nb]
-        ctrl = torch.empty(25 * nb, dtype=torch.uint8, pin_memory=True)
+        slot = self._host_slot()
+        ctrl = slot['ctrl'][:25 * nb]
         ctrl[:8 * nb].view(torch.int64).copy_(idx if self._resident else torch.arange(nb))
         torch.index_select(self.targets, 0, idx, out=ctrl[8 * nb:16 * nb].view(torch.int64))
         if crop is not None:
@@ -174,7 +192,7 @@ class DeviceBatchLoader:
             ctrl[24 * nb:].copy_(flip)
         stage = None
         if not self._resident:      # host gather into pinned staging, then ONE uint8 copy (a quarter of the f32 batch)
-            stage = torch.empty((nb,) + tuple(self.data.shape[1:]), dtype=torch.uint8, pin_memory=True)
+            stage = slot['stage'][:nb]
             torch.index_select(self.data, 0, idx, out=stage)
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._side):
@@ -187,6 +205,7 @@ class DeviceBatchLoader:
             y = dctrl[8 * nb:16 * nb].view(torch.int64)
             ev = torch.cuda.Event()
             ev.record(self._side)
+            slot['busy'] = ev          # the host buffers may be rewritten once the copies queued before this event are done
         for t in (x, dctrl):        # allocated on the side stream, consumed on the caller's stream
             t.record_stream(cur)
         return x, y, ev, (ctrl, stage)

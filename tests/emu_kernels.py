@@ -205,6 +205,36 @@ class EmuKernels:
         din[..., :C] = v.grad.permute(0, 2, 3, 1).to(EmuKernels.store)
 
     @classmethod
+    def maxpool_pad_fwd(cls, x, N, H, W, C, ld_in, k, stride, pad, out, ld_out):
+        cls.launches += 1
+        v = torch.nan_to_num(x.float()[..., :C]).permute(0, 3, 1, 2)
+        out[..., :C] = torch.nn.functional.max_pool2d(v, k, stride, pad).permute(0, 2, 3, 1).to(EmuKernels.store)
+
+    @classmethod
+    def maxpool_pad_bwd(cls, x, N, H, W, C, ld_in, k, stride, pad, dout, ld_dout, din, ld_din):
+        cls.launches += 1
+        with torch.enable_grad():
+            v = torch.nan_to_num(x.float()[..., :C]).permute(0, 3, 1, 2).clone().requires_grad_(True)
+            o = torch.nn.functional.max_pool2d(v, k, stride, pad)
+            o.backward(torch.nan_to_num(dout.float()[..., :C]).permute(0, 3, 1, 2))
+        din[..., :C] = v.grad.permute(0, 2, 3, 1).to(EmuKernels.store)
+
+    @classmethod
+    def avgpool(cls, src, ld_src, dst, ld_dst, N, H, W, C, k, backward):
+        cls.launches += 1
+        s = torch.nan_to_num(src.float()[..., :C])
+        if not backward:
+            dst[..., :C] = s.view(N, H // k, k, W // k, k, C).mean((2, 4)).to(EmuKernels.store)
+        else:
+            dst[..., :C] = (s / (k * k)).repeat_interleave(k, 1).repeat_interleave(k, 2).to(EmuKernels.store)
+
+    @classmethod
+    def add_act(cls, a, ld_a, b, ld_b, P, C, act, out, ld_out):
+        cls.launches += 1
+        v = cls._flat(a, P, ld_a)[:, :C].float() + cls._flat(b, P, ld_b)[:, :C].float()
+        cls._flat(out, P, ld_out)[:, :C] = _act(v, act).to(EmuKernels.store)
+
+    @classmethod
     def upsample2(cls, src, ld_src, dst, ld_dst, N, H, W, C, backward):
         cls.launches += 1
         s = src.float()[..., :C]

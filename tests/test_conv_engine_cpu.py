@@ -169,3 +169,37 @@ def test_input_gradient_in_eval_mode(pkg, ce, monkeypatch, spec, shape, act):
     for m in seq:
         if isinstance(m, torch.nn.BatchNorm2d):
             assert int(m.num_batches_tracked) == 0
+
+
+def test_resnet18_features_native_stack(pkg, ce, monkeypatch):
+    """torchvision resnet18 minus fc (the reference's ResOrDenseNetFeatures, conv.py:247-272): 7x7 stride-2 stem,
+    padded overlapping max pool, BasicBlocks with identity and conv1x1 shortcuts, global average pool -- one native stack,
+    forward and every gradient against torch fp32"""
+    monkeypatch.setattr(EmuKernels, 'store', torch.float32)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', torch.float32)
+    torch.manual_seed(0)
+    from jointvae_b200.module.vae_layers.conv import ResOrDenseNetFeatures
+    seq = ResOrDenseNetFeatures('resnet18', (3, 64, 64), pretrained=False)
+    for m in seq.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            m.weight.data = m.weight.data.to(torch.bfloat16).float()
+    ref = copy.deepcopy(seq)
+    seq.train(), ref.train()
+    x = torch.randn(2, 3, 64, 64).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    xin = x.clone().requires_grad_(True)
+    n0 = EmuKernels.launches
+    got = ce.run(list(seq), xin)
+    assert EmuKernels.launches - n0 >= 40
+    assert tuple(got.shape) == tuple(want.shape) == (2, 512, 1, 1)
+    assert _rel(got, want) < 1e-3, _rel(got, want)
+    go = torch.randn_like(want)
+    want.backward(go)
+    got.backward(go)
+    gmax = max(float(p.grad.norm()) for p in ref.parameters())
+    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, k
+        err = float((p.grad.double() - q.grad.double()).norm())
+        assert err <= 5e-3 * float(q.grad.norm()) + 5e-4 * gmax, (k, err, float(q.grad.norm()))
+    assert _rel(xin.grad, xr.grad) < 5e-3

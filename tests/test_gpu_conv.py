@@ -32,6 +32,9 @@ CASES = [
     ('input/leaky', 'conv32', (3, 32, 32), 8, False, None),
     ('output/leaky', 'deconv32', (64, 1, 1), 16, True, 'linear'),
     ('output/leaky', 'deconv32', (64, 1, 1), 8, False, 'sigmoid'),
+    # torchvision ResNet features (conv.py:247-272; BASELINE configs[3]): 7x7 stride-2 stem, padded overlapping max pool,
+    # residual blocks with identity / conv1x1 stride-2 shortcuts, global average pool
+    ('input', 'resnet18', (3, 64, 64), 16, True, None),
 ]
 
 
@@ -61,11 +64,12 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
     assert pkg._native.launch_count() > n0
     assert tuple(got.shape) == tuple(want.shape)
     assert torch.isfinite(got.float()).all()
-    assert _rel(got, want) < 2e-2, _rel(got, want)
-    go = torch.randn_like(want)
-    want.backward(go)
     with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
         lo = lib(x.contiguous(memory_format=torch.channels_last))
+    # 2e-2 (north_star's bf16 tolerance), or the cuDNN-bf16 noise floor for deep stacks (resnet18: 20 BatchNorm layers)
+    assert _rel(got, want) < max(2e-2, 1.5 * _rel(lo.float(), want)), (_rel(got, want), _rel(lo.float(), want))
+    go = torch.randn_like(want)
+    want.backward(go)
     lo.backward(go.to(lo.dtype))
     g = go.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if where == 'output' else go
     got.backward(g)
@@ -217,3 +221,47 @@ def test_input_gradient_in_eval_mode(pkg, spec, shape, N, act):
     print('input-gradient error: native', e, 'cudnn-bf16', e_lib)
     assert e < max(0.05, 2.0 * e_lib), (e, e_lib)
     assert all(int(m.num_batches_tracked) == 0 for m in seq if isinstance(m, torch.nn.BatchNorm2d))
+
+
+@pytest.mark.parametrize('C,H,W,k,s,p', [(64, 32, 32, 3, 2, 1), (8, 9, 7, 3, 2, 1), (3, 8, 8, 2, 1, 0), (16, 6, 6, 3, 1, 1)])
+def test_padded_overlapping_maxpool(pkg, C, H, W, k, s, p):
+    """jvae_maxpool_pad_fwd / bwd against torch (ResNet stem MaxPool2d(3, 2, 1) and other padded / overlapping windows),
+    with ties: bf16 inputs on a coarse grid make equal maxima common, the first one in scan order must get the gradient"""
+    nat = pkg._native
+    torch.manual_seed(0)
+    N, ld = 5, (C + 7) // 8 * 8
+    x = (torch.randint(-3, 4, (N, H, W, ld), device=DEV).float() / 2).to(torch.bfloat16)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    out = torch.empty(N, Ho, Wo, ld, dtype=torch.bfloat16, device=DEV)
+    nat.maxpool_pad_fwd(x, N, H, W, C, ld, k, s, p, out, ld)
+    xr = x[..., :C].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    want = torch.nn.functional.max_pool2d(xr, k, s, p)
+    assert torch.equal(out[..., :C].float().permute(0, 3, 1, 2), want)
+    go = torch.randn(N, Ho, Wo, ld, device=DEV).to(torch.bfloat16)
+    want.backward(go[..., :C].float().permute(0, 3, 1, 2))
+    din = torch.empty_like(x)
+    nat.maxpool_pad_bwd(x, N, H, W, C, ld, k, s, p, go, ld, din, ld)
+    got = din[..., :C].float().permute(0, 3, 1, 2)
+    assert float((got - xr.grad).abs().max()) <= 2e-2 * float(xr.grad.abs().max())      # sums of up to 4 bf16 gradients
+
+
+@pytest.mark.parametrize('C,H,k', [(512, 2, 2), (64, 8, 4), (3, 6, 3), (16, 1, 1)])
+def test_avgpool_and_residual_join(pkg, C, H, k):
+    nat = pkg._native
+    torch.manual_seed(1)
+    N, ld = 4, (C + 7) // 8 * 8
+    x = torch.randn(N, H, H, ld, device=DEV).to(torch.bfloat16)
+    out = torch.empty(N, H // k, H // k, ld, dtype=torch.bfloat16, device=DEV)
+    nat.avgpool(x, ld, out, ld, N, H, H, C, k, False)
+    want = torch.nn.functional.avg_pool2d(x[..., :C].float().permute(0, 3, 1, 2), k)
+    assert torch.allclose(out[..., :C].float().permute(0, 3, 1, 2), want, rtol=1e-2, atol=1e-2)
+    g = torch.randn_like(out)
+    dx = torch.empty_like(x)
+    nat.avgpool(g, ld, dx, ld, N, H, H, C, k, True)
+    wantg = (g[..., :C].float() / (k * k)).repeat_interleave(k, 1).repeat_interleave(k, 2)
+    assert torch.allclose(dx[..., :C].float(), wantg, rtol=1e-2, atol=1e-3)
+    a, b = torch.randn_like(x), torch.randn_like(x)
+    o = torch.empty_like(x)
+    for act, fn in ((1, torch.relu), (0, lambda t: t)):
+        nat.add_act(a, ld, b, ld, N * H * H, C, act, o, ld)
+        assert torch.allclose(o[..., :C].float(), fn(a[..., :C].float() + b[..., :C].float()), rtol=1e-2, atol=1e-2)
