@@ -85,12 +85,16 @@ class NativeKernels:
                                     Wo, Cout, ld_out, out_s, out_o, bias, act, stats, bn=bn)
 
     @staticmethod
-    def wgrad(g, Cg, x, Cx, taps, in_stride, dw):
-        """dw (Cg, Cx, T) fp32 (the torch weight layout with the kernel window flattened) += sum_px g x_shifted"""
+    def wgrad(g, Cg, x, Cx, taps, in_stride, dw, swapped=False):
+        """dw (Cg, Cx, T) fp32 (the torch weight layout with the kernel window flattened) += sum_px g x_shifted.
+        swapped: dw is (Cx, Cg, T) instead (the roles of the two tensors were exchanged by the caller)"""
         N, Hq, Wq, ld_g = g.shape
         _, H, W, ld_x = x.shape
         T = len(taps[0])
-        nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, Cx * T, T)
+        if swapped:
+            nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, T, Cg * T)
+        else:
+            nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, Cx * T, T)
 
     @staticmethod
     def gemm(mode, M, N, K, a, b, bias=None, act=0, out_bf16=None, out_f32=None):
@@ -207,6 +211,12 @@ class ConvStep:
         # phases of the data gradient that no tap reaches (kernel < stride) stay zero
         self.dgrad_sparse = (not self.gemm1x1) and (not self.transposed) and len(self.dgrad_ops) < min(s, H) * min(s, W)
         self.wgrad_taps = [(i - p, j - p) for i in range(k) for j in range(k)]
+        # stride-1 Conv2d with few output channels (the image head, 32 -> 3): exchange the roles in the weight-gradient kernel
+        # (grid tensor = x, gathered tensor = dy, taps negated): the kernel stacks taps of the GATHERED tensor along M, so the
+        # narrow tensor packs twice as many taps per MMA (sum_p dy[p] x[p + t] = sum_q x[q] dy[q - t])
+        self.wgrad_swapped = (not self.transposed) and s == 1 and (self.Ho, self.Wo) == (H, W) and \
+            cblk_of(min(self.Co, 64)) < cblk_of(min(Ci, 64))
+        self.wgrad_taps_neg = [(-a, -b) for a, b in self.wgrad_taps]
         self._packed = None
         self._packed_folded = None
         self._ctaps = {}
@@ -412,6 +422,9 @@ class ConvStep:
                 dw = live if live is not None else K.zeros(tuple(w.shape), x)
                 if self.transposed:      # grid tensor = x, gathered tensor = dy   -> W.grad (Ci, Co, k, k)
                     K.wgrad(x, self.Ci, dy, self.Co, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Ci, self.Co, kk))
+                elif self.wgrad_swapped:  # grid tensor = x, gathered tensor = dy, negated taps -> W.grad (Co, Ci, k, k)
+                    K.wgrad(x, self.Ci, dy, self.Co, self._taps('wn', self.wgrad_taps_neg), 1, dw.view(self.Co, self.Ci, kk),
+                            swapped=True)
                 else:                    # grid tensor = dy, gathered tensor = x   -> W.grad (Co, Ci, k, k)
                     K.wgrad(dy, self.Co, x, self.Ci, self._taps('w', self.wgrad_taps), self.s, dw.view(self.Co, self.Ci, kk))
                 grads['w'] = None if live is not None else dw

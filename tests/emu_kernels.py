@@ -90,14 +90,15 @@ class EmuKernels:
         view[..., Cout:] = 0
 
     @classmethod
-    def wgrad(cls, g, Cg, x, Cx, taps, in_stride, dw):
+    def wgrad(cls, g, Cg, x, Cx, taps, in_stride, dw, swapped=False):
         cls.launches += 1
         N, Hq, Wq, _ = g.shape
         gf, xf = g.float()[..., :Cg], x.float()[..., :Cx]
         assert not torch.isnan(gf).any() and not torch.isnan(xf).any()
-        assert dw.shape == (Cg, Cx, len(taps[0]))
+        assert dw.shape == ((Cx, Cg, len(taps[0])) if swapped else (Cg, Cx, len(taps[0])))
         for t in range(len(taps[0])):
-            dw[:, :, t] += torch.einsum('nhwa,nhwb->ab', gf, cls._shifted(xf, taps[0][t], taps[1][t], in_stride, Hq, Wq))
+            v = torch.einsum('nhwa,nhwb->ab', gf, cls._shifted(xf, taps[0][t], taps[1][t], in_stride, Hq, Wq))
+            dw[:, :, t] += v.t() if swapped else v
 
     @classmethod
     def gemm(cls, mode, M, N, K, a, b, bias=None, act=0, out_bf16=None, out_f32=None):
