@@ -623,10 +623,15 @@ __global__ void __launch_bounds__(ELBO_THREADS, LG <= 4 ? 12 : 8) elbo_train_fwd
     if (b < a.B) train_latent_warp(a, b, threadIdx.x & 31);
     return;
   }
-  const int sid = (int)blockIdx.x - nlat;
-  const int b = sid % a.B, g = sid / a.B;   // b fastest: neighbouring CTAs stream neighbouring rows
-  if (!stream_and_elect<XR_BF16, LG>(a, b, g, red, 1)) return;
-  if (threadIdx.x == 0) train_finalize(a, b);
+  // streaming CTAs: when the items (sample, group of draws) exceed one resident wave, every CTA takes the same number of
+  // items in turn instead of leaving a partial second wave (the host sizes the grid: items / ceil(items / wave))
+  const int nstream = (int)gridDim.x - nlat, items = a.B * a.G;
+  for (int sid = (int)blockIdx.x - nlat; sid < items; sid += nstream) {
+    const int b = sid % a.B, g = sid / a.B;   // b fastest: neighbouring CTAs stream neighbouring rows
+    const bool last = stream_and_elect<XR_BF16, LG>(a, b, g, red, 1);
+    if (last && threadIdx.x == 0) train_finalize(a, b);
+    __syncthreads();                          // the election's shared state is reused by the next item
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1539,7 +1544,16 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
     }
   }
   // latent CTAs (one warp per sample) first, then the streaming CTAs (none without a reconstruction term)
-  const int grid = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32) + (a.has_xreco ? a.B * a.G : 0);
+  int grid = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
+  if (a.has_xreco) {
+    const int items = a.B * a.G;
+    static const int wave_env = getenv("JVAE_ELBO_WAVE") ? atoi(getenv("JVAE_ELBO_WAVE")) : 12;   // resident CTAs per SM; 0: one CTA per item
+    const int wave = wave_env * sm_count() - grid;
+    // between one and two waves (c2: 2048 items, 1648 slots) a partial second wave costs ~1.2 us of a 17 us launch: two items
+    // per CTA instead.  With several waves the hardware scheduler's refill beats a static split (measured at B = 2048).
+    const int per_cta = (wave_env > 0 && wave > 0 && items > wave && items <= 2 * wave) ? 2 : 1;
+    grid += (items + per_cta - 1) / per_cta;
+  }
 #define JVAE_ELBO_LAUNCH(kern, smem_)                                                              \
   do {                                                                                           \
     const int lg_ = elbo_lg();                                                                   \
