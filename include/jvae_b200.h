@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 9
+#define JVAE_ABI_VERSION 10
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -280,6 +280,17 @@ int jvae_maxpool_pad_bwd(const void* in, int N, int H, int W, int C, int ld_in, 
  * src (N,H/k,W/k,C) / k^2 spread over the windows */
 int jvae_avgpool(const void* src, int ld_src, void* dst, int ld_dst, int N, int H, int W, int C, int k, int backward,
                  void* stream);
+/* Separable form of a k x k stride-1 'same' convolution with few output channels (k * Co <= 16, Co <= 4: the image head 32 -> 3 of
+ * the deconv presets, conv-models.ini:25): the tensor-core kernels run the 1 x k convolution to k * Co channels,
+ * T[r][ty*Co + co] = sum_tx sum_ci x[r + (0, tx - pad)][ci] W[co][ci][ty][tx], and
+ *   jvae_vsum_rows:   out[q][co] = act(bias[co] + sum_ty T[q + (ty - pad, 0)][ty*Co + co]); stats (2, Co) f64 (optional) +=
+ *                     sum / sum of squares of the pre-activation (BatchNorm2d batch statistics);
+ *   jvae_vstack_rows: U[r][ty*Co + co] = dy[r - (ty - pad, 0)][co], the gradient of T (zero outside the image, zero padding
+ *                     channels up to ld_u): the 1 x k kernel's data / weight gradients then run on U.
+ * k taps instead of k^2 in the three tensor-core passes. */
+int jvae_vsum_rows(const void* T, int ld_t, int N, int H, int W, int k, int pad, int Co, const float* bias, int act, double* stats,
+                   void* out, int ld_out, void* stream);
+int jvae_vstack_rows(const void* dy, int ld_dy, int N, int H, int W, int k, int pad, int Co, void* U, int ld_u, void* stream);
 /* out = act(a + b) over P pixels x C channels: the join of a residual block (out += identity; relu); act = NONE adds two
  * gradient branches */
 int jvae_add_act(const void* a, int ld_a, const void* b, int ld_b, size_t P, int C, int act, void* out, int ld_out,

@@ -107,9 +107,11 @@ def lib():
     L.jvae_maxpool_pad_bwd.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P]
     L.jvae_avgpool.argtypes = [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_add_act.argtypes = [P, c_int, P, c_int, c_size_t, c_int, c_int, P, c_int, P]
+    L.jvae_vsum_rows.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, P]
+    L.jvae_vstack_rows.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
     L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
-    if L.jvae_abi_version() != 9:
+    if L.jvae_abi_version() != 10:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -452,6 +454,15 @@ def maxpool_pad_bwd(inp, N, H, W, C, ld_in, k, stride, pad, dout, ld_dout, din, 
 
 def avgpool(src, ld_src, dst, ld_dst, N, H, W, C, k, backward=False):
     check(lib().jvae_avgpool(rawptr(src), ld_src, rawptr(dst), ld_dst, N, H, W, C, k, int(backward), stream()))
+
+
+def vsum_rows(T, ld_t, N, H, W, k, pad, Co, bias, act, stats, out, ld_out):
+    check(lib().jvae_vsum_rows(rawptr(T), ld_t, N, H, W, k, pad, Co, rawptr(bias), act, rawptr(stats), rawptr(out), ld_out,
+                               stream()))
+
+
+def vstack_rows(dy, ld_dy, N, H, W, k, pad, Co, U, ld_u):
+    check(lib().jvae_vstack_rows(rawptr(dy), ld_dy, N, H, W, k, pad, Co, rawptr(U), ld_u, stream()))
 
 
 def add_act(a, ld_a, b, ld_b, P, C, act, out, ld_out):

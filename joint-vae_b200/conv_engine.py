@@ -19,6 +19,8 @@ streaming pass (csrc/norm.cu), its backward two.
 `K` is the kernel backend: `NativeKernels` (ctypes -> CUDA) in the product.  tests/ substitute a torch emulation of the
 same entry points to check the tap tables / weight arrangements on machines without a GPU; the product never does.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -112,6 +114,8 @@ class NativeKernels:
     maxpool_pad_bwd = staticmethod(nat.maxpool_pad_bwd)
     avgpool = staticmethod(nat.avgpool)
     add_act = staticmethod(nat.add_act)
+    vsum_rows = staticmethod(nat.vsum_rows)
+    vstack_rows = staticmethod(nat.vstack_rows)
     taps_arg = staticmethod(nat.taps_arg)
 
 
@@ -217,6 +221,15 @@ class ConvStep:
         self.wgrad_swapped = (not self.transposed) and s == 1 and (self.Ho, self.Wo) == (H, W) and \
             cblk_of(min(self.Co, 64)) < cblk_of(min(Ci, 64))
         self.wgrad_taps_neg = [(-a, -b) for a, b in self.wgrad_taps]
+        # narrow image heads (32 -> 3, k5): the k x k 'same' convolution runs as a 1 x k convolution to k * Co channels on the
+        # tensor cores followed by a vertical shift-and-add (include/jvae_b200.h: jvae_vsum_rows / jvae_vstack_rows): k taps
+        # instead of k^2 in the forward, data-gradient and weight-gradient kernels
+        self.separable = (not self.transposed) and (not self.gemm1x1) and s == 1 and k > 1 and 2 * p == k - 1 and \
+            self.Co <= 4 and k * self.Co <= 16 and W >= 8 and os.environ.get('JVAE_CONV_SEPARABLE', '1') != '0'
+        if self.separable:
+            self.sep_C, self.sep_ld = k * self.Co, r8(k * self.Co)
+            self.sep_fwd_taps = [(0, j - p) for j in range(k)]
+            self.sep_bwd_taps = [(0, p - j) for j in range(k)]
         self._packed = None
         self._packed_folded = None
         self._ctaps = {}
@@ -280,6 +293,12 @@ class ConvStep:
                 g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
                 g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
             d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
+            if self.separable:      # wd (Co, Ci, ky, kx): rows (ky, co) of the 1 x k kernel, and its transpose for the data gradient
+                kq = self.k
+                d['sep_fwd'] = pack_gather_weights(wd.permute(2, 0, 3, 1).reshape(kq * self.Co, kq, self.Ci),
+                                                   list(range(kq)), self.Ci)
+                d['sep_bwd'] = pack_gather_weights(wd.permute(1, 3, 2, 0).reshape(self.Ci, kq, kq * self.Co),
+                                                   list(range(kq)), kq * self.Co)
             if want_bwd:
                 d['bwd'] = [pack_gather_weights(g_b, op['idx'], self.Co) for op in self.dgrad_ops]
         setattr(self, slot, (key, d))
@@ -304,6 +323,8 @@ class ConvStep:
                    out_bf16=y.view(N, kk * self.Co))
             if bn_train:
                 K.bn_stats(y, N * kk, self.Co, self.ld_y, stats)
+        elif self.separable:
+            self._sep_forward(x, pk, bias, fused_act, stats, y)
         else:
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
                 K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
@@ -323,6 +344,15 @@ class ConvStep:
         st['y'], st['save'], st['bn_train'] = y, save, bn_train
         return a
 
+    def _sep_forward(self, x, pk, bias, act, stats, out):
+        """1 x k convolution to k * Co channels (tensor cores), then the vertical shift-and-add with bias / activation / stats"""
+        N = x.shape[0]
+        T = K.empty((N, self.H, self.W, self.sep_ld), x)
+        wm = pk['sep_fwd']
+        K.gather(x, self.Ci, wm, wm.shape[0], self._taps('sf', self.sep_fwd_taps), 1, self.H, self.W, T, self.sep_C, (1, 1),
+                 (0, 0), None, 0, None)
+        K.vsum_rows(T, self.sep_ld, N, self.H, self.W, self.k, self.p, self.Co, bias, act, stats, out, out.shape[-1])
+
     def _forward_folded(self, x, st):
         """inference: conv + folded BatchNorm + activation in one kernel, no intermediate tensor"""
         N = x.shape[0]
@@ -332,6 +362,8 @@ class ConvStep:
             kk = self.k * self.k
             K.gemm(nat.GEMM_NT, N, kk * self.Co, self.Ci, x.view(N, x.shape[-1]), pk['bm'], bias=pk['bias'], act=self.act,
                    out_bf16=a.view(N, kk * self.Co))
+        elif self.separable:
+            self._sep_forward(x, pk, pk['b'], self.act, None, a)
         else:
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
                 K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
@@ -413,6 +445,26 @@ class ConvStep:
                     K.gemm(nat.GEMM_NN, N, self.Ci, kk * self.Co, dy2, pk['bm'], out_f32=tmp)
                     dx = K.zeros(x.shape, x, torch.bfloat16)
                     dx.view(N, ldx)[:, :self.Ci] = tmp
+        elif self.separable:
+            kq = self.k
+            U = K.empty((N, self.H, self.W, self.sep_ld), x)      # gradient of the 1 x k stage's output
+            K.vstack_rows(dy, dy.shape[-1], N, self.H, self.W, kq, self.p, self.Co, U, self.sep_ld)
+            if not folded:
+                dwa = K.zeros((self.sep_C, self.Ci, kq), x)        # rows (ky, co), then ci, kx
+                if cblk_of(self.sep_C) < cblk_of(min(self.Ci, 64)):
+                    K.wgrad(x, self.Ci, U, self.sep_C, self._taps('sb', self.sep_bwd_taps), 1, dwa, swapped=True)
+                else:
+                    K.wgrad(U, self.sep_C, x, self.Ci, self._taps('sf', self.sep_fwd_taps), 1, dwa)
+                upd = dwa.view(kq, self.Co, self.Ci, kq).permute(1, 2, 0, 3)      # -> (co, ci, ky, kx)
+                live = _live_grad(self.conv.weight, x)
+                if live is not None:
+                    live.add_(upd)
+                grads['w'] = None if live is not None else upd.contiguous()
+            if need_dx:
+                dx = K.empty(x.shape, x)
+                wm = pk['sep_bwd']
+                K.gather(U, self.sep_C, wm, wm.shape[0], self._taps('sb', self.sep_bwd_taps), 1, self.H, self.W, dx, self.Ci,
+                         (1, 1), (0, 0), None, 0, None)
         else:
             # the kernel accumulates straight into the torch layout; when the Parameter already owns a dense fp32 .grad
             # (the optimizer's flat gradient buffer, zeroed by zero_grad) it accumulates THERE and autograd gets None

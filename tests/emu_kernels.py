@@ -230,6 +230,34 @@ class EmuKernels:
             dst[..., :C] = (s / (k * k)).repeat_interleave(k, 1).repeat_interleave(k, 2).to(EmuKernels.store)
 
     @classmethod
+    def vsum_rows(cls, T, ld_t, N, H, W, k, pad, Co, bias, act, stats, out, ld_out):
+        cls.launches += 1
+        t = torch.nan_to_num(T.float())
+        acc = torch.zeros(N, H, W, Co)
+        for ty in range(k):
+            sh = ty - pad                           # out[y] += T[y + sh][ty*Co : ty*Co + Co]
+            lo, hi = max(0, -sh), min(H, H - sh)
+            if hi > lo:
+                acc[:, lo:hi] += t[:, lo + sh:hi + sh, :, ty * Co:(ty + 1) * Co]
+        if bias is not None:
+            acc = acc + bias.float()
+        if stats is not None:
+            stats[0] += acc.sum((0, 1, 2)).double()
+            stats[1] += (acc * acc).sum((0, 1, 2)).double()
+        out[..., :Co] = _act(acc, act).to(EmuKernels.store)
+
+    @classmethod
+    def vstack_rows(cls, dy, ld_dy, N, H, W, k, pad, Co, U, ld_u):
+        cls.launches += 1
+        g = torch.nan_to_num(dy.float())[..., :Co]
+        U.zero_()
+        for ty in range(k):
+            sh = ty - pad                           # U[r][ty] = dy[r - sh]
+            lo, hi = max(0, sh), min(H, H + sh)
+            if hi > lo:
+                U[:, lo:hi, :, ty * Co:(ty + 1) * Co] = g[:, lo - sh:hi - sh].to(EmuKernels.store)
+
+    @classmethod
     def add_act(cls, a, ld_a, b, ld_b, P, C, act, out, ld_out):
         cls.launches += 1
         v = cls._flat(a, P, ld_a)[:, :C].float() + cls._flat(b, P, ld_b)[:, :C].float()

@@ -265,3 +265,41 @@ def test_avgpool_and_residual_join(pkg, C, H, k):
     for act, fn in ((1, torch.relu), (0, lambda t: t)):
         nat.add_act(a, ld, b, ld, N * H * H, C, act, o, ld)
         assert torch.allclose(o[..., :C].float(), fn(a[..., :C].float() + b[..., :C].float()), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('k,Co,ld_t,ld_y,H,W', [(5, 3, 16, 8, 32, 32), (5, 3, 16, 3, 9, 8), (3, 4, 16, 8, 8, 8), (3, 1, 8, 8, 10, 12),
+                                                (7, 2, 16, 2, 8, 8), (3, 3, 16, 8, 16, 16), (5, 1, 16, 8, 28, 28),
+                                                (3, 1, 16, 8, 8, 24)])
+def test_separable_head_row_kernels(pkg, k, Co, ld_t, ld_y, H, W):
+    """jvae_vsum_rows / jvae_vstack_rows (vertical stage of the separable narrow-output convolution), vectorised and generic
+    layouts, against the index arithmetic written out in torch; the two are adjoint"""
+    nat = pkg._native
+    torch.manual_seed(0)
+    N, p = 3, (k - 1) // 2
+    T = torch.randn(N, H, W, ld_t, device=DEV).to(torch.bfloat16)
+    bias = torch.randn(Co, device=DEV)
+    out = torch.full((N, H, W, ld_y), 7.0, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(2, Co, dtype=torch.float64, device=DEV)
+    nat.vsum_rows(T, ld_t, N, H, W, k, p, Co, bias, 1, stats, out, ld_y)
+    acc = torch.zeros(N, H, W, Co, device=DEV)
+    for ty in range(k):
+        sh = ty - p
+        lo, hi = max(0, -sh), min(H, H - sh)
+        acc[:, lo:hi] += T.float()[:, lo + sh:hi + sh, :, ty * Co:(ty + 1) * Co]
+    acc = acc + bias
+    assert torch.allclose(out[..., :Co].float(), torch.relu(acc), rtol=1e-2, atol=1e-2)
+    assert torch.allclose(stats[0], acc.sum((0, 1, 2)).double(), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[1], (acc * acc).sum((0, 1, 2)).double(), rtol=1e-4, atol=1e-2)
+    dy = torch.randn(N, H, W, ld_y, device=DEV).to(torch.bfloat16)
+    U = torch.full((N, H, W, ld_t), 7.0, dtype=torch.bfloat16, device=DEV)
+    nat.vstack_rows(dy, ld_y, N, H, W, k, p, Co, U, ld_t)
+    want = torch.zeros(N, H, W, ld_t, device=DEV)
+    for ty in range(k):
+        sh = ty - p
+        lo, hi = max(0, sh), min(H, H + sh)
+        want[:, lo:hi, :, ty * Co:(ty + 1) * Co] = dy.float()[:, lo - sh:hi - sh, :, :Co]
+    assert torch.equal(U.float(), want)
+    # adjointness: <vsum(T) - bias, dy> = <T, vstack(dy)> over the k * Co real channels
+    lhs = ((acc - bias) * dy.float()[..., :Co]).sum()
+    rhs = (T.float()[..., :k * Co] * want[..., :k * Co]).sum()
+    assert abs(float(lhs - rhs)) <= 1e-3 * max(1.0, abs(float(lhs)))
