@@ -26,7 +26,8 @@ class Sigma(Parameter):
             value = 0
         learned = learned or bool(input_dim)
         is_log = is_log or learned
-        v = np.log(value) if is_log else value
+        with np.errstate(divide='ignore'):      # a coded sigma starts from value 0 -> log 0 = -inf, as in the reference (layers.py:84-87)
+            v = np.log(value) if is_log else value
         return super().__new__(cls, torch.zeros(sdim).fill_(v), requires_grad=learned)
 
     def __init__(self, value=None, learned=False, is_rmse=False, sdim=1, input_dim=False, reach=1, decay=0,
