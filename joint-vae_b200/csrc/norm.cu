@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_apply_fwd_kernel(const Bn
 }
 
 // ------------------------------------------------------------------------------------------------ BN backward
+constexpr int BN_REDUCE_BLOCKS = 3;      // resident blocks per SM of the backward reduction (one wave)
 struct BnBwd {
   const __nv_bfloat16* da; const __nv_bfloat16* y; __nv_bfloat16* dy;
   size_t P; int C, ld_da, ld_y, ld_dy, nchunk, ppb, act;
@@ -195,19 +196,21 @@ struct BnBwd {
 };
 
 template <int V>
-__global__ void __launch_bounds__(NORM_MAX_THREADS, 2) bn_bwd_reduce_kernel(const BnBwd a) {
+__global__ void __launch_bounds__(NORM_MAX_THREADS, BN_REDUCE_BLOCKS) bn_bwd_reduce_kernel(const BnBwd a) {
   extern __shared__ double s_acc[];
   const int chunk = threadIdx.x % a.nchunk, pl = threadIdx.x / a.nchunk;
-  float mean[V], rstd[V], scale[V], shift[V], acc[2][V];
+  // registers: only scale / shift live through the loop (the activation mask needs z); sum g xhat is recovered at the end
+  // from sum g y, so four blocks of 256 threads fit per SM and their load / compute phases interleave
+  float scale[V], shift[V], acc[2][V];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const int c = chunk * V + j;
-    mean[j] = a.save[c]; rstd[j] = a.save[a.C + c];
+    const float mean = a.save[c], rstd = a.save[a.C + c];
     const float g = a.gamma ? a.gamma[c] : 1.f, b = a.beta ? a.beta[c] : 0.f;
-    scale[j] = g * rstd[j]; shift[j] = b - mean[j] * scale[j];
+    scale[j] = g * rstd; shift[j] = b - mean * scale[j];
     acc[0][j] = acc[1][j] = 0.f;
   }
-  constexpr int U = 4;
+  constexpr int U = 2;
   const size_t step = (size_t)gridDim.x * a.ppb;
   for (size_t p0 = (size_t)blockIdx.x * a.ppb + pl; p0 < a.P; p0 += U * step) {
     float g[U][V], y[U][V];
@@ -228,8 +231,13 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS, 2) bn_bwd_reduce_kernel(cons
       for (int j = 0; j < V; ++j) {
         const float gz = g[u][j] * act_grad_z(fmaf(y[u][j], scale[j], shift[j]), a.act);
         acc[0][j] += gz;
-        acc[1][j] += gz * (y[u][j] - mean[j]) * rstd[j];
+        acc[1][j] = fmaf(gz, y[u][j], acc[1][j]);
       }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) {      // sum g xhat = (sum g y - mean sum g) rstd, per thread before the cross-thread reduction
+    const int c = chunk * V + j;
+    acc[1][j] = (acc[1][j] - a.save[c] * acc[0][j]) * a.save[a.C + c];
   }
   block_channel_reduce<V, 2>(acc, chunk, a.C, s_acc, a.sums);
 }
@@ -792,7 +800,7 @@ int jvae_bn_bwd(const void* da, int ld_da, const void* y, int ld_y, size_t P, in
   a.save = save_mean_rstd; a.gamma = gamma; a.beta = beta; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
   if (!skip_reduce) {
     JVAE_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), (cudaStream_t)stream));
-    const Geo gr = make_geo(P, C, vec ? 8 : 1, 2);     // one resident wave: the per-block reduction tail runs once
+    const Geo gr = make_geo(P, C, vec ? 8 : 1, BN_REDUCE_BLOCKS);     // one resident wave: the per-block reduction tail runs once
     NORM_DISPATCH(vec, bn_bwd_reduce_kernel, gr, 2 * C * sizeof(double), (cudaStream_t)stream, a);
   }
   NORM_DISPATCH(vec, bn_bwd_apply_kernel, g, 0, (cudaStream_t)stream, a);
