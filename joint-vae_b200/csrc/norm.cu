@@ -7,6 +7,8 @@
 // one channel otherwise) for the whole kernel and walks over pixels, so per-channel parameters live in registers and
 // per-channel reductions need one shared-memory + one global atomic per block.
 #include "common.cuh"
+#include <mutex>
+#include <unordered_map>
 #include <initializer_list>
 
 namespace jvae {
@@ -749,10 +751,33 @@ static bool vec_ok(int C, std::initializer_list<int> lds, std::initializer_list<
 
 using namespace jvae;
 
+// all kernels here are grid-stride: the grid never exceeds what is resident at once (occupancy x SMs), so there is no partial
+// second wave of blocks (bn_apply_fwd: 1184 blocks on 740 slots before)
+template <typename Kern>
+static int resident_grid(Kern kern, int threads, size_t smem, int want) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> cache;
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kern)) ^ ((uint64_t)threads << 48) ^
+                       ((uint64_t)smem << 32);
+  int occ = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) occ = it->second;
+  }
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = occ;
+  }
+  const long long cap = (long long)occ * sm_count();
+  return (int)(want < cap ? want : cap);
+}
+
 #define NORM_DISPATCH(vec, kernel, geo, smem, st, ...)                                             \
   do {                                                                                             \
-    if (vec) kernel<8><<<geo.grid, geo.threads, smem, st>>>(__VA_ARGS__);                          \
-    else kernel<1><<<geo.grid, geo.threads, smem, st>>>(__VA_ARGS__);                              \
+    if (vec) kernel<8><<<resident_grid(kernel<8>, geo.threads, smem, geo.grid), geo.threads, smem, st>>>(__VA_ARGS__);   \
+    else kernel<1><<<resident_grid(kernel<1>, geo.threads, smem, geo.grid), geo.threads, smem, st>>>(__VA_ARGS__);       \
     JVAE_LAUNCH_CHECK();                                                                           \
   } while (0)
 
@@ -919,10 +944,10 @@ int jvae_vsum_rows(const void* T, int ld_t, int N, int H, int W, int k, int pad,
   const __nv_bfloat16* Tp = reinterpret_cast<const __nv_bfloat16*>(T);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (fixed && k == 5 && Co == 3) vsum_rows_fixed_kernel<5, 3><<<(int)blocks, 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 3 && Co == 3) vsum_rows_fixed_kernel<3, 3><<<(int)blocks, 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 5 && Co == 1) vsum_rows_fixed_kernel<5, 1><<<(int)blocks, 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 3 && Co == 1) vsum_rows_fixed_kernel<3, 1><<<(int)blocks, 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
+  if (fixed && k == 5 && Co == 3) vsum_rows_fixed_kernel<5, 3><<<resident_grid(vsum_rows_fixed_kernel<5, 3>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
+  else if (fixed && k == 3 && Co == 3) vsum_rows_fixed_kernel<3, 3><<<resident_grid(vsum_rows_fixed_kernel<3, 3>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
+  else if (fixed && k == 5 && Co == 1) vsum_rows_fixed_kernel<5, 1><<<resident_grid(vsum_rows_fixed_kernel<5, 1>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
+  else if (fixed && k == 3 && Co == 1) vsum_rows_fixed_kernel<3, 1><<<resident_grid(vsum_rows_fixed_kernel<3, 1>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
   else vsum_rows_kernel<<<(int)blocks, 256, 0, st>>>(Tp, ld_t, N, H, W, k, pad, Co, bias, act, stats, op, ld_out);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
@@ -940,10 +965,10 @@ int jvae_vstack_rows(const void* dy, int ld_dy, int N, int H, int W, int k, int 
   const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(dy);
   __nv_bfloat16* up = reinterpret_cast<__nv_bfloat16*>(U);
   cudaStream_t st = (cudaStream_t)stream;
-  if (fixed && k == 5 && Co == 3) vstack_rows_fixed_kernel<5, 3><<<(int)blocks, 256, 0, st>>>(dp, N, H, W, up);
-  else if (fixed && k == 3 && Co == 3) vstack_rows_fixed_kernel<3, 3><<<(int)blocks, 256, 0, st>>>(dp, N, H, W, up);
-  else if (fixed && k == 5 && Co == 1) vstack_rows_fixed_kernel<5, 1><<<(int)blocks, 256, 0, st>>>(dp, N, H, W, up);
-  else if (fixed && k == 3 && Co == 1) vstack_rows_fixed_kernel<3, 1><<<(int)blocks, 256, 0, st>>>(dp, N, H, W, up);
+  if (fixed && k == 5 && Co == 3) vstack_rows_fixed_kernel<5, 3><<<resident_grid(vstack_rows_fixed_kernel<5, 3>, 256, 0, (int)blocks), 256, 0, st>>>(dp, N, H, W, up);
+  else if (fixed && k == 3 && Co == 3) vstack_rows_fixed_kernel<3, 3><<<resident_grid(vstack_rows_fixed_kernel<3, 3>, 256, 0, (int)blocks), 256, 0, st>>>(dp, N, H, W, up);
+  else if (fixed && k == 5 && Co == 1) vstack_rows_fixed_kernel<5, 1><<<resident_grid(vstack_rows_fixed_kernel<5, 1>, 256, 0, (int)blocks), 256, 0, st>>>(dp, N, H, W, up);
+  else if (fixed && k == 3 && Co == 1) vstack_rows_fixed_kernel<3, 1><<<resident_grid(vstack_rows_fixed_kernel<3, 1>, 256, 0, (int)blocks), 256, 0, st>>>(dp, N, H, W, up);
   else vstack_rows_kernel<<<(int)blocks, 256, 0, st>>>(dp, ld_dy, N, H, W, k, pad, Co, up, ld_u);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
