@@ -281,7 +281,7 @@ def run_native(args, wl):
                     sc(i)
                 timed(sc, 5)               # settles the caching allocator for this model's shapes
                 nat.PROFILE = {'elbo_eval_fwd': []}
-                ms_c = min(timed(sc, 5), timed(sc, 5))      # best of two 5-batch runs
+                ms_c = min(timed(sc, 5), timed(sc, 5), timed(sc, 5))      # best of three 5-batch runs
                 ev = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
                 nat.PROFILE = None
             sweep.append({'C': C_, 'K': 256, 'L': wl['ctor']['test_latent_sampling'], 'samples_per_s': world * B * 5 / (ms_c * 1e-3),
