@@ -60,6 +60,31 @@ class _LazyMeasures(Mapping):
         return repr(dict(self._force()))
 
 
+def _develop_starred(methods, methods_params):
+    """utils/save_load/dictify.py:198-212 (in place): 'softkl*' -> softkl-1, softkl-2, ... (one entry per temperature)"""
+    starred = []
+    for m in list(methods):
+        if m.endswith('*'):
+            methods += methods_params.get(m[:-1], [])
+            starred.append(m)
+    for m in starred:
+        methods.remove(m)
+    return methods
+
+
+def _make_list(o, default_for_all):
+    """utils/misc.py:1-13"""
+    if isinstance(o, str):
+        o = [o]
+    if o is None:
+        return []
+    if o and o[0] in ('all', 'default'):
+        return type(default_for_all)(default_for_all)
+    if o and o[0] == 'first':
+        return [next(iter(default_for_all))]
+    return o
+
+
 class ClassificationVariationalNetwork(nn.Module):
     """X -- features -- encoder -- Z -- decoder -- imager -- X^ ;  Z -- classifier -- Y^   (cvae.py:60-81)"""
 
@@ -727,6 +752,52 @@ class ClassificationVariationalNetwork(nn.Module):
                           'thresholds': thr}      # the reference stores list(dict) = the two key names here
         if update_self_ood:
             self.ood_results.setdefault(epoch, {})[set_name] = results
+        return results
+
+    def misclassification_detection_rates(self, recorder, predict_methods='all', misclass_methods='all', epoch='last',
+                                          update_self_results=True):
+        """The arithmetic of cvae.py:1913-2079 on a LossRecorder of the test set (the reference loads `record-<set>.pth`
+        through its result registry; here the recorder is passed in): per predict method the correct / missed split and the
+        accuracy, per misclassification score the ROC table of correct against missed samples (device sort / searchsorted,
+        utils/roc_curves.py of this package) and the precision at the kept thresholds.  Results use the reference's keys
+        and, with update_self_results, land in self.testing[epoch][predict_method][score] as there."""
+        from .utils.roc_curves import roc_curve
+        methods = {}
+        for which, asked, all_methods in (('predict', predict_methods, self.predict_methods),
+                                          ('miss', misclass_methods, self.misclass_methods)):
+            developed = _develop_starred(all_methods, self.methods_params)          # in place, as the reference does
+            methods[which] = _make_list(asked, developed)
+            for m in methods[which]:
+                assert m in all_methods, m
+        tensors = dict(recorder._tensors)
+        logits = tensors.pop('logits').T
+        y = tensors.pop('y_true')
+        losses = tensors
+        kept_tpr = [pc / 100 for pc in range(90, 100)]
+        epoch = self.trained if epoch == 'last' else epoch
+        sampling = self._latent_samplings['eval']
+        results = {}
+        for pm in methods['predict']:
+            if not methods['miss']:
+                continue
+            y_ = self.predict_after_evaluate(logits, losses, method=pm)
+            correct, missed = (y_ == y), (y_ != y)
+            n_correct, n_missed = int(correct.sum()), int(missed.sum())
+            acc = n_correct / (n_correct + n_missed)
+            scores = self.batch_dist_measures(logits, losses, methods['miss'])
+            results[pm] = {'n': int(y.numel()), 'epochs': epoch, 'sampling': sampling, 'accuracy': acc}
+            for m in methods['miss']:
+                v = scores[m].reshape(-1).double()
+                auc, fpr, tpr, thr = roc_curve(v[correct], v[missed], *kept_tpr)
+                t_low = torch.as_tensor(np.asarray(thr['low'], dtype=np.float64), device=v.device)
+                pos = v[None, :] >= t_low[:, None]                      # (thresholds, samples), cvae.py:2010-2016
+                tp = (pos & correct[None]).sum(1).double()
+                fp = (pos & missed[None]).sum(1).double()
+                precision = (tp / (tp + fp)).tolist()
+                results[pm][m] = {'n': int(y.numel()), 'epochs': epoch, 'sampling': sampling, 'tpr': list(tpr), 'fpr': list(fpr),
+                                  'auc': auc, 'precision': precision}
+        if update_self_results:
+            self.testing.setdefault(epoch, {}).update(results)
         return results
 
     # ------------------------------------------------------------------------------------------ persistence
