@@ -443,6 +443,12 @@ class ClassificationVariationalNetwork(nn.Module):
                     if res['total'].shape[0] == 1:
                         res['total'] = res['total'].squeeze(0)
                 self._fused = {'scores': r['scores'], 'preds': r['preds'], 'total': res['total']}
+        if self.training and self.x_is_generated and self.sigma.decay and not self.sigma.learned and not self.sigma.is_rmse:
+            # cvae.py:768-771: a decaying sigma moves towards reach * rmse of the batch after every training evaluate (no sync:
+            # the update stays on the device unless a max_step is set)
+            sd = self.sigma.data.float().reshape(-1)[:1]
+            s2 = (2 * sd).exp() if self.sigma.is_log else sd ** 2
+            self.sigma.update(rmse=(res['wmse'].detach() * s2).mean().sqrt())
         # same key order as the reference's dict (cvae.py:726-902)
         for k in ('kl', 'zdist', 'var_kl', 'total'):
             batch_losses[k] = res[k]

@@ -237,7 +237,7 @@ def run_case(cvae_mod, name, kw, eval_part=True):
         if p.grad is not None:
             out['train.grad.' + k] = t2n(p.grad)
     for k, v in model.state_dict().items():
-        if 'running_' in k or 'num_batches' in k:
+        if 'running_' in k or 'num_batches' in k or k == 'sigma':
             out['train.sd_after.' + k] = t2n(v)
 
     # ---------------- eval / scoring step, cvae.py:1629-1677

@@ -20,6 +20,12 @@ CASES = {
         latent_dim=8, latent_sampling=3, test_latent_sampling=4, gamma=0, beta=1.0, output_activation='sigmoid',
         sigma={'input_dim': [1, 8, 8], 'sdim': 1},
         prior={'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 31}),
+    # constant sigma decaying towards reach * rmse of every training batch (layers.py:146-168, cvae.py:768-771)
+    'sig_mlp_cvae_decay': dict(
+        input_shape=(1, 8, 8), num_labels=5, type='cvae', encoder=[32, 16], decoder=[16, 32], classifier=[],
+        latent_dim=8, latent_sampling=3, test_latent_sampling=4, gamma=0, beta=1.0, output_activation='sigmoid',
+        sigma={'value': 0.5, 'decay': 0.1, 'reach': 2.0},
+        prior={'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 32}),
 }
 
 if __name__ == '__main__':

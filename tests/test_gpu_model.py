@@ -55,6 +55,11 @@ def test_sigma_coded_matches_reference(pkg):
     _run(pkg, 'sig_mlp_cvae_coded')
 
 
+def test_sigma_decay_matches_reference(pkg):
+    """constant sigma decaying towards reach * rmse after every training evaluate (layers.py:146-168, cvae.py:768-771)"""
+    _run(pkg, 'sig_mlp_cvae_decay')
+
+
 def test_y_is_coded_train_step_matches_reference(pkg):
     """y_is_coded=True: the one-hot label enters the encoder (layers.py:366-369); train step against the reference
     (its label-free evaluation fails in the reference itself, tests/golden/make_ycoded_golden.py)"""
@@ -86,6 +91,8 @@ def _run(pkg, name, eval_part=True):
     if cfg['type'] != 'vib':
         assert tuple(x_reco.shape) == d['train.x_reco'].shape
         assert rel(x_reco.detach().float().cpu().numpy(), d['train.x_reco']) < tol
+    if 'train.sd_after.sigma' in d.files:      # Sigma.update(rmse=...) / update(v=...) side effect of the training evaluate
+        assert rel(net.sigma.data.detach().cpu().numpy().reshape(-1), d['train.sd_after.sigma'].reshape(-1)) < tol
     if cfg['prior'].get('distribution') == 'uniform':
         return _eval(pkg, net, d, cfg, x, tol)
     losses['total'].mean().backward()
