@@ -875,13 +875,38 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
     const float n = sqrtf(dist);
     tilt = (n > 0.f) ? (n - a.tau) / n : 0.f;
   }
+  // uniform-with-gaussian-tail prior (priors.py:429-476): kl = max(sum_k (Elogq + neg), sum_k (Elogq + alpha)) [+ (w - 1) aux];
+  // the max is taken on the sums, so the branch is per sample
+  bool uni_first = true;
+  if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+    __shared__ float red_u[32];
+    float dist = 0.f, tr = 0.f, aux = 0.f;
+    for (int k = tid; k < K; k += ELBO_THREADS)
+      kl_dim_terms(a, a.mu[(size_t)b * K + k], a.lv[(size_t)b * K + k], a.means[(size_t)c * K + k], 1.f, dist, tr, aux);
+    tr = block_sum(tr, red_u);
+    aux = block_sum(aux, red_u);
+    uni_first = tr >= aux;      // torch.max(a, b) back-propagates into a where a >= b (ties: half each; measure-zero here)
+  }
   for (int k = tid; k < K; k += ELBO_THREADS) {
     const float mu = a.mu[(size_t)b * K + k], lv = a.lv[(size_t)b * K + k];
     const float m = a.means[(size_t)c * K + k];
     const float T = (a.var_dim == JVAE_VAR_SCALAR) ? Tc : a.inv_trans[(size_t)c * K + k];
     const float t2 = T * T;
     float dmu, dlv;
-    if (a.prior_kind == JVAE_PRIOR_TILTED) {
+    if (a.prior_kind == JVAE_PRIOR_UNIFORM) {
+      // d/d(mu - m) and d/d(log_var) of Elogq + neg (first branch) or of Elogq + alpha (second branch, and the (w - 1) term)
+      const float d = mu - m, tau = a.tau, A = a.alpha - 0.5f * LOG2PI_F;
+      const float span = 2.f * 1.7320508075688772f * expf(0.5f * lv);
+      const float lo = d - 0.5f * span, hi = d + 0.5f * span;
+      const float lo_ = tau * fminf(fmaxf(lo / tau, -1.f), 1.f), hi_ = tau * fminf(fmaxf(hi / tau, -1.f), 1.f);
+      const float dlo = (fabsf(lo) < tau) ? 1.f : 0.f, dhi = (fabsf(hi) < tau) ? 1.f : 0.f;      // hardtanh slopes
+      const float neg_d = d + A * (dhi - dlo) / span - (hi_ * hi_ * dhi - lo_ * lo_ * dlo) / (2.f * span);
+      const float neg_lv = span * span / 24.f + A * ((dhi + dlo) * 0.25f - (hi_ - lo_) / (2.f * span))
+                           - ((hi_ * hi_ * dhi + lo_ * lo_ * dlo) * 0.125f - (hi_ * hi_ * hi_ - lo_ * lo_ * lo_) / (12.f * span));
+      const float gk = gb * a.beta;
+      dmu = uni_first ? gk * neg_d : 0.f;
+      dlv = gk * ((uni_first ? neg_lv - 0.5f : -0.5f) + (a.var_w - 1.f) * -0.5f);
+    } else if (a.prior_kind == JVAE_PRIOR_TILTED) {
       dmu = gb * a.beta * tilt * t2 * (mu - m);
       dlv = 0.f;
     } else {
@@ -1593,10 +1618,6 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
                         float* d_inv_trans, float* d_sigma, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_cfg(cfg, __func__);
   if (rc) return rc;
-  if (cfg->prior_kind == JVAE_PRIOR_UNIFORM) {
-    set_error("%s: backward of the uniform-with-gaussian-tail prior is not implemented", __func__);
-    return JVAE_ERR_UNSUPPORTED;
-  }
   if (cfg->sigma_is_rmse) {
     set_error("%s: backward with sigma=rmse is not implemented", __func__);
     return JVAE_ERR_UNSUPPORTED;

@@ -92,8 +92,6 @@ def test_train_fwd_bwd(pkg, case, xr_dtype):
     for k in ('kl', 'zdist', 'var_kl', 'wmse', 'cross_x', 'cross_y', 'total', 'dzdist'):
         close(out[k], ref[k], what=k)
     assert int(out['finite'].item()) != 0
-    if kind == 'uniform':
-        return
     g = torch.full((B,), 1.0 / B, device=DEV)
     d_xr, d_mu, d_lv, d_lg, d_means, d_it, d_sigma = nat.elbo_train_bwd(
         cfg, g, d['x'], d['xr'], d['mu'], d['lv'], d['logits'], d['y'], d['means'], d['T'], sig, out['wmse'],
@@ -123,6 +121,21 @@ def test_train_fwd_bwd(pkg, case, xr_dtype):
         close(d_lg * B, rb['logits'] * B, what='d_logits')
         close(d_means, rb['means'], what='d_means')
         close(d_sigma, np.array([rb['sigma']]), what='d_sigma')
+    elif kind == 'uniform':   # torch autograd of priors.py:429-476 written out (hardtanh tails, max of the two sums)
+        import torch.nn.functional as F
+        mu, lv, means = d['mu'].clone().requires_grad_(), d['lv'].clone().requires_grad_(), d['means'].clone().requires_grad_()
+        tau, alpha, cst = c['tau'], c['prior'].alpha, float(np.log(2 * np.pi))
+        span = 2 * np.sqrt(3) * (0.5 * lv).exp()
+        dd = mu - means[d['y']]
+        a_, b_ = tau * F.hardtanh((dd - 0.5 * span) / tau), tau * F.hardtanh((dd + 0.5 * span) / tau)
+        elogq = -0.5 * lv - 0.5 * np.log(12)
+        neg = (cst + dd.square() + span.square() / 12) / 2 + (alpha - cst / 2) * (b_ - a_) / span - (b_.pow(3) - a_.pow(3)) / span / 6
+        var_kl = (elogq + alpha).sum(-1)
+        kl = torch.max(elogq.sum(-1) + neg.sum(-1), var_kl) + (var_w - 1) * var_kl
+        (beta * kl / B).sum().backward()
+        close(d_mu * B, (mu.grad * B).cpu().numpy(), what='d_mu uniform')
+        close(d_lv * B, (lv.grad * B).cpu().numpy(), what='d_lv uniform')
+        close(d_means, means.grad.cpu().numpy(), what='d_means uniform')
     else:   # tilted: check against torch autograd of the same formula
         mu = d['mu'].clone().requires_grad_()
         m = d['means'][d['y']]

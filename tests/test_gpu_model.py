@@ -93,8 +93,6 @@ def _run(pkg, name, eval_part=True):
         assert rel(x_reco.detach().float().cpu().numpy(), d['train.x_reco']) < tol
     if 'train.sd_after.sigma' in d.files:      # Sigma.update(rmse=...) / update(v=...) side effect of the training evaluate
         assert rel(net.sigma.data.detach().cpu().numpy().reshape(-1), d['train.sd_after.sigma'].reshape(-1)) < tol
-    if cfg['prior'].get('distribution') == 'uniform':
-        return _eval(pkg, net, d, cfg, x, tol)
     losses['total'].mean().backward()
     checked = 0
     pairs = {k: p for k, p in net.named_parameters() if 'train.grad.' + k in d.files}
