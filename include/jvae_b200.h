@@ -110,7 +110,8 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Train backward of sum_b g[b]*total[b] (SURVEY.md §8a backward contract; the reference uses
- * autograd over the same lines).  g (B) f32 (= 1/B for total.mean()).  wmse (B): saved forward output.
+ * autograd over the same lines).  g (B) f32 (= 1/B for total.mean()).  wmse (B): saved forward output `wmse`; with
+ * sigma_is_rmse pass the forward's `cross_x` instead (the per-sample sigma^2 = mse is recovered from it; d_sigma is not written).
  *   d_x_reco (L+1,B,D) [slab 0 written as zeros]; d_mu, d_log_var (B,K) f32: DIRECT terms only
  *   (the path through z is added by jvae_sample_bwd); d_logits (L+1,B,C); d_means (C,K) f32;
  *   d_inv_trans like inv_trans (NULL unless var_dim is diag/full); d_sigma: 1 f32 (B with sigma_per_sample). */

@@ -774,7 +774,12 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
   const float gb = a.g[b];
   const int D = a.D, K = a.K, C = a.C;
   float sig = 1.f;
-  if (a.has_xreco) {
+  if (a.has_xreco && a.sigma_is_rmse) {
+    // sigma^2 := this sample's mean squared error (cvae.py:662-670); it is not detached in the reference, but wmse = mse / sigma^2
+    // is then constant and cross_x = D/2 (log mse + 1 + log 2pi): d/dx_reco = (x_reco - x) / (L mse), the usual formula with
+    // sigma^2 = mse.  The caller passes cross_x in the wmse slot: mse = exp(2 cross_x / D - 1 - log 2pi).
+    sig = expf(a.wmse_in[b] / (float)D - 0.5f - 0.5f * LOG2PI_F);
+  } else if (a.has_xreco) {
     const float s = a.sigma[(size_t)a.sigma_stride * b];
     sig = a.sigma_is_log ? expf(s) : s;
   }
@@ -856,7 +861,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_train_bwd_kernel(ElboArgs a
   long long yb = a.y[b];
   if (yb < 0 || yb >= C) yb = 0;
   const int c = a.conditional ? (int)yb : 0;
-  if (a.has_xreco && a.d_sigma && tid == 0) {
+  if (a.has_xreco && a.d_sigma && !a.sigma_is_rmse && tid == 0) {
     // cross_x = D/2 (2 log sigma + wmse + log 2pi), wmse ~ sigma^-2
     float ds = gb * (float)D * (1.f - a.wmse_in[b]);
     if (!a.sigma_is_log) ds /= sig;
@@ -1618,10 +1623,6 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
                         float* d_inv_trans, float* d_sigma, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_cfg(cfg, __func__);
   if (rc) return rc;
-  if (cfg->sigma_is_rmse) {
-    set_error("%s: backward with sigma=rmse is not implemented", __func__);
-    return JVAE_ERR_UNSUPPORTED;
-  }
   JVAE_CHECK_ARG(g && mu && log_var && y && means && inv_trans, "g, mu, log_var, y, means, inv_trans are required");
   JVAE_CHECK_ARG(!cfg->has_xreco || (x && x_reco && sigma && wmse), "x, x_reco, sigma, wmse are required when has_xreco");
   JVAE_CHECK_ARG(!cfg->has_logits || logits, "logits is required when has_logits");

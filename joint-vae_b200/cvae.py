@@ -408,7 +408,9 @@ class ClassificationVariationalNetwork(nn.Module):
         cfg = self._elbo_cfg(B, L, xr_k, logits_k, beta, gw, kl_var_weighting)
         cfg.prior_stats_ready = int(prior_ready)
         sig = self.sigma if self.x_is_generated else None
-        sigma_seen = self.sigma.data       # the `sigma` measure is read before any update (cvae.py:624)
+        # the `sigma` measure is read before any update (cvae.py:624); the decaying / rmse update is in place: snapshot then
+        updates_in_place = self.training and self.x_is_generated and self.sigma.decay and not self.sigma.learned
+        sigma_seen = self.sigma.data.clone() if updates_in_place else self.sigma.data
         if self.x_is_generated and self.sigma.coded:       # cvae.py:631-634: one log sigma per sample from the encoder's head
             sig = sigma_coded.reshape(-1).float().contiguous()
             self.sigma.update(v=sigma_coded.detach().reshape(-1, *self.sigma.output_dim))
@@ -443,12 +445,20 @@ class ClassificationVariationalNetwork(nn.Module):
                     if res['total'].shape[0] == 1:
                         res['total'] = res['total'].squeeze(0)
                 self._fused = {'scores': r['scores'], 'preds': r['preds'], 'total': res['total']}
-        if self.training and self.x_is_generated and self.sigma.decay and not self.sigma.learned and not self.sigma.is_rmse:
-            # cvae.py:768-771: a decaying sigma moves towards reach * rmse of the batch after every training evaluate (no sync:
-            # the update stays on the device unless a max_step is set)
-            sd = self.sigma.data.float().reshape(-1)[:1]
-            s2 = (2 * sd).exp() if self.sigma.is_log else sd ** 2
-            self.sigma.update(rmse=(res['wmse'].detach() * s2).mean().sqrt())
+        mse_rmse = None
+        if self.x_is_generated and self.sigma.is_rmse:
+            # sigma^2 := per-sample mse (cvae.py:662-670); recovered from cross_x = D/2 (log mse + 1 + log 2 pi)
+            D_ = float(np.prod(self.input_shape))
+            mse_rmse = (2 * res['cross_x'].detach() / D_ - 1 - math.log(2 * math.pi)).exp()
+        if self.training and self.x_is_generated and self.sigma.decay and not self.sigma.learned:
+            # cvae.py:768-771: a decaying / rmse-tracking sigma moves towards reach * rmse of the batch after every training
+            # evaluate (no sync: the update stays on the device unless a max_step is set)
+            if mse_rmse is not None:
+                mse_b = mse_rmse
+            else:
+                sd = self.sigma.data.float().reshape(-1)[:1]
+                mse_b = res['wmse'].detach() * ((2 * sd).exp() if self.sigma.is_log else sd ** 2)
+            self.sigma.update(rmse=mse_b.mean().sqrt())
         # same key order as the reference's dict (cvae.py:726-902)
         for k in ('kl', 'zdist', 'var_kl', 'total'):
             batch_losses[k] = res[k]
@@ -464,13 +474,13 @@ class ClassificationVariationalNetwork(nn.Module):
 
         logits_out = res['logits'] if res.get('logits') is not None else y_est[1:].mean(0)
         measures = self._lazy_measures(x, batch_losses, batch, current_measures, sigma_seen,
-                                       sig.detach() if (self.x_is_generated and self.sigma.coded) else None)
+                                       sig.detach() if (self.x_is_generated and self.sigma.coded) else None, mse_rmse)
         out = (x_reco, logits_out, batch_losses, measures)
         if z_output:
             out += (mu, log_var, z)
         return out
 
-    def _lazy_measures(self, x, losses, batch, current, sigma_data=None, sigma_coded=None):
+    def _lazy_measures(self, x, losses, batch, current, sigma_data=None, sigma_coded=None, mse_rmse=None):
         names = ['sigma']
         if self.x_is_generated:
             names += ['xpow', 'mse', 'rmse', 'dB']
@@ -489,6 +499,8 @@ class ClassificationVariationalNetwork(nn.Module):
                     s2 = 1.0 if self.sigma.is_rmse else dev[0] ** 2
                     if sigma_coded is not None:       # per-sample sigma^2 (cvae.py:644-645, 674)
                         s2 = (2 * sigma_coded).exp() if self.sigma.is_log else sigma_coded ** 2
+                    if mse_rmse is not None:          # sigma = rmse: mse = wmse * sigma^2 with wmse = 1 (cvae.py:662-674)
+                        s2 = mse_rmse
                     dev += [x.float().pow(2).mean().reshape(1), (losses['wmse'] * s2).mean().reshape(1)]
                 if conditional:
                     m = self.encoder.prior.mean

@@ -252,7 +252,9 @@ class _ElboTrainFn(torch.autograd.Function):
     def forward(ctx, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, cfg):
         out = nat.elbo_train_fwd(cfg, x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma)
         ctx.cfg = cfg
-        ctx.save_for_backward(x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma, out['wmse'])
+        # the backward kernel recovers the per-sample sigma^2 of sigma=rmse from cross_x (include/jvae_b200.h)
+        ctx.save_for_backward(x, x_reco, mu, log_var, logits, y, means, inv_trans, sigma,
+                              out['cross_x'] if cfg.sigma_is_rmse else out['wmse'])
         ctx.set_materialize_grads(False)
         names = ('kl', 'zdist', 'var_kl', 'wmse', 'cross_x', 'cross_y', 'total', 'dzdist')
         ctx.mark_non_differentiable(out['finite'])

@@ -26,6 +26,12 @@ CASES = {
         latent_dim=8, latent_sampling=3, test_latent_sampling=4, gamma=0, beta=1.0, output_activation='sigmoid',
         sigma={'value': 0.5, 'decay': 0.1, 'reach': 2.0},
         prior={'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 32}),
+    # sigma^2 := the sample's own mean squared error (train.py --sigma rmse; cvae.py:662-670), the parameter tracks reach * rmse
+    'sig_mlp_cvae_rmse': dict(
+        input_shape=(1, 8, 8), num_labels=5, type='cvae', encoder=[32, 16], decoder=[16, 32], classifier=[],
+        latent_dim=8, latent_sampling=3, test_latent_sampling=4, gamma=0, beta=1.0, output_activation='sigmoid',
+        sigma={'is_rmse': True},
+        prior={'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 33}),
 }
 
 if __name__ == '__main__':

@@ -60,6 +60,11 @@ def test_sigma_decay_matches_reference(pkg):
     _run(pkg, 'sig_mlp_cvae_decay')
 
 
+def test_sigma_rmse_matches_reference(pkg):
+    """sigma = rmse (train.py --sigma rmse; cvae.py:662-670): per-sample sigma^2 = mse in the fused forward AND backward"""
+    _run(pkg, 'sig_mlp_cvae_rmse')
+
+
 def test_y_is_coded_train_step_matches_reference(pkg):
     """y_is_coded=True: the one-hot label enters the encoder (layers.py:366-369); train step against the reference
     (its label-free evaluation fails in the reference itself, tests/golden/make_ycoded_golden.py)"""
