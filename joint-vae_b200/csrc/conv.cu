@@ -1214,7 +1214,8 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   p.BN = Cout_pad > 256 ? 256 : Cout_pad;
   if (Cout_pad > 256) JVAE_CHECK_ARG((Cout_pad % 256) == 0, "Cout_pad > 256 must be a multiple of 256");
   // small maps (vgg19's 512-channel layers at 2x2: 16 pixel tiles): narrower channel tiles until the CTAs cover the SMs
-  while (p.BN > 64 && (p.BN % 32) == 0 && 2 * p.tiles_x * p.tiles_y * p.tiles_n * (Cout_pad / p.BN) <= sm_count()) p.BN /= 2;
+  static const bool narrow = !(getenv("JVAE_CONV_NARROW") && atoi(getenv("JVAE_CONV_NARROW")) == 0);
+  while (narrow && p.BN > 64 && (p.BN % 32) == 0 && 2 * p.tiles_x * p.tiles_y * p.tiles_n * (Cout_pad / p.BN) <= sm_count()) p.BN /= 2;
   p.n_tiles_n = Cout_pad / p.BN;
   p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
   p.Cblk = cblk_of(Cin); p.nCk = (Cin + p.Cblk - 1) / p.Cblk; p.ntaps = ntaps; p.in_stride = in_stride;
