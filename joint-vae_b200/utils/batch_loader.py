@@ -40,7 +40,7 @@ class DeviceBatchLoader:
 
     def __init__(self, data, targets, batch_size, device='cuda', data_augmentation=(), transformer='simple', out_shape=None,
                  crop_padding=None, shuffle=True, drop_last=False, rng='vectorised', seed=None, resident=None,
-                 max_resident_bytes=32 << 30):
+                 max_resident_bytes=32 << 30, rank=None, world_size=None):
         self.data = _as_u8_nhwc(data)
         n, H, W, C = self.data.shape
         self.targets = torch.as_tensor(np.asarray(targets) if not torch.is_tensor(targets) else targets).long().reshape(-1)
@@ -63,11 +63,21 @@ class DeviceBatchLoader:
         if rng not in ('torchvision', 'vectorised'):
             raise ValueError("rng must be 'torchvision' or 'vectorised'")
         self.rng = rng
-        self._gen = torch.Generator()
+        # data-parallel training (distributed.py): every rank walks the SAME permutation (shared seed) and keeps the samples
+        # rank, rank + world_size, ...; the augmentation decisions come from a per-rank generator
+        self.rank, self.world_size = (0, 1) if world_size in (None, 1) else (int(rank), int(world_size))
+        if not 0 <= self.rank < self.world_size:
+            raise ValueError('rank must be in [0, world_size)')
+        if self.world_size > 1 and (seed is None or rng != 'vectorised'):
+            raise ValueError("sharding across ranks needs rng='vectorised' and the same explicit seed on every rank")
+        self._gen = torch.Generator()          # permutation
+        self._gen_aug = torch.Generator()      # flip / crop draws
         if seed is not None:
             self._gen.manual_seed(int(seed))
+            self._gen_aug.manual_seed(int(seed) + 7919 * (self.rank + 1))
         else:
             self._gen.seed()
+            self._gen_aug.seed()
 
         oH, oW, off_y, off_x = H, W, 0, 0
         if transformer in ('simple', 'tensor', None):
@@ -95,8 +105,12 @@ class DeviceBatchLoader:
         #                                         costs a cudaHostAlloc, milliseconds)
 
     # ------------------------------------------------------------------ host side: which samples, which decisions
-    def __len__(self):
+    def _n_local(self):
         n = self.data.shape[0]
+        return len(range(self.rank, n, self.world_size))
+
+    def __len__(self):
+        n = self._n_local()
         return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
 
     def _epoch_order(self):
@@ -133,14 +147,16 @@ class DeviceBatchLoader:
                         crop[s, 1] = int(torch.randint(0, span, size=(1,)).item())
         else:
             if want_flip:
-                flip = (torch.rand(nb, generator=self._gen) < 0.5).to(torch.uint8)
+                flip = (torch.rand(nb, generator=self._gen_aug) < 0.5).to(torch.uint8)
             if self._crop_draws:
-                crop = torch.randint(0, span, (nb, 2), generator=self._gen, dtype=torch.int32)
+                crop = torch.randint(0, span, (nb, 2), generator=self._gen_aug, dtype=torch.int32)
         return flip, crop
 
     def plan_epoch(self):
         """generator of (index int64 (nb), flip, crop) per batch: everything the kernel needs besides the images"""
         order = self._epoch_order()
+        if self.world_size > 1:
+            order = order[self.rank::self.world_size]
         n, bs = order.numel(), self.batch_size
         for lo in range(0, n, bs):
             idx = order[lo:lo + bs]

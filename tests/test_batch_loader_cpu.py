@@ -86,3 +86,27 @@ def test_argument_errors(pkg):
         DeviceBatchLoader(data, targets, 2, transformer='crop')
     with pytest.raises(Exception):          # no CPU fallback
         next(iter(DeviceBatchLoader(data, targets, 2, device='cpu')))
+
+
+def test_rank_sharding_partitions_every_epoch(pkg):
+    """data-parallel use: all ranks walk the same permutation and keep every world_size-th sample"""
+    from jointvae_b200.utils.batch_loader import DeviceBatchLoader
+    data, targets = _images(50, 8, 8, 3)
+    loaders = [DeviceBatchLoader(data, targets, 4, data_augmentation=['flip', 'crop'], seed=5, rank=r, world_size=3)
+               for r in range(3)]
+    assert [len(l) for l in loaders] == [5, 5, 4]
+    for epoch in range(2):
+        plans = [list(l.plan_epoch()) for l in loaders]
+        idx = [torch.cat([p[0] for p in pl]) for pl in plans]
+        assert sorted(torch.cat(idx).tolist()) == list(range(50))            # a partition of the dataset
+        assert [i.numel() for i in idx] == [17, 17, 16]
+        if epoch == 0:
+            first = idx
+        else:
+            assert any(not torch.equal(a, b) for a, b in zip(first, idx))    # a new permutation every epoch
+        # augmentation decisions differ between ranks
+        assert not torch.equal(plans[0][0][2], plans[1][0][2])
+    with pytest.raises(ValueError):
+        DeviceBatchLoader(data, targets, 4, rank=0, world_size=2)                     # no shared seed
+    with pytest.raises(ValueError):
+        DeviceBatchLoader(data, targets, 4, seed=1, rng='torchvision', rank=0, world_size=2)
