@@ -205,3 +205,32 @@ def test_resnet18_features_native_stack(pkg, ce, monkeypatch):
         err = float((p.grad.double() - q.grad.double()).norm())
         assert err <= 5e-3 * float(q.grad.norm()) + 5e-4 * gmax, (k, err, float(q.grad.norm()))
     assert _rel(xin.grad, xr.grad) < 5e-3
+
+
+def test_resnet18_eval_mode_forward_and_input_gradient(pkg, ce, monkeypatch):
+    """eval mode (running statistics folded into every conv of the residual blocks and shortcuts): forward against torch, and
+    the input gradient ODIN needs, through the residual joins"""
+    monkeypatch.setattr(EmuKernels, 'store', torch.float32)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', torch.float32)
+    torch.manual_seed(1)
+    from jointvae_b200.module.vae_layers.conv import ResOrDenseNetFeatures
+    seq = ResOrDenseNetFeatures('resnet18', (3, 32, 32), pretrained=False)
+    for m in seq.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+    seq.eval()
+    x = torch.randn(2, 3, 32, 32).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    want = seq(xr)
+    go = torch.randn_like(want)
+    want.backward(go)
+    xin = x.clone().requires_grad_(True)
+    got = ce.run(list(seq), xin)
+    # folded weights are rounded to bf16 (the torch side keeps fp32 weights): 20 layers deep
+    assert _rel(got, want) < 3e-2, _rel(got, want)
+    got.backward(go)
+    assert xin.grad is not None and _rel(xin.grad, xr.grad) < 0.15, _rel(xin.grad, xr.grad)
+    assert all(int(m.num_batches_tracked) == 0 for m in seq.modules() if isinstance(m, torch.nn.BatchNorm2d))
