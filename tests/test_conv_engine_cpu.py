@@ -234,3 +234,48 @@ def test_resnet18_eval_mode_forward_and_input_gradient(pkg, ce, monkeypatch):
     got.backward(go)
     assert xin.grad is not None and _rel(xin.grad, xr.grad) < 0.15, _rel(xin.grad, xr.grad)
     assert all(int(m.num_batches_tracked) == 0 for m in seq.modules() if isinstance(m, torch.nn.BatchNorm2d))
+
+
+@pytest.mark.parametrize('kind', ['basic', 'basic_down', 'bottleneck', 'bottleneck_proj', 'bottleneck_down'])
+def test_residual_blocks_exact(pkg, ce, monkeypatch, kind):
+    """torchvision BasicBlock / Bottleneck (identity, conv1x1 projection, conv1x1 stride-2 shortcut) as ResidualStep: with
+    fp32 storage in the emulation forward, input gradient and every parameter gradient equal torch's to rounding"""
+    from torchvision.models.resnet import BasicBlock, Bottleneck
+    nn = torch.nn
+    monkeypatch.setattr(EmuKernels, 'store', torch.float32)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', torch.float32)
+    torch.manual_seed(0)
+    if kind == 'basic':
+        block, shape = BasicBlock(16, 16), (16, 8, 8)
+    elif kind == 'basic_down':
+        block = BasicBlock(16, 32, stride=2, downsample=nn.Sequential(nn.Conv2d(16, 32, 1, stride=2, bias=False), nn.BatchNorm2d(32)))
+        shape = (16, 8, 8)
+    elif kind == 'bottleneck':
+        block, shape = Bottleneck(64, 16), (64, 6, 6)
+    elif kind == 'bottleneck_proj':
+        block = Bottleneck(16, 16, downsample=nn.Sequential(nn.Conv2d(16, 64, 1, bias=False), nn.BatchNorm2d(64)))
+        shape = (16, 6, 6)
+    else:
+        block = Bottleneck(32, 16, stride=2, downsample=nn.Sequential(nn.Conv2d(32, 64, 1, stride=2, bias=False), nn.BatchNorm2d(64)))
+        shape = (32, 8, 8)
+    for m in block.modules():
+        if isinstance(m, nn.Conv2d):
+            m.weight.data = m.weight.data.to(torch.bfloat16).float()
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+    seq = nn.Sequential(block)
+    ref = copy.deepcopy(seq)
+    seq.train(), ref.train()
+    x = torch.randn(6, *shape).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    want = ref(xr)
+    go = torch.randn_like(want)
+    want.backward(go)
+    xin = x.clone().requires_grad_(True)
+    got = ce.run(list(seq), xin)
+    assert _rel(got, want) < 1e-5
+    got.backward(go)
+    assert _rel(xin.grad, xr.grad) < 1e-4
+    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and _rel(p.grad, q.grad) < 1e-4, (k, _rel(p.grad, q.grad))
