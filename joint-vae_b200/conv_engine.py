@@ -49,6 +49,10 @@ _ACT_CODE = {nn.ReLU: 1, nn.Sigmoid: 2, nn.Identity: 0, nn.LeakyReLU: 3}
 # registers / the constant bank.
 import os as _os
 FUSE_BN_REDUCE = _os.environ.get('JVAE_FUSE_BN_REDUCE', '0') == '1'
+# opt-in, NOT yet measured on the GPU (DESIGN.md section 6, vgg19's 512-channel layers at 2x2): 'same' stride-1 convolutions on
+# maps of at most 2x2 pixels as ONE dense GEMM over (pixel, channel) pairs -- every (output pixel, input pixel) pair is exactly
+# one filter tap, so nothing is wasted on padding taps and the launch fills the machine (M = batch, N = K = pixels * channels)
+DENSE_SMALL = _os.environ.get('JVAE_CONV_DENSE_SMALL', '0') == '1'
 
 
 # ------------------------------------------------------------------------------------------------ kernel backend
@@ -199,6 +203,12 @@ class ConvStep:
         self.out_shape = (self.Co, self.Ho, self.Wo)
         self.gemm1x1 = (self.transposed and H == 1 and W == 1 and p == 0 and conv.output_padding[0] == 0
                         and self.Co % 8 == 0)
+        self.dense_small = DENSE_SMALL and (not self.transposed) and (not self.gemm1x1) and s == 1 and k > 1 and 2 * p == k - 1 \
+            and H * W <= 4 and Ci % 8 == 0 and self.Co % 8 == 0 and not final_dense
+        if self.dense_small:      # (output pixel q, input pixel r) -> filter tap (ry - qy + p, rx - qx + p) when inside the window
+            self.dense_pairs = [(qy * W + qx, ry * W + rx, ry - qy + p, rx - qx + p)
+                                for qy in range(H) for qx in range(W) for ry in range(H) for rx in range(W)
+                                if 0 <= ry - qy + p < k and 0 <= rx - qx + p < k]
         self.final_dense = final_dense
         self.ld_y = r8(self.Co) if (bn is not None or not final_dense) else self.Co
         self.ld_a = self.Co if final_dense else r8(self.Co)
@@ -294,6 +304,13 @@ class ConvStep:
                 g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
                 g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
             d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
+            if self.dense_small:     # W_eff[(q, co), (r, ci)] = W[co][ci][tap(q, r)]
+                hw = self.H * self.W
+                weff = torch.zeros((hw, self.Co, hw, self.Ci), dtype=torch.float32, device=w.device)
+                for q, r, ty, tx in self.dense_pairs:
+                    weff[q, :, r, :] = wd[:, :, ty, tx]
+                d['dense'] = weff.view(hw * self.Co, hw * self.Ci).to(torch.bfloat16).contiguous()
+                d['dense_bias'] = b0.repeat(hw).contiguous() if b0 is not None else None
             if self.separable:      # wd (Co, Ci, ky, kx): rows (ky, co) of the 1 x k kernel, and its transpose for the data gradient
                 kq = self.k
                 d['sep_fwd'] = pack_gather_weights(wd.permute(2, 0, 3, 1).reshape(kq * self.Co, kq, self.Ci),
@@ -324,6 +341,12 @@ class ConvStep:
                    out_bf16=y.view(N, kk * self.Co))
             if bn_train:
                 K.bn_stats(y, N * kk, self.Co, self.ld_y, stats)
+        elif self.dense_small:
+            hw = self.H * self.W
+            K.gemm(nat.GEMM_NT, N, hw * self.Co, hw * self.Ci, x.view(N, hw * self.Ci), pk['dense'], bias=pk['dense_bias'],
+                   act=fused_act, out_bf16=y.view(N, hw * self.Co))
+            if bn_train:
+                K.bn_stats(y, N * hw, self.Co, self.ld_y, stats)
         elif self.separable:
             self._sep_forward(x, pk, bias, fused_act, stats, y)
         else:
@@ -363,6 +386,10 @@ class ConvStep:
             kk = self.k * self.k
             K.gemm(nat.GEMM_NT, N, kk * self.Co, self.Ci, x.view(N, x.shape[-1]), pk['bm'], bias=pk['bias'], act=self.act,
                    out_bf16=a.view(N, kk * self.Co))
+        elif self.dense_small:
+            hw = self.H * self.W
+            K.gemm(nat.GEMM_NT, N, hw * self.Co, hw * self.Ci, x.view(N, hw * self.Ci), pk['dense'], bias=pk['dense_bias'],
+                   act=self.act, out_bf16=a.view(N, hw * self.Co))
         elif self.separable:
             self._sep_forward(x, pk, pk['b'], self.act, None, a)
         else:
@@ -446,6 +473,22 @@ class ConvStep:
                     K.gemm(nat.GEMM_NN, N, self.Ci, kk * self.Co, dy2, pk['bm'], out_f32=tmp)
                     dx = K.zeros(x.shape, x, torch.bfloat16)
                     dx.view(N, ldx)[:, :self.Ci] = tmp
+        elif self.dense_small:
+            hw = self.H * self.W
+            dy2, x2 = dy.view(N, hw * self.Co), x.view(N, hw * self.Ci)
+            if not folded:
+                dweff = K.empty((hw * self.Co, hw * self.Ci), x, torch.float32)
+                K.gemm(nat.GEMM_TN, hw * self.Co, hw * self.Ci, N, dy2, x2, out_f32=dweff)
+                dw4 = dweff.view(hw, self.Co, hw, self.Ci)
+                w = self.conv.weight
+                live = _live_grad(w, x)
+                dw = live if live is not None else K.zeros(tuple(w.shape), x)
+                for q, r, ty, tx in self.dense_pairs:          # fold the (pixel, pixel) blocks back onto their taps
+                    dw[:, :, ty, tx] += dw4[q, :, r, :]
+                grads['w'] = None if live is not None else dw
+            if need_dx:
+                dx = K.empty(x.shape, x)
+                K.gemm(nat.GEMM_NN, N, hw * self.Ci, hw * self.Co, dy2, pk['dense'], out_bf16=dx.view(N, hw * self.Ci))
         elif self.separable:
             kq = self.k
             U = K.empty((N, self.H, self.W, self.sep_ld), x)      # gradient of the 1 x k stage's output

@@ -279,3 +279,47 @@ def test_residual_blocks_exact(pkg, ce, monkeypatch, kind):
     assert _rel(xin.grad, xr.grad) < 1e-4
     for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
         assert p.grad is not None and _rel(p.grad, q.grad) < 1e-4, (k, _rel(p.grad, q.grad))
+
+
+@pytest.mark.parametrize('shape,spec', [((16, 2, 2), '[x3+1]16-24'), ((8, 1, 2), '[x3+1]16'), ((16, 2, 1), '[x5+2]8-8')])
+def test_dense_small_map_form(pkg, ce, monkeypatch, shape, spec):
+    """opt-in JVAE_CONV_DENSE_SMALL: 'same' convolutions on maps of at most 2x2 pixels as one dense GEMM over (pixel, channel)
+    pairs (the vgg19 tail); forward, input gradient and parameter gradients equal torch's with fp32 storage"""
+    monkeypatch.setattr(ce, 'DENSE_SMALL', True)
+    monkeypatch.setattr(EmuKernels, 'store', torch.float32)
+    monkeypatch.setattr(EmuKernels, 'act_dtype', torch.float32)
+    torch.manual_seed(0)
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=True, where='input')
+    for m in seq:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.uniform_(-0.3, 0.3)
+        elif hasattr(m, 'weight'):
+            m.weight.data = m.weight.data.to(torch.bfloat16).float()
+    ref = copy.deepcopy(seq)
+    for mode in ('train', 'eval'):
+        getattr(seq, mode)(), getattr(ref, mode)()
+        x = torch.randn(6, *shape).to(torch.bfloat16).float()
+        xr = x.clone().requires_grad_(True)
+        want = ref(xr)
+        go = torch.randn_like(want)
+        want.backward(go)
+        xin = x.clone().requires_grad_(True)
+        ce._stacks.clear()
+        got = ce.run(list(seq), xin)
+        stack = next(iter(ce._stacks.values()))
+        assert all(s.dense_small for s in stack.steps if isinstance(s, ce.ConvStep))
+        tol = 1e-4 if mode == 'train' else 2e-2        # eval folds BatchNorm into bf16 weights
+        assert _rel(got, want) < tol
+        for p in seq.parameters():
+            p.grad = None
+        got.backward(go)
+        assert _rel(xin.grad, xr.grad) < max(tol, 1e-3)
+        if mode == 'train':
+            gmax = max(float(q.grad.norm()) for q in ref.parameters())
+            for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+                # a conv bias in front of train-mode BatchNorm has an exactly zero gradient here, rounding noise in autograd
+                err = float((p.grad.double() - q.grad.double()).norm())
+                assert p.grad is not None and err <= 1e-3 * float(q.grad.norm()) + 1e-4 * gmax, (k, err)
+        for q in ref.parameters():
+            q.grad = None
