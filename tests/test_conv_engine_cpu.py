@@ -323,3 +323,23 @@ def test_dense_small_map_form(pkg, ce, monkeypatch, shape, spec):
                 assert p.grad is not None and err <= 1e-3 * float(q.grad.norm()) + 1e-4 * gmax, (k, err)
         for q in ref.parameters():
             q.grad = None
+
+
+def test_c2_stack_plan(pkg, ce):
+    """which execution form every layer of the flagship stacks takes (BASELINE configs[1]: vgg19 features, deconv32 imager)"""
+    build = pkg.module.vae_layers.build_de_conv_layers
+    imager = build((128, 1, 1), 'deconv32', batch_norm=True, where='output', output_activation='linear')
+    st = ce.ConvStack(list(imager), (128, 1, 1), True)
+    convs = [s for s in st.steps if isinstance(s, ce.ConvStep)]
+    assert [s.gemm1x1 for s in convs] == [True] + [False] * 6             # ConvTranspose2d on the 1x1 latent map is a plain GEMM
+    assert [s.separable for s in convs] == [False] * 6 + [True]           # 32 -> 3 k5 head: 1 x 5 pass + row kernels
+    assert convs[-1].wgrad_swapped and not any(s.wgrad_swapped for s in convs[:-1])
+    assert [len(s.fwd_ops) if s.fwd_ops else 0 for s in convs] == [0, 1, 4, 1, 4, 1, 1]      # stride-2 deconvs: 4 sub-pixel phases
+    assert not any(s.dense_small for s in convs)                          # opt-in only
+    assert st.out_shape == (3, 32, 32)
+    feats = build((3, 32, 32), 'vgg19', batch_norm=True, where='input')
+    sf = ce.ConvStack(list(feats), (3, 32, 32), False)
+    fconvs = [s for s in sf.steps if isinstance(s, ce.ConvStep)]
+    assert len(fconvs) == 16 and len([s for s in sf.steps if isinstance(s, ce.PoolStep)]) == 5
+    assert not any(s.separable or s.gemm1x1 or s.dgrad_sparse for s in fconvs)
+    assert sf.out_shape == (512, 1, 1)
