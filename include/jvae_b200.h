@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 10
+#define JVAE_ABI_VERSION 11
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -308,6 +308,30 @@ int jvae_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
 /* NCHW f32 -> NHWC bf16 (optionally padding channels to c_pad with zeros) and back */
 int jvae_nchw_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
 int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight re-packing.  The reference re-reads its live nn.Parameters in every step (cvae.py:2424-2461: forward, backward,
+ * optimizer.step on the same tensors).  Here the optimizer updates ONE flat fp32 buffer in place and the tensor-core
+ * kernels read bf16 copies in their own arrangements ([Cout_pad][tap][Cin chunk], transposed for the data gradient,
+ * 1 x k rows of the separable image head, (pixel, co) rows of the 1x1 -> k x k GEMM, plain casts of Linear weights);
+ * jvae_pack_weights rebuilds every arrangement of a whole layer stack in ONE launch, once per step.
+ * A job describes one destination tensor dst[r][t][c] (r < rows_pad, t < T, c < cols_pad, dense, zero where r >= rows or
+ * c >= cols):  dst[r][t][c] = src[(r / R0) * s_r1 + (r % R0) * s_r0 + taps[tap_off + t] * s_t + (c / C0) * s_c1 + (c % C0) * s_c0]
+ * (strides in elements).  cols_pad must be a multiple of 8.  The job table and the tap table live in device memory; jobs are
+ * sorted by first_block, job j owning blocks [first_block_j, first_block_j + jvae_pack_job_blocks(rows_pad, T, cols_pad)).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jvae_pack_job {
+  const float* src;         /* fp32 parameter (device) */
+  void* dst;                /* bf16 (or f32 when dst_f32) destination (device, 16-byte aligned) */
+  int64_t s_r1, s_r0, s_t, s_c1, s_c0;
+  int32_t rows, rows_pad, R0;
+  int32_t T, tap_off;
+  int32_t cols, cols_pad, C0;
+  int32_t dst_f32;
+  int32_t first_block;
+} jvae_pack_job;
+int jvae_pack_job_blocks(long long rows_pad, int T, int cols_pad);
+int jvae_pack_weights(const jvae_pack_job* jobs_dev, int n_jobs, const int32_t* taps_dev, int total_blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Input batches.  Replaces, for datasets held as uint8 (N, H, W, C) arrays (torchvision's

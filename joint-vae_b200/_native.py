@@ -45,6 +45,13 @@ class BatchCfg(ctypes.Structure):          # include/jvae_b200.h: jvae_batch_cfg
                                               'post_off_x')]
 
 
+class PackJob(ctypes.Structure):          # include/jvae_b200.h: jvae_pack_job
+    _fields_ = [('src', ctypes.c_void_p), ('dst', ctypes.c_void_p)] + \
+               [(n, ctypes.c_int64) for n in ('s_r1', 's_r0', 's_t', 's_c1', 's_c0')] + \
+               [(n, ctypes.c_int32) for n in ('rows', 'rows_pad', 'R0', 'T', 'tap_off', 'cols', 'cols_pad', 'C0', 'dst_f32',
+                                              'first_block')]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -111,7 +118,9 @@ def lib():
     L.jvae_vstack_rows.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
     L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
-    if L.jvae_abi_version() != 10:
+    L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
+    L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
+    if L.jvae_abi_version() != 11:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -347,6 +356,15 @@ def batch_u8_to_f32(cfg, src, index, flip, crop_ij, out):
     check(lib().jvae_batch_u8_to_f32(ctypes.byref(cfg), ptr(src), src.shape[0], ptr(index), index.numel(), ptr(flip),
                                      ptr(crop_ij), ptr(out), stream()))
     return out
+
+
+def pack_job_blocks(rows_pad, T, cols_pad):
+    return int(lib().jvae_pack_job_blocks(rows_pad, T, cols_pad))
+
+
+def pack_weights(jobs_dev, n_jobs, taps_dev, total_blocks):
+    """include/jvae_b200.h: jvae_pack_weights (job table and tap table are device tensors built by conv_engine.PackPlan)"""
+    check(lib().jvae_pack_weights(rawptr(jobs_dev), n_jobs, rawptr(taps_dev), total_blocks, stream()))
 
 
 def grad_sqnorm(grad, out):

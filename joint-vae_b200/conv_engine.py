@@ -25,6 +25,7 @@ import torch
 from torch import nn
 
 from . import _native as nat
+from . import engine
 
 
 def r8(n):
@@ -166,6 +167,104 @@ def pack_gather_weights(G, idx, cin):
     return out.view(out.shape[0], T * nck * cb)
 
 
+def pack_spec(name, src, rows, cols, taps, s_r0, s_c0, s_t=1, rows_pad=None, cols_pad=None, R0=None, s_r1=0, C0=None,
+              s_c1=0, f32=False, index=None):
+    """One destination of the native weight re-pack (include/jvae_b200.h: jvae_pack_job):
+    dst[r][t][c] = src[(r // R0) * s_r1 + (r % R0) * s_r0 + taps[t] * s_t + (c // C0) * s_c1 + (c % C0) * s_c0], zero where
+    r >= rows or c >= cols; dst is (rows_pad, T * cols_pad) dense.  `src` names the parameter ('w' or 'b')."""
+    return dict(name=name, index=index, src=src, rows=rows, rows_pad=rows_pad or rows, R0=R0 or rows, s_r1=s_r1, s_r0=s_r0,
+                taps=list(taps), s_t=s_t, cols=cols, cols_pad=cols_pad or cols, C0=C0 or cols, s_c1=s_c1, s_c0=s_c0, f32=f32)
+
+
+def gather_spec(name, index, Co, cin, idx, s_row, s_col):
+    """spec of pack_gather_weights(G, idx, cin) with G[co, t, ci] = w.flat[co * s_row + t + ci * s_col]"""
+    cb = cblk_of(cin)
+    nck = (cin + cb - 1) // cb
+    return pack_spec(name, 'w', Co, cin, idx, s_row, s_col, rows_pad=cout_pad_of(Co), cols_pad=nck * cb, index=index)
+
+
+def run_pack_spec(sp, src):
+    """torch execution of one pack job (any device): the definition the CUDA kernel is tested against"""
+    flat = src.detach().reshape(-1).float()
+    r = torch.arange(sp['rows_pad'], device=flat.device)
+    c = torch.arange(sp['cols_pad'], device=flat.device)
+    t = torch.tensor(sp['taps'], device=flat.device, dtype=torch.long)
+    ro = torch.div(r, sp['R0'], rounding_mode='floor') * sp['s_r1'] + (r % sp['R0']) * sp['s_r0']
+    co = torch.div(c, sp['C0'], rounding_mode='floor') * sp['s_c1'] + (c % sp['C0']) * sp['s_c0']
+    idx = ro[:, None, None] + (t * sp['s_t'])[None, :, None] + co[None, None, :]
+    ok = (r < sp['rows'])[:, None, None] & (c < sp['cols'])[None, None, :]
+    ok = ok.expand_as(idx)
+    out = torch.zeros(idx.shape, dtype=torch.float32, device=flat.device)
+    out[ok] = flat[idx[ok]]
+    out = out.reshape(sp['rows_pad'], len(sp['taps']) * sp['cols_pad'])
+    return out if sp['f32'] else out.to(torch.bfloat16)
+
+
+class PackPlan:
+    """Every bf16 weight arrangement of a stack's convolutions, rebuilt by ONE kernel launch (csrc/pack.cu) whenever
+    the parameters changed: optimizer step (engine.PARAM_EPOCH), in-place torch writes (_version), re-pointed storage
+    (data_ptr: Optimizer._flatten, .to(device)).  The reference reads its live nn.Parameters in every step
+    (cvae.py:2424-2461); this is that read."""
+
+    def __init__(self, steps):
+        self.steps = [s for s in steps if s.pack_specs()]
+        self.params = []
+        for s in self.steps:
+            self.params += [p for p in (s.conv.weight, s.conv.bias) if p is not None]
+        self.key = None
+        self.epoch = -1
+        self.ptrs = None
+        self.jobs_dev = self.taps_dev = None
+        self.n_jobs = self.blocks = 0
+
+    def _build(self):
+        jobs, taps = [], []
+        first = 0
+        for s in self.steps:
+            w = s.conv.weight
+            assert w.dtype == torch.float32 and w.is_contiguous(), 'conv weights must be dense fp32'
+            pk = {'b': s.conv.bias.detach() if s.conv.bias is not None else None}
+            for sp in s.pack_specs():
+                src = w if sp['src'] == 'w' else s.conv.bias
+                T = len(sp['taps'])
+                dst = torch.empty((sp['rows_pad'], T * sp['cols_pad']), dtype=torch.float32 if sp['f32'] else torch.bfloat16,
+                                  device=w.device)
+                assert sp['cols_pad'] % 8 == 0 and dst.data_ptr() % 16 == 0
+                j = nat.PackJob(src=src.data_ptr(), dst=dst.data_ptr(), s_r1=sp['s_r1'], s_r0=sp['s_r0'], s_t=sp['s_t'],
+                                s_c1=sp['s_c1'], s_c0=sp['s_c0'], rows=sp['rows'], rows_pad=sp['rows_pad'], R0=sp['R0'], T=T,
+                                tap_off=len(taps), cols=sp['cols'], cols_pad=sp['cols_pad'], C0=sp['C0'],
+                                dst_f32=int(sp['f32']), first_block=first)
+                first += nat.pack_job_blocks(sp['rows_pad'], T, sp['cols_pad'])
+                taps += sp['taps']
+                jobs.append(j)
+                if sp['index'] is None:
+                    pk[sp['name']] = s.pack_view(sp, dst)
+                else:
+                    pk.setdefault(sp['name'], []).append(dst)
+            s._pk = pk
+        import ctypes
+        arr = (nat.PackJob * len(jobs))(*jobs)
+        dev = self.steps[0].conv.weight.device
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        self.jobs_dev = raw.to(dev)
+        self.taps_dev = torch.tensor(taps, dtype=torch.int32).to(dev)
+        self.n_jobs, self.blocks = len(jobs), first
+
+    def ensure(self):
+        if not self.steps:
+            return
+        ptrs = tuple(p.data_ptr() for p in self.params)
+        key = (engine.PARAM_EPOCH[0], ptrs) + tuple(p._version for p in self.params)
+        self.epoch = engine.PARAM_EPOCH[0]
+        if key == self.key:
+            return
+        if ptrs != self.ptrs:
+            self._build()
+            self.ptrs = ptrs
+        nat.pack_weights(self.jobs_dev, self.n_jobs, self.taps_dev, self.blocks)
+        self.key = key
+
+
 def _live_grad(p, like):
     """the Parameter's own dense fp32 .grad (the optimizer's flat gradient buffer, zeroed by zero_grad) when the native
     kernels can accumulate into it directly; autograd then receives None for that parameter"""
@@ -257,15 +356,58 @@ class ConvStep:
             c = self._ctaps[key] = K.taps_arg(taps)
         return c
 
+    def pack_specs(self):
+        """jobs of the native re-pack for the training-mode (unfolded) weights: the same arrangements _pack() builds with
+        torch ops (tests/test_conv_engine_cpu.py checks them against each other); [] when this layer keeps the torch path"""
+        if self.dense_small:
+            return []
+        kk, k, Co, Ci = self.k * self.k, self.k, self.Co, self.Ci
+        if self.gemm1x1:      # W (Ci, Co, k, k): Bm[(yx, co)][ci] = W[ci][co][yx]; bias repeated per output pixel
+            sp = [pack_spec('bm', 'w', kk * Co, Ci, [0], kk, Co * kk, R0=Co, s_r1=1, cols_pad=r8(Ci))]
+            if self.conv.bias is not None:
+                sp.append(pack_spec('bias', 'b', kk, Co, [0], 0, 1, f32=True))
+            return sp
+        # strides of W.flat for (output channel, input channel); the tap index has stride 1 in both layouts
+        s_co, s_ci = (kk, Co * kk) if self.transposed else (Ci * kk, kk)
+        sp = [gather_spec('fwd', i, Co, Ci, op['idx'], s_co, s_ci) for i, op in enumerate(self.fwd_ops)]
+        sp += [gather_spec('bwd', i, Ci, Co, op['idx'], s_ci, s_co) for i, op in enumerate(self.dgrad_ops)]
+        if self.separable:    # rows (ky, co) of the 1 x k kernel over kx taps; and [ci][kx][(ky, co)] for the data gradient
+            cb = cblk_of(Ci)
+            sp.append(pack_spec('sep_fwd', 'w', k * Co, Ci, range(k), s_co, s_ci, R0=Co, s_r1=k,
+                                rows_pad=cout_pad_of(k * Co), cols_pad=((Ci + cb - 1) // cb) * cb))
+            cb = cblk_of(k * Co)
+            sp.append(pack_spec('sep_bwd', 'w', Ci, k * Co, range(k), s_ci, s_co, C0=Co, s_c1=k,
+                                rows_pad=cout_pad_of(Ci), cols_pad=((k * Co + cb - 1) // cb) * cb))
+        return sp
+
+    def pack_view(self, sp, dst):
+        if sp['name'] == 'bm':
+            return dst[:, :self.Ci]
+        if sp['name'] == 'bias':
+            return dst.view(-1)
+        return dst
+
     def _pack(self, fold_bn=False, want_bwd=None):
-        """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict).
+        """bf16 weight arrangements, refreshed when the Parameter changes (optimizer step / load_state_dict / in-place
+        writes).  Training-mode weights on the GPU come from the stack's PackPlan (one native launch per stack and step);
+        this torch formulation serves the BatchNorm-folded inference weights, the opt-in dense form and the CPU emulation.
         fold_bn (inference with running statistics): BatchNorm is folded into the weights and the bias, so the layer is
         ONE kernel: W' = W * gamma * rstd, b' = (b - mean) * gamma * rstd + beta."""
         w = self.conv.weight
-        key = (w._version, w.device, w.data_ptr())
+        if not fold_bn and K is NativeKernels and not self.dense_small:
+            plan = getattr(self, 'plan', None)
+            if plan is None:                      # a step used outside a ConvStack
+                plan = self.plan = PackPlan([self])
+            if plan.epoch != engine.PARAM_EPOCH[0] or plan.key is None:      # full check at the stack's entry points
+                plan.ensure()
+            return self._pk
+        key = (engine.PARAM_EPOCH[0], w._version, w.device, w.data_ptr())
+        if self.conv.bias is not None:
+            key += (self.conv.bias._version,)
         slot = '_packed'
         if fold_bn:
             bn = self.bn
+            key += (engine.STATS_EPOCH[0],)
             key += tuple(t._version for t in (bn.running_mean, bn.running_var) if t is not None)
             key += tuple(t._version for t in (bn.weight, bn.bias) if t is not None)
             slot = '_packed_folded'
@@ -365,6 +507,8 @@ class ConvStep:
                        bn.bias.detach() if bn.affine else None, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
                        bn.running_mean if track or not bn_train else None, bn.running_var if track or not bn_train else None,
                        bn.num_batches_tracked if track else None, bn_train, self.act, a, self.ld_a, save)
+        if track:
+            engine.bump_stats()      # the kernel wrote running_mean / running_var behind the version counters
         st['y'], st['save'], st['bn_train'] = y, save, bn_train
         return a
 
@@ -790,11 +934,22 @@ class ConvStack:
         self.steps = steps
         self.out_shape = shape
         self.parameters = [p for s in steps for p in s.params()]
+        convs = []
+        for stp in steps:
+            if isinstance(stp, ConvStep):
+                convs.append(stp)
+            elif isinstance(stp, ResidualStep):
+                convs += stp.chain + ([stp.ds] if stp.ds is not None else [])
+        self.plan = PackPlan(convs)
+        for c in convs:
+            c.plan = self.plan
 
     def forward(self, x, training):
         """x (N, C, H, W) fp32 / bf16 NCHW -> (output tensor, saved state)"""
         C, H, W = self.in_shape
         N = x.shape[0]
+        if K is NativeKernels and training:
+            self.plan.ensure()
         t = K.to_nhwc(x.reshape(N, C, H, W), r8(C))
         state = []
         for s in self.steps:

@@ -645,12 +645,13 @@ class ClassificationVariationalNetwork(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------ training
-    def train_step(self, x, y, kl_var_weighting=1., gamma_weighting=1., check_every=0):
+    def train_step(self, x, y, kl_var_weighting=1., gamma_weighting=1., check_every=0, batch=0, current_measures=None):
         """One optimisation step = the body of the reference's batch loop (cvae.py:2427-2461): zero_grad, evaluate with
-        beta, backward of total.mean(), clip, Adam.  No host sync unless check_every divides the step count, in which
-        case the device-side finite flag replaces the reference's per-parameter isnan scan (cvae.py:2454-2457)."""
+        beta (batch index and the epoch's running measures passed through, cvae.py:2441-2449), backward of total.mean(),
+        clip, Adam.  No host sync unless check_every divides the step count, in which case the device-side finite flag
+        replaces the reference's per-parameter isnan scan (cvae.py:2454-2457)."""
         self.optimizer.zero_grad()
-        _, _, losses, measures = self.evaluate(x, y, batch=self._steps, with_beta=True,
+        _, _, losses, measures = self.evaluate(x, y, batch=batch, current_measures=current_measures, with_beta=True,
                                                kl_var_weighting=kl_var_weighting, gamma_weighting=gamma_weighting)
         loss = losses['total'].mean()
         loss.backward()
@@ -661,27 +662,42 @@ class ClassificationVariationalNetwork(nn.Module):
             raise FloatingPointError('non-finite loss at step {}'.format(self._steps))
         return losses, measures
 
+    @staticmethod
+    def warmup_weighting(epoch, warmup):
+        """cvae.py:2432-2433: the ramp of the KL variance term / of gamma at `epoch` (0-based) for warmup = (w0, w1)"""
+        return max(0., min(1., (epoch + 1 - warmup[0]) / (warmup[1] + 1)))
+
     def train_model(self, batches, epochs=1, warmup=(0, 0), warmup_gamma=(0, 0), check_every=100, on_batch=None):
         """Epoch loop over an iterable of (x, y) device batches with the reference's warm-up ramps for the KL variance
-        term and gamma (cvae.py:2293, 2420-2493).  Dataset handling, checkpoints and console tables of the reference's
+        term and gamma, the per-epoch running measures (batch index i and the previous batch's measures feed the next
+        evaluate) and the per-epoch mean losses of the history (cvae.py:2293, 2402-2493).  The loss means accumulate on
+        the device and are read once per epoch.  Dataset handling, checkpoints and console tables of the reference's
         train_model stay outside the hot path."""
         history = self.train_history
         for epoch in range(history['epochs'], epochs):
             self.encoder.prior.thaw_means(epoch)
             self.train()
-            kw = min(1., max(0., (epoch - warmup[0]) / (warmup[1] - warmup[0]))) if warmup[1] > warmup[0] else 1.
-            gw = min(1., max(0., (epoch - warmup_gamma[0]) / (warmup_gamma[1] - warmup_gamma[0]))) \
-                if warmup_gamma[1] > warmup_gamma[0] else 1.
-            last = None
+            kw = self.warmup_weighting(epoch, warmup)
+            gw = self.warmup_weighting(epoch, warmup_gamma)
+            measures, sums, n = {}, None, 0
             for i, (x, y) in enumerate(batches):
-                last = self.train_step(x, y, kl_var_weighting=kw, gamma_weighting=gw, check_every=check_every)
+                losses, measures = self.train_step(x, y, kl_var_weighting=kw, gamma_weighting=gw, check_every=check_every,
+                                                   batch=i, current_measures=measures)
+                vec = torch.stack([v.detach().float().mean() for v in losses.values()])
+                sums = vec if sums is None else sums + vec
+                keys, n = list(losses), n + 1
                 if on_batch is not None:
-                    on_batch(epoch, i, *last)
-            self.optimizer.update_lr()
+                    on_batch(epoch, i, losses, measures)
+            self.eval()
             history['epochs'] = epoch + 1
             self.trained = epoch + 1
-            if last is not None:
-                history[epoch] = {'train_loss': {k: float(v.mean()) for k, v in last[0].items()}}
+            history[epoch] = {}
+            if n:
+                mean = (sums / n).tolist()          # the epoch's single read-back
+                history[epoch]['train_loss'] = dict(zip(keys, mean))
+                history[epoch]['train_measures'] = dict(measures)
+            history[epoch]['lr'] = self.optimizer.lr
+            self.optimizer.update_lr()
         self.eval()
         return history
 
@@ -787,7 +803,7 @@ class ClassificationVariationalNetwork(nn.Module):
             methods[which] = _make_list(asked, developed)
             for m in methods[which]:
                 assert m in all_methods, m
-        tensors = dict(recorder._tensors)
+        tensors = {k: recorder[k] for k in recorder}      # narrowed to the recorded samples (the buffers grow by doubling)
         logits = tensors.pop('logits').T
         y = tensors.pop('y_true')
         losses = tensors

@@ -14,6 +14,9 @@ def attach(net, bf16_bucket=True, group=None):
     with torch.no_grad():
         for t in list(net.parameters()) + list(net.buffers()):
             dist.broadcast(t.data, src=0, group=group)
+    from . import engine
+    engine.bump_params()          # .data writes do not move autograd's version counters
+    engine.bump_stats()
     opt = net.optimizer
     if bf16_bucket and next(net.parameters()).is_cuda:
         opt.grad_dtype = torch.bfloat16

@@ -21,6 +21,23 @@ POLICY = {
     'conv': os.environ.get('JVAE_CONV', 'native'),
 }
 _rng_offset = itertools.count(1)
+
+# Parameter epochs.  The fused Adam (csrc/optim.cu) and the BatchNorm kernels (running statistics) write parameters and
+# buffers through raw pointers, which autograd's version counters never see.  Every cache of derived weights (bf16
+# operand arrangements, BatchNorm-folded inference weights) therefore keys on these explicit counters as well:
+# bump_params() after anything that rewrites parameters in place (Optimizer.step, broadcasts on .data),
+# bump_stats() after a train-mode BatchNorm pass updated its running statistics.
+PARAM_EPOCH = [0]
+STATS_EPOCH = [0]
+
+
+def bump_params():
+    PARAM_EPOCH[0] += 1
+
+
+def bump_stats():
+    STATS_EPOCH[0] += 1
+
 _library_stacks = set()
 
 
@@ -54,10 +71,14 @@ def _weight_bf16(w):
     """bf16 copy of a weight, cached per Parameter object (weak reference: a recycled id() never hits a stale entry)"""
     key = id(w)
     hit = _wcache.get(key)
-    if hit is not None and hit[2]() is w and hit[0] == (w._version, w.data_ptr()) and hit[1].device == w.device:
+    ver = (PARAM_EPOCH[0], w._version, w.data_ptr())
+    if hit is not None and hit[2]() is w and hit[0] == ver and hit[1].device == w.device:
         return hit[1]
+    if len(_wcache) > 256:       # temporaries (the concatenated head weights) leave dead entries behind
+        for k in [k for k, v in _wcache.items() if v[2]() is None]:
+            del _wcache[k]
     wb = _bf16_ld8(w.detach())
-    _wcache[key] = ((w._version, w.data_ptr()), wb, weakref.ref(w))
+    _wcache[key] = (ver, wb, weakref.ref(w))
     return wb
 
 

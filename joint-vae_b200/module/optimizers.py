@@ -81,7 +81,7 @@ class Optimizer:
             f['views'][id(p)] = sl
             off += sz
         self._flat = f
-        engine._wcache.clear()
+        engine.bump_params()
 
     def _ensure_flat(self):
         ps = self._trainable()
@@ -130,7 +130,9 @@ class Optimizer:
 
     def step(self):
         if self._opt is not None:
-            return self._opt.step()
+            r = self._opt.step()
+            engine.bump_params()
+            return r
         self._ensure_flat()
         f = self._flat
         g = f['g']
@@ -146,7 +148,7 @@ class Optimizer:
         nat.adam_step(f['p'], f['m'], f['v'], g, f['norm2'], max_norm=max_norm, lr=self._lr, beta1=self.betas[0],
                       beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self._step)
         self._clip_now = False
-        engine._wcache.clear()       # parameters changed in place behind autograd's version counters
+        engine.bump_params()         # parameters changed in place behind autograd's version counters
 
     def update_lr(self):
         if not self.lr_decay:

@@ -17,7 +17,7 @@ def pytest_configure(config):
 def golden_names():
     """model fixtures (tests/golden/make_golden.py); roc_cases.npz belongs to tests/test_roc_golden.py, odin_*.npz to
     tests/test_gpu_odin.py, wim_*.npz to tests/test_gpu_wim.py, cat_*.npz to tests/test_gpu_categorical.py"""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('roc_', 'odin_', 'wim_', 'cat_', 'sig_', 'ycoded_', 'misclass_')))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('roc_', 'odin_', 'wim_', 'cat_', 'sig_', 'ycoded_', 'misclass_', 'multistep_', 'full_')))
 
 
 @pytest.fixture(scope='session')

@@ -343,3 +343,26 @@ def test_c2_stack_plan(pkg, ce):
     assert len(fconvs) == 16 and len([s for s in sf.steps if isinstance(s, ce.PoolStep)]) == 5
     assert not any(s.separable or s.gemm1x1 or s.dgrad_sparse for s in fconvs)
     assert sf.out_shape == (512, 1, 1)
+
+
+@pytest.mark.parametrize('where,spec,shape,bn,out_act', CASES)
+def test_pack_specs_equal_torch_packing(pkg, ce, where, spec, shape, bn, out_act):
+    """The job table of the native weight re-pack (csrc/pack.cu, one launch per stack and step) describes exactly the
+    arrangements ConvStep._pack builds with torch ops: every job, executed by its torch definition (run_pack_spec), is
+    bit-equal to the torch-packed tensor.  The CUDA kernel is checked against run_pack_spec on the GPU."""
+    torch.manual_seed(1)
+    where, _, act = where.partition('/')
+    kw = dict(output_activation=out_act) if where == 'output' else {}
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=bn, where=where, activation=act or 'relu', **kw)
+    stack = ce.ConvStack(list(seq), shape, where == 'output')
+    n = 0
+    for stp in stack.plan.steps:
+        want = stp._pack()                      # torch formulation (K is the emulation here)
+        for sp in stp.pack_specs():
+            src = stp.conv.weight if sp['src'] == 'w' else stp.conv.bias
+            got = stp.pack_view(sp, ce.run_pack_spec(sp, src))
+            ref = want[sp['name']] if sp['index'] is None else want[sp['name']][sp['index']]
+            assert got.shape == ref.shape and got.dtype == ref.dtype, (sp['name'], got.shape, ref.shape)
+            assert torch.equal(got, ref), sp['name']
+            n += 1
+    assert n >= 2
