@@ -409,8 +409,8 @@ class ClassificationVariationalNetwork(nn.Module):
         cfg.prior_stats_ready = int(prior_ready)
         sig = self.sigma if self.x_is_generated else None
         # the `sigma` measure is read before any update (cvae.py:624); the decaying / rmse update is in place: snapshot then
-        updates_in_place = self.training and self.x_is_generated and self.sigma.decay and not self.sigma.learned
-        sigma_seen = self.sigma.data.clone() if updates_in_place else self.sigma.data
+        # ... and so is the optimizer's (flat parameter buffer): in training the lazy measures read snapshots
+        sigma_seen = self.sigma.data.clone() if self.training else self.sigma.data
         if self.x_is_generated and self.sigma.coded:       # cvae.py:631-634: one log sigma per sample from the encoder's head
             sig = sigma_coded.reshape(-1).float().contiguous()
             self.sigma.update(v=sigma_coded.detach().reshape(-1, *self.sigma.output_dim))
@@ -474,13 +474,16 @@ class ClassificationVariationalNetwork(nn.Module):
 
         logits_out = res['logits'] if res.get('logits') is not None else y_est[1:].mean(0)
         measures = self._lazy_measures(x, batch_losses, batch, current_measures, sigma_seen,
-                                       sig.detach() if (self.x_is_generated and self.sigma.coded) else None, mse_rmse)
+                                       sig.detach() if (self.x_is_generated and self.sigma.coded) else None, mse_rmse,
+                                       means0.detach().clone() if self.training else means0.detach())
         out = (x_reco, logits_out, batch_losses, measures)
         if z_output:
             out += (mu, log_var, z)
         return out
 
-    def _lazy_measures(self, x, losses, batch, current, sigma_data=None, sigma_coded=None, mse_rmse=None):
+    def _lazy_measures(self, x, losses, batch, current, sigma_data=None, sigma_coded=None, mse_rmse=None, means=None):
+        """the reference computes these floats inside evaluate (cvae.py:622-762), i.e. BEFORE the optimizer step that
+        follows a training evaluate; read lazily they must come from snapshots of sigma and of the class means"""
         names = ['sigma']
         if self.x_is_generated:
             names += ['xpow', 'mse', 'rmse', 'dB']
@@ -503,9 +506,9 @@ class ClassificationVariationalNetwork(nn.Module):
                         s2 = mse_rmse
                     dev += [x.float().pow(2).mean().reshape(1), (losses['wmse'] * s2).mean().reshape(1)]
                 if conditional:
-                    m = self.encoder.prior.mean
-                    dev += [m.pow(2).mean().reshape(1), self.encoder.capacity().reshape(1),
-                            self.encoder.dict_min_distance().reshape(1)]
+                    m = self.encoder.prior.mean if means is None else means
+                    dev += [m.pow(2).mean().reshape(1), self.encoder.capacity(m).reshape(1),
+                            self.encoder.dict_min_distance(m).reshape(1)]
                 v = torch.cat([d.float() for d in dev]).tolist()      # the single sync
             run = lambda k, val: (current.get(k, 0.) * batch + val) / (batch + 1)
             out = {'sigma': v[0], 'zdist': run('zdist', v[1]), 'var_kl': run('var_kl', v[2])}

@@ -90,39 +90,38 @@ class Sigma(Parameter):
             delta = self.max_step if delta > 0 else -self.max_step
         self.data += delta
 
-    def __format__(self, spec):
-        if spec.endswith(('f', 'g', 'e')):
-            return self.value.__format__(spec)
-        if spec.endswith('i'):
-            if self.is_rmse:
-                return 'e'
-            if self.coded:
-                return 'C' if self.per_dim else 'c'
-            if self.learned:
-                return 'l'
-        return str(self)
+    # ---- text forms (job listings / logs).  Only `params`, `value` and `update` above are on the hot path.
+    def _kind(self):
+        """(one-letter code, description) of how this sigma is obtained"""
+        if self.is_rmse:
+            seen = '' if self._rmse is np.nan else ' ({:g})'.format(float(self._rmse))
+            return 'e', 'rmse' + seen
+        if self.coded:
+            return ('C', 'coded mask') if self.per_dim else ('c', 'coded scalar')
+        if self.learned:
+            return 'l', '{:g}->rmse[l] ({:g})'.format(self.sigma0, self.value)
+        if self.decay:
+            target = ('' if self.reach == 1 else '{:g}*'.format(self.reach)) + 'rmse'
+            cap = '<{:g}'.format(self.max_step) if self.max_step else ''
+            return None, '{:g}->{}[-{:g}*{}]'.format(self.sigma0, target, self.decay, cap)
+        return None, '{:g}'.format(float(self.data.detach().reshape(-1)[0]))
 
     def __str__(self):
-        if self.is_rmse:
-            return 'rmse' if self._rmse is np.nan else f'rmse ({self._rmse:g})'
-        if self.coded:
-            return 'coded {}'.format('mask' if self.per_dim else 'scalar')
-        if self.learned:
-            return f'{self.sigma0:g}->rmse[l] ({self.value:g})'
-        if not self.decay:
-            with torch.no_grad():
-                return f'{self.data.item():g}'
-        mult = '' if self.reach == 1 else f'{self.reach:g}*'
-        mx = f'<{self.max_step:g}' if self.max_step else ''
-        return f'{self.sigma0:g}->{mult}rmse[-{self.decay:g}*{mx}]'
+        return self._kind()[1]
+
+    def __format__(self, spec):
+        if spec and spec[-1] in 'fge':            # numeric format: the current value
+            return format(self.value, spec)
+        code, text = self._kind()
+        return code if (spec.endswith('i') and code) else text
 
     def __repr__(self):
         if self.is_rmse:
             return 'Sigma will be RMSE'
-        s = super().__repr__()
-        if self.decay:
-            return s[:-1] + f', decaying to {self.reach}*mse with rate {self.decay})'
-        return s
+        base = super().__repr__()
+        if not self.decay:
+            return base
+        return '{}, decaying to {}*mse with rate {})'.format(base[:-1], self.reach, self.decay)
 
 
 class Sampling(nn.Module):
@@ -205,15 +204,15 @@ class Encoder(nn.Module):
         self._sampling_size = v
         self.sampling.sampling_size = v
 
-    def capacity(self):
-        """upper bound of I(Z;Y) from the class means (layers.py:323-336)"""
-        m = self.prior.mean
+    def capacity(self, m=None):
+        """upper bound of I(Z;Y) from the class means (layers.py:323-336); m: a snapshot of the means"""
+        m = self.prior.mean if m is None else m
         C = self.num_labels
         cdm = torch.cdist(m, m)
         return np.log(C) - 1 / C * torch.exp(-cdm.pow(2) / 4).sum(0).log().sum()
 
-    def dict_min_distance(self):
-        m = self.prior.mean
+    def dict_min_distance(self, m=None):
+        m = self.prior.mean if m is None else m
         C = self.num_labels
         diag = 2 * m.norm(dim=1).max() * torch.eye(C, device=m.device)
         return (torch.cdist(m, m) + diag).min()

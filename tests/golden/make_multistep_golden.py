@@ -6,8 +6,11 @@ The body of the reference's batch loop (cvae.py:2424-2461) -- zero_grad, evaluat
 current_measures=...), total.mean().backward(), optimizer.clip, optimizer.step -- is driven for 3 batches on a conv + BatchNorm
 cvae with its own Optimizer (Adam, L2 weight decay, clipping), then eval, then one more train step, then eval again.  Every
 step re-reads the live parameters (and, in eval, the BatchNorm running statistics the training steps moved), so a product
-whose packed / folded weight copies go stale after the first optimizer step cannot match.  A large learning rate makes the
-steps matter (every weight moves by ~lr per Adam step).
+whose packed / folded weight copies go stale after the first optimizer step cannot match.  The learning rates make the
+steps matter (the loss falls by a third in three steps).  The conv case runs Adam with eps = 1 (a keyword the reference's
+Optimizer forwards to torch.optim.Adam, optimizers.py:44): updates are then proportional to the gradient, so the trajectory is
+a well-conditioned function of the gradients; with the default eps the first Adam steps are sign(g) * lr per element, which turns
+bf16-level gradient noise on near-zero elements into full-size steps (the MLP case keeps the default eps).
 
 Stored: per step the per-sample losses, the chained running measures and the batch-mean losses; the state_dict after step 3;
 the per-class eval losses / logits after step 3 and after step 4.
@@ -27,9 +30,9 @@ STEPS = 3
 OPT = {'optim_type': 'adam', 'lr': 1e-2, 'weight_decay': 3e-5, 'grad_clipping': 100}
 
 
-def run(cvae_mod, base, name, B):
+def run(cvae_mod, base, name, B, opt=None):
     kw = json.loads(json.dumps(CASES[base]))
-    kw['optimizer'] = dict(OPT)
+    kw['optimizer'] = dict(opt or OPT)
     ctor = json.loads(json.dumps(kw))
     ctor['input_shape'] = tuple(ctor['input_shape'])
     torch.manual_seed(4321)
@@ -95,5 +98,5 @@ if __name__ == '__main__':
     os.chdir('/tmp')
     mod = import_reference()
     torch.set_num_threads(1)
-    run(mod, 'conv_cvae_bn', 'multistep_conv_cvae_bn', 64)
+    run(mod, 'conv_cvae_bn', 'multistep_conv_cvae_bn', 64, opt=dict(OPT, eps=1.0))
     run(mod, 'mlp_cvae', 'multistep_mlp_cvae', 32)
