@@ -30,7 +30,10 @@ CASES = {
     'full_c2': (_conv(10, 128), 32),
     'full_c3': (_conv(100, 256), 32),
     'full_c4': (_conv(20, 256, features='resnet18', upsampler='ivgg', shape=(3, 64, 64), L=8), 16),
+    # c2 with BatchNorm parameters in the chaotic regime (see fill_state_): reported against loose bounds only
+    'full_c2x': (_conv(10, 128), 32),
 }
+CHAOTIC = {'full_c2x'}
 NPROJ = 16
 
 
@@ -46,8 +49,19 @@ def _rs(key, salt=0):
     return np.random.RandomState((zlib.crc32(key.encode()) + salt) & 0x7fffffff)
 
 
-def fill_state_(module):
-    """in place: every entry of module.state_dict() from a generator seeded by its key"""
+def fill_state_(module, chaotic=False):
+    """in place: every entry of module.state_dict() from a generator seeded by its key.
+
+    BatchNorm scale / shift are drawn so that the train-mode network is WELL CONDITIONED (scale in [0.25, 0.75], shift in
+    [0.5, 1]: most pre-activations sit on the linear side of the ReLU).  With scale ~ 1, shift ~ 0 a deep random BatchNorm +
+    ReLU stack is chaotic: measured on vgg19 in train mode, a 1e-3 perturbation (bf16 rounding of the weights alone, fp32
+    everywhere else) grows 1.2x per layer to 3.6e-2 at the features, so no bf16 implementation can be compared at 2e-2 there
+    (`chaotic=True` keeps that regime for a loosely-bounded case)."""
+    bn_keys = {}
+    for mname, m in module.named_modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            bn_keys[mname + '.weight'] = 'scale'
+            bn_keys[mname + '.bias'] = 'shift'
     with torch.no_grad():
         for k, v in module.state_dict().items():
             if 'num_batches_tracked' in k or k == 'sigma' or k.endswith('_var_parameter'):
@@ -59,9 +73,11 @@ def fill_state_(module):
                 a = rs.normal(0.0, 0.1, shape)
             elif k.endswith('prior.mean'):
                 a = rs.normal(0.0, 1.0, shape)
-            elif v.dim() == 1 and k.endswith('weight'):          # BatchNorm scale
-                a = rs.uniform(0.5, 1.5, shape)
-            elif v.dim() == 1:                                    # biases, BatchNorm shifts
+            elif bn_keys.get(k) == 'scale':
+                a = rs.uniform(0.5, 1.5, shape) if chaotic else rs.uniform(0.25, 0.75, shape)
+            elif bn_keys.get(k) == 'shift':
+                a = rs.uniform(-0.1, 0.1, shape) if chaotic else rs.uniform(0.5, 1.0, shape)
+            elif v.dim() == 1:                                    # biases
                 a = rs.uniform(-0.1, 0.1, shape)
             else:
                 fan = v.numel() // shape[0]
@@ -120,7 +136,7 @@ def build_oracle(pkg, name):
     from oracle.torch_model import OracleNet, describe_model, describe_seq
     torch.manual_seed(0)
     model = pkg.ClassificationVariationalNetwork(**ctor_kwargs(name))
-    fill_state_(model)
+    fill_state_(model, chaotic=name in CHAOTIC)
     feats = model.features
     try:
         describe_seq(feats)
@@ -138,12 +154,21 @@ def build_oracle(pkg, name):
     return model, net
 
 
-def oracle_outputs(pkg, name, train_backward=True):
-    """the oracle's eval losses / scores / predictions and its training losses + gradients for a case"""
+def oracle_outputs(pkg, name, train_backward=True, bf16_operands=False):
+    """the oracle's eval losses / scores / predictions and its training losses + gradients for a case.
+    bf16_operands: the same fp32 computation after rounding every GEMM / convolution weight and the input image to bf16 --
+    the error this alone causes is the floor of ANY implementation with bf16 tensor-core operands (north_star mandates
+    them), before a single activation is rounded."""
     from oracle import elbo_numpy as on
     model, net = build_oracle(pkg, name)
     kw = CASES[name][0]
     x, y, eps_tr, eps_te = inputs(name)
+    if bf16_operands:
+        with torch.no_grad():
+            for p in net.parameters():
+                if p.dim() > 1 and not any(p is q for q in (net.encoder.prior.mean, net.encoder.prior._var_parameter)):
+                    p.copy_(p.to(torch.bfloat16).float())
+        x = x.to(torch.bfloat16).float()
     n = lambda t: None if t is None else t.detach().numpy()
     prior = on.Prior(n(net.encoder.prior.mean), n(net.encoder.prior._var_parameter), var_dim='scalar', conditional=True)
     skw = dict(sigma_value=float(net.sigma[0]), sigma_is_log=bool(net.arch['sigma']['is_log']),

@@ -37,7 +37,7 @@ def run(cvae_mod, name):
         model = cvae_mod.ClassificationVariationalNetwork(**fc.ctor_kwargs(name))
     finally:
         torchvision.models.resnet18 = orig
-    fc.fill_state_(model)
+    fc.fill_state_(model, chaotic=name in fc.CHAOTIC)
     x, y, eps_tr, eps_te = fc.inputs(name)
     out = {'n_params': np.array(sum(p.numel() for p in model.parameters()))}
     # ---------------- eval / scoring (cvae.py:1629-1687) on the generated running statistics

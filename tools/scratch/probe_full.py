@@ -12,7 +12,7 @@ for name in (sys.argv[1:] or list(fc.CASES)):
     d = np.load(f'tests/golden/{name}.npz')
     torch.manual_seed(0)
     net = pkg.ClassificationVariationalNetwork(**fc.ctor_kwargs(name))
-    fc.fill_state_(net)
+    fc.fill_state_(net, chaotic=name in fc.CHAOTIC)
     net = net.to(DEV)
     x, y, eps_tr, eps_te = [t.to(DEV) for t in fc.inputs(name)]
     net.eval()
