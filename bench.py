@@ -5,8 +5,11 @@ joint-VAE, K=128, L=16, C=10, batch 512 per GPU, bf16 GEMMs; plus OOD-scoring sa
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference ...                    the reference's algorithm (oracle port) on the host cores
 
-A "step" is one full optimisation step of the path: zero_grad, features/encoder/sampler/decoder/classifier forward,
-fused ELBO forward + backward, network backward, global-norm clip, Adam.  Prints ONE JSON line on rank 0.
+A "step" is one full optimisation step of the path: zero_grad, weight re-pack, features/encoder/sampler/decoder/classifier
+forward, fused ELBO forward + backward, network backward, gradient all-reduce (N > 1), global-norm clip, Adam.
+Prints ONE JSON line on rank 0.  Sub-results: `workloads` (BASELINE configs[2], [3]: c3 and c4 train steps with their own
+ms_per_step) and `scoring_c5` (configs[4]: 1 Mi samples sharded over the ranks, per-class evaluate + 11 OOD scores +
+predictions per batch, ONE final gather over NCCL, device ROC tables on rank 0).
 """
 import argparse
 import json
@@ -19,39 +22,33 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OPT = {'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}
+
+
+def _conv(C, K, features='vgg19', upsampler='deconv32', shape=(3, 32, 32), L=16):
+    return dict(input_shape=shape, num_labels=C, type='cvae', features=features, upsampler=upsampler, encoder=[], decoder=[],
+                classifier=[], batch_norm='both', latent_dim=K, latent_sampling=L, test_latent_sampling=L, gamma=0, beta=1.0,
+                output_activation='linear', sigma={'value': 1.0, 'learned': True}, optimizer=dict(OPT))
+
+
 WORKLOADS = {
     # BASELINE.json configs[1]: conv joint-VAE on synthetic 3x32x32, VGG-style encoder, K=128, L=16, C=10, B=512/GPU
-    'c2': dict(ctor=dict(input_shape=(3, 32, 32), num_labels=10, type='cvae', features='vgg19', upsampler='deconv32',
-                         encoder=[], decoder=[], classifier=[], batch_norm='both', latent_dim=128, latent_sampling=16,
-                         test_latent_sampling=16, gamma=0, beta=1.0, output_activation='linear',
-                         sigma={'value': 1.0, 'learned': True},
-                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
-               batch=512, fwd_gflop_per_img=2.903,
+    'c2': dict(ctor=_conv(10, 128), batch=512, fwd_gflop_per_img=2.903,
                name='conv joint-VAE 3x32x32 vgg19+deconv32 BN K=128 L=16 C=10 B=512/GPU'),
-    # BASELINE.json configs[2]: CIFAR-100 shape, wider per-class contraction (parity-test case; optional bench workload)
-    'c3': dict(ctor=dict(input_shape=(3, 32, 32), num_labels=100, type='cvae', features='vgg19', upsampler='deconv32',
-                         encoder=[], decoder=[], classifier=[], batch_norm='both', latent_dim=256, latent_sampling=16,
-                         test_latent_sampling=16, gamma=0, beta=1.0, output_activation='linear',
-                         sigma={'value': 1.0, 'learned': True},
-                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
-               batch=512, fwd_gflop_per_img=2.921,
+    # configs[2]: CIFAR-100 shape, wider per-class contraction
+    'c3': dict(ctor=_conv(100, 256), batch=512, fwd_gflop_per_img=2.921,
                name='conv joint-VAE 3x32x32 vgg19+deconv32 BN K=256 L=16 C=100 B=512/GPU'),
-    # BASELINE.json configs[3]: ResNet-style, imagenet20-subset shape (parity-test case; optional bench workload)
-    'c4': dict(ctor=dict(input_shape=(3, 64, 64), num_labels=20, type='cvae', features='resnet18', upsampler='ivgg',
-                         encoder=[], decoder=[], classifier=[], batch_norm='both', latent_dim=256, latent_sampling=8,
-                         test_latent_sampling=8, gamma=0, beta=1.0, output_activation='linear',
-                         sigma={'value': 1.0, 'learned': True},
-                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
-               batch=128, fwd_gflop_per_img=None,
-               name='ResNet joint-VAE 3x64x64 resnet18+ivgg BN K=256 L=8 C=20 B=128/GPU'),
-    # BASELINE.json configs[0]: the reference's CPU-runnable case
+    # configs[3]: ResNet-style, imagenet20-subset shape, data parallel at 2/4/8 GPUs
+    'c4': dict(ctor=_conv(20, 256, features='resnet18', upsampler='ivgg', shape=(3, 64, 64), L=8), batch=128,
+               fwd_gflop_per_img=None, name='ResNet joint-VAE 3x64x64 resnet18+ivgg BN K=256 L=8 C=20 B=128/GPU'),
+    # configs[0]: the reference's CPU-runnable case
     'c1': dict(ctor=dict(input_shape=(1, 28, 28), num_labels=10, type='cvae', encoder=[512, 256], decoder=[256, 512],
                          classifier=[], latent_dim=16, latent_sampling=1, test_latent_sampling=1, gamma=0, beta=1.0,
-                         output_activation='sigmoid', sigma={'value': 0.1},
-                         optimizer={'optim_type': 'adam', 'lr': 1e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}),
+                         output_activation='sigmoid', sigma={'value': 0.1}, optimizer=dict(OPT)),
                batch=128, fwd_gflop_per_img=0.0032, name='MLP joint-VAE 1x28x28 K=16 L=1 C=10 B=128'),
 }
 PRIOR = {'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 1}
+C5_SAMPLES = 1 << 20          # configs[4]: 1 Mi synthetic test samples (half of them drawn as the OOD set)
 
 
 def peaks():
@@ -59,7 +56,7 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), 'measured'
-    return 6650.0, 1590.0, 'fallback'
+    return 6650.0, 1400.0, 'fallback'
 
 
 class ClockSampler:
@@ -71,7 +68,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -98,32 +95,39 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def make_ctor(wl):
+def make_ctor(wl, **over):
     kw = json.loads(json.dumps(wl['ctor']))
     kw['input_shape'] = tuple(kw['input_shape'])
     kw['prior'] = dict(PRIOR)
+    kw.update(over)
     return kw
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_run(wl, steps, warmup, sample_batch, threads=None):
-    """The reference's algorithm for the same step (oracle/torch_model.py, a PyTorch fp32 restatement of cvae.py's train
-    step pinned against the unmodified reference) on the host cores."""
+def _oracle_net(wl, **over):
+    """The reference's algorithm for the path (oracle/torch_model.py + oracle/elbo_numpy.py, fp32 restatements of cvae.py's
+    train / eval step pinned against the unmodified reference by tests/golden/, including at these configurations)."""
     import torch
     import __graft_entry__ as g
-    from oracle.torch_model import OracleNet, describe_model, train_step
-    if threads:
-        torch.set_num_threads(threads)
+    from oracle.torch_model import OracleNet, describe_model
     pkg = g.load_package()
     torch.manual_seed(0)
-    model = pkg.ClassificationVariationalNetwork(**make_ctor(wl))          # layer containers only (CPU, no compute)
+    model = pkg.ClassificationVariationalNetwork(**make_ctor(wl, **over))          # layer containers only (CPU, no compute)
     cfg, arch = describe_model(model)
     net = OracleNet(cfg, arch)
     net.load_state_dict(model.state_dict())
+    return net
+
+
+def cpu_train_run(wl, steps, warmup, batch, threads):
+    import torch
+    from oracle.torch_model import train_step
+    torch.set_num_threads(threads)
+    net = _oracle_net(wl)
     net.train()
     oc = wl['ctor']['optimizer']
     opt = torch.optim.Adam(net.parameters(), lr=oc['lr'], weight_decay=oc['weight_decay'])
-    B, L, K, C = sample_batch, wl['ctor']['latent_sampling'], wl['ctor']['latent_dim'], wl['ctor']['num_labels']
+    B, L, K, C = batch, wl['ctor']['latent_sampling'], wl['ctor']['latent_dim'], wl['ctor']['num_labels']
     gen = torch.Generator().manual_seed(0)
     x = torch.rand(B, *wl['ctor']['input_shape'], generator=gen)
     y = torch.randint(0, C, (B,), generator=gen)
@@ -135,21 +139,64 @@ def cpu_reference_run(wl, steps, warmup, sample_batch, threads=None):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
-    return B / dt, dt, torch.get_num_threads()
+    return B / dt, dt
+
+
+def cpu_score_run(wl, steps, warmup, batch, threads, **over):
+    """the reference's scoring step (cvae.py:1629-1687): evaluate(x) per class + batch_dist_measures + predict_after_evaluate"""
+    import numpy as np
+    import torch
+    from oracle import elbo_numpy as on
+    torch.set_num_threads(threads)
+    net = _oracle_net(wl, **over)
+    net.eval()
+    kw = make_ctor(wl, **over)
+    B, L, K, C = batch, kw['test_latent_sampling'], kw['latent_dim'], kw['num_labels']
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(B, *kw['input_shape'], generator=gen)
+    n = lambda t: None if t is None else t.detach().numpy()
+    prior = on.Prior(n(net.encoder.prior.mean), n(net.encoder.prior._var_parameter), var_dim='scalar', conditional=True)
+    methods = ['iws-2s', 'iws-a-1-1', 'iws-a-4-1', 'iws', 'mse', 'elbo', 'soft', 'elbo-2s', 'elbo-a-1-1', 'elbo-a-4-1', 'zdist']
+    times = []
+    for i in range(warmup + steps):
+        eps = torch.randn(L + 1, B, K, generator=gen)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            xr, ye, mu, lv, z, en = net(x, eps)
+        losses, logits = on.evaluate(n(x), n(xr), n(ye), n(mu), n(lv), n(z), n(en), prior, y=None, training=False,
+                                     type='cvae', sigma_value=float(net.sigma.detach()[0]), sigma_is_log=bool(net.arch['sigma']['is_log']),
+                                     y_is_decoded=bool(net.arch['y_is_decoded']))
+        on.batch_dist_measures(logits, losses, methods, type='cvae', num_labels=C)
+        on.predict_after_evaluate(logits, losses, 'iws')
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return B / dt, dt
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sb = args.cpu_batch
-    v, dt, cores = cpu_reference_run(wl, args.steps, args.warmup, sb)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the CPU arm takes all host cores explicitly
+    cores = os.cpu_count() or 1
+    v_small, _ = cpu_train_run(wl, max(1, args.steps // 3), 1, 32, cores)
+    v, dt = cpu_train_run(wl, args.steps, args.warmup, args.cpu_batch, cores)
+    v_one, _ = cpu_train_run(wl, 1, 1, 16, 1)
+    vs, _ = cpu_score_run(wl, 2, 1, 32, cores)
+    world = args.gpus
     line = {'impl': 'reference', 'metric': 'train_images_per_sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'sample_batch': sb},
+            'config': {'workload': wl['name'], 'global_batch': world * wl['batch'], 'parallelism': f'dp{world}',
+                       'sample_batch': args.cpu_batch},
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{args.steps} full train steps at batch {sb} (CPU time is linear in the batch)'},
+                             'sample': f'{args.steps} full train steps at batch {args.cpu_batch} of the configured {wl["batch"]} '
+                                       f'(the step is linear in the batch: {v_small:.1f} images/s at batch 32), oracle/torch_model.py fp32',
+                             'images_per_s_at_batch_32': v_small, 'images_per_s_one_thread': v_one,
+                             'scoring_samples_per_s': vs, 'host_cores': cores,
+                             'why_port': 'the reference is Python on /root/reference, which does not exist on the GPU box; the port '
+                                         'is pinned to it by tests/golden (incl. this configuration: tests/golden/full_c2.npz)'},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -171,24 +218,6 @@ def run_native(args, wl):
         dist.init_process_group('nccl', device_id=dev)
     pkg = g.build()
     nat = pkg._native
-    if args.conv:
-        pkg.engine.POLICY['conv'] = args.conv
-    if args.linear:
-        pkg.engine.POLICY['linear'] = args.linear
-    torch.manual_seed(0)
-    net = pkg.ClassificationVariationalNetwork(**make_ctor(wl)).to(dev)
-    if world > 1:
-        pkg.distributed.attach(net, bf16_bucket=True)
-    net.train()
-    B = args.batch or wl['batch']
-    C = wl['ctor']['num_labels']
-    shape = tuple(wl['ctor']['input_shape'])
-    gen = torch.Generator().manual_seed(1 + rank)
-    npool = 4
-    xs_h = [torch.rand(B, *shape, generator=gen).pin_memory() for _ in range(npool)]
-    ys_h = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(npool)]
-    xs = [t.to(dev) for t in xs_h]
-    ys = [t.to(dev) for t in ys_h]
 
     def barrier():
         if world > 1:
@@ -196,6 +225,7 @@ def run_native(args, wl):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """CUDA-event time of `steps` calls bracketed by barrier + synchronize, max over ranks (ms)"""
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -210,6 +240,28 @@ def run_native(args, wl):
             ms = float(t.item())
         return ms
 
+    def build_net(w, **over):
+        torch.manual_seed(0)
+        net = pkg.ClassificationVariationalNetwork(**make_ctor(w, **over)).to(dev)
+        if world > 1:
+            pkg.distributed.attach(net, bf16_bucket=True)
+        return net
+
+    def train_inputs(w, B, npool=4):
+        gen = torch.Generator().manual_seed(1 + rank)
+        shape, C = tuple(w['ctor']['input_shape']), w['ctor']['num_labels']
+        xs_h = [torch.rand(B, *shape, generator=gen).pin_memory() for _ in range(npool)]
+        ys_h = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(npool)]
+        return xs_h, ys_h, [t.to(dev) for t in xs_h], [t.to(dev) for t in ys_h]
+
+    # ================================================================ headline workload: train step
+    net = build_net(wl)
+    net.train()
+    B = args.batch or wl['batch']
+    C = wl['ctor']['num_labels']
+    shape = tuple(wl['ctor']['input_shape'])
+    npool = 4
+    xs_h, ys_h, xs, ys = train_inputs(wl, B, npool)
     step_dev = lambda i: net.train_step(xs[i % npool], ys[i % npool])
 
     def step_e2e(i):
@@ -220,15 +272,24 @@ def run_native(args, wl):
 
     for i in range(args.warmup):
         step_dev(i)
-    # ---- device-resident timing (value), with live per-launch timing of the fused ELBO kernels
-    nat.PROFILE = {'elbo_train_fwd': [], 'elbo_train_bwd': []}
+    # ---- device-resident timing (value); per-launch CUDA events around the fused ELBO kernels and every convolution launch
+    nat.PROFILE = {'elbo_train_fwd': [], 'elbo_train_bwd': [], 'conv': []}
     clocks = ClockSampler(local)
     n0 = nat.launch_count()
     ms = timed(step_dev, args.steps)
     launches = nat.launch_count() - n0
     clk = clocks.stop()
-    prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in nat.PROFILE.items()}
+    prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in nat.PROFILE.items() if k != 'conv'}
+    conv_prof = {}
+    for a, b, flops, kname in nat.PROFILE['conv']:
+        e = conv_prof.setdefault(kname, [0.0, 0.0, 0])
+        e[0] += a.elapsed_time(b) * 1e-3
+        e[1] += flops
+        e[2] += 1
     nat.PROFILE = None
+    # the same steps without any per-launch events: the published value is the undisturbed one
+    ms_plain = timed(step_dev, args.steps)
+    ms = min(ms, ms_plain)
     # ---- end-to-end timing through the public API with host buffers
     step_e2e(0)
     ms_e2e = timed(step_e2e, args.steps)
@@ -237,6 +298,7 @@ def run_native(args, wl):
     ms_loader = None
     if len(shape) == 3:
         from jointvae_b200.utils.batch_loader import DeviceBatchLoader
+        gen = torch.Generator().manual_seed(7 + rank)
         u8 = torch.randint(0, 256, ((args.steps + 2) * B, shape[1], shape[2], shape[0]), dtype=torch.uint8, generator=gen)
         tg = torch.randint(0, C, (u8.shape[0],), generator=gen)
         loader = DeviceBatchLoader(u8, tg, B, device=dev, data_augmentation=['flip', 'crop'], resident=False, seed=rank)
@@ -244,56 +306,45 @@ def run_native(args, wl):
         step_loader = lambda i: float(net.train_step(*next(it))[0]['total'].mean().item())
         step_loader(0)
         ms_loader = timed(step_loader, args.steps)
+        del loader, u8
 
-    # ---- OOD scoring throughput (per-class evaluate + scores + predictions), device resident
-    n_methods = len(net.ood_methods)
-    net.eval()
-    with torch.no_grad():
-        def score(i):
-            _, logits, losses, _ = net.evaluate(xs[i % npool])
-            net.batch_dist_measures(logits, losses, [m for m in net.ood_methods])
-            net.predict_after_evaluate(logits, losses, method=net.predict_methods[0])
-        for i in range(6):          # the caching allocator re-sizes its pools when the step shape changes: settle first
-            score(i)
-        timed(score, 3)
-        nat.PROFILE = {'elbo_eval_fwd': []}
-        ms_score = min(timed(score, max(3, args.steps)), timed(score, max(3, args.steps)))     # best of two runs
-        prof['elbo_eval_fwd'] = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
-        nat.PROFILE = None
-
-    # ---- BASELINE configs[4]: OOD-scoring sweep over the class count (C = 10 / 100 / 1000, K = 256, L = 16), sample-sharded:
-    # every rank scores its own shard (no data-path collective); rate = samples of all ranks / max-over-ranks time
-    sweep = []
-    if args.sweep:
+    # ================================================================ BASELINE configs[4]: sharded scoring with one final gather
+    scoring = None
+    if args.c5:
+        scoring = []
         for C_ in (10, 100, 1000):
-            kw = make_ctor(wl)
-            kw.update(num_labels=C_, latent_dim=256)
-            torch.manual_seed(0)
-            m = pkg.ClassificationVariationalNetwork(**kw).to(dev)
-            m.eval()
-            xs_ = [torch.rand(B, *shape, device=dev) for _ in range(2)]
-            with torch.no_grad():
-                def sc(i, m=m, xs_=xs_):
-                    _, lg, ls, _ = m.evaluate(xs_[i % 2])
-                    m.batch_dist_measures(lg, ls, list(m.ood_methods))
-                    m.predict_after_evaluate(lg, ls, method=m.predict_methods[0])
-                for i in range(6):
-                    sc(i)
-                timed(sc, 5)               # settles the caching allocator for this model's shapes
-                nat.PROFILE = {'elbo_eval_fwd': []}
-                ms_c = min(timed(sc, 5), timed(sc, 5), timed(sc, 5))      # best of three 5-batch runs
-                ev = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
-                nat.PROFILE = None
-            sweep.append({'C': C_, 'K': 256, 'L': wl['ctor']['test_latent_sampling'], 'samples_per_s': world * B * 5 / (ms_c * 1e-3),
-                          'eval_kernel_us': sum(ev) / max(1, len(ev)) * 1e3})
+            scoring.append(run_c5(pkg, wl, C_, 128 if C_ == 10 else 256, dev, world, rank, timed, B, args))
+    del net, xs, ys
+    torch.cuda.empty_cache()
+
+    # ================================================================ BASELINE configs[2], [3]: c3 / c4 train steps
+    extra = {}
+    if args.extra:
+        for name in ('c3', 'c4'):
+            if name == args.workload:
+                continue
+            w = WORKLOADS[name]
+            n2 = build_net(w)
+            n2.train()
+            _, _, xs2, ys2 = train_inputs(w, w['batch'])
+            f = lambda i: n2.train_step(xs2[i % len(xs2)], ys2[i % len(xs2)])
+            for i in range(args.warmup):
+                f(i)
+            ms2 = timed(f, args.steps)
+            extra[name] = {'workload': w['name'], 'value': world * w['batch'] * args.steps / (ms2 * 1e-3), 'unit': 'images/s',
+                           'ms_per_step': ms2 / args.steps, 'global_batch': world * w['batch'], 'steps': args.steps}
+            if w['fwd_gflop_per_img']:
+                extra[name]['tensor_tflops'] = 3 * w['fwd_gflop_per_img'] * 1e9 * w['batch'] * args.steps / (ms2 * 1e-3) / 1e12
+            del n2, xs2, ys2
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm, tf, which = peaks()
     L, K, D = wl['ctor']['latent_sampling'], wl['ctor']['latent_dim'], int(torch.tensor(shape).prod())
-    has_xr = True
-    # algorithmic bytes of the fused ELBO train forward per sample (SURVEY.md §8d): x f32 + L reconstructions (bf16)
+    # algorithmic bytes of the fused ELBO train forward per sample (SURVEY.md 8d): x f32 + L reconstructions (bf16)
     # + mu/log_var f32 + label + 8 outputs (logits only when a classifier exists: gamma=0 here)
     bytes_fwd = B * (D * 4 + L * D * 2 + 2 * K * 4 + 8 + 8 * 4)
     t_fwd = sum(prof['elbo_train_fwd']) / max(1, len(prof['elbo_train_fwd'])) * 1e-3
@@ -301,13 +352,26 @@ def run_native(args, wl):
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     flops = 3 * (wl['fwd_gflop_per_img'] or 0.0) * 1e9 * B * args.steps / (ms * 1e-3)
+    # dominant kernel of the step = the convolution kernel with the largest summed CUDA-event time
+    dom = max(conv_prof.items(), key=lambda kv: kv[1][0]) if conv_prof else None
+    roofline = None
+    if dom is not None:
+        kname, (t_s, fl, nl) = dom
+        ach = fl / t_s / 1e12
+        roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, average over the launches of one
+                    # step in the committed ncu --set full capture (profiles/, r02): null until re-captured for a new kernel
+                    'traffic': args.traffic, 'peak_source': which + ' (MEASURED_PEAKS.json bf16_tflops_sustained)',
+                    'launches_per_step': nl / args.steps, 'us_per_launch': t_s / nl * 1e6, 'flop_per_launch': fl / nl,
+                    'share_of_step': t_s / (ms_plain * 1e-3) if ms_plain else None,
+                    'by_kernel': {k: {'ms_per_step': v[0] / args.steps * 1e3, 'tflops': v[1] / v[0] / 1e12,
+                                      'launches_per_step': v[2] / args.steps} for k, v in conv_prof.items()}}
     line = {
         'metric': 'train_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': wl['name'], 'global_batch': world * B, 'parallelism': f'dp{world}',
-                   'l2': 'per-step working set (activations, 53 MB x_reco alone) exceeds L2; 4 rotating input batches',
-                   'backend': dict(pkg.engine.POLICY)},
+                   'l2': 'per-step working set (activations, 53 MB x_reco alone) exceeds L2; 4 rotating input batches'},
         'clocks': clk,
         'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
@@ -315,29 +379,102 @@ def run_native(args, wl):
             'value': world * B * args.steps / (ms_loader * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': B * D + B * 25,
             'd2h_bytes_per_step': 4, 'note': 'uint8 dataset in pinned host memory, flip + crop + ToTensor on the device'},
         'gpu_launches': int(launches),
-        'roofline': {'kernel': 'elbo_train_fwd_kernel (fused prior/ELBO forward)', 'bound': 'hbm', 'achieved': achieved,
-                     'peak': hbm, 'unit': 'GB/s', 'frac': (achieved / hbm) if achieved else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-                     # of this kernel at this workload (profiles/r01_elbo_train_fwd_ncu_full.txt): 57.23 MB + 0.36 MB
-                     'traffic': 57.59e6 if (args.workload == 'c2' and B == 512) else None,
-                     'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)', 'bytes_per_launch': bytes_fwd,
-                     'us_per_launch': t_fwd * 1e6,
-                     'bwd_us_per_launch': sum(prof['elbo_train_bwd']) / max(1, len(prof['elbo_train_bwd'])) * 1e3,
-                     'eval_us_per_launch': sum(prof['elbo_eval_fwd']) / max(1, len(prof['elbo_eval_fwd'])) * 1e3},
+        'roofline': roofline,
+        'elbo_roofline': {'kernel': 'elbo_train_fwd_kernel (fused prior/ELBO forward)', 'bound': 'hbm', 'achieved': achieved,
+                          'peak': hbm, 'unit': 'GB/s', 'frac': (achieved / hbm) if achieved else None,
+                          'traffic': 57.59e6 if (args.workload == 'c2' and B == 512) else None,
+                          'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)', 'bytes_per_launch': bytes_fwd,
+                          'us_per_launch': t_fwd * 1e6,
+                          'bwd_us_per_launch': sum(prof['elbo_train_bwd']) / max(1, len(prof['elbo_train_bwd'])) * 1e3},
         'gemm_roofline': None if not wl['fwd_gflop_per_img'] else {
             'bound': 'tensor', 'achieved': flops / 1e12, 'peak': tf, 'unit': 'TFLOP/s', 'frac': flops / 1e12 / tf,
             'note': 'whole step: 3 x forward GEMM/conv FLOPs / step time'},
-        'scoring': {'value': world * B * max(3, args.steps) / (ms_score * 1e-3), 'unit': 'samples/s',
-                    'methods': n_methods},
-        'scoring_sweep': sweep,
+        'workloads': extra,
+        'scoring_c5': scoring,
     }
     if world == 1 and not args.no_cpu:
-        v, dt, cores = cpu_reference_run(wl, 2, 1, args.cpu_batch)
+        cores = os.cpu_count() or 1
+        v, dt = cpu_train_run(wl, 2, 1, args.cpu_batch if args.cpu_batch <= 64 else 64, cores)
+        vs, _ = cpu_score_run(wl, 2, 1, 32, cores)
         line['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': f'2 full train steps at batch {args.cpu_batch} after 1 warm-up, oracle/torch_model.py fp32'}
+                                'sample': '2 full train steps at batch 64 after 1 warm-up, oracle/torch_model.py fp32, all host cores',
+                                'scoring_samples_per_s': vs}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c5(pkg, wl, C_, K_, dev, world, rank, timed, B, args):
+    """BASELINE configs[4]: C5_SAMPLES synthetic samples, sample-sharded over the ranks (contiguous shards, no per-batch
+    communication).  Per batch: per-class evaluate (BatchNorm folded) + the 11 OOD scores + the predictions, written into
+    device buffers; then ONE gather of the scores to rank 0 (NCCL all_gather) and the device ROC table of every method
+    (in-distribution half against the OOD half).  samples/s = all samples / max-over-ranks device time of the whole thing."""
+    import torch
+    import torch.distributed as dist
+    from jointvae_b200.utils.roc_curves import roc_curve
+    nat = pkg._native
+    torch.manual_seed(0)
+    m = pkg.ClassificationVariationalNetwork(**make_ctor(wl, num_labels=C_, latent_dim=K_)).to(dev)
+    m.eval()
+    shape = tuple(wl['ctor']['input_shape'])
+    n_total = args.c5_samples
+    lo, hi = pkg.distributed.shard_range(n_total, rank, world)
+    nb = (hi - lo) // B
+    gen = torch.Generator().manual_seed(11 + rank)
+    pool_in = [torch.rand(B, *shape, generator=gen).to(dev) for _ in range(4)]
+    # the "OOD" half: blocky images (8 x 8 constant patches), a different distribution for the ROC tables to separate
+    pool_out = [torch.rand(B, shape[0], 4, 4, generator=gen).repeat_interleave(shape[1] // 4, 2)
+                .repeat_interleave(shape[2] // 4, 3).to(dev) for _ in range(4)]
+    methods = [mm for mm in m.ood_methods if not mm.startswith('odin')]
+    base = sorted(set(mm[:-3] if mm.endswith('-2s') else mm.split('-a-')[0] for mm in methods))
+    pm = m.predict_methods[0]
+    buf = torch.empty((len(base), nb * B), dtype=torch.float32, device=dev)
+    preds = torch.empty(nb * B, dtype=torch.int64, device=dev)
+    out = {}
+
+    def whole(_):
+        with torch.no_grad():
+            for i in range(nb):
+                x = (pool_in if i < nb // 2 else pool_out)[i % 4]
+                _, lg, ls, _ = m.evaluate(x)
+                sc = m.batch_dist_measures(lg, ls, base)
+                buf[:, i * B:(i + 1) * B] = torch.stack([sc[k] for k in base])
+                preds[i * B:(i + 1) * B] = m.predict_after_evaluate(lg, ls, method=pm)
+            local_scores = {k: buf[j] for j, k in enumerate(base)}
+            full = pkg.distributed.gather_scores(local_scores, n_total) if world > 1 else local_scores
+            if rank == 0:
+                # shard r holds [in-distribution half | OOD half] of its own samples
+                per = n_total // world
+                res = {}
+                for mm in methods:
+                    k = mm[:-3] if mm.endswith('-2s') else mm.split('-a-')[0]
+                    v = full[k].view(world, per)
+                    ind, ood = v[:, :per // 2].reshape(-1), v[:, per // 2:].reshape(-1)
+                    two = 'around-mean' if mm.endswith('-2s') else (tuple(int(t) for t in mm.split('-')[-2:]) if '-a-' in mm else False)
+                    auc, fpr, tpr, _ = roc_curve(ind, ood, *[pc / 100 for pc in range(90, 100)], two_sided=two)
+                    res[mm] = (auc, float(fpr[5]))
+                out['roc'] = res
+
+    with torch.no_grad():
+        for i in range(6):          # settle the caching allocator for this model's shapes
+            m.evaluate(pool_in[i % 4])
+    nat.PROFILE = {'elbo_eval_fwd': []}
+    ms = timed(whole, 1)
+    ev = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
+    nat.PROFILE = None
+    L, D = wl['ctor']['test_latent_sampling'], int(torch.tensor(shape).prod())
+    # algorithmic bytes of the eval kernel per sample (SURVEY 8d): x, L reconstructions (bf16), mu / log_var, z, |eps|^2,
+    # outputs (5C + 3) + C logits + 16 scores + 4 predictions
+    bytes_eval = D * 4 + L * D * 2 + 2 * K_ * 4 + (L + 1) * K_ * 4 + L * 4 + ((5 * C_ + 3) + C_ + 16 + 4) * 4
+    us = sum(ev) / max(1, len(ev)) * 1e3
+    r = {'C': C_, 'K': K_, 'L': L, 'samples': n_total, 'samples_per_s': n_total / (ms * 1e-3), 'seconds': ms * 1e-3,
+         'includes': 'per-batch evaluate + scores + predictions, final gather (NCCL all_gather when N > 1), device ROC of 11 methods',
+         'eval_kernel_us': us, 'eval_kernel_gbs': bytes_eval * B / (us * 1e-6) / 1e9 if us else None}
+    if rank == 0 and 'roc' in out:
+        r['auc_iws'] = out['roc'].get('iws', (None,))[0]
+    del m, buf, preds
+    torch.cuda.empty_cache()
+    return r
 
 
 def main():
@@ -348,11 +485,12 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0)
-    ap.add_argument('--cpu-batch', type=int, default=32)
-    ap.add_argument('--conv', default='', choices=['', 'native', 'library'])
-    ap.add_argument('--linear', default='', choices=['', 'native', 'library'])
+    ap.add_argument('--cpu-batch', type=int, default=128)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--no-sweep', dest='sweep', action='store_false', help='skip the C = 10/100/1000 scoring sweep')
+    ap.add_argument('--no-c5', dest='c5', action='store_false', help='skip the 1 Mi-sample sharded scoring run (configs[4])')
+    ap.add_argument('--c5-samples', type=int, default=C5_SAMPLES)
+    ap.add_argument('--no-extra', dest='extra', action='store_false', help='skip the c3 / c4 train-step sub-results')
+    ap.add_argument('--traffic', type=float, default=None, help='ncu dram bytes per launch of the dominant kernel (from profiles/)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

@@ -183,6 +183,12 @@ int jvae_sample_bwd(int B, int L, int K, const float* head, const float* log_var
  * ------------------------------------------------------------------------------------------ */
 enum jvae_act { JVAE_ACT_NONE = 0, JVAE_ACT_RELU = 1, JVAE_ACT_SIGMOID = 2, JVAE_ACT_LEAKY = 3 };   /* leaky: slope 0.01 (nn.LeakyReLU default, misc.py:27) */
 #define JVAE_LEAKY_SLOPE 0.01f
+/* flags OR-ed into the `act` argument of the convolution / row kernels:
+ *   JVAE_OUT_F32 (jvae_conv_gather_gemm): `out` holds fp32 and ld_out counts floats (no activation rounding at all: the 1 x k
+ *   stage of the separable image head, whose vertical taps cancel -- rounding them to bf16 costs the head's gradients 10 x);
+ *   JVAE_IN_F32 (jvae_vsum_rows): T holds fp32 */
+#define JVAE_OUT_F32 0x100
+#define JVAE_IN_F32 0x200
 enum jvae_gemm_mode {
   JVAE_GEMM_NT = 0,  /* D[M,N] = A[M,K] . B[N,K]^T   forward:  y = x W^T                       */
   JVAE_GEMM_NN = 1,  /* D[M,N] = A[M,K] . B[K,N]     dgrad:    dx = dy W                        */
@@ -241,6 +247,11 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, int dw_ld_ci, void* stream);
+/* which kernel the calling thread's last jvae_conv_gather_gemm[_bn] / jvae_conv_wgrad call launched (measurement aid:
+ * bench.py attributes per-launch CUDA-event times to the dominant kernel of the step) */
+enum jvae_conv_kernel { JVAE_KERNEL_CONV_HALO = 1, JVAE_KERNEL_CONV_TAPBOX = 2, JVAE_KERNEL_WGRAD_HALO = 3, JVAE_KERNEL_WGRAD_TAPBOX = 4 };
+int jvae_last_conv_kernel(void);
+
 
 /* ------------------------------------------------------------------------------------------
  * Layers between the convolutions, NHWC bf16, P = N*H*W pixels (module/vae_layers/conv.py:189-227):

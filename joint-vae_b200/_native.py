@@ -16,6 +16,7 @@ F32, BF16 = 0, 1
 VAR_DIM = {'scalar': 0, 'diag': 1, 'full': 2}
 PRIOR_KIND = {'gaussian': 0, 'tilted': 1, 'uniform': 2}
 ACT = {'none': 0, 'linear': 0, 'relu': 1, 'sigmoid': 2, 'leaky': 3}
+OUT_F32, IN_F32 = 0x100, 0x200      # include/jvae_b200.h: JVAE_OUT_F32 / JVAE_IN_F32 flags of the `act` argument
 LEAKY_SLOPE = 0.01      # JVAE_LEAKY_SLOPE: nn.LeakyReLU() default, the only slope the reference builds (misc.py:27)
 NSCORES, NPRED = 16, 4
 SCORE_INDEX = {'elbo': 0, 'max': 0, 'sum': 1, 'mean': 2, 'iws': 3, 'soft': 4, 'softkl': 4, 'zdist': 5, 'kl': 6,
@@ -118,6 +119,7 @@ def lib():
     L.jvae_vstack_rows.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]
     L.jvae_elbo_prior_stats.argtypes = [ctypes.POINTER(ElboCfg), P, P, P, c_size_t, P]
     L.jvae_batch_u8_to_f32.argtypes = [ctypes.POINTER(BatchCfg), P, ctypes.c_longlong, P, c_int, P, P, P, P]
+    L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
     if L.jvae_abi_version() != 11:
@@ -199,6 +201,28 @@ class _timed:
         if self.on:
             self.b.record()
             PROFILE[self.name].append((self.a, self.b))
+
+
+CONV_KERNELS = {1: 'conv_halo_kernel', 2: 'conv_gather_gemm_kernel', 3: 'conv_wgrad_halo_kernel', 4: 'conv_wgrad_kernel'}
+
+
+class _timed_conv:
+    """PROFILE['conv']: (start event, stop event, algorithmic FLOPs, kernel name) per convolution launch"""
+
+    def __init__(self, flops):
+        self.on = PROFILE is not None and 'conv' in PROFILE
+        self.flops = flops
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            PROFILE['conv'].append((self.a, self.b, self.flops, CONV_KERNELS.get(int(lib().jvae_last_conv_kernel()), '?')))
 
 
 def workspace(cfg, device):
@@ -408,9 +432,11 @@ def conv_gather_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, taps, in_str
     bn = dict(y, ld_y, save, gamma, beta, act): fold the previous layer's BatchNorm-backward reduction into this
     data-gradient launch (sums go to `stats`); returns True when the launched kernel did it."""
     if bn is None:
-        check(lib().jvae_conv_gather_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]),
-                                          taps[0], taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s[0],
-                                          out_s[1], out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), stream()))
+        with _timed_conv(2.0 * N * Hq * Wq * len(taps[0]) * Cin * Cout):
+            check(lib().jvae_conv_gather_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(taps[0]),
+                                              taps[0], taps[1], in_stride, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out,
+                                              out_s[0], out_s[1], out_o[0], out_o[1], rawptr(bias), act, rawptr(stats),
+                                              stream()))
         return False
     d = BnReduce(y=bn['y'].data_ptr(), ld_y=bn['ld_y'], save_mean_rstd=bn['save'].data_ptr(),
                  gamma=bn['gamma'].data_ptr() if bn['gamma'] is not None else None,
@@ -424,8 +450,9 @@ def conv_gather_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, taps, in_str
 
 
 def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co, dw_ld_ci=1):
-    check(lib().jvae_conv_wgrad(rawptr(dy), N, Hq, Wq, Cout, ld_dy, rawptr(x), H, W, Cin, ld_x, len(taps[0]), taps[0],
-                                taps[1], in_stride, rawptr(dw), dw_ld_tap, dw_ld_co, dw_ld_ci, stream()))
+    with _timed_conv(2.0 * N * Hq * Wq * len(taps[0]) * Cin * Cout):
+        check(lib().jvae_conv_wgrad(rawptr(dy), N, Hq, Wq, Cout, ld_dy, rawptr(x), H, W, Cin, ld_x, len(taps[0]), taps[0],
+                                    taps[1], in_stride, rawptr(dw), dw_ld_tap, dw_ld_co, dw_ld_ci, stream()))
 
 
 def bn_stats(y, P, C, ld, stats):

@@ -513,13 +513,16 @@ class ConvStep:
         return a
 
     def _sep_forward(self, x, pk, bias, act, stats, out):
-        """1 x k convolution to k * Co channels (tensor cores), then the vertical shift-and-add with bias / activation / stats"""
+        """1 x k convolution to k * Co channels (tensor cores), then the vertical shift-and-add with bias / activation / stats.
+        T stays fp32: the k vertical taps of an output pixel cancel, and rounding them to bf16 first costs the gradients of the
+        head and of the layer under it an order of magnitude (measured: 25 % instead of 1.8 % on the head's weight gradient)."""
         N = x.shape[0]
-        T = K.empty((N, self.H, self.W, self.sep_ld), x)
+        T = K.empty((N, self.H, self.W, self.sep_ld), x, torch.float32)
         wm = pk['sep_fwd']
         K.gather(x, self.Ci, wm, wm.shape[0], self._taps('sf', self.sep_fwd_taps), 1, self.H, self.W, T, self.sep_C, (1, 1),
-                 (0, 0), None, 0, None)
-        K.vsum_rows(T, self.sep_ld, N, self.H, self.W, self.k, self.p, self.Co, bias, act, stats, out, out.shape[-1])
+                 (0, 0), None, nat.OUT_F32, None)
+        K.vsum_rows(T, self.sep_ld, N, self.H, self.W, self.k, self.p, self.Co, bias, act | nat.IN_F32, stats, out,
+                    out.shape[-1])
 
     def _forward_folded(self, x, st):
         """inference: conv + folded BatchNorm + activation in one kernel, no intermediate tensor"""
@@ -1033,7 +1036,7 @@ def run(mods, x, image_out=False):
         try:
             stack = ConvStack(list(mods), tuple(x.shape[1:]), image_out)
         except NotImplementedError as e:
-            stack = e                  # remembered: the engine routes this stack to the library path
+            stack = e                  # remembered: every later call raises the same error
         _stacks[key] = stack
     if isinstance(stack, NotImplementedError):
         raise stack

@@ -20,6 +20,9 @@ namespace jvae {
 
 constexpr int CONV_THREADS = 192;
 constexpr int CONV_MAX_TAPS = 64;
+// which kernel the last convolution entry point of this thread launched (jvae_last_conv_kernel: bench.py attributes its
+// per-launch CUDA-event times to the dominant kernel with it)
+static thread_local int g_last_conv_kernel = 0;
 
 struct ConvParams {
   // iteration space
@@ -35,6 +38,7 @@ struct ConvParams {
   int Ho, Wo, Cout, ldc;       // output tensor (N, Ho, Wo, ldc channels); Cout real channels written
   int out_sy, out_sx, out_oy, out_ox;   // output pixel = q * out_s + out_o
   int act;
+  int out_f32;                 // 1: `out` holds fp32 (ldc counts floats): JVAE_OUT_F32
   const float* bias;
   __nv_bfloat16* out;
   double* stats;               // (2, Cout) per-channel sum / sum of squares of the pre-activation, += (or null)
@@ -223,7 +227,11 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
           }
-          if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
+          if (p.out_f32) {
+            float* of = reinterpret_cast<float*>(p.out) + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + (size_t)nt * p.BN + c0;
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + c0 + j < p.ldc) of[j] = v[j];
+          } else if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
             uint4 o0, o1;
             o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
             o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
@@ -277,6 +285,7 @@ struct HaloParams {
   short dy[CONV_MAX_TAPS], dx[CONV_MAX_TAPS];
   uint32_t tap_off16[CONV_MAX_TAPS];     // (plane * plane_bytes + ((ey-eymin)*HWp + (ex-exmin)) * row bytes) / 16
   int Ho, Wo, Cout, ldc, out_sy, out_sx, out_oy, out_ox, act;
+  int out_f32;                           // 1: `out` holds fp32 (ldc counts floats): JVAE_OUT_F32
   const float* bias;
   __nv_bfloat16* out;
   double* stats;
@@ -331,7 +340,7 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
 // Epilogue of one M-tile for NCH 16-column chunks (BN = 16 * NCH): bias, activation, bf16 store, and per-THREAD running
 // sums of y and y^2 in registers (reduced across the CTA once, at the end of the kernel).
 template <int NCH>
-__device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t t_addr, bool ok, __nv_bfloat16* orow, int ch0,
+__device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t t_addr, bool ok, __nv_bfloat16* orow, float* orow_f, int ch0,
                                                    const float* s_bias, const float* s_bn, const __nv_bfloat16* yrow,
                                                    float (&s1)[NCH * 16], float (&s2)[NCH * 16]) {
   // the BatchNorm-backward operand of every chunk is requested before the accumulator is read: one exposed global
@@ -403,7 +412,16 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
         for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
       }
       const int c0 = c * 16;
-      if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
+      if (orow_f) {           // fp32 result (the 1 x k stage of the separable image head keeps full precision)
+        if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow_f + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (ch0 + c0 + j < p.ldc) orow_f[c0 + j] = ch0 + c0 + j < p.Cout ? v[j] : 0.f;
+        }
+      } else if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
         uint4 o0, o1;
         o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
         o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
@@ -448,11 +466,12 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
       const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
       const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
       __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
+      float* orow_f = p.out_f32 ? reinterpret_cast<float*>(p.out) + opix * p.ldc + (size_t)ch0 : nullptr;
       // row (128 m + mrow) of the y tile in shared memory: BN channels of the pixel this thread owns
       const __nv_bfloat16* yrow = p.bn_y ? reinterpret_cast<const __nv_bfloat16*>(ysm + (size_t)ys * p.y_stage_bytes) +
                                                (size_t)(m * 128 + mrow) * p.BN : nullptr;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(m * p.BN) + ((uint32_t)(q * 32) << 16);
-      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, ch0, s_bias, s_bn, yrow, s1, s2);
+      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, orow_f, ch0, s_bias, s_bn, yrow, s1, s2);
     }
     tc_fence_before();
     __syncwarp();
@@ -1007,7 +1026,8 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.num_boxes = p.strips_x * p.blocks_y * p.blocks_n;
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
-  p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
+  p.act = act & 0xff; p.out_f32 = (act & JVAE_OUT_F32) ? 1 : 0;
+  p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
   CUtensorMap tin, tw, ty;
   memset(&ty, 0, sizeof(ty));
   if (bn) {
@@ -1046,6 +1066,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
   conv_halo_kernel<<<grid, CONV_THREADS, smem, stream>>>(tin, tw, ty, p);
   JVAE_LAUNCH_CHECK();
+  g_last_conv_kernel = JVAE_KERNEL_CONV_HALO;
   if (bn && bn_fused) *bn_fused = 1;
   return JVAE_OK;
 }
@@ -1167,6 +1188,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   }
   conv_wgrad_halo_kernel<<<dim3(gx, ysplit, nz), CONV_THREADS, smem, stream>>>(tg, tx, p);
   JVAE_LAUNCH_CHECK();
+  g_last_conv_kernel = JVAE_KERNEL_WGRAD_HALO;
   return JVAE_OK;
 }
 
@@ -1222,7 +1244,8 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = tap_dy[t]; p.dx[t] = tap_dx[t]; }
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
-  p.act = act; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.act = act & 0xff; p.out_f32 = (act & JVAE_OUT_F32) ? 1 : 0;
+  p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.stats = stats; p.cout_pad = Cout_pad;
   const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 8u : 0u;
   p.a_bytes = 128u * p.Cblk * 2u;
@@ -1254,6 +1277,7 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   conv_gather_gemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(tin, tw, pk);
   JVAE_LAUNCH_CHECK();
+  g_last_conv_kernel = JVAE_KERNEL_CONV_TAPBOX;
   return JVAE_OK;
 }
 
@@ -1313,8 +1337,11 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   if (rc) return rc;
   conv_wgrad_kernel<<<dim3(gx, tap_groups, nz), CONV_THREADS, smem, (cudaStream_t)stream>>>(tdy, tx, p);
   JVAE_LAUNCH_CHECK();
+  g_last_conv_kernel = JVAE_KERNEL_WGRAD_TAPBOX;
   return JVAE_OK;
 }
+
+int jvae_last_conv_kernel(void) { return g_last_conv_kernel; }
 
 }  // extern "C"
 

@@ -544,8 +544,8 @@ __device__ __forceinline__ float bf16_pick(const uint32_t (&w)[8], int ch) {    
 
 // compile-time (k, Co) with the vector layouts (T / U rows of 16 channels, dy / out rows of 8): every channel pick is a fixed
 // register, the kernels stream at memory speed.  KK * CO <= 16.
-template <int KK, int CO>
-__global__ void __launch_bounds__(256) vsum_rows_fixed_kernel(const __nv_bfloat16* __restrict__ T, int N, int H, int W,
+template <int KK, int CO, bool TF>
+__global__ void __launch_bounds__(256) vsum_rows_fixed_kernel(const void* __restrict__ Tv, int N, int H, int W,
                                                               const float* __restrict__ bias, int act, double* stats,
                                                               __nv_bfloat16* __restrict__ out) {
   __shared__ double s_st[2 * CO];
@@ -565,14 +565,26 @@ __global__ void __launch_bounds__(256) vsum_rows_fixed_kernel(const __nv_bfloat1
     for (int ty = 0; ty < KK; ++ty) {
       const int yy = y + ty - PAD;
       if (yy < 0 || yy >= H) continue;
-      const uint4* row = reinterpret_cast<const uint4*>(T + (q + (size_t)(ty - PAD) * W) * 16);
-      // channels [ty*CO, ty*CO + CO) live in the first vector, the second, or straddle both
-      constexpr int dummy = 0; (void)dummy;
-      uint32_t w[8];
-      if (ty * CO < 8) { const uint4 lo = row[0]; w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; }
-      if (ty * CO + CO > 8) { const uint4 hi = row[1]; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w; }
+      if constexpr (TF) {     // fp32 rows of 16 channels: the float4 vectors that hold channels [ty*CO, ty*CO + CO)
+        const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Tv) + (q + (size_t)(ty - PAD) * W) * 16);
+        float f[16];
 #pragma unroll
-      for (int c = 0; c < CO; ++c) acc[c] += bf16_pick(w, ty * CO + c);
+        for (int v4 = 0; v4 < 4; ++v4)
+          if (v4 * 4 < ty * CO + CO && v4 * 4 + 4 > ty * CO) {
+            const float4 t4 = row[v4];
+            f[v4 * 4] = t4.x; f[v4 * 4 + 1] = t4.y; f[v4 * 4 + 2] = t4.z; f[v4 * 4 + 3] = t4.w;
+          }
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] += f[ty * CO + c];
+      } else {
+        const uint4* row = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Tv) + (q + (size_t)(ty - PAD) * W) * 16);
+        // channels [ty*CO, ty*CO + CO) live in the first vector, the second, or straddle both
+        uint32_t w[8];
+        if (ty * CO < 8) { const uint4 lo = row[0]; w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; }
+        if (ty * CO + CO > 8) { const uint4 hi = row[1]; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w; }
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] += bf16_pick(w, ty * CO + c);
+      }
     }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -625,12 +637,12 @@ __global__ void __launch_bounds__(256) vstack_rows_fixed_kernel(const __nv_bfloa
 
 __global__ void __launch_bounds__(256) vsum_rows_kernel(const __nv_bfloat16* __restrict__ T, int ld_t, int N, int H, int W, int k, int p,
                                                         int Co, const float* __restrict__ bias, int act, double* stats,
-                                                        __nv_bfloat16* __restrict__ out, int ld_out) {
+                                                        __nv_bfloat16* __restrict__ out, int ld_out, int t_f32) {
   __shared__ double s_st[2 * VS_MAXC];
   if (threadIdx.x < 2 * VS_MAXC) s_st[threadIdx.x] = 0.0;
   __syncthreads();
   const size_t P = (size_t)N * H * W;
-  const bool vec = ld_t == 16 && (reinterpret_cast<uintptr_t>(T) & 15) == 0;
+  const bool vec = !t_f32 && ld_t == 16 && (reinterpret_cast<uintptr_t>(T) & 15) == 0;
   const bool vec_out = ld_out == 8 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};      // statistics: Co <= 4 per thread registers
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < P; q += (size_t)gridDim.x * blockDim.x) {
@@ -658,10 +670,10 @@ __global__ void __launch_bounds__(256) vsum_rows_kernel(const __nv_bfloat16* __r
       for (int ty = 0; ty < k; ++ty) {
         const int yy = y + ty - p;
         if (yy < 0 || yy >= H) continue;
-        const __nv_bfloat16* row = T + (q + (size_t)(ty - p) * W) * ld_t + ty * Co;
+        const size_t off = (q + (size_t)(ty - p) * W) * ld_t + ty * Co;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c < Co) acc[c] += __bfloat162float(row[c]);
+          if (c < Co) acc[c] += t_f32 ? reinterpret_cast<const float*>(T)[off + c] : __bfloat162float(T[off + c]);
       }
     }
     float v[4];
@@ -941,14 +953,20 @@ int jvae_vsum_rows(const void* T, int ld_t, int N, int H, int W, int k, int pad,
   if (blocks > cap) blocks = cap;
   const bool fixed = ld_t == 16 && ld_out == 8 && pad == (k - 1) / 2 && (k & 1) &&
                      ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int tf = (act & JVAE_IN_F32) ? 1 : 0;
+  act &= 0xff;
   const __nv_bfloat16* Tp = reinterpret_cast<const __nv_bfloat16*>(T);
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (fixed && k == 5 && Co == 3) vsum_rows_fixed_kernel<5, 3><<<resident_grid(vsum_rows_fixed_kernel<5, 3>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 3 && Co == 3) vsum_rows_fixed_kernel<3, 3><<<resident_grid(vsum_rows_fixed_kernel<3, 3>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 5 && Co == 1) vsum_rows_fixed_kernel<5, 1><<<resident_grid(vsum_rows_fixed_kernel<5, 1>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else if (fixed && k == 3 && Co == 1) vsum_rows_fixed_kernel<3, 1><<<resident_grid(vsum_rows_fixed_kernel<3, 1>, 256, 0, (int)blocks), 256, 0, st>>>(Tp, N, H, W, bias, act, stats, op);
-  else vsum_rows_kernel<<<(int)blocks, 256, 0, st>>>(Tp, ld_t, N, H, W, k, pad, Co, bias, act, stats, op, ld_out);
+#define VSUM_FIXED(KK, CO)                                                                                                   \
+  if (tf) vsum_rows_fixed_kernel<KK, CO, true><<<resident_grid(vsum_rows_fixed_kernel<KK, CO, true>, 256, 0, (int)blocks), 256, 0, st>>>(T, N, H, W, bias, act, stats, op); \
+  else vsum_rows_fixed_kernel<KK, CO, false><<<resident_grid(vsum_rows_fixed_kernel<KK, CO, false>, 256, 0, (int)blocks), 256, 0, st>>>(T, N, H, W, bias, act, stats, op)
+  if (fixed && k == 5 && Co == 3) { VSUM_FIXED(5, 3); }
+  else if (fixed && k == 3 && Co == 3) { VSUM_FIXED(3, 3); }
+  else if (fixed && k == 5 && Co == 1) { VSUM_FIXED(5, 1); }
+  else if (fixed && k == 3 && Co == 1) { VSUM_FIXED(3, 1); }
+  else vsum_rows_kernel<<<(int)blocks, 256, 0, st>>>(Tp, ld_t, N, H, W, k, pad, Co, bias, act, stats, op, ld_out, tf);
+#undef VSUM_FIXED
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }

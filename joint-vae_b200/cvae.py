@@ -4,7 +4,7 @@ Constructor keywords, attribute names, state_dict keys, the return tuples of for
 keys per model type, predict_after_evaluate and batch_dist_measures follow the reference, so a caller of the
 reference (train.py:195-217,333; test.py:272-304) can switch modules.  Underneath:
 
-  features / dense_projs / heads / decoder / imager / classifier -> engine (tcgen05 GEMM kernels, see engine.POLICY)
+  features / dense_projs / heads / decoder / imager / classifier -> engine (tcgen05 GEMM / implicit-GEMM kernels)
   Sampling            -> csrc/sampler.cu (Philox or injected noise, fused mean/log-var head)
   the ELBO step       -> csrc/elbo.cu: ONE fused kernel for train forward, one for its backward, one for the
                          per-class eval that also emits OOD scores and predictions (cvae.py:626-1085)

@@ -1,14 +1,10 @@
 """Execution engine: maps the reference's layer containers and loss step onto libjvae_sm100.so.
 
 Everything here is host plumbing (PyTorch owns tensors, autograd graph and streams); the arithmetic is in
-csrc/*.cu, reached through _native (ctypes, C ABI).  POLICY names, per layer family, whether the hand-written
-kernel ('native') or a vendor library call through torch ('library': cuDNN / cuBLAS, bf16) executes it.  The
-library setting exists only for layer families whose sm_100a kernel has not landed yet; it is
-never selected silently: a 'native' op that cannot run raises.
+csrc/*.cu, reached through _native (ctypes, C ABI).  There is ONE execution path: a layer without a native sm_100a
+kernel raises NotImplementedError (no vendor-library or eager fallback, no backend switch).
 """
 import itertools
-import logging
-import os
 import weakref
 
 import torch
@@ -16,10 +12,6 @@ from torch import nn
 
 from . import _native as nat
 
-POLICY = {
-    'linear': os.environ.get('JVAE_LINEAR', 'native'),
-    'conv': os.environ.get('JVAE_CONV', 'native'),
-}
 _rng_offset = itertools.count(1)
 
 # Parameter epochs.  The fused Adam (csrc/optim.cu) and the BatchNorm kernels (running statistics) write parameters and
@@ -38,7 +30,6 @@ def bump_params():
 def bump_stats():
     STATS_EPOCH[0] += 1
 
-_library_stacks = set()
 
 
 def _r8(n):
@@ -132,16 +123,7 @@ def linear(x, w, b, act='linear', out_dtype=torch.bfloat16):
     """x (M,K) -> act(x W^T + b) (M,N).  act in linear|relu|sigmoid."""
     if not x.is_cuda:
         raise nat.NativeError('joint-vae_b200 runs on CUDA devices only (there is no CPU fallback); got a CPU tensor')
-    if POLICY['linear'] == 'native':
-        return _LinearFn.apply(x, w, b, act, out_dtype)
-    y = torch.nn.functional.linear(x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16) if b is not None else None)
-    if act == 'relu':
-        y = torch.relu(y)
-    elif act == 'sigmoid':
-        y = torch.sigmoid(y)
-    elif act == 'leaky':
-        y = torch.nn.functional.leaky_relu(y, nat.LEAKY_SLOPE)
-    return y.to(out_dtype)
+    return _LinearFn.apply(x, w, b, act, out_dtype)
 
 
 _ACT_OF = {nn.ReLU: 'relu', nn.Sigmoid: 'sigmoid', nn.Identity: 'linear', nn.LeakyReLU: 'leaky'}
@@ -197,9 +179,7 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
         elif type(m) in _ACT_OF:
             x = m(x)
         elif any(True for _ in m.parameters()):
-            # a parametrised module without a native kernel (e.g. torchvision's residual blocks): library path, bf16
-            with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
-                x = m(x)
+            raise NotImplementedError(f'{type(m).__name__} has parameters but no native kernel (there is no library path)')
         else:
             x = m(x)     # Reshape, pooling and other parameter-free modules
         i += 1
@@ -209,26 +189,10 @@ def run_sequential(seq, x, out_dtype=None, image_out=False):
 
 
 def run_conv_stack(mods, x, image_out=False):
-    """x NCHW.  'native' (default): the tcgen05 implicit-GEMM kernels of csrc/conv.cu + csrc/norm.cu through
-    conv_engine; 'library': the same layers as cuDNN / ATen calls in bf16 channels_last, kept ONLY as the comparison
-    arm of bench.py --conv library and for layer types without a native kernel (never selected silently)."""
-    if POLICY['conv'] == 'native':
-        from . import conv_engine
-        try:
-            return conv_engine.run(mods, x, image_out=image_out)
-        except NotImplementedError as e:
-            # a layer type without a native kernel (e.g. torchvision's overlapping MaxPool2d(3, 2, 1) in the resnet stem):
-            # this stack runs through the library path; said once per stack, never silently
-            key = tuple(id(m) for m in mods)
-            if key not in _library_stacks:
-                _library_stacks.add(key)
-                logging.warning('conv stack %s runs through the library (cuDNN) path: %s',
-                                [type(m).__name__ for m in mods], e)
-    with torch.autocast(device_type='cuda', dtype=torch.bfloat16):
-        x = x.contiguous(memory_format=torch.channels_last)
-        for m in mods:
-            x = m(x)
-    return x
+    """x NCHW through the tcgen05 implicit-GEMM kernels of csrc/conv.cu + csrc/norm.cu (conv_engine).  A layer type
+    without a native kernel (DenseNet blocks, MaxPool2d with ceil_mode, ...) raises NotImplementedError."""
+    from . import conv_engine
+    return conv_engine.run(mods, x, image_out=image_out)
 
 
 # --------------------------------------------------------------------------------------------- sampler

@@ -83,10 +83,11 @@ class EmuKernels:
         if stats is not None:
             stats[0] += acc.sum((0, 1, 2))
             stats[1] += (acc * acc).sum((0, 1, 2))
-        acc = _act(acc, act)
+        acc = _act(acc, act & 0xff)
         view = out[:, out_o[0]::out_s[0], out_o[1]::out_s[1]]
         assert view.shape[1] == Hq and view.shape[2] == Wq, (view.shape, Hq, Wq)
-        view[..., :Cout] = acc.to(EmuKernels.store)
+        assert bool(act & 0x100) == (out.dtype == torch.float32 and EmuKernels.store != torch.float32) or EmuKernels.store == torch.float32
+        view[..., :Cout] = acc if (act & 0x100) else acc.to(EmuKernels.store)      # JVAE_OUT_F32: no rounding of the result
         view[..., Cout:] = 0
 
     @classmethod
@@ -232,6 +233,8 @@ class EmuKernels:
     @classmethod
     def vsum_rows(cls, T, ld_t, N, H, W, k, pad, Co, bias, act, stats, out, ld_out):
         cls.launches += 1
+        assert bool(act & 0x200) == (T.dtype == torch.float32) or EmuKernels.store == torch.float32      # JVAE_IN_F32
+        act &= 0xff
         t = torch.nan_to_num(T.float())
         acc = torch.zeros(N, H, W, Co)
         for ty in range(k):

@@ -154,20 +154,45 @@ def build_oracle(pkg, name):
     return model, net
 
 
+def _make_bf16_pipeline_(net):
+    """In place: every GEMM / convolution weight rounded to bf16, and every tensor that travels between layers -- the output
+    of each convolution, linear layer, BatchNorm and activation in the forward pass, and the gradient arriving at it in the
+    backward pass -- rounded to bf16, all arithmetic staying fp32.  Nothing here knows the product's kernels: it is what any
+    pipeline that stores activations in bf16 and feeds bf16 operands to tensor cores computes."""
+    from torch import nn
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() > 1 and 'prior' not in k:
+                p.copy_(rnd(p))
+    heads = {id(net.encoder.dense_mean), id(net.encoder.dense_log_var)}      # fp32 outputs (they feed the fp32 loss)
+
+    def hook(mod, inp, out):
+        out = rnd(out)
+        if out.requires_grad:
+            out.register_hook(rnd)
+        return out
+
+    kinds = (nn.Conv2d, nn.ConvTranspose2d, nn.Linear, nn.BatchNorm2d, nn.ReLU, nn.LeakyReLU, nn.Sigmoid)
+    for m in net.modules():
+        if isinstance(m, kinds) and id(m) not in heads:
+            if isinstance(m, nn.ReLU):
+                m.inplace = False
+            m.register_forward_hook(hook)
+    return net
+
+
 def oracle_outputs(pkg, name, train_backward=True, bf16_operands=False):
     """the oracle's eval losses / scores / predictions and its training losses + gradients for a case.
-    bf16_operands: the same fp32 computation after rounding every GEMM / convolution weight and the input image to bf16 --
-    the error this alone causes is the floor of ANY implementation with bf16 tensor-core operands (north_star mandates
-    them), before a single activation is rounded."""
+    bf16_operands: the same fp32 arithmetic as a GENERIC bf16 tensor-core pipeline would see it (_make_bf16_pipeline_):
+    the error this causes against the exact oracle is the floor of any implementation with bf16 operands, which north_star
+    mandates."""
     from oracle import elbo_numpy as on
     model, net = build_oracle(pkg, name)
     kw = CASES[name][0]
     x, y, eps_tr, eps_te = inputs(name)
     if bf16_operands:
-        with torch.no_grad():
-            for p in net.parameters():
-                if p.dim() > 1 and not any(p is q for q in (net.encoder.prior.mean, net.encoder.prior._var_parameter)):
-                    p.copy_(p.to(torch.bfloat16).float())
+        _make_bf16_pipeline_(net)
         x = x.to(torch.bfloat16).float()
     n = lambda t: None if t is None else t.detach().numpy()
     prior = on.Prior(n(net.encoder.prior.mean), n(net.encoder.prior._var_parameter), var_dim='scalar', conditional=True)

@@ -39,14 +39,9 @@ def build(pkg, d):
 SUPPORTED = golden_names()
 
 
-@pytest.mark.parametrize('linear', ['native', 'library'])
 @pytest.mark.parametrize('name', SUPPORTED)
-def test_train_and_eval_match_reference(pkg, name, linear):
-    pkg.engine.POLICY['linear'] = linear
-    try:
-        _run(pkg, name)
-    finally:
-        pkg.engine.POLICY['linear'] = 'native'
+def test_train_and_eval_match_reference(pkg, name):
+    _run(pkg, name)
 
 
 def test_sigma_coded_matches_reference(pkg):
@@ -71,12 +66,36 @@ def test_y_is_coded_train_step_matches_reference(pkg):
     _run(pkg, 'ycoded_mlp_cvae', eval_part=False)
 
 
+def _bf16_operand_floor(d, cfg):
+    """per-tensor gradient error of the fp32 oracle when only its GEMM / conv weights and the input are rounded to bf16"""
+    from oracle.torch_model import OracleNet
+    arch = json.loads(str(d['arch']))
+    net = OracleNet(cfg, arch).load_numpy_state(d)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() > 1 and 'prior' not in k:
+                p.copy_(p.to(torch.bfloat16).float())
+    net.train()
+    x = torch.from_numpy(d['x']).to(torch.bfloat16).float()
+    losses, _ = net.train_losses(x, torch.from_numpy(d['y']), torch.from_numpy(d['eps_train']), beta=cfg['beta'],
+                                 gamma=cfg['gamma'] or 0.0, kl_var_weighting=float(d['train.kl_var_weighting']),
+                                 gamma_weighting=float(d['train.gamma_weighting']))
+    losses['total'].mean().backward()
+    out = {}
+    for k, p in net.named_parameters():
+        gk = 'train.grad.' + k
+        if p.grad is not None and gk in d.files:
+            gr = d[gk].astype(np.float64)
+            out[k] = float(np.linalg.norm(p.grad.numpy().astype(np.float64) - gr) / max(1e-30, np.linalg.norm(gr)))
+    return out
+
+
 def _run(pkg, name, eval_part=True):
     d = np.load(os.path.join(GOLDEN, name + '.npz'))
     cfg, net = build(pkg, d)
     x = torch.from_numpy(d['x']).to(DEV)
     y = torch.from_numpy(d['y']).to(DEV)
-    tol = 3e-2
+    tol = 2e-2      # north_star's tolerance for bf16 GEMM operands
     # ---------------- train step
     net.train()
     net.encoder.sampling.injected_eps = torch.from_numpy(d['eps_train']).to(DEV)
@@ -102,19 +121,21 @@ def _run(pkg, name, eval_part=True):
     checked = 0
     pairs = {k: p for k, p in net.named_parameters() if 'train.grad.' + k in d.files}
     gmax = max(float(np.linalg.norm(d['train.grad.' + k].astype(np.float64))) for k in pairs)
-    # bf16 operands in every GEMM / conv of the chain, bf16 activations between conv layers: per-tensor error relative
-    # to the tensor's norm.  Conv stacks with BatchNorm at the fixtures' tiny batch amplify activation rounding through
-    # the batch statistics (tests/test_conv_engine_cpu.py isolates this), and a conv bias in front of a train-mode
-    # BatchNorm has an exactly-zero gradient here where autograd leaves rounding noise: absolute floor from gmax.
-    conv_model = cfg.get('features') is not None
-    tol_g = 0.25 if conv_model else 0.1
+    # Per-tensor error relative to the tensor's norm: 2e-2 (north_star), or 2.5 x the error that rounding the GEMM / conv
+    # weights and the input to bf16 ALONE causes in the fp32 oracle (the floor of any bf16-operand implementation: ReLU /
+    # max-pool decisions and tiny-batch BatchNorm statistics flip on 1e-3 perturbations), whichever is larger.  A conv bias
+    # in front of a train-mode BatchNorm has an exactly-zero gradient here where autograd leaves rounding noise: absolute
+    # floor from the largest gradient norm.  Priors the torch oracle does not restate (tilted / uniform) keep 0.1.
+    floor = _bf16_operand_floor(d, cfg) if ('tilted' not in name and 'uniform' not in name and 'sig_' not in name
+                                            and 'ycoded' not in name) else None
     for k, p in pairs.items():
         gk = 'train.grad.' + k
         assert p.grad is not None, k
         g, gr = p.grad.detach().float().cpu().numpy().astype(np.float64), d[gk].astype(np.float64)
         nr = np.linalg.norm(gr)
         assert np.isfinite(g).all(), k
-        assert np.linalg.norm(g - gr) <= tol_g * nr + 0.02 * gmax + 1e-6, (k, np.linalg.norm(g - gr), nr, gmax)
+        tol_g = 0.1 if floor is None else max(2e-2, 2.5 * floor.get(k, 0.0))
+        assert np.linalg.norm(g - gr) <= tol_g * nr + 0.02 * gmax + 1e-6, (k, np.linalg.norm(g - gr) / max(nr, 1e-30), tol_g)
         checked += 1
     assert checked >= 4
     for k in d.files:
@@ -138,14 +159,20 @@ def _eval(pkg, net, d, cfg, x, tol):
         assert rel(logits.float().cpu().numpy(), d['eval.logits']) < tol
         methods = json.loads(str(d['eval.methods']))
         dm = net.batch_dist_measures(logits, losses, methods)
+        from full_cases import rank_agreement
         for m in methods:
             want = d['eval.measure.' + m]
             got = dm[m].float().cpu().numpy()
-            if m in ('nstd', 'IYx', 'mag'):      # ill-conditioned functions of near-equal exponentials
+            # rank order (what OOD / misclassification ROC curves see): identical on every pair of samples whose reference
+            # scores differ by more than the margin 2 * tol * scale
+            agree, frac = rank_agreement(got, want, tol)
+            assert agree == 1.0, (m, agree, frac)
+            if m in ('nstd', 'IYx', 'mag'):      # ill-conditioned functions of near-equal exponentials: rank order only
                 continue
-            assert rel(got, want) < 5e-2, (m, rel(got, want))
-        # predictions: exact w.r.t. our own losses (kernel arg-min == torch arg-min), and equal to the reference's
-        # wherever the reference's decision margin exceeds the bf16 tolerance
+            assert rel(got, want) < tol, (m, rel(got, want))
+        # predictions: exact w.r.t. our own losses (kernel arg-min == torch arg-min), and equal to the reference's on
+        # every sample whose decision margin in the reference exceeds the tolerance
+        margin_key = {'iws': ('iws', -1.0), 'closest': ('zdist', 1.0), 'loss': ('total', 1.0), 'esty': (None, -1.0)}
         for m in json.loads(str(d['eval.predict_methods'])):
             got = net.predict_after_evaluate(logits, losses, method=m).cpu().numpy()
             want = d['eval.pred.' + m]
@@ -153,7 +180,13 @@ def _eval(pkg, net, d, cfg, x, tol):
             plain = net.predict_after_evaluate(logits, losses, method=m).cpu().numpy()
             net._fused = f
             assert (got == plain).all(), m
-            assert (got == want).mean() >= 0.8, (m, got, want)
+            key, sign = margin_key[m]
+            ref = sign * (d['eval.logits'].T if key is None else d['eval.loss.' + key]).astype(np.float64)
+            if ref.ndim == 1:
+                continue
+            srt = np.sort(ref, axis=0)
+            clear = (srt[1] - srt[0]) > 2 * tol * np.maximum(1.0, np.abs(srt[0]))
+            assert (got[clear] == want[clear]).all(), (m, got, want)
 
 
 @pytest.mark.parametrize('act', ['relu', 'leaky', 'sigmoid', 'linear'])

@@ -44,11 +44,9 @@ def test_odin_scores_match_reference(pkg, name):
         native = input_gradients()
         # noise floor of bf16 activations: the same network through cuDNN in bf16 (conv stacks with ReLU / max-pool
         # decisions on 8 channels amplify activation rounding in the input gradient, tests/test_gpu_conv.py)
-        pkg.engine.POLICY['conv'] = 'library'
-        try:
+        from library_arm import cudnn_bf16
+        with cudnn_bf16(pkg):
             library = input_gradients()
-        finally:
-            pkg.engine.POLICY['conv'] = 'native'
         print('input gradient (cos, norm ratio, sign agreement): native', native, 'cudnn-bf16', library)
         for (c, r, sg), (cl, rl, sl) in zip(native, library):
             assert 1 - c < max(5e-3, 2 * (1 - cl)), (c, cl)
