@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 11
+#define JVAE_ABI_VERSION 12
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -370,13 +370,23 @@ int jvae_batch_u8_to_f32(const jvae_batch_cfg* cfg, const void* src, long long n
  * Optimizer (module/optimizers.py:79-81,120-121: clip_grad_norm_ then Adam with L2 weight decay)
  * on one flat f32 parameter / gradient buffer.  grad may be the bf16 all-reduced bucket.
  * ------------------------------------------------------------------------------------------ */
-/* norm2_out[0] += sum(grad^2) (zero it first); grad_dtype is a jvae_dtype */
-int jvae_grad_sqnorm(const void* grad, int grad_dtype, size_t n, float* norm2_out, void* stream);
+/* The flat buffers hold the trainable parameters back to back, each starting on a multiple of JVAE_OPT_CHUNK elements;
+ * chunk_seg[i / JVAE_OPT_CHUNK] = index of the parameter that owns element i (int32, n / JVAE_OPT_CHUNK entries, device).
+ * torch.optim.Adam keeps a step count per parameter and skips parameters whose grad is None (here: whose slice of the zeroed
+ * flat gradient stayed all zero, e.g. the classifier of a cvae with gamma = 0, cvae.py:216-218): seg_active (nseg int32,
+ * ZEROED by the caller before jvae_grad_sqnorm) receives 1 for every parameter with a non-zero gradient element, seg_step
+ * (nseg int32, device) holds the per-parameter step counts, seg_bc (nseg x 2 f32) is scratch for the bias corrections.
+ * Nothing of the step count lives on the host, so a captured CUDA graph of the step replays correctly. */
+#define JVAE_OPT_CHUNK 256
+/* norm2_out[0] += sum(grad^2) (zero it first); grad_dtype is a jvae_dtype; chunk_seg / seg_active: both or neither */
+int jvae_grad_sqnorm(const void* grad, int grad_dtype, size_t n, float* norm2_out, const int32_t* chunk_seg, int32_t* seg_active,
+                     void* stream);
 /* p,m,v (n) f32; clip_coef = min(1, max_norm/(sqrt(norm2)+1e-6)) computed on device from norm2;
- * max_norm <= 0 disables clipping; step is the 1-based Adam step count */
+ * max_norm <= 0 disables clipping.  Two launches: per-parameter step counts / bias corrections, then the update. */
 int jvae_adam_step(float* p, float* m, float* v, const void* grad, int grad_dtype, size_t n,
                    const float* norm2, float max_norm, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int step, float grad_scale, void* stream);
+                   float weight_decay, int nseg, const int32_t* chunk_seg, const int32_t* seg_active, int32_t* seg_step,
+                   float* seg_bc, float grad_scale, void* stream);
 
 /* self-test of the tensor-core kernels against naive CUDA-core references run on the device;
  * prints a report to stdout, returns the number of failed cases */

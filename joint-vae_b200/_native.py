@@ -85,9 +85,9 @@ def lib():
     L.jvae_cast_bf16_f32.argtypes = [P, P, c_size_t, P]
     L.jvae_nchw_to_nhwc_bf16.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P]
     L.jvae_nhwc_bf16_to_nchw.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P]
-    L.jvae_grad_sqnorm.argtypes = [P, c_int, c_size_t, P, P]
+    L.jvae_grad_sqnorm.argtypes = [P, c_int, c_size_t, P, P, P, P]
     L.jvae_adam_step.argtypes = [P, P, P, P, c_int, c_size_t, P, c_float, c_float, c_float, c_float, c_float,
-                                 c_float, c_int, c_float, P]
+                                 c_float, c_int, P, P, P, P, c_float, P]
     for name in ('jvae_gemm_bf16', 'jvae_selftest'):
         if not hasattr(L, name):
             raise NativeError(f'{LIB_PATH} does not export {name}: stale build')
@@ -122,7 +122,7 @@ def lib():
     L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
-    if L.jvae_abi_version() != 11:
+    if L.jvae_abi_version() != 12:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -391,14 +391,19 @@ def pack_weights(jobs_dev, n_jobs, taps_dev, total_blocks):
     check(lib().jvae_pack_weights(rawptr(jobs_dev), n_jobs, rawptr(taps_dev), total_blocks, stream()))
 
 
-def grad_sqnorm(grad, out):
-    check(lib().jvae_grad_sqnorm(ptr(grad), dtype_code(grad), grad.numel(), ptr(out), stream()))
+OPT_CHUNK = 256      # include/jvae_b200.h: JVAE_OPT_CHUNK
 
 
-def adam_step(p, m, v, grad, norm2, *, max_norm, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def grad_sqnorm(grad, out, chunk_seg=None, seg_active=None):
+    check(lib().jvae_grad_sqnorm(ptr(grad), dtype_code(grad), grad.numel(), ptr(out), ptr(chunk_seg), ptr(seg_active), stream()))
+
+
+def adam_step(p, m, v, grad, norm2, *, max_norm, lr, beta1, beta2, eps, weight_decay, chunk_seg, seg_active, seg_step, seg_bc,
+              grad_scale=1.0):
+    """include/jvae_b200.h: jvae_adam_step (per-parameter step counts on the device; gradient-less parameters are skipped)"""
     check(lib().jvae_adam_step(ptr(p), ptr(m), ptr(v), ptr(grad), dtype_code(grad), p.numel(), ptr(norm2),
-                               float(max_norm or 0.0), lr, beta1, beta2, eps, weight_decay, int(step), grad_scale,
-                               stream()))
+                               float(max_norm or 0.0), lr, beta1, beta2, eps, weight_decay, seg_active.numel(), ptr(chunk_seg),
+                               ptr(seg_active), ptr(seg_step), ptr(seg_bc), grad_scale, stream()))
 
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2

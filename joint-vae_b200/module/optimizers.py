@@ -42,7 +42,7 @@ class Optimizer:
                 raise NotImplementedError('amsgrad is not implemented by the fused Adam kernel')
             self._opt = None
             self._flat = None
-            self._step = 0
+            self._pending_state = {}          # id(param) -> loaded Adam state waiting for the flat buffers
         elif optim_type == 'sgd':
             # secondary optimizer of the reference: plain torch.optim.SGD (library), not on the measured path
             self._opt = optim.SGD(self._params, lr=lr, weight_decay=weight_decay, **kw)
@@ -54,6 +54,8 @@ class Optimizer:
         return [p for p in self._params if p.requires_grad]
 
     def _flatten(self):
+        """Re-point the trainable parameters (and their .grad) to slices of flat buffers; every slice starts on a multiple of
+        JVAE_OPT_CHUNK elements so that a chunk belongs to one parameter (include/jvae_b200.h: chunk_seg)."""
         ps = self._trainable()
         if not ps:
             raise RuntimeError('no trainable parameter')
@@ -61,25 +63,39 @@ class Optimizer:
         if dev.type != 'cuda':
             raise nat.NativeError('the fused Adam kernel needs the parameters on a CUDA device (no CPU fallback)')
         old = self._flat
-        sizes = [(p.numel() + 3) & ~3 for p in ps]          # keep every view 16-byte aligned
-        n = sum(sizes)
+        CH = nat.OPT_CHUNK
+        sizes = [(p.numel() + CH - 1) // CH * CH for p in ps]
+        n, nseg = sum(sizes), len(ps)
+        aux = torch.zeros(1 + nseg, device=dev)                  # [norm2 | seg_active (int32 view)]: one zero_() per step
         f = {'ids': [id(p) for p in ps], 'n': n, 'p': torch.zeros(n, device=dev), 'm': torch.zeros(n, device=dev),
-             'v': torch.zeros(n, device=dev), 'g': torch.zeros(n, device=dev), 'norm2': torch.zeros(1, device=dev),
-             'views': {}}
+             'v': torch.zeros(n, device=dev), 'g': torch.zeros(n, device=dev), 'aux': aux, 'norm2': aux[:1],
+             'seg_active': aux[1:].view(torch.int32), 'seg_step': torch.zeros(nseg, dtype=torch.int32, device=dev),
+             'seg_bc': torch.zeros(2 * nseg, device=dev), 'views': {}, 'seg': {}}
+        f['chunk_seg'] = torch.repeat_interleave(torch.arange(nseg, dtype=torch.int32),
+                                                 torch.tensor([sz // CH for sz in sizes])).to(dev)
         off = 0
-        for p, sz in zip(ps, sizes):
+        steps = [0] * nseg
+        for i, (p, sz) in enumerate(zip(ps, sizes)):
             sl = slice(off, off + p.numel())
             f['p'][sl].copy_(p.data.reshape(-1))
-            if old is not None and id(p) in old['views']:
+            if id(p) in self._pending_state:                      # Adam state from load_state_dict
+                st = self._pending_state.pop(id(p))
+                f['m'][sl].copy_(st['exp_avg'].reshape(-1))
+                f['v'][sl].copy_(st['exp_avg_sq'].reshape(-1))
+                steps[i] = int(st['step'])
+            elif old is not None and id(p) in old['views']:
                 osl = old['views'][id(p)]
                 f['m'][sl].copy_(old['m'][osl])
                 f['v'][sl].copy_(old['v'][osl])
+                steps[i] = int(old['seg_step'][old['seg'][id(p)]])
             if p.grad is not None:
                 f['g'][sl].copy_(p.grad.reshape(-1))
             p.data = f['p'][sl].view(p.shape)
             p.grad = f['g'][sl].view(p.shape)
             f['views'][id(p)] = sl
+            f['seg'][id(p)] = i
             off += sz
+        f['seg_step'].copy_(torch.tensor(steps, dtype=torch.int32))
         self._flat = f
         engine.bump_params()
 
@@ -141,12 +157,12 @@ class Optimizer:
         if self.allreduce is not None:
             g = self.allreduce(g)
         max_norm = self.grad_clipping if self._clip_now else 0.0
-        if max_norm:
-            f['norm2'].zero_()
-            nat.grad_sqnorm(g, f['norm2'])
-        self._step += 1
+        f['aux'].zero_()
+        # one pass over the gradient: squared norm for the clip AND the per-parameter "has a gradient" flags
+        nat.grad_sqnorm(g, f['norm2'], f['chunk_seg'], f['seg_active'])
         nat.adam_step(f['p'], f['m'], f['v'], g, f['norm2'], max_norm=max_norm, lr=self._lr, beta1=self.betas[0],
-                      beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self._step)
+                      beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, chunk_seg=f['chunk_seg'],
+                      seg_active=f['seg_active'], seg_step=f['seg_step'], seg_bc=f['seg_bc'])
         self._clip_now = False
         engine.bump_params()         # parameters changed in place behind autograd's version counters
 
@@ -172,35 +188,31 @@ class Optimizer:
         # the flat buffers follow the parameters lazily (see _ensure_flat)
 
     def state_dict(self, *a, **k):
-        """torch.optim.Adam-compatible layout: state[i] = {step, exp_avg, exp_avg_sq} per trainable parameter."""
+        """torch.optim.Adam's layout: `state` indexed by the position of the parameter in the FULL parameter list the optimizer
+        was given (frozen ones included, as torch does), one {step, exp_avg, exp_avg_sq} per parameter that was ever updated."""
         if self._opt is not None:
             return self._opt.state_dict(*a, **k)
         state = {}
         if self._flat is not None:
             f = self._flat
-            for i, p in enumerate(self._trainable()):
+            steps = f['seg_step'].tolist()
+            for i, p in enumerate(self._params):
+                if id(p) not in f['views'] or steps[f['seg'][id(p)]] == 0:
+                    continue
                 sl = f['views'][id(p)]
-                state[i] = {'step': torch.tensor(float(self._step)), 'exp_avg': f['m'][sl].view(p.shape).clone(),
+                state[i] = {'step': torch.tensor(float(steps[f['seg'][id(p)]])), 'exp_avg': f['m'][sl].view(p.shape).clone(),
                             'exp_avg_sq': f['v'][sl].view(p.shape).clone()}
         group = {'lr': self._lr, 'betas': self.betas, 'eps': self.eps, 'weight_decay': self.weight_decay,
-                 'amsgrad': False, 'params': list(range(len(self._trainable())))}
+                 'amsgrad': False, 'params': list(range(len(self._params)))}
         return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd, *a, **k):
         if self._opt is not None:
             return self._opt.load_state_dict(sd, *a, **k)
         self._lr = sd['param_groups'][0]['lr']
-        if sd['state']:
-            self._ensure_flat()
-            f = self._flat
-            for i, p in enumerate(self._trainable()):
-                st = sd['state'].get(i)
-                if st is None:
-                    continue
-                sl = f['views'][id(p)]
-                f['m'][sl].copy_(st['exp_avg'].reshape(-1))
-                f['v'][sl].copy_(st['exp_avg_sq'].reshape(-1))
-                self._step = int(st['step'])
+        self._pending_state = {id(self._params[int(i)]): st for i, st in sd['state'].items() if int(i) < len(self._params)}
+        if self._pending_state and self._trainable() and self._trainable()[0].is_cuda:
+            self._flatten()            # the loaded moments and step counts enter the flat buffers
 
     def __str__(self):
         return self.__format__('10')

@@ -113,19 +113,28 @@ def projected_error(key, g, ref_norm, ref_proj):
 
 
 def rank_agreement(got, want, tol):
-    """Rank order of a per-sample score: over all pairs (i, j) whose reference scores differ by more than the margin
-    2 * tol * scale, the fraction ordered the same way, and the fraction of pairs that clear the margin."""
+    """Rank order of a per-sample score (what the ROC tables of OOD / misclassification detection see).
+    -> (fraction of ALL sample pairs ordered as in the reference, fraction of the pairs whose reference scores differ by more
+    than the margin tol * scale that are ordered as in the reference, fraction of pairs beyond that margin).
+    Note that pairs further apart than twice the largest value error keep their order by arithmetic; the informative figures
+    are the all-pairs agreement and the agreement beyond a margin SMALLER than the value tolerance."""
     got, want = np.asarray(got, np.float64).reshape(-1), np.asarray(want, np.float64).reshape(-1)
     ok = np.isfinite(want) & np.isfinite(got)
     got, want = got[ok], want[ok]
     scale = max(1e-12, float(np.abs(want).max()))
-    dw = want[:, None] - want[None, :]
-    dg = got[:, None] - got[None, :]
-    clear = dw > 2 * tol * scale
-    n = int(clear.sum())
-    if n == 0:
-        return 1.0, 0.0
-    return float((dg[clear] > 0).mean()), n / max(1, got.size * (got.size - 1) // 2)
+    iu = np.triu_indices(got.size, 1)
+    dw = (want[:, None] - want[None, :])[iu]
+    dg = (got[:, None] - got[None, :])[iu]
+    same = np.sign(dw) == np.sign(dg)
+    clear = np.abs(dw) > tol * scale
+    return float(same.mean()) if same.size else 1.0, (float(same[clear].mean()) if clear.any() else 1.0), float(clear.mean()) if clear.size else 0.0
+
+
+ILL_CONDITIONED = ('nstd', 'IYx', 'mag', 'softiws')      # functions of near-equal exponentials of losses ~ 1e3..1e4
+
+
+def ill_conditioned(method):
+    return method.split('-')[0] in ILL_CONDITIONED
 
 
 def build_oracle(pkg, name):

@@ -278,32 +278,87 @@ def test_philox_sampler_statistics(pkg):
 
 
 def test_adam_matches_torch(pkg):
+    """flat Adam over three parameters (slices start on JVAE_OPT_CHUNK multiples) against torch.optim.Adam + clip_grad_norm_:
+    the second parameter never receives a gradient -- torch skips it (grad is None: no weight decay, no step count), and so
+    does the kernel (all-zero slice of the zeroed flat gradient); the third one gets its first gradient at step 2, so its
+    bias correction runs one step behind the first one's (per-parameter step counts, kept on the device)."""
     nat = pkg._native
     torch.manual_seed(0)
-    n = 100003
-    p0 = torch.randn(n, device=DEV)
-    g = torch.randn(n, device=DEV) * 3
-    ref = torch.nn.Parameter(p0.clone())
-    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=3e-5)
-    pad = (n + 3) & ~3
-    p, m, v = torch.zeros(pad, device=DEV), torch.zeros(pad, device=DEV), torch.zeros(pad, device=DEV)
-    p[:n] = p0
-    gp = torch.zeros(pad, device=DEV)
-    norm2 = torch.zeros(1, device=DEV)
-    for step in range(1, 4):
-        gp[:n] = g * step
-        ref.grad = (g * step).clone()
-        torch.nn.utils.clip_grad_norm_([ref], 100.0)
+    CH = nat.OPT_CHUNK
+    sizes = [100003, 777, 4099]
+    refs = [torch.nn.Parameter(torch.randn(n, device=DEV)) for n in sizes]
+    opt = torch.optim.Adam(refs, lr=1e-3, weight_decay=3e-5)
+    pads = [(n + CH - 1) // CH * CH for n in sizes]
+    offs = [sum(pads[:i]) for i in range(3)]
+    N = sum(pads)
+    p, m, v, gp = (torch.zeros(N, device=DEV) for _ in range(4))
+    for r, o, n in zip(refs, offs, sizes):
+        p[o:o + n] = r.detach()
+    chunk_seg = torch.repeat_interleave(torch.arange(3, dtype=torch.int32), torch.tensor([q // CH for q in pads])).to(DEV)
+    aux = torch.zeros(4, device=DEV)
+    norm2, seg_active = aux[:1], aux[1:].view(torch.int32)
+    seg_step, seg_bc = torch.zeros(3, dtype=torch.int32, device=DEV), torch.zeros(6, device=DEV)
+    g0, g2 = torch.randn(sizes[0], device=DEV) * 3, torch.randn(sizes[2], device=DEV)
+    for step in range(1, 5):
+        gp.zero_()
+        gp[offs[0]:offs[0] + sizes[0]] = g0 * step
+        refs[0].grad, refs[1].grad, refs[2].grad = (g0 * step).clone(), None, None
+        if step >= 2:
+            gp[offs[2]:offs[2] + sizes[2]] = g2 * step
+            refs[2].grad = (g2 * step).clone()
+        torch.nn.utils.clip_grad_norm_(refs, 100.0)
         opt.step()
-        norm2.zero_()
-        nat.grad_sqnorm(gp, norm2)
-        nat.adam_step(p, m, v, gp, norm2, max_norm=100.0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=3e-5, step=step)
-        close(p[:n], ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-6, what=f'step {step}')
+        aux.zero_()
+        nat.grad_sqnorm(gp, norm2, chunk_seg, seg_active)
+        nat.adam_step(p, m, v, gp, norm2, max_norm=100.0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=3e-5,
+                      chunk_seg=chunk_seg, seg_active=seg_active, seg_step=seg_step, seg_bc=seg_bc)
+        for r, o, n in zip(refs, offs, sizes):
+            close(p[o:o + n], r.detach().cpu().numpy(), rtol=1e-5, atol=1e-6, what=f'step {step}')
+    assert seg_step.tolist() == [4, 0, 3]
+    assert torch.equal(p[offs[1]:offs[1] + sizes[1]], refs[1].detach())          # untouched, bit for bit
     # bf16 gradient bucket
     g16 = nat.cast_f32_bf16(gp)
     norm2.zero_()
     nat.grad_sqnorm(g16, norm2)
     close(norm2, np.array([float((g16.float() ** 2).sum())]), rtol=1e-4)
+
+
+def test_optimizer_state_dict_uses_torch_indexing(pkg):
+    """state_dict()['state'] is indexed by the position in the FULL parameter list (frozen prior means / variance in the middle
+    of a cvae's parameters shift the indices of everything after them in torch.optim.Adam), carries per-parameter steps, and a
+    state written that way loads back (module/optimizers.py:57-61 of the reference passes these through to torch)."""
+    torch.manual_seed(0)
+    mk = lambda: pkg.ClassificationVariationalNetwork((1, 8, 8), 5, type='cvae', encoder=[16], decoder=[16], classifier=[],
+                                                      latent_dim=8, latent_sampling=2, gamma=0, sigma={'value': 0.5},
+                                                      prior={'init_mean': 1.0, 'learned_means': False, 'var_dim': 'scalar'},
+                                                      optimizer={'optim_type': 'adam', 'lr': 1e-2}).to(DEV)
+    net = mk()
+    net.train()
+    x, y = torch.rand(6, 1, 8, 8, device=DEV), torch.randint(0, 5, (6,), device=DEV)
+    for _ in range(2):
+        net.train_step(x, y)
+    params = list(net.parameters())
+    sd = net.optimizer.state_dict()
+    assert sd['param_groups'][0]['params'] == list(range(len(params)))
+    frozen = [i for i, q in enumerate(params) if not q.requires_grad]
+    unused = [i for i, (k, q) in enumerate(net.named_parameters()) if k.startswith('classifier')]
+    assert frozen and unused
+    assert all(i not in sd['state'] for i in frozen + unused)          # torch has no state for them either
+    used = [i for i in range(len(params)) if i not in frozen + unused]
+    assert sorted(sd['state']) == used
+    assert all(float(sd['state'][i]['step']) == 2.0 and sd['state'][i]['exp_avg'].shape == params[i].shape for i in used)
+    # the same state loads into torch.optim.Adam built on the same parameter list, and back into a fresh network
+    topt = torch.optim.Adam(params, lr=1e-2)
+    topt.load_state_dict(sd)
+    other = mk()
+    other.load_state_dict(net.state_dict())
+    other.optimizer.load_state_dict(topt.state_dict())
+    other.train()
+    net.encoder.sampling.injected_eps = other.encoder.sampling.injected_eps = torch.randn(3, 6, 8, device=DEV)
+    a, _ = net.train_step(x, y)
+    b, _ = other.train_step(x, y)
+    for (k, q), (_, r) in zip(net.named_parameters(), other.named_parameters()):
+        assert torch.allclose(q, r, rtol=1e-5, atol=1e-6), k
 
 
 def test_layout_kernels(pkg):

@@ -37,9 +37,9 @@ def test_oracle_matches_reference_at_baseline_config(pkg, name):
     kw = fc.CASES[name][0]
     dm = on.batch_dist_measures(ev['logits'], ev['losses'], methods, type='cvae', num_labels=kw['num_labels'])
     for m in methods:
-        if m in ('nstd', 'IYx', 'mag'):      # ill-conditioned in fp32 on both sides: rank order with a margin instead
-            agree, _ = fc.rank_agreement(dm[m], d['eval.measure.' + m], 1e-3)
-            assert agree == 1.0, m
+        if fc.ill_conditioned(m):            # ill-conditioned in fp32 on both sides: rank order beyond a margin instead
+            _, agree, _ = fc.rank_agreement(dm[m], d['eval.measure.' + m], 1e-3)
+            assert agree >= 0.999, m
             continue
         close(dm[m], d['eval.measure.' + m], what='score ' + m)
     for m in json.loads(str(d['eval.predict_methods'])):
