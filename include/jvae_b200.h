@@ -166,9 +166,11 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
  *   writes mu, log_var = clip(raw,-20,20) (B,K) f32; z (L+1,B,K) f32 and optional bf16 copy z_bf16;
  *   eps_out (L,B,K) f32 (slabs 1..L) and eps_norm (L,B).  is_sampled: layers.py:243.
  *   uniform != 0 draws U(-sqrt3, sqrt3) instead (layers.py:237).
+ *   The Philox stream position is offset + *offset_dev (offset_dev: one uint64 on the device, or NULL): a caller that
+ *   advances the device word after every call gets fresh noise from a replayed CUDA graph of the step.
  * ------------------------------------------------------------------------------------------ */
 int jvae_sample_fwd(int B, int L, int K, const float* head, const float* eps_in,
-                    uint64_t seed, uint64_t offset, int is_sampled, int uniform,
+                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int is_sampled, int uniform,
                     float* mu, float* log_var, float* z, void* z_bf16, float* eps_out, float* eps_norm,
                     void* stream);
 /* d_head (B,2K) = [d_mu_direct + sum_l dz | (d_lv_direct + sum_l dz*0.5*exp(lv/2)*eps) * 1[|raw|<=20]] */

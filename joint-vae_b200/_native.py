@@ -79,7 +79,7 @@ def lib():
     L.jvae_elbo_train_fwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 19 + [c_size_t, P]
     L.jvae_elbo_train_bwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 19 + [c_size_t, P]
     L.jvae_elbo_eval_fwd.argtypes = [ctypes.POINTER(ElboCfg)] + [P] * 23 + [c_size_t, P]
-    L.jvae_sample_fwd.argtypes = [c_int, c_int, c_int, P, P, c_u64, c_u64, c_int, c_int, P, P, P, P, P, P, P]
+    L.jvae_sample_fwd.argtypes = [c_int, c_int, c_int, P, P, c_u64, c_u64, P, c_int, c_int, P, P, P, P, P, P, P]
     L.jvae_sample_bwd.argtypes = [c_int, c_int, c_int, P, P, P, P, c_int, P, P, c_int, P, P]
     L.jvae_cast_f32_bf16.argtypes = [P, P, c_size_t, P]
     L.jvae_cast_bf16_f32.argtypes = [P, P, c_size_t, P]
@@ -325,14 +325,14 @@ def elbo_eval_fwd(cfg, x, x_reco, mu, log_var, z, eps_norm, logits, means, inv_t
                 dzdist=dzdist, logits=logits_out, scores=scores, preds=preds)
 
 
-def sample_fwd(head, L, K, eps_in=None, seed=0, offset=0, is_sampled=True, uniform=False, want_bf16=False):
+def sample_fwd(head, L, K, eps_in=None, seed=0, offset=0, is_sampled=True, uniform=False, want_bf16=False, offset_dev=None):
     """head (B,2K) f32 -> mu, log_var (B,K), z (L+1,B,K), z_bf16|None, eps (L,B,K), eps_norm (L,B)"""
     dev = head.device
     B = head.shape[0]
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     mu, lv, z, eps, en = f(B, K), f(B, K), f(L + 1, B, K), f(L, B, K), f(L, B)
     z16 = torch.empty((L + 1, B, K), dtype=torch.bfloat16, device=dev) if want_bf16 else None
-    check(lib().jvae_sample_fwd(B, L, K, ptr(head), ptr(eps_in), seed, offset, int(is_sampled), int(uniform), ptr(mu),
+    check(lib().jvae_sample_fwd(B, L, K, ptr(head), ptr(eps_in), seed, offset, ptr(offset_dev), int(is_sampled), int(uniform), ptr(mu),
                                 ptr(lv), ptr(z), ptr(z16), ptr(eps), ptr(en), stream()))
     return mu, lv, z, z16, eps, en
 

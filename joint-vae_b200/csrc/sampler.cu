@@ -39,12 +39,14 @@ __device__ __forceinline__ float draw(uint64_t seed, uint64_t offset, uint64_t i
 // one CTA per sample b
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_fwd_kernel(int B, int L, int K, const float* __restrict__ head,
                                                                     const float* __restrict__ eps_in, uint64_t seed,
-                                                                    uint64_t offset, int is_sampled, int uniform,
+                                                                    uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                                                                    int is_sampled, int uniform,
                                                                     float* mu_o, float* lv_o, float* z,
                                                                     __nv_bfloat16* z16, float* eps_o, float* eps_norm) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float samp = is_sampled ? 1.f : 0.f;
+  if (offset_dev) offset += *offset_dev;      // stream position kept on the device (CUDA-graph replays draw fresh noise)
   // slab 0 and the clipped head
   for (int k = threadIdx.x; k < K; k += SAMPLE_THREADS) {
     const float m = head[(size_t)b * 2 * K + k];
@@ -108,12 +110,12 @@ using namespace jvae;
 extern "C" {
 
 int jvae_sample_fwd(int B, int L, int K, const float* head, const float* eps_in, uint64_t seed, uint64_t offset,
-                    int is_sampled, int uniform, float* mu, float* log_var, float* z, void* z_bf16, float* eps_out,
-                    float* eps_norm, void* stream) {
+                    const uint64_t* offset_dev, int is_sampled, int uniform, float* mu, float* log_var, float* z, void* z_bf16,
+                    float* eps_out, float* eps_norm, void* stream) {
   JVAE_CHECK_ARG(B > 0 && L >= 0 && K > 0, "B, K > 0 and L >= 0");
   JVAE_CHECK_ARG(head != nullptr, "head is required");
-  sample_fwd_kernel<<<B, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(B, L, K, head, eps_in, seed, offset, is_sampled,
-                                                                     uniform, mu, log_var, z,
+  sample_fwd_kernel<<<B, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(B, L, K, head, eps_in, seed, offset, offset_dev,
+                                                                     is_sampled, uniform, mu, log_var, z,
                                                                      reinterpret_cast<__nv_bfloat16*>(z_bf16), eps_out,
                                                                      eps_norm);
   JVAE_LAUNCH_CHECK();

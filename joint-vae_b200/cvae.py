@@ -37,10 +37,16 @@ VERSION = 2.
 
 
 class _LazyMeasures(Mapping):
-    """total_measures of the reference (python floats, cvae.py:622-762) computed on first access with ONE sync."""
+    """total_measures of the reference (python floats, cvae.py:622-762) computed on first access with ONE sync.
+    `make(batch, current)` builds the thunk for a batch index and the previous running measures, so the same device-side
+    sources can be read again after a replayed step (rebind)."""
 
-    def __init__(self, names, thunk):
-        self._names, self._thunk, self._vals = list(names), thunk, None
+    def __init__(self, names, make, batch=0, current=None):
+        self._names, self._make, self._vals = list(names), make, None
+        self._thunk = make(batch, current or {})
+
+    def rebind(self, batch, current):
+        return _LazyMeasures(self._names, self._make, batch, current)
 
     def _force(self):
         if self._vals is None:
@@ -491,9 +497,8 @@ class ClassificationVariationalNetwork(nn.Module):
         conditional = self.encoder.prior.conditional
         if conditional:
             names += ['ld-norm', 'imut-zy', 'd-mind']
-        current = current or {}
-
-        def thunk():
+        def make(batch, current):
+          def thunk():
             with torch.no_grad():
                 sd = (self.sigma.data if sigma_data is None else sigma_data).float().reshape(-1)[:1]
                 dev = [sd if not self.sigma.is_log else sd.exp(),
@@ -522,8 +527,9 @@ class ClassificationVariationalNetwork(nn.Module):
             if conditional:
                 out['ld-norm'], out['imut-zy'], out['d-mind'] = v[i], v[i + 1], v[i + 2]
             return out
+          return thunk
 
-        return _LazyMeasures(names, thunk)
+        return _LazyMeasures(names, make, batch, current)
 
     # ------------------------------------------------------------------------------------------ predictions / scores
     def predict(self, x, method=None, **kw):
@@ -648,11 +654,21 @@ class ClassificationVariationalNetwork(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------ training
-    def train_step(self, x, y, kl_var_weighting=1., gamma_weighting=1., check_every=0, batch=0, current_measures=None):
+    def train_step(self, x, y, kl_var_weighting=1., gamma_weighting=1., check_every=0, batch=0, current_measures=None,
+                   graph=False):
         """One optimisation step = the body of the reference's batch loop (cvae.py:2427-2461): zero_grad, evaluate with
         beta (batch index and the epoch's running measures passed through, cvae.py:2441-2449), backward of total.mean(),
         clip, Adam.  No host sync unless check_every divides the step count, in which case the device-side finite flag
-        replaces the reference's per-parameter isnan scan (cvae.py:2454-2457)."""
+        replaces the reference's per-parameter isnan scan (cvae.py:2454-2457).
+        graph=True: the same step replayed from a CUDA graph (captured on the third call with a given batch shape /
+        weighting / learning rate; the first two run eagerly), which removes the ~180 kernel launches' host cost per step.
+        Every per-step quantity lives on the device (Adam step counts, Philox position, BatchNorm counters), so a replay
+        is the same arithmetic as an eager step."""
+        if graph and self._graph_ok(x):
+            return self._train_step_graphed(x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures)
+        return self._train_step_eager(x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures)
+
+    def _train_step_eager(self, x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures):
         self.optimizer.zero_grad()
         _, _, losses, measures = self.evaluate(x, y, batch=batch, current_measures=current_measures, with_beta=True,
                                                kl_var_weighting=kl_var_weighting, gamma_weighting=gamma_weighting)
@@ -665,12 +681,47 @@ class ClassificationVariationalNetwork(nn.Module):
             raise FloatingPointError('non-finite loss at step {}'.format(self._steps))
         return losses, measures
 
+    def _graph_ok(self, x):
+        """steps a replayed graph reproduces: Philox noise (an injected tensor would be frozen into the graph), the fused
+        Adam (its state is on the device), sigma not updated from the host, a single process (the NCCL all-reduce of the
+        data-parallel step stays eager)"""
+        opt = self.optimizer
+        return (x.is_cuda and self.encoder.sampling.injected_eps is None and opt._opt is None and opt.allreduce is None
+                and not (self.sigma.decay and not self.sigma.learned) and not self.sigma.coded)
+
+    def _train_step_graphed(self, x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures):
+        key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, float(kl_var_weighting), float(gamma_weighting),
+               float(self.optimizer.lr), self.latent_sampling, str(x.device), self.optimizer.grad_clipping)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        st = graphs.setdefault(key, {'calls': 0})
+        st['calls'] += 1
+        if 'graph' not in st:
+            if st['calls'] <= 2:       # eager: every lazy initialisation (flat buffers, packing tables, workspaces) happens here
+                return self._train_step_eager(x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures)
+            sx, sy = x.clone(), y.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):      # records the step on a side stream; nothing executes yet
+                losses, measures = self._train_step_eager(sx, sy, kl_var_weighting, gamma_weighting, 0, 0, None)
+            self._steps -= 1
+            st.update(graph=g, x=sx, y=sy, losses=losses, measures=measures, flag=self._finite_flag)
+        st['x'].copy_(x, non_blocking=True)
+        st['y'].copy_(y, non_blocking=True)
+        st['graph'].replay()
+        self._steps += 1
+        self._finite_flag = st['flag']
+        engine.bump_params()           # the replay rewrote parameters and BatchNorm statistics behind every version counter
+        engine.bump_stats()
+        if check_every and self._steps % check_every == 0 and int(self._finite_flag.item()) == 0:
+            raise FloatingPointError('non-finite loss at step {}'.format(self._steps))
+        return st['losses'], st['measures'].rebind(batch, current_measures)
+
     @staticmethod
     def warmup_weighting(epoch, warmup):
         """cvae.py:2432-2433: the ramp of the KL variance term / of gamma at `epoch` (0-based) for warmup = (w0, w1)"""
         return max(0., min(1., (epoch + 1 - warmup[0]) / (warmup[1] + 1)))
 
-    def train_model(self, batches, epochs=1, warmup=(0, 0), warmup_gamma=(0, 0), check_every=100, on_batch=None):
+    def train_model(self, batches, epochs=1, warmup=(0, 0), warmup_gamma=(0, 0), check_every=100, on_batch=None, graph=False):
         """Epoch loop over an iterable of (x, y) device batches with the reference's warm-up ramps for the KL variance
         term and gamma, the per-epoch running measures (batch index i and the previous batch's measures feed the next
         evaluate) and the per-epoch mean losses of the history (cvae.py:2293, 2402-2493).  The loss means accumulate on
@@ -685,7 +736,7 @@ class ClassificationVariationalNetwork(nn.Module):
             measures, sums, n = {}, None, 0
             for i, (x, y) in enumerate(batches):
                 losses, measures = self.train_step(x, y, kl_var_weighting=kw, gamma_weighting=gw, check_every=check_every,
-                                                   batch=i, current_measures=measures)
+                                                   batch=i, current_measures=measures, graph=graph)
                 vec = torch.stack([v.detach().float().mean() for v in losses.values()])
                 sums = vec if sums is None else sums + vec
                 keys, n = list(losses), n + 1

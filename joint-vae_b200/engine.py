@@ -4,7 +4,6 @@ Everything here is host plumbing (PyTorch owns tensors, autograd graph and strea
 csrc/*.cu, reached through _native (ctypes, C ABI).  There is ONE execution path: a layer without a native sm_100a
 kernel raises NotImplementedError (no vendor-library or eager fallback, no backend switch).
 """
-import itertools
 import weakref
 
 import torch
@@ -12,7 +11,7 @@ from torch import nn
 
 from . import _native as nat
 
-_rng_offset = itertools.count(1)
+_rng_counters = {}      # device -> int64[1]: position of the sampler's Philox stream
 
 # Parameter epochs.  The fused Adam (csrc/optim.cu) and the BatchNorm kernels (running statistics) write parameters and
 # buffers through raw pointers, which autograd's version counters never see.  Every cache of derived weights (bf16
@@ -201,8 +200,15 @@ class _SampleFn(torch.autograd.Function):
     def forward(ctx, head, eps_in, L, is_sampled, uniform, seed, offset):
         K = head.shape[1] // 2
         head = nat.f32c(head.detach())
+        ctr = None
+        if eps_in is None:      # Philox stream position on the device, advanced after every draw (graph replays stay fresh)
+            ctr = _rng_counters.get(head.device)
+            if ctr is None:
+                ctr = _rng_counters[head.device] = torch.zeros(1, dtype=torch.int64, device=head.device)
         mu, lv, z, _, eps, en = nat.sample_fwd(head, L, K, eps_in=nat.f32c(eps_in), seed=seed, offset=offset,
-                                               is_sampled=is_sampled, uniform=uniform)
+                                               is_sampled=is_sampled, uniform=uniform, offset_dev=ctr)
+        if ctr is not None:
+            ctr.add_(1)
         ctx.save_for_backward(head, lv, eps)
         ctx.dims = (L, K, is_sampled)
         ctx.mark_non_differentiable(eps, en)
@@ -226,7 +232,7 @@ def sample(head, L, eps_in=None, is_sampled=True, uniform=False):
     if not head.is_cuda:
         raise nat.NativeError('joint-vae_b200 runs on CUDA devices only (there is no CPU fallback); got a CPU tensor')
     seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    return _SampleFn.apply(head, eps_in, L, is_sampled, uniform, seed, next(_rng_offset))
+    return _SampleFn.apply(head, eps_in, L, is_sampled, uniform, seed, 0)
 
 
 # --------------------------------------------------------------------------------------------- fused ELBO

@@ -1,0 +1,52 @@
+"""train_step(graph=True): the optimisation step replayed from a CUDA graph is the same arithmetic as the eager step -- Adam's
+per-parameter step counts, the Philox position of the sampler and the BatchNorm counters live on the device, so nothing is
+frozen into the graph.  Two identical networks, same seed and Philox position: one steps eagerly, the other through the graph
+(two eager calls, capture, replays); parameters, BatchNorm statistics and losses must agree to the round-off of fp32 atomics."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _net(pkg):
+    torch.manual_seed(0)
+    return pkg.ClassificationVariationalNetwork(
+        (3, 16, 16), 4, type='cvae', features='[x3+1]8-8-M-16:2-16', upsampler='[x3+1]16x4+0-16-8:2++1-8:2++1-!3x3+1',
+        batch_norm='both', encoder=[], decoder=[], classifier=[], latent_dim=16, latent_sampling=3, gamma=0, beta=1.0,
+        output_activation='linear', sigma={'value': 1.0, 'learned': True},
+        prior={'init_mean': 1.0, 'learned_means': True, 'var_dim': 'scalar', 'seed': 8},
+        optimizer={'optim_type': 'adam', 'lr': 3e-3, 'weight_decay': 3e-5, 'grad_clipping': 100}).to(DEV)
+
+
+def test_graphed_steps_equal_eager_steps(pkg):
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.rand(32, 3, 16, 16, generator=g).to(DEV) for _ in range(7)]
+    ys = [torch.randint(0, 4, (32,), generator=g).to(DEV) for _ in range(7)]
+    out = {}
+    for mode in ('eager', 'graph'):
+        net = _net(pkg)
+        net.train()
+        for c in pkg.engine._rng_counters.values():
+            c.zero_()
+        losses, cur = [], {}
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            ls, cur = net.train_step(x, y, batch=i, current_measures=cur, graph=(mode == 'graph'))
+            losses.append(ls['total'].detach().clone())
+            meas = dict(cur)
+        if mode == 'graph':
+            assert any('graph' in st for st in net._graphs.values()), 'the step was never captured'
+        net.eval()
+        with torch.no_grad():
+            net.encoder.sampling.injected_eps = torch.zeros(4, 32, 16, device=DEV)
+            _, _, ev, _ = net.evaluate(xs[0])
+        out[mode] = (losses, {k: v.detach().clone() for k, v in net.state_dict().items()}, meas, ev['total'].clone())
+    (la, sa, ma, ea), (lb, sb, mb, eb) = out['eager'], out['graph']
+    for i, (a, b) in enumerate(zip(la, lb)):
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-3), (i, float((a - b).abs().max()))
+    for k in sa:
+        assert torch.allclose(sa[k].float(), sb[k].float(), rtol=1e-3, atol=2e-5), (k, float((sa[k].float() - sb[k].float()).abs().max()))
+    for k in ma:
+        assert abs(ma[k] - mb[k]) <= 1e-3 * max(1.0, abs(ma[k])), (k, ma[k], mb[k])
+    # evaluation after graphed training reads the replayed parameters / running statistics (folded copies refreshed)
+    assert torch.allclose(ea, eb, rtol=2e-4, atol=1e-2)

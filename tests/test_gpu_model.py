@@ -164,8 +164,8 @@ def _eval(pkg, net, d, cfg, x, tol):
             want = d['eval.measure.' + m]
             got = dm[m].float().cpu().numpy()
             # rank order (what OOD / misclassification ROC curves see): the reference's on every pair of samples whose
-            # reference scores differ by more than 1e-3 x scale
-            every, beyond, frac = rank_agreement(got, want, 1e-3)
+            # reference scores differ by more than 1e-2 x scale (half of what the value tolerance guarantees)
+            every, beyond, frac = rank_agreement(got, want, 1e-2)
             if ill_conditioned(m):      # functions of near-equal exponentials: loosely bounded
                 assert beyond >= 0.9, (m, every, beyond)
                 continue

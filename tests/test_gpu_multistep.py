@@ -128,8 +128,10 @@ def test_adam_steps_then_eval_match_reference(pkg, name):
         for m, got in preds.items():
             ref = d[f'{tag}.loss.' + ('iws' if m == 'iws' else 'zdist')].astype(np.float64)
             srt = np.sort(ref if m == 'closest' else -ref, axis=0)
-            clear = (srt[1] - srt[0]) > 2 * 2e-2 * np.maximum(1.0, np.abs(srt[0]))
-            assert clear.any()
+            r = ref if m == 'closest' else -ref
+            # margin against the part of the loss that differs between classes (the reconstruction term is common to all)
+            clear = (srt[1] - srt[0]) > 2 * 2e-2 * np.maximum(1.0, np.abs(r - r.mean(0)).max(0))
+            assert clear.mean() > 0.2, clear.mean()
             assert (got[clear] == d[f'{tag}.pred.{m}'][clear]).all(), (tag, m)
 
 
