@@ -276,6 +276,8 @@ def run_native(args, wl):
         step_dev(i)
     # ---- device-resident timing (value); per-launch CUDA events around the fused ELBO kernels and every convolution launch
     # (eager steps: per-launch events cannot be recorded inside a replayed graph)
+    for i in range(2):          # the capture above emptied the caching allocator: let the eager pools settle again
+        step_eager(i)
     nat.PROFILE = {'elbo_train_fwd': [], 'elbo_train_bwd': [], 'conv': []}
     n0 = nat.launch_count()
     ms_eager = timed(step_eager, args.steps)

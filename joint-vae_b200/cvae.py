@@ -696,12 +696,21 @@ class ClassificationVariationalNetwork(nn.Module):
         st = graphs.setdefault(key, {'calls': 0})
         st['calls'] += 1
         if 'graph' not in st:
+            # The warm-up steps and the capture share ONE side stream: autograd's AccumulateGrad nodes remember the stream they
+            # were created on, and a node created on the default stream would pull the capture across streams.
+            side = self.__dict__.setdefault('_graph_stream', None) or torch.cuda.Stream(device=x.device)
+            self._graph_stream = side
+            cur = torch.cuda.current_stream(x.device)
+            side.wait_stream(cur)
             if st['calls'] <= 2:       # eager: every lazy initialisation (flat buffers, packing tables, workspaces) happens here
-                return self._train_step_eager(x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures)
+                with torch.cuda.stream(side):
+                    out = self._train_step_eager(x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures)
+                cur.wait_stream(side)
+                return out
             sx, sy = x.clone(), y.clone()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):      # records the step on a side stream; nothing executes yet
+            with torch.cuda.graph(g, stream=side):      # records the step; nothing executes yet
                 losses, measures = self._train_step_eager(sx, sy, kl_var_weighting, gamma_weighting, 0, 0, None)
             self._steps -= 1
             st.update(graph=g, x=sx, y=sy, losses=losses, measures=measures, flag=self._finite_flag)
