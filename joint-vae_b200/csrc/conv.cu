@@ -273,6 +273,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 // in exchange the input is read from L2 ~1.7x instead of 25x (k = 5), and the layer's weights stay resident in shared
 // memory (or stream per tap when they do not fit, amortised over the MT M-tiles of the box).
 // ------------------------------------------------------------------------------------------------
+constexpr int HALO_MAX_CK = 128;
 struct HaloParams {
   int N, Hq, Wq;
   int RT, NBt, HHs, HWp, MT;            // rows / images per box, slots per image, halo width (pixels), M-tiles per box
@@ -299,6 +300,15 @@ struct HaloParams {
   int ystages;
   uint32_t stage_bytes, box_bytes, w_tap_bytes, w_bytes, tmem_cols, acc_stride;
   int stages, resident, wstages;
+  // Vertical tap stacking (G > 1): one M row stands for G consecutive output rows (slots) of one pixel column; the N side of an
+  // MMA stacks the weights of up to G vertically adjacent taps, D[(row group, px)][(j, co)] += X[slot g*G + u][px + x][ci] *
+  // W[tap (e = u - j, x)][co][ci] for every j that has such a tap.  An MMA then does count * BN columns instead of BN for the
+  // same A-operand fetch, which is what bounds the N <= 64 layers.  Chunks = (plane, x, u) triples.
+  int G, nck;
+  uint32_t ck_a16[HALO_MAX_CK];          // A start shift: (plane * plane_bytes + (u * HWp + x) * row bytes) / 16
+  unsigned short ck_b16[HALO_MAX_CK];    // B start shift: position of the chunk's first tap block * w_tap_bytes / 16
+  unsigned char ck_cnt[HALO_MAX_CK], ck_j0[HALO_MAX_CK], ck_fresh[HALO_MAX_CK];
+  short w_pos[CONV_MAX_TAPS];            // position of tap t's weight block in shared memory (resident weights)
 };
 
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
@@ -333,6 +343,27 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
     } else {
       umma_commit(&wempty_bar[ws]);
       if (++ws == (uint32_t)p.wstages) { ws = 0; wph ^= 1; }
+    }
+  }
+}
+
+// All MMAs of one box with vertical tap stacking (HaloParams::G > 1): M-tiles outer, chunks inner.  The chunks flagged fresh come
+// first and cover every column block of the tile exactly once (they overwrite), the others accumulate.
+template <int KSTEPS>
+__device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0, uint32_t a_hi, uint32_t a_lo0, uint32_t m_step16,
+                                               uint32_t b_hi, uint32_t b_lo_base, uint32_t idesc0) {
+  const uint32_t gbn = (uint32_t)(p.G * p.BN);
+  for (int m = 0; m < p.MT; ++m) {
+    const uint32_t a_m = a_lo0 + (uint32_t)m * m_step16;
+    const uint32_t d_m = d0 + (uint32_t)m * gbn;
+    for (int c = 0; c < p.nck; ++c) {
+      const uint32_t a_lo = a_m + p.ck_a16[c], b_lo = b_lo_base + p.ck_b16[c];
+      const uint32_t d = d_m + (uint32_t)p.ck_j0[c] * (uint32_t)p.BN;
+      const uint32_t idesc = idesc0 | ((((uint32_t)p.ck_cnt[c] * (uint32_t)p.BN) >> 3) << 17);
+      const uint32_t acc0 = p.ck_fresh[c] ? 0u : 1u;
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k)
+        umma_bf16(d, desc64(a_hi, a_lo + 2u * k), desc64(b_hi, b_lo + 2u * k), idesc, k == 0 ? acc0 : 1u);
     }
   }
 }
@@ -458,20 +489,22 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
     if (p.bn_y) mbar_wait(&yfull_bar[ys], (it / p.ystages) & 1);
     mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
     tc_fence_after();
-    int slot = mrow >> 3;
-    for (int m = 0; m < p.MT; ++m, slot += 16) {
-      const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
-      const int qy = by * p.RT + yy, n = mm * p.NBt + nb;
-      const bool ok = (nb < p.NBt) && (yy < p.RT) && (qy < p.Hq) && (qx < p.Wq) && (n < p.N);
-      const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
-      const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
-      __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
-      float* orow_f = p.out_f32 ? reinterpret_cast<float*>(p.out) + opix * p.ldc + (size_t)ch0 : nullptr;
-      // row (128 m + mrow) of the y tile in shared memory: BN channels of the pixel this thread owns
-      const __nv_bfloat16* yrow = p.bn_y ? reinterpret_cast<const __nv_bfloat16*>(ysm + (size_t)ys * p.y_stage_bytes) +
-                                               (size_t)(m * 128 + mrow) * p.BN : nullptr;
-      const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(m * p.BN) + ((uint32_t)(q * 32) << 16);
-      halo_epilogue_tile<NCH>(p, t_addr, ok, orow, orow_f, ch0, s_bias, s_bn, yrow, s1, s2);
+    for (int m = 0; m < p.MT; ++m) {
+      for (int j = 0; j < p.G; ++j) {        // G = 1: one output row per M row; G > 1: column block j of the row group
+        const int slot = (m * 16 + (mrow >> 3)) * p.G + j;
+        const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
+        const int qy = by * p.RT + yy, n = mm * p.NBt + nb;
+        const bool ok = (nb < p.NBt) && (yy < p.RT) && (qy < p.Hq) && (qx < p.Wq) && (n < p.N);
+        const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
+        const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+        __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
+        float* orow_f = p.out_f32 ? reinterpret_cast<float*>(p.out) + opix * p.ldc + (size_t)ch0 : nullptr;
+        // row (128 m + mrow) of the y tile in shared memory: BN channels of the pixel this thread owns (G = 1 only)
+        const __nv_bfloat16* yrow = p.bn_y ? reinterpret_cast<const __nv_bfloat16*>(ysm + (size_t)ys * p.y_stage_bytes) +
+                                                 (size_t)(m * 128 + mrow) * p.BN : nullptr;
+        const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)((m * p.G + j) * p.BN) + ((uint32_t)(q * 32) << 16);
+        halo_epilogue_tile<NCH>(p, t_addr, ok, orow, orow_f, ch0, s_bias, s_bn, yrow, s1, s2);
+      }
     }
     tc_fence_before();
     __syncwarp();
@@ -565,7 +598,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       if (p.resident) {
         mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
         for (int t = 0; t < p.ntaps; ++t)
-          tma_load_2d(wsm + (size_t)t * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
+          tma_load_2d(wsm + (size_t)(p.G > 1 ? p.w_pos[t] : t) * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
       }
       auto load_box = [&](int box, uint32_t it) {
         int m = box;
@@ -604,7 +637,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
       const uint32_t idesc = make_idesc_bf16(128, p.BN, false, false);
       const uint32_t swz = (p.Cblk == 64) ? SWZ_128B : (p.Cblk == 32 ? SWZ_64B : SWZ_32B);
-      const uint32_t sbo_a = (uint32_t)p.HWp * rb, sbo_b = 8u * rb;
+      const uint32_t sbo_a = (uint32_t)(p.G * p.HWp) * rb, sbo_b = 8u * rb;      // 8-row groups of A: one slot (row group) apart
       // descriptor words: lo = start >> 4 | LBO(16 B) << 16; hi = SBO >> 4 | version 1 << 14 | swizzle << 29
       const uint32_t a_hi = ((sbo_a >> 4) & 0x3fffu) | (1u << 14) | (swz << 29);
       const uint32_t b_hi = ((sbo_b >> 4) & 0x3fffu) | (1u << 14) | (swz << 29);
@@ -629,7 +662,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           case 4: HALO_BOX(KS, 4); break;                                              \
           default: HALO_BOX(KS, 5); break;                                             \
         }
-        if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
+        if (p.G > 1) {
+          const uint32_t idesc0 = make_idesc_bf16(128, 0, false, false);
+          if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+          else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+          else halo_mma_box_g<1>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+        } else if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
 #undef HALO_BOX_M
 #undef HALO_BOX
         umma_commit(&empty_bar[s]);
@@ -989,39 +1027,126 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   const uint32_t budget = 200u * 1024u;
   const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 8u : 0u;
   const uint32_t w_res = (uint32_t)ntaps * p.w_tap_bytes;
-  // best (NBt) for resident and streamed weights
-  double best_eff = 0.0;
-  for (int resident = 1; resident >= 0; --resident) {
-    const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
-    for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
-      const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
-      const uint32_t plane = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
-      const uint32_t stage = plane * (uint32_t)p.nplanes;
-      const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
-      if (pow2_ceil(2 * MT * p.BN) > 512) break;
-      if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage > budget) break;
-      if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
-      const double eff = (double)(nbt * p.RT) / (16.0 * MT) * (resident ? 1.0 : 0.97);
-      if (eff > best_eff + 0.02) {
-        best_eff = eff; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
-        p.w_bytes = wb; p.y_stage_bytes = ystage;
-      }
-    }
-    if (best_eff > 0.0 && resident) break;               // resident weights fit: take them
+  const int ksteps = p.Cblk >> 4;
+  // modelled cycles of one 128 x n x 16 MMA with both operands in shared memory (measured: profiles/r01_umma_rate_probe.txt):
+  // the tensor pipe needs n / 2, the operand fetch (4 KB of A + 32 n bytes of B at 128 B / cycle) 32 + n / 4
+  auto mma_cycles = [](int n) { const double t = n / 2.0, f = 32.0 + n / 4.0; return t > f ? t : f; };
+
+  // ---- tap rectangles per parity plane (vertical stacking needs, for every tap column, a contiguous run of tap rows)
+  struct Col { int pl, x, e_lo, e_hi; };
+  std::vector<Col> cols;
+  bool stackable = bn == nullptr && getenv("JVAE_CONV_NOSTACK") == nullptr;
+  for (int t = 0; t < ntaps && stackable; ++t) {
+    const int x = tex[t] - dxmin, e = tey[t] - dymin;
+    Col* c = nullptr;
+    for (auto& q : cols) if (q.pl == tpl[t] && q.x == x) c = &q;
+    if (!c) { cols.push_back({tpl[t], x, e, e}); continue; }
+    c->e_lo = min(c->e_lo, e); c->e_hi = max(c->e_hi, e);
   }
-  if (best_eff <= 0.0) return 1;
+  if (stackable) {
+    int covered = 0;
+    for (auto& q : cols) covered += q.e_hi - q.e_lo + 1;
+    stackable = covered == ntaps;                          // no holes, no duplicates
+  }
+
+  // ---- choose (G, resident, images per box): most useful output rows per modelled MMA cycle
+  double best = 0.0;
+  int bestG = 1;
+  uint32_t best_extent = 0;
+  for (int G = 1; G <= 8; ++G) {
+    if (G > 1 && (!stackable || G * p.BN > 256)) break;
+    for (int resident = 1; resident >= 0; --resident) {
+      if (G > 1 && !resident) continue;
+      const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
+      bool found = false;
+      for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
+        const int S = nbt * p.HHs;
+        const int groups = (S - ey + G - 1) / G, MT = (groups + 15) / 16;
+        if (nbt > 1 && p.RT < Hq) break;                   // several row blocks per image: one image per box
+        if (pow2_ceil(2 * MT * G * p.BN) > 512) break;
+        // a plane holds the box; the MMAs of the last (partly filled) M-tile read up to slot 16 MT G + ey - 1: past the box they
+        // fetch whatever follows in shared memory (the next plane / stage / the weights) into rows that are discarded, so only
+        // the END of the last stage's last plane has to stay inside the allocation
+        const uint32_t plane = G == 1 ? (((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u)
+                                      : (((uint32_t)S * p.HWp * rb + 1023u) & ~1023u);
+        const uint32_t extent = (uint32_t)(16 * MT * G + ey) * p.HWp * rb;      // bytes an M-tile sweep can touch in a plane
+        const uint32_t stage = plane * (uint32_t)p.nplanes;
+        const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
+        const uint32_t over = extent > plane ? extent - plane : 0u;             // overshoot of the very last plane
+        const uint32_t tail = over > wb + 3u * ystage ? over - wb - 3u * ystage : 0u;
+        if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail > budget + (G > 1 ? 20u * 1024u : 0u)) break;
+        double cyc = 0.0;
+        if (G == 1) cyc = (double)MT * ntaps * ksteps * mma_cycles(p.BN) * (resident ? 1.0 : 1.03);
+        else
+          for (auto& q : cols)
+            for (int u = q.e_lo; u <= q.e_hi + G - 1; ++u) {
+              const int j0 = max(0, u - q.e_hi), j1 = min(G - 1, u - q.e_lo);
+              cyc += (double)MT * ksteps * mma_cycles((j1 - j0 + 1) * p.BN);
+            }
+        const double score = (double)(nbt * p.RT) / cyc;
+        if (score > best * 1.02) {
+          best = score; bestG = G; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
+          p.w_bytes = wb + tail; p.y_stage_bytes = ystage; best_extent = extent;
+        }
+        found = true;
+      }
+      if (found && resident) break;                        // resident weights fit: take them
+    }
+  }
+  if (best <= 0.0) return 1;
+  p.G = bestG;
+  (void)best_extent;
   p.wstages = p.resident ? 1 : 4;
-  if ((size_t)p.stage_bytes + (size_t)p.HWp * rb * 16 >= (1u << 18)) return 1;        // descriptor start field is 14 bits of 16 B
+  if ((size_t)p.stage_bytes + (size_t)(p.G * p.HWp) * rb * 16 >= (1u << 18)) return 1;      // descriptor start field is 14 bits of 16 B
+  if (((uint32_t)(p.G * p.HWp) * rb >> 4) > 0x3fffu) return 1;                              // SBO field
   for (int t = 0; t < ntaps; ++t)
     p.tap_off16[t] = ((uint32_t)tpl[t] * p.plane_bytes + (uint32_t)((tey[t] - dymin) * p.HWp + (tex[t] - dxmin)) * rb) >> 4;
+  if (p.G > 1) {
+    // weight blocks in shared memory: per tap column, rows of taps DESCENDING (the column block j of a chunk reads tap e = u - j)
+    int pos = 0, nck = 0;
+    std::vector<int> col_base(cols.size());
+    for (size_t ci = 0; ci < cols.size(); ++ci) {
+      col_base[ci] = pos;
+      for (int t = 0; t < ntaps; ++t)
+        if (tpl[t] == cols[ci].pl && tex[t] - dxmin == cols[ci].x) p.w_pos[t] = (short)(pos + cols[ci].e_hi - (tey[t] - dymin));
+      pos += cols[ci].e_hi - cols[ci].e_lo + 1;
+    }
+    auto add_chunk = [&](size_t ci, int u, int fresh) {
+      const Col& q = cols[ci];
+      const int j0 = max(0, u - q.e_hi), j1 = min(p.G - 1, u - q.e_lo);
+      p.ck_a16[nck] = ((uint32_t)q.pl * p.plane_bytes + (uint32_t)(u * p.HWp + q.x) * rb) >> 4;
+      p.ck_b16[nck] = (unsigned short)(((uint32_t)(col_base[ci] + q.e_hi - (u - j0)) * p.w_tap_bytes) >> 4);
+      p.ck_cnt[nck] = (unsigned char)(j1 - j0 + 1); p.ck_j0[nck] = (unsigned char)j0; p.ck_fresh[nck] = (unsigned char)fresh;
+      ++nck;
+    };
+    // fresh chunks: a disjoint cover of the G column blocks out of the first tap column
+    std::vector<int> fresh_u;
+    for (int jn = 0; jn < p.G;) {
+      const int u = jn + cols[0].e_hi;
+      fresh_u.push_back(u);
+      jn = min(p.G - 1, u - cols[0].e_lo) + 1;
+    }
+    for (int u : fresh_u) add_chunk(0, u, 1);
+    for (size_t ci = 0; ci < cols.size(); ++ci)
+      for (int u = cols[ci].e_lo; u <= cols[ci].e_hi + p.G - 1; ++u) {
+        if (ci == 0 && std::find(fresh_u.begin(), fresh_u.end(), u) != fresh_u.end()) continue;
+        if (nck >= HALO_MAX_CK) return 1;
+        add_chunk(ci, u, 0);
+      }
+    p.nck = nck;
+    if ((((uint32_t)pos * p.w_tap_bytes) >> 4) > 0xffffu) return 1;
+  }
   p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
   p.ystages = bn ? 3 : 0;
   p.y_box_bytes = bn ? (uint32_t)(p.NBt * p.HHs) * 8u * (uint32_t)p.BN * 2u : 0u;
-  p.stages = (int)((budget - p.w_bytes - stats_bytes - 1792u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
+  {
+    const uint32_t bud = budget + (p.G > 1 ? 20u * 1024u : 0u);
+    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
+  }
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
-  p.acc_stride = (uint32_t)(p.MT * p.BN);
-  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.MT * p.BN < 32 ? 32 : 2 * p.MT * p.BN);
+  p.acc_stride = (uint32_t)(p.MT * p.G * p.BN);
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.MT * p.G * p.BN < 32 ? 32 : 2 * p.MT * p.G * p.BN);
   p.strips_x = (Wq + 7) / 8; p.blocks_y = (Hq + p.RT - 1) / p.RT; p.blocks_n = (N + p.NBt - 1) / p.NBt;
   p.num_boxes = p.strips_x * p.blocks_y * p.blocks_n;
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
