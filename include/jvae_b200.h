@@ -398,6 +398,9 @@ int jvae_selftest(int verbose);
 int jvae_probe_descriptors(int verbose);
 /* diagnostic: measured cycles per tcgen05.mma for small N and for 1..8 independent accumulators (prints a table) */
 int jvae_probe_mma_rate(void);
+/* diagnostic: fills the shared memory and TMEM of every SM with `pattern` (tests use it to show that no kernel result depends on
+ * what an earlier kernel left on the SM) */
+int jvae_probe_poison(unsigned pattern, void* stream);
 
 #ifdef __cplusplus
 }

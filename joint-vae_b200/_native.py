@@ -94,6 +94,7 @@ def lib():
     L.jvae_gemm_bf16.argtypes = [c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, P, c_int, P]
     L.jvae_selftest.argtypes = [c_int]
     L.jvae_probe_descriptors.argtypes = [c_int]
+    L.jvae_probe_poison.argtypes = [ctypes.c_uint, P]
     I16P = ctypes.POINTER(ctypes.c_int16)
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
                                         c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int,

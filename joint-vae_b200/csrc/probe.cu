@@ -194,3 +194,37 @@ int probe_mma_rate() {
 }  // namespace jvae
 
 extern "C" int jvae_probe_mma_rate(void) { return jvae::probe_mma_rate(); }
+
+// ------------------------------------------------------------------------------------------------
+// Poison probe: fills the shared memory (220 KB per SM) and all 512 TMEM columns of every SM with a bit pattern, so that
+// a kernel whose results depend on whatever a previous kernel left there shows up as a difference between two patterns.
+namespace jvae {
+__global__ void __launch_bounds__(128, 1) probe_poison_kernel(uint32_t pattern, int nwords) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_slot;
+  uint32_t* w = reinterpret_cast<uint32_t*>(smem_raw);
+  for (int i = threadIdx.x; i < nwords; i += 128) w[i] = pattern;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  for (int c = 0; c < 512; c += 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c), "r"(pattern) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+}  // namespace jvae
+
+extern "C" int jvae_probe_poison(unsigned pattern, void* stream) {
+  static bool attr = false;
+  const int bytes = 220 * 1024;
+  if (!attr) { cudaFuncSetAttribute(jvae::probe_poison_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); attr = true; }
+  jvae::probe_poison_kernel<<<148 * 4, 128, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(pattern, bytes / 4);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
