@@ -62,16 +62,31 @@ struct ElboArgs {
   float* tdiag;             // (Cp, K)
   float* full_dist;         // train: (B); eval: (L+1, Cp, B)
   float* d_full_T;          // (Cp, K, K) gradient
+  // eval with many classes: the cross terms z_r . m_c of the norm-expanded distances come from ONE tcgen05 GEMM (operands split
+  // into bf16 hi / lo parts, three products, fp32 accumulation) run before the kernel; cross[(r * B + b) * cross_ld + c]
+  const float* cross;
+  const float* mnorm;       // (Cp) ||m_c||^2
+  int cross_ld;
   // TMA-staged train forward
   int tma_lg, tma_stages;
   unsigned int tma_stage_bytes;
 };
 
 struct WsLayout {
-  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, ce, tdiag, full_dist, total;
+  size_t counters, dnv, zero_bytes, mse, dict_mean, logdet, lat, ce, tdiag, full_dist, tc_a, tc_b, tc_cross, tc_mnorm, total;
+  int tc_ld, tc_cpad;
 };
+// classes from which the eval kernel takes its distances from the tensor-core cross-term GEMM (JVAE_ELBO_TC_MINC overrides)
+static int tc_min_classes() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JVAE_ELBO_TC_MINC"); v = e ? atoi(e) : 32; if (v < 1) v = 1; }
+  return v;
+}
+static bool tc_eligible(int K, int Cp, int var_dim, int prior_kind, int conditional) {
+  return conditional && var_dim == JVAE_VAR_SCALAR && prior_kind == JVAE_PRIOR_GAUSSIAN && (K % 8) == 0 && Cp >= tc_min_classes();
+}
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false) {
+static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false, bool tc = false) {
   WsLayout w;
   w.counters = 0;
   w.zero_bytes = (size_t)B * 4;
@@ -83,7 +98,14 @@ static WsLayout ws_layout(int B, int L, int K, int Cp, bool full = false) {
   w.ce = w.lat + align256((size_t)B * 16);
   w.tdiag = w.ce + align256((size_t)(L > 0 ? L : 1) * B * 4);
   w.full_dist = w.tdiag + (full ? align256((size_t)Cp * K * 4) : 0);
-  w.total = w.full_dist + (full ? align256((size_t)(L + 1) * Cp * B * 4) : 0);
+  w.tc_a = w.full_dist + (full ? align256((size_t)(L + 1) * Cp * B * 4) : 0);
+  w.tc_cpad = (Cp + 63) & ~63;                 // rows of the class operand (whole 64-row TMA boxes stay inside the buffer)
+  w.tc_ld = (Cp + 3) & ~3;
+  const size_t R = (size_t)(L + 1) * B;
+  w.tc_b = w.tc_a + (tc ? align256(R * 3 * K * 2) : 0);
+  w.tc_cross = w.tc_b + (tc ? align256((size_t)w.tc_cpad * 3 * K * 2) : 0);
+  w.tc_mnorm = w.tc_cross + (tc ? align256(R * w.tc_ld * 4) : 0);
+  w.total = w.tc_mnorm + (tc ? align256((size_t)Cp * 4) : 0);
   return w;
 }
 
@@ -979,6 +1001,35 @@ __device__ __forceinline__ int block_first_index(const float* v, int n, float ta
   return r;
 }
 
+// Operands of the cross-term GEMM (eval with many classes).  A value v is split as hi = bf16(v), lo = bf16(v - hi); rows of
+// the sample operand hold [hi | lo | hi], rows of the class operand [hi | hi | lo], so one bf16 GEMM over 3K columns returns
+// hi.hi + lo.hi + hi.lo (the dropped lo.lo term is 2^-16 of a product).  blockIdx.x < R: row r * B + b of (mu; z[1..L]);
+// then one block per class, which also leaves ||m_c||^2 in fp32.
+__global__ void __launch_bounds__(128) dist_split_kernel(const float* __restrict__ mu, const float* __restrict__ z,
+                                                         const float* __restrict__ means, int R, int B, int K, int Cp,
+                                                         __nv_bfloat16* __restrict__ xa, __nv_bfloat16* __restrict__ xb,
+                                                         float* __restrict__ mnorm) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const bool is_class = row >= R;
+  const float* src = is_class ? means + (size_t)(row - R) * K : (row < B ? mu + (size_t)row * K : z + (size_t)row * K);
+  __nv_bfloat16* dst = is_class ? xb + (size_t)(row - R) * 3 * K : xa + (size_t)row * 3 * K;
+  float nrm = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const float v = src[k];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+    dst[k] = hi;
+    dst[K + k] = is_class ? hi : lo;
+    dst[2 * K + k] = is_class ? lo : hi;
+    nrm = fmaf(v, v, nrm);
+  }
+  if (is_class) {
+    nrm = block_sum(nrm, red);
+    if (threadIdx.x == 0) mnorm[row - R] = nrm;
+  }
+}
+
 template <bool XR_BF16, int LG>
 __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a) {
   extern __shared__ float sm[];
@@ -1080,7 +1131,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
   // ---- fast class loop (Gaussian prior, scalar variance, K <= 256: the default model).  ||T(z - m)||^2 is expanded as
   // T^2 (||z||^2 - 2 z.m + ||m||^2): per class only the L+1 dot products z_l . m_c remain (class mean in registers, 8
   // latent dims per lane, four rows reduced at a time), ||z_l||^2 and sum exp(log_var) are per-sample scalars.
-  const bool fast = a.var_dim == JVAE_VAR_SCALAR && a.prior_kind == JVAE_PRIOR_GAUSSIAN && K <= 256;
+  const bool fast = a.var_dim == JVAE_VAR_SCALAR && a.prior_kind == JVAE_PRIOR_GAUSSIAN && (K <= 256 || a.cross);
   if (fast) {
     for (int r = wid; r <= (do_iws ? L : 0); r += ELBO_THREADS / 32) {
       float t = 0.f;
@@ -1092,7 +1143,35 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_eval_fwd_kernel(ElboArgs a)
     for (int k = tid; k < K; k += ELBO_THREADS) sexp += expf(evar[k]);
     sexp = block_sum(sexp, red);       // contains the __syncthreads that publishes s_zn
     const int nrows = do_iws ? L + 1 : 1;
-    for (int c = wid; c < Cp; c += ELBO_THREADS / 32) {
+    // many classes: one THREAD per class, the dot products z_r . m_c read from the tensor-core GEMM's output (consecutive
+    // classes = consecutive addresses); the log importance weights are evaluated twice (max, then sum) instead of staged
+    for (int c = tid; c < (a.cross ? Cp : 0); c += ELBO_THREADS) {
+      const float Tc = a.inv_trans[c], T2 = Tc * Tc, logdet = a.logdet[c], mn = a.mnorm[c];
+      const float* cr = a.cross + (size_t)b * a.cross_ld + c;
+      const size_t rs = (size_t)B * a.cross_ld;
+      const float dist = fmaxf(T2 * (s_zn[0] - 2.f * __ldg(cr) + mn), 0.f);
+      float kl, var_kl, iws = 0.f;
+      kl_finish(a, dist, T2 * sexp, 0.f, slv, logdet, &kl, &var_kl);
+      if (do_iws) {
+        const float off = -0.5f * (float)K * LOG2PI_F - 0.5f * logdet;
+        float mxl = -CUDART_INF_F;
+        for (int l = 1; l <= L; ++l) {
+          const float d = fmaxf(T2 * (s_zn[l] - 2.f * __ldg(cr + (size_t)l * rs) + mn), 0.f);
+          mxl = fmaxf(mxl, base_l[l - 1] + off - 0.5f * d);
+        }
+        float se = 0.f;
+        for (int l = 1; l <= L; ++l) {
+          const float d = fmaxf(T2 * (s_zn[l] - 2.f * __ldg(cr + (size_t)l * rs) + mn), 0.f);
+          se += expf(base_l[l - 1] + off - 0.5f * d - mxl);
+        }
+        iws = se / (float)L + mxl;  // cvae.py:870: mean_l exp(.) + max, no log
+      }
+      s_kl[c] = kl;
+      s_zd[c] = dist;
+      s_vk[c] = var_kl;
+      s_iws[c] = iws;
+    }
+    for (int c = wid; c < (a.cross ? 0 : Cp); c += ELBO_THREADS / 32) {
       const float Tc = a.inv_trans[c], T2 = Tc * Tc, logdet = a.logdet[c];
       float mreg[8], mn = 0.f;
 #pragma unroll
@@ -1444,7 +1523,8 @@ static void fill_args(ElboArgs& a, const jvae_elbo_cfg* cfg, void* workspace) {
   a.sigma_is_log = cfg->sigma_is_log; a.sigma_is_rmse = cfg->sigma_is_rmse;
   a.beta = cfg->beta; a.gamma_w = cfg->gamma_w; a.var_w = cfg->var_w; a.tau = cfg->tau; a.alpha = cfg->alpha;
   const bool full = cfg->var_dim == JVAE_VAR_FULL;
-  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp, full);
+  const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp, full,
+                               tc_eligible(cfg->K, a.Cp, cfg->var_dim, cfg->prior_kind, cfg->conditional));
   char* p = reinterpret_cast<char*>(workspace);
   if (full) {
     a.tdiag = reinterpret_cast<float*>(p + w.tdiag);
@@ -1507,7 +1587,9 @@ extern "C" {
 
 size_t jvae_elbo_workspace_bytes(const jvae_elbo_cfg* cfg) {
   if (!cfg) return 0;
-  return ws_layout(cfg->B, cfg->L, cfg->K, cfg->conditional ? cfg->C : 1, cfg->var_dim == JVAE_VAR_FULL).total;
+  const int Cp = cfg->conditional ? cfg->C : 1;
+  return ws_layout(cfg->B, cfg->L, cfg->K, Cp, cfg->var_dim == JVAE_VAR_FULL,
+                   tc_eligible(cfg->K, Cp, cfg->var_dim, cfg->prior_kind, cfg->conditional)).total;
 }
 
 int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_reco, const float* mu,
@@ -1710,6 +1792,23 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
   if (a.categorical) {
     rc = categorical_prepass(a, st);
     if (rc) return rc;
+  }
+  if (tc_eligible(a.K, a.Cp, a.var_dim, a.prior_kind, a.conditional)) {
+    // cross terms of every (row, class) pair on the tensor cores: (R x 3K) . (Cp x 3K)^T -> fp32 (R x Cp)
+    const bool rows_z = a.z && a.eps_norm && (a.has_xreco || a.categorical);
+    const int R = rows_z ? (a.L + 1) * a.B : a.B;
+    const WsLayout w = ws_layout(a.B, a.L, a.K, a.Cp, false, true);
+    char* wp = reinterpret_cast<char*>(workspace);
+    __nv_bfloat16* xa = reinterpret_cast<__nv_bfloat16*>(wp + w.tc_a);
+    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(wp + w.tc_b);
+    float* cross = reinterpret_cast<float*>(wp + w.tc_cross);
+    float* mnorm = reinterpret_cast<float*>(wp + w.tc_mnorm);
+    dist_split_kernel<<<R + a.Cp, 128, 0, st>>>(mu, z, means, R, a.B, a.K, a.Cp, xa, xb, mnorm);
+    JVAE_LAUNCH_CHECK();
+    rc = jvae_gemm_bf16(JVAE_GEMM_NT, R, a.Cp, 3 * a.K, xa, 3 * a.K, xb, 3 * a.K, nullptr, JVAE_ACT_NONE, nullptr, cross, w.tc_ld,
+                        nullptr, 0, stream);
+    if (rc) return rc;
+    a.cross = cross; a.mnorm = mnorm; a.cross_ld = w.tc_ld;
   }
   const int grid = a.B * a.G;
   if (smem > 48 * 1024) {

@@ -66,7 +66,10 @@ CASES = [
     (5, 3, 8, 4, 77, 'scalar', 'gaussian'),        # ragged D: scalar path
     (12, 4, 32, 7, 192, 'scalar', 'tilted'),
     (12, 4, 32, 7, 192, 'scalar', 'uniform'),
-    (4, 9, 256, 1000, 512, 'scalar', 'gaussian'),
+    (4, 9, 256, 1000, 512, 'scalar', 'gaussian'),      # C >= 32: eval distances from the tensor-core cross-term GEMM
+    (64, 16, 256, 100, 3072, 'scalar', 'gaussian'),    # c3's latent shape
+    (130, 4, 128, 40, 96, 'scalar', 'gaussian'),       # ragged row / class tiles of the GEMM
+    (9, 2, 320, 64, 192, 'scalar', 'gaussian'),        # K > 256
     (19, 3, 40, 7, 192, 'full', 'gaussian'),
     (70, 2, 130, 3, 64, 'full', 'gaussian'),
 ]

@@ -29,7 +29,7 @@ def bench(fn, n=20):
     return ts[len(ts) // 2], ts[0]
 
 
-for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (2048, 16, 128, 10, 3072)]:
+for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (512, 16, 256, 1000, 3072), (2048, 16, 128, 10, 3072)]:
     x = torch.rand(B, D, device=dev)
     xr = torch.rand(L + 1, B, D, device=dev).bfloat16()
     mu, lv = torch.randn(B, K, device=dev), torch.randn(B, K, device=dev) * 0.1
