@@ -278,11 +278,14 @@ def run_native(args, wl):
     # (eager steps: per-launch events cannot be recorded inside a replayed graph)
     for i in range(2):          # the capture above emptied the caching allocator: let the eager pools settle again
         step_eager(i)
-    nat.PROFILE = {'elbo_train_fwd': [], 'elbo_train_bwd': [], 'conv': []}
+    nat.PROFILE = {'conv': []}
+    nat.profile_drain()
+    nat.profile_native(True)        # fused ELBO kernels: events recorded inside the library right around the launch
     n0 = nat.launch_count()
     ms_eager = timed(step_eager, args.steps)
     launches = nat.launch_count() - n0
-    prof = {k: [a.elapsed_time(b) for a, b in v] for k, v in nat.PROFILE.items() if k != 'conv'}
+    nat.profile_native(False)
+    prof = nat.profile_drain()
     conv_prof = {}
     for a, b, flops, kname in nat.PROFILE['conv']:
         e = conv_prof.setdefault(kname, [0.0, 0.0, 0])
@@ -467,10 +470,11 @@ def run_c5(pkg, wl, C_, K_, dev, world, rank, timed, B, args):
     with torch.no_grad():
         for i in range(6):          # settle the caching allocator for this model's shapes
             m.evaluate(pool_in[i % 4])
-    nat.PROFILE = {'elbo_eval_fwd': []}
+    nat.profile_drain()
+    nat.profile_native(True)
     ms = timed(whole, 1)
-    ev = [a.elapsed_time(b) for a, b in nat.PROFILE['elbo_eval_fwd']]
-    nat.PROFILE = None
+    nat.profile_native(False)
+    ev = nat.profile_drain().get('elbo_eval_fwd', [])
     L, D = wl['ctor']['test_latent_sampling'], int(torch.tensor(shape).prod())
     # algorithmic bytes of the eval kernel per sample: x, L reconstructions (bf16), mu / log_var, z, |eps|^2,
     # outputs (5C + 3) + C logits + 16 scores + 4 predictions

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 12
+#define JVAE_ABI_VERSION 13
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -389,6 +389,13 @@ int jvae_adam_step(float* p, float* m, float* v, const void* grad, int grad_dtyp
                    const float* norm2, float max_norm, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int nseg, const int32_t* chunk_seg, const int32_t* seg_active, int32_t* seg_step,
                    float* seg_bc, float grad_scale, void* stream);
+
+/* Per-launch profile: while enabled, the fused ELBO entry points bracket their main kernel launch with CUDA events recorded
+ * on the launching stream inside the library (tags below); jvae_profile_drain waits for them, returns (tag, milliseconds)
+ * pairs and forgets them.  Enable only around eager launches (event records are not stream-capture safe). */
+enum jvae_prof_tag { JVAE_PROF_ELBO_TRAIN_FWD = 1, JVAE_PROF_ELBO_TRAIN_BWD = 2, JVAE_PROF_ELBO_EVAL_FWD = 3 };
+int jvae_profile_enable(int on);
+int jvae_profile_drain(int32_t* tags, float* ms, int max_records);
 
 /* self-test of the tensor-core kernels against naive CUDA-core references run on the device;
  * prints a report to stdout, returns the number of failed cases */

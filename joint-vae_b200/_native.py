@@ -95,6 +95,8 @@ def lib():
     L.jvae_selftest.argtypes = [c_int]
     L.jvae_probe_descriptors.argtypes = [c_int]
     L.jvae_probe_poison.argtypes = [ctypes.c_uint, P]
+    L.jvae_profile_enable.argtypes = [c_int]
+    L.jvae_profile_drain.argtypes = [P, P, c_int]
     I16P = ctypes.POINTER(ctypes.c_int16)
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
                                         c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int,
@@ -123,7 +125,7 @@ def lib():
     L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
-    if L.jvae_abi_version() != 12:
+    if L.jvae_abi_version() != 13:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -185,6 +187,25 @@ _ws_cache = {}
 # bench.py sets PROFILE = {'elbo_train_fwd': [], ...}: CUDA event pairs recorded on the launching stream around the
 # named entry point (the roofline's per-launch duration is measured live inside the timed region)
 PROFILE = None
+
+
+PROF_TAGS = {1: 'elbo_train_fwd', 2: 'elbo_train_bwd', 3: 'elbo_eval_fwd'}
+
+
+def profile_native(on):
+    """per-launch events recorded INSIDE the library around the fused ELBO kernels (include/jvae_b200.h: jvae_profile_enable)"""
+    check(lib().jvae_profile_enable(int(bool(on))))
+
+
+def profile_drain(max_records=1 << 16):
+    """-> {entry point: [ms per launch]} of the launches profiled since the last drain (synchronises)"""
+    tags = (ctypes.c_int32 * max_records)()
+    ms = (ctypes.c_float * max_records)()
+    n = lib().jvae_profile_drain(tags, ms, max_records)
+    out = {}
+    for i in range(n):
+        out.setdefault(PROF_TAGS.get(tags[i], str(tags[i])), []).append(float(ms[i]))
+    return out
 
 
 class _timed:

@@ -46,6 +46,10 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int sm_count();   // SMs of the current device (cached)
 
+// per-launch profile (runtime.cu): events recorded inside the library right around a kernel launch when enabled
+void* prof_begin(int tag, cudaStream_t st);
+void prof_end(void* h, cudaStream_t st);
+
 // ---------------------------------------------------------------- small device utilities
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -657,6 +657,78 @@ __global__ void __launch_bounds__(ELBO_THREADS, LG <= 4 ? 12 : 8) elbo_train_fwd
 }
 
 // ------------------------------------------------------------------------------------------------
+// Train forward, register-staged streaming (bf16 reconstructions, D a multiple of 8): ONE item (sample b, LG draws) per CTA and
+// every load of U vector rounds issued before the first use (U * LG 16-byte x_reco loads + 2 U x loads in flight per thread:
+// at c2, D = 3072 = 3 * 128 vectors, the whole item is one memory round trip).  The warp partials meet in shared memory;
+// thread 0 alone adds them in a fixed order (deterministic), publishes ws_mse, counts the sample's arrival with one
+// acq_rel atomic and, if it is the last of the sample's G + 1 arrivals, finalises: one barrier per CTA, no fence / barrier chain.
+// ------------------------------------------------------------------------------------------------
+template <int LG, int U, int MINB>
+__global__ void __launch_bounds__(ELBO_THREADS, MINB) elbo_train_fwd_v2_kernel(ElboArgs a) {
+  __shared__ float s_part[ELBO_THREADS / 32][LG];
+  const int nlat = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
+  if ((int)blockIdx.x < nlat) {
+    const int b = (int)blockIdx.x * (ELBO_THREADS / 32) + (threadIdx.x >> 5);
+    if (b < a.B) train_latent_warp(a, b, threadIdx.x & 31);
+    return;
+  }
+  const int sid = (int)blockIdx.x - nlat;
+  const int b = sid % a.B, g = sid / a.B;
+  const int D = a.D, nvec = D >> 3;
+  const int l0 = 1 + g * LG, nl = min(LG, a.L + 1 - l0);
+  const size_t slab = (size_t)a.B * D;
+  const __nv_bfloat16* r0 = reinterpret_cast<const __nv_bfloat16*>(a.xr) + (size_t)l0 * slab + (size_t)b * D;
+  const float4* xb = reinterpret_cast<const float4*>(a.x + (size_t)b * D);
+  float acc[LG];
+#pragma unroll
+  for (int j = 0; j < LG; ++j) acc[j] = 0.f;
+  for (int v0 = threadIdx.x; v0 < nvec; v0 += U * ELBO_THREADS) {
+    uint4 r[U][LG];
+    float4 x0[U], x1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * ELBO_THREADS;
+#pragma unroll
+      for (int j = 0; j < LG; ++j)
+        if (v < nvec && j < nl) r[u][j] = ld_stream16(r0 + (size_t)j * slab + (size_t)v * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * ELBO_THREADS;
+      if (v < nvec) { x0[u] = __ldg(xb + 2 * v); x1[u] = __ldg(xb + 2 * v + 1); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * ELBO_THREADS;
+#pragma unroll
+      for (int j = 0; j < LG; ++j)
+        if (v < nvec && j < nl) sq_acc8(acc[j], x0[u], x1[u], r[u][j]);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < LG; ++j) {
+    const float t = warp_sum(acc[j]);
+    if (lane == 0) s_part[wid][j] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < nl; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ELBO_THREADS / 32; ++w) t += s_part[w][j];
+      a.ws_mse[(size_t)(l0 - 1 + j) * a.B + b] = t;
+    }
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&a.counters[b]) : "memory");
+    if (old == (unsigned int)a.G) {       // G streaming CTAs + the latent warp
+      a.counters[b] = 0;
+      train_finalize(a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA-staged persistent variant of the train forward (opt-in, JVAE_ELBO_TMA=1; rows must be 16-byte aligned): one CTA per SM;
 // a producer thread streams work items (sample b, group of tma_lg draws) = the x row + tma_lg x_reco rows as 1-D bulk
 // copies into a ring of shared-memory stages (up to ~180 KB in flight per SM, full-row DRAM bursts); 12 consumer warps
@@ -1655,6 +1727,28 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
       return JVAE_OK;
     }
   }
+  // register-staged variant (bf16 reconstructions, vector-aligned rows); JVAE_ELBO_V2 = 0 disables, 1..5 picks the shape
+  static const int v2 = getenv("JVAE_ELBO_V2") ? atoi(getenv("JVAE_ELBO_V2")) : 1;
+  if (a.has_xreco && a.xr_bf16 && (a.D & 7) == 0 && v2 > 0) {
+    const int nlat = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
+#define JVAE_ELBO_V2_LAUNCH(LG_, U_, MINB_)                                                   \
+    do {                                                                                      \
+      a.G = (a.L + LG_ - 1) / LG_;                                                            \
+      elbo_train_fwd_v2_kernel<LG_, U_, MINB_><<<nlat + a.B * a.G, ELBO_THREADS, 0, st>>>(a); \
+    } while (0)
+    void* prof = prof_begin(JVAE_PROF_ELBO_TRAIN_FWD, st);
+    switch (v2) {
+      case 2: JVAE_ELBO_V2_LAUNCH(4, 3, 4); break;
+      case 3: JVAE_ELBO_V2_LAUNCH(4, 2, 6); break;
+      case 4: JVAE_ELBO_V2_LAUNCH(2, 2, 8); break;
+      case 5: JVAE_ELBO_V2_LAUNCH(1, 3, 7); break;
+      default: JVAE_ELBO_V2_LAUNCH(2, 3, 6); break;      // measured best at B = 512 and B = 2048 (tools/elbo_tune.py)
+    }
+#undef JVAE_ELBO_V2_LAUNCH
+    prof_end(prof, st);
+    JVAE_LAUNCH_CHECK();
+    return JVAE_OK;
+  }
   // latent CTAs (one warp per sample) first, then the streaming CTAs (none without a reconstruction term)
   int grid = (a.B + ELBO_THREADS / 32 - 1) / (ELBO_THREADS / 32);
   if (a.has_xreco) {
@@ -1681,7 +1775,9 @@ int jvae_elbo_train_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_
       else kern<false, 8><<<grid, ELBO_THREADS, smem_, st>>>(a);                                 \
     }                                                                                            \
   } while (0)
+  void* prof = prof_begin(JVAE_PROF_ELBO_TRAIN_FWD, st);
   JVAE_ELBO_LAUNCH(elbo_train_fwd_kernel, 0);
+  prof_end(prof, st);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }
@@ -1744,7 +1840,9 @@ int jvae_elbo_train_bwd(const jvae_elbo_cfg* cfg, const float* g, const float* x
     JVAE_LAUNCH_CHECK();
   }
   const int grid = a.B * a.G;
+  void* prof = prof_begin(JVAE_PROF_ELBO_TRAIN_BWD, st);
   JVAE_ELBO_LAUNCH(elbo_train_bwd_kernel, 0);
+  prof_end(prof, st);
   JVAE_LAUNCH_CHECK();
   if (full) {
     full_prior_bwd_kernel<<<a.B, 128, 2 * (size_t)a.K * sizeof(float), st>>>(a);
@@ -1793,6 +1891,7 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
     rc = categorical_prepass(a, st);
     if (rc) return rc;
   }
+  void* prof = prof_begin(JVAE_PROF_ELBO_EVAL_FWD, st);      // the cross-term GEMM is part of the figure
   if (tc_eligible(a.K, a.Cp, a.var_dim, a.prior_kind, a.conditional)) {
     // cross terms of every (row, class) pair on the tensor cores: (R x 3K) . (Cp x 3K)^T -> fp32 (R x Cp)
     const bool rows_z = a.z && a.eps_norm && (a.has_xreco || a.categorical);
@@ -1818,6 +1917,7 @@ int jvae_elbo_eval_fwd(const jvae_elbo_cfg* cfg, const float* x, const void* x_r
 #undef JVAE_EVAL_ATTR
   }
   JVAE_ELBO_LAUNCH(elbo_eval_fwd_kernel, smem);
+  prof_end(prof, st);
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }

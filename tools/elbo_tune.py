@@ -29,6 +29,29 @@ def bench(fn, n=20):
     return ts[len(ts) // 2], ts[0]
 
 
+def bench_graph(make, nbuf=6, n=10):
+    """steady-state time per launch: nbuf launches on rotating reconstruction buffers (together larger than L2) replayed from
+    a CUDA graph, so neither the CPU launch path nor the event pair is in the figure"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(nbuf): make(i)()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for i in range(nbuf): make(i)()
+    ts = []
+    for i in range(n + 2):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        if i >= 2: ts.append(a.elapsed_time(b) * 1e3 / nbuf)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (512, 16, 256, 1000, 3072), (2048, 16, 128, 10, 3072)]:
     x = torch.rand(B, D, device=dev)
     xr = torch.rand(L + 1, B, D, device=dev).bfloat16()
@@ -48,6 +71,21 @@ for (B, L, K, C, D) in [(512, 16, 128, 10, 3072), (512, 16, 256, 100, 3072), (51
     t_f = bench(lambda: nat.elbo_train_fwd(cfg, x, xr, mu, lv, None, y, means, T, sig))
     t_b = bench(lambda: nat.elbo_train_bwd(cfg, gvec, x, xr, mu, lv, None, y, means, T, sig, out['wmse']))
     t_e = bench(lambda: nat.elbo_eval_fwd(cfg, x, xr, mu, lv, z, en, None, means, T, sig))
+    nat.profile_drain(); nat.profile_native(True)
+    for fn in (lambda: nat.elbo_train_fwd(cfg, x, xr, mu, lv, None, y, means, T, sig),
+               lambda: nat.elbo_train_bwd(cfg, gvec, x, xr, mu, lv, None, y, means, T, sig, out['wmse']),
+               lambda: nat.elbo_eval_fwd(cfg, x, xr, mu, lv, z, en, None, means, T, sig)):
+        for i in range(12):
+            flush.zero_(); fn()
+    nat.profile_native(False)
+    pr = {k: sorted(v)[len(v) // 2] * 1e3 for k, v in nat.profile_drain().items()}
+    print('   events inside the library (L2 flushed): ' + ' | '.join(f'{k} {v:.1f} us' for k, v in pr.items()), flush=True)
+    xrs = [torch.rand(L + 1, B, D, device=dev).bfloat16() for _ in range(6)]
+    dxs = [torch.empty(L + 1, B, D, device=dev, dtype=torch.bfloat16) for _ in range(6)]
+    g_f = bench_graph(lambda i: (lambda: nat.elbo_train_fwd(cfg, x, xrs[i], mu, lv, None, y, means, T, sig)))
+    g_e = bench_graph(lambda i: (lambda: nat.elbo_eval_fwd(cfg, x, xrs[i], mu, lv, z, en, None, means, T, sig)))
+    print(f'   graph-replayed, rotating buffers: fwd {g_f:.2f} us = {bytes_fwd / g_f / 1e3:.0f} GB/s | eval {g_e:.2f} us = '
+          f'{(bytes_fwd + B * L * K * 4) / g_e / 1e3:.0f} GB/s', flush=True)
     print(f'LG={os.environ.get("JVAE_ELBO_LG", "4")} B={B} L={L} K={K} C={C}: fwd {t_f[0]:.1f} us (min {t_f[1]:.1f}) = '
           f'{bytes_fwd / t_f[0] / 1e3:.0f} GB/s | bwd {t_b[0]:.1f} us = {(bytes_fwd + B * L * D * 2) / t_b[0] / 1e3:.0f} GB/s | '
           f'eval {t_e[0]:.1f} us = {(bytes_fwd + B * L * K * 4) / t_e[0] / 1e3:.0f} GB/s', flush=True)
