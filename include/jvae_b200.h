@@ -318,6 +318,12 @@ int jvae_upsample2(const void* src, int ld_src, void* dst, int ld_dst, int N, in
 /* f32 -> bf16 cast of n elements (weights repack, activations) */
 int jvae_cast_f32_bf16(const float* src, void* dst, size_t n, void* stream);
 int jvae_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
+/* Patch matrix of a convolution (weight gradient on small maps as ONE TN GEMM, nn.Conv2d in conv.py:189-219): row (n, y, x) of
+ * out (N*Hq*Wq, ld_out) holds column ci * ntaps + t = x[n, y * in_stride + dy_t, x * in_stride + dx_t, ci], zero outside the
+ * map; x is NHWC bf16 with channel stride ld_x.  The column order is torch's (Cin, kh, kw), so
+ * jvae_gemm_bf16(TN, Cout, Cin * ntaps, N*Hq*Wq, dY, ld_dy, out, ld_out, ..., accumulate) adds the weight gradient to .grad */
+int jvae_im2col_bf16(const void* x, int N, int H, int W, int C, int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx,
+                     int in_stride, int Hq, int Wq, void* out, int ld_out, void* stream);
 /* NCHW f32 -> NHWC bf16 (optionally padding channels to c_pad with zeros) and back */
 int jvae_nchw_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
 int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);

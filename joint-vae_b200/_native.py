@@ -96,6 +96,7 @@ def lib():
     L.jvae_probe_descriptors.argtypes = [c_int]
     L.jvae_probe_poison.argtypes = [ctypes.c_uint, P]
     L.jvae_profile_enable.argtypes = [c_int]
+    L.jvae_im2col_bf16.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_int16), c_int, c_int, c_int, P, c_int, P]
     L.jvae_profile_drain.argtypes = [P, P, c_int]
     I16P = ctypes.POINTER(ctypes.c_int16)
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
@@ -444,6 +445,12 @@ def rawptr(t):
     if not t.is_cuda:
         raise NativeError('libjvae_sm100 works on CUDA tensors only (got a CPU tensor); there is no CPU fallback')
     return c_void_p(t.data_ptr())
+
+
+def im2col(x, N, H, W, C, ld_x, taps, in_stride, Hq, Wq, out):
+    """include/jvae_b200.h: jvae_im2col_bf16; out (N*Hq*Wq, >= C*T) bf16"""
+    check(lib().jvae_im2col_bf16(rawptr(x), N, H, W, C, ld_x, len(taps[0]), taps[0], taps[1], in_stride, Hq, Wq, rawptr(out),
+                                 out.stride(0), stream()))
 
 
 def taps_arg(taps):

@@ -54,6 +54,8 @@ FUSE_BN_REDUCE = _os.environ.get('JVAE_FUSE_BN_REDUCE', '0') == '1'
 # maps of at most 2x2 pixels as ONE dense GEMM over (pixel, channel) pairs -- every (output pixel, input pixel) pair is exactly
 # one filter tap, so nothing is wasted on padding taps and the launch fills the machine (M = batch, N = K = pixels * channels)
 DENSE_SMALL = _os.environ.get('JVAE_CONV_DENSE_SMALL', '0') == '1'
+# weight gradients on maps of at most this many pixels go through a patch matrix + one TN GEMM (0 disables)
+IM2COL_MAXPIX = int(_os.environ.get('JVAE_CONV_IM2COL_MAXPIX', '16'))
 
 
 # ------------------------------------------------------------------------------------------------ kernel backend
@@ -98,6 +100,16 @@ class NativeKernels:
         N, Hq, Wq, ld_g = g.shape
         _, H, W, ld_x = x.shape
         T = len(taps[0])
+        if (not swapped and Hq * Wq <= IM2COL_MAXPIX and Cx % 8 == 0 and Cg >= 128 and Cx >= 64 and T in (1, 4, 9, 25)
+                and dw.is_contiguous()):
+            # small maps with many channels (vgg19's 512-channel layers at 4 x 4 and 2 x 2): the per-tap kernels have no reuse
+            # there; one patch matrix in torch's (Cin, kh, kw) column order + ONE TN GEMM accumulating into .grad instead
+            P = N * Hq * Wq
+            cols = torch.empty((P, Cx * T), dtype=torch.bfloat16, device=g.device)
+            nat.im2col(x, N, H, W, Cx, ld_x, taps, in_stride, Hq, Wq, cols)
+            nat.gemm_bf16(2, Cg, Cx * T, P, g.view(P, ld_g), ld_g, cols, Cx * T, out_f32=dw.view(Cg, Cx * T), ldd=Cx * T,
+                          accumulate=True)
+            return
         if swapped:
             nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, T, Cg * T)
         else:

@@ -55,6 +55,38 @@ __global__ void __launch_bounds__(EW_THREADS) nhwc_to_nchw_kernel(const __nv_bfl
   }
 }
 
+// Patch matrix of a convolution on a SMALL map (weight gradient of the 512-channel vgg19 layers at 4 x 4 and 2 x 2): row
+// q = (n, y, x) of `out` holds column ci * T + t = X[n, y * s + dy_t, x * s + dx_t, ci] (zero outside the map), i.e. the
+// columns follow torch's (Cin, kh, kw) weight order, so dW = dY^T . out is the weight gradient in torch's layout (one TN GEMM
+// accumulating straight into .grad).  One thread per (row, 8 channels): T 16-byte loads, a register transpose, T 16-byte stores.
+struct TapList { short dy[32], dx[32]; };
+template <int T>
+__global__ void __launch_bounds__(EW_THREADS) im2col_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                            int Hq, int Wq, int stride, const TapList taps,
+                                                            __nv_bfloat16* __restrict__ out, int ldo) {
+  const int cg = C >> 3;
+  const size_t total = (size_t)N * Hq * Wq * cg;
+  for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % cg);
+    const size_t q = i / cg;
+    const int xq = (int)(q % Wq), yq = (int)((q / Wq) % Hq), n = (int)(q / ((size_t)Wq * Hq));
+    __nv_bfloat16 v[8 * T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int yy = yq * stride + taps.dy[t], xx = xq * stride + taps.dx[t];
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        u = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * ldx + (size_t)g * 8);
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c * T + t] = e[c];
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + q * (size_t)ldo + (size_t)g * 8 * T);
+#pragma unroll
+    for (int t = 0; t < T; ++t) o[t] = reinterpret_cast<const uint4*>(v)[t];
+  }
+}
+
 // gather + augmentation + ToTensor of one batch (include/jvae_b200.h: jvae_batch_u8_to_f32).  One thread per output
 // element, x fastest: coalesced f32 stores; the uint8 source rows of an image (<= a few KB) stay in L1 / L2.
 struct BatchArgs {
@@ -147,6 +179,33 @@ int jvae_batch_u8_to_f32(const jvae_batch_cfg* cfg, const void* src, long long n
   a.B = B; a.H = cfg->H; a.W = cfg->W; a.C = cfg->C; a.oH = cfg->out_H; a.oW = cfg->out_W;
   a.crop_pad = cfg->crop_pad; a.flip_first = cfg->flip_first; a.off_y = cfg->post_off_y; a.off_x = cfg->post_off_x;
   batch_u8_to_f32_kernel<<<ew_grid((size_t)B * a.C * a.oH * a.oW), EW_THREADS, 0, (cudaStream_t)stream>>>(a);
+  JVAE_LAUNCH_CHECK();
+  return JVAE_OK;
+}
+
+int jvae_im2col_bf16(const void* x, int N, int H, int W, int C, int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx,
+                     int in_stride, int Hq, int Wq, void* out, int ld_out, void* stream) {
+  JVAE_CHECK_ARG(x && out && tap_dy && tap_dx, "x, out and the tap lists are required");
+  JVAE_CHECK_ARG(N > 0 && H > 0 && W > 0 && Hq > 0 && Wq > 0 && in_stride > 0, "bad dims");
+  JVAE_CHECK_ARG(C > 0 && (C % 8) == 0 && (ld_x % 8) == 0 && ld_x >= C, "C and ld_x must be multiples of 8");
+  JVAE_CHECK_ARG(ld_out >= C * ntaps && (ld_out % 8) == 0, "ld_out must cover C * ntaps columns and be a multiple of 8");
+  JVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "buffers must be 16-byte aligned");
+  if (ntaps != 9 && ntaps != 25 && ntaps != 1 && ntaps != 4) {
+    set_error("jvae_im2col_bf16: windows of 1, 4, 9 or 25 taps only (ntaps=%d)", ntaps);
+    return JVAE_ERR_UNSUPPORTED;
+  }
+  TapList tl;
+  for (int t = 0; t < ntaps; ++t) { tl.dy[t] = tap_dy[t]; tl.dx[t] = tap_dx[t]; }
+  const size_t total = (size_t)N * Hq * Wq * (C / 8);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ntaps) {
+    case 1: im2col_kernel<1><<<ew_grid(total), EW_THREADS, 0, st>>>(xp, N, H, W, C, ld_x, Hq, Wq, in_stride, tl, op, ld_out); break;
+    case 4: im2col_kernel<4><<<ew_grid(total), EW_THREADS, 0, st>>>(xp, N, H, W, C, ld_x, Hq, Wq, in_stride, tl, op, ld_out); break;
+    case 9: im2col_kernel<9><<<ew_grid(total), EW_THREADS, 0, st>>>(xp, N, H, W, C, ld_x, Hq, Wq, in_stride, tl, op, ld_out); break;
+    default: im2col_kernel<25><<<ew_grid(total), EW_THREADS, 0, st>>>(xp, N, H, W, C, ld_x, Hq, Wq, in_stride, tl, op, ld_out); break;
+  }
   JVAE_LAUNCH_CHECK();
   return JVAE_OK;
 }

@@ -303,3 +303,21 @@ def test_separable_head_row_kernels(pkg, k, Co, ld_t, ld_y, H, W):
     lhs = ((acc - bias) * dy.float()[..., :Co]).sum()
     rhs = (T.float()[..., :k * Co] * want[..., :k * Co]).sum()
     assert abs(float(lhs - rhs)) <= 1e-3 * max(1.0, abs(float(lhs)))
+
+
+@pytest.mark.parametrize('k,stride,H,C', [(3, 1, 4, 64), (3, 1, 2, 136), (5, 1, 3, 8), (2, 2, 4, 16), (1, 1, 2, 8)])
+def test_im2col_matches_unfold(pkg, k, stride, H, C):
+    """jvae_im2col_bf16 (patch matrix of the small-map weight gradient) against torch's unfold: same (Cin, kh, kw) column order"""
+    import torch.nn.functional as F
+    nat = pkg._native
+    N, pad = 5, (k // 2 if stride == 1 else 0)
+    ld = C + 8
+    x = torch.randn(N, H, H, ld, device=DEV).to(torch.bfloat16)
+    Hq = (H + 2 * pad - k) // stride + 1
+    taps = nat.taps_arg([(ky - pad, kx - pad) for ky in range(k) for kx in range(k)])
+    out = torch.full((N * Hq * Hq, C * k * k + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    nat.im2col(x, N, H, H, C, ld, taps, stride, Hq, Hq, out)
+    want = F.unfold(x[..., :C].permute(0, 3, 1, 2).float(), k, padding=pad, stride=stride)      # (N, C k k, Hq Hq)
+    want = want.permute(0, 2, 1).reshape(N * Hq * Hq, C * k * k)
+    assert torch.equal(out[:, :C * k * k].float(), want)
+    assert (out[:, C * k * k:] == 7.0).all()          # columns past C * T are left alone
