@@ -398,10 +398,18 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t
     }
     if (ch0 + c * 16 >= p.Cout) continue;      // warp-uniform
     float v[16];
+    if (p.bias) {      // four 16-byte shared loads per chunk (the LSU shares the shared-memory pipe with the MMA operand fetch)
+      float bb[16];
+      const uint32_t sb = smem_u32(s_bias + c * 16);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float t = __uint_as_float(r[c % RG][j]) + s_bias[c * 16 + j];
-      v[j] = ok ? t : 0.f;
+      for (int j = 0; j < 16; j += 4)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(sb + 4u * j));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ok ? __uint_as_float(r[c % RG][j]) + bb[j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ok ? __uint_as_float(r[c % RG][j]) : 0.f;
     }
     if (p.bn_y) {
       if (ok) {     // BatchNorm-backward sums of the previous layer: mask and xhat recomputed from its saved pre-BN output
@@ -538,7 +546,158 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+// Fast epilogue (every launch without a fused BatchNorm-backward operand), run by EIGHT warps.  The ncu source view of the
+// generic role above showed ~420 warp instructions per 32-channel accumulator block, of which ~90 are the work, executed by one
+// epilogue warp per scheduler at an IPC of 0.15: the accumulator drain, not the MMAs, paced the narrow layers (the MMA thread
+// spent its time waiting for a free accumulator).  Two changes:
+//   * a per-thread table in shared memory holds, for each of the MT * G accumulator blocks of a box, the thread's output offset
+//     from the box origin and its (row, image) inside the box: a block costs one 8-byte shared load and four compares instead of
+//     a division and the pointer arithmetic; rows that are not written skip the arithmetic, dead blocks skip the TMEM load;
+//   * two warps per TMEM lane quarter (set = 0 / 1): a set takes every other 16-channel chunk of each block (every other block
+//     for 16-channel tiles), so a scheduler interleaves two independent drains and a thread keeps statistics for at most 32
+//     channels.
+template <int NCH, bool STATS>
+__device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                   double* s_stats, const float* s_bias, int2* s_tab, int warp, int lane, int nt,
+                                                   int box0, int box_step) {
+  constexpr int LC = (NCH + 1) / 2;              // chunks a thread handles at most
+  const int set = (warp - 2) >> 2;               // warps 2..5: set 0, warps 6..9: set 1
+  const int q = warp & 3;
+  const int mrow = q * 32 + lane;
+  const int ch0 = nt * p.BN;
+  const int nblk = p.MT * p.G;
+  const int c_first = NCH == 1 ? 0 : set;        // chunks c_first, c_first + 2
+  if (set == 0) {
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int m = blk / p.G, j = blk - m * p.G;
+      const int slot = (m * 16 + (mrow >> 3)) * p.G + j;
+      const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
+      const bool valid = nb < p.NBt && yy < p.RT;
+      s_tab[blk * 128 + mrow] = make_int2(valid ? ((nb * p.Ho + yy * p.out_sy) * p.Wo) * p.ldc : -1, yy | (nb << 16));
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");      // the table is shared by the two warps of a lane quarter
+  float s1[STATS ? LC * 16 : 1], s2[STATS ? LC * 16 : 1];
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < LC * 16; ++j) s1[j] = s2[j] = 0.f;
+  }
+  const bool has_bias = p.bias != nullptr;
+  const uint32_t sb = smem_u32(s_bias);
+  const bool vec_bf16 = (p.ldc & 7) == 0, vec_f32 = (p.ldc & 3) == 0;
+  uint32_t it = 0;
+  for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
+    const uint32_t acc = it & 1;
+    int mm = box;
+    const int sx = mm % p.strips_x; mm /= p.strips_x;
+    const int by = mm % p.blocks_y; mm /= p.blocks_y;
+    const int qx = sx * 8 + (mrow & 7);
+    const bool pxok = qx < p.Wq;
+    const int ylim = p.Hq - by * p.RT, nlim = p.N - mm * p.NBt;
+    const size_t base = (((size_t)(mm * p.NBt) * p.Ho + (size_t)(by * p.RT * p.out_sy + p.out_oy)) * p.Wo +
+                         (size_t)(qx * p.out_sx + p.out_ox)) * p.ldc + (size_t)ch0;
+    mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+    tc_fence_after();
+    for (int blk = (NCH == 1 ? set : 0); blk < nblk; blk += (NCH == 1 ? 2 : 1)) {
+      const int2 e = s_tab[blk * 128 + mrow];
+      const bool ok = pxok && e.x >= 0 && (e.y & 0xffff) < ylim && (e.y >> 16) < nlim;
+      if (!__any_sync(0xffffffffu, ok)) continue;
+      const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(blk * p.BN) + ((uint32_t)(q * 32) << 16);
+      uint32_t r[LC][16];
+#pragma unroll
+      for (int lc = 0; lc < LC; ++lc)
+        if (c_first + 2 * lc < NCH) tmem_ld_32x16(t_addr + (uint32_t)((c_first + 2 * lc) * 16), r[lc]);
+      tmem_ld_wait();
+      if (!ok) continue;
+#pragma unroll
+      for (int lc = 0; lc < LC; ++lc) {
+        const int c = c_first + 2 * lc;
+        if (c >= NCH || ch0 + c * 16 >= p.Cout) continue;      // warp-uniform
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[lc][j]);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(sb + 4u * (c * 16 + j)));
+            v[j] += b0; v[j + 1] += b1; v[j + 2] += b2; v[j + 3] += b3;
+          }
+        }
+        if (STATS) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { s1[lc * 16 + j] += v[j]; s2[lc * 16 + j] = fmaf(v[j], v[j], s2[lc * 16 + j]); }
+        }
+        if (p.act == JVAE_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == JVAE_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        } else if (p.act == JVAE_ACT_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
+        }
+        const int c0 = c * 16;
+        const size_t off = base + (size_t)e.x + (size_t)c0;
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + off;
+          if (ch0 + c0 + 16 <= p.ldc && vec_f32) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + c0 + j < p.ldc) o[j] = ch0 + c0 + j < p.Cout ? v[j] : 0.f;
+          }
+        } else {
+          __nv_bfloat16* o = p.out + off;
+          if (ch0 + c0 + 16 <= p.ldc && vec_bf16) {
+            uint4 o0, o1;
+            o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+            o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+            *reinterpret_cast<uint4*>(o) = o0;
+            *reinterpret_cast<uint4*>(o + 8) = o1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + c0 + j < p.ldc) o[j] = __float2bfloat16(ch0 + c0 + j < p.Cout ? v[j] : 0.f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+  }
+  if (STATS) {
+    // CTA-level reduction of the per-thread sums: warp butterfly (16 values at a time), then shared + global atomics
+#pragma unroll
+    for (int lc = 0; lc < LC; ++lc) {
+      const int c = c_first + 2 * lc;
+      float a[16], b[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { a[j] = s1[STATS ? lc * 16 + j : 0]; b[j] = s2[STATS ? lc * 16 + j : 0]; }
+      int chn;
+      const float t1 = warp_sum16(a, lane, &chn);
+      const float t2 = warp_sum16(b, lane, &chn);
+      if (c < NCH && (lane & 1) == 0 && ch0 + c * 16 + chn < p.Cout) {
+        atomicAdd(&s_stats[ch0 + c * 16 + chn], (double)t1);
+        atomicAdd(&s_stats[p.cout_pad + ch0 + c * 16 + chn], (double)t2);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < 2 * p.cout_pad; i += 256) {
+      const int ch = i % p.cout_pad;
+      const double val = s_stats[i];
+      if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
+    }
+  }
+}
+
+constexpr int HALO_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -560,7 +719,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (int)blockIdx.x % p.n_tiles_n;
   float* s_bn = s_bias + 64;                                               // [4][64]: mean, rstd, scale, shift (bn_y launches)
-  for (int i = threadIdx.x; i < p.BN; i += CONV_THREADS) {
+  int2* s_tab = reinterpret_cast<int2*>(s_bn + 256);                       // [MT * G][128]: per-thread block table (fast epilogue)
+  for (int i = threadIdx.x; i < p.BN; i += HALO_THREADS) {
     const int ch = nt * p.BN + i;
     s_bias[i] = (p.bias && ch < p.Cout) ? p.bias[ch] : 0.f;
     if (p.bn_y) {
@@ -574,13 +734,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const uint32_t rb = (uint32_t)p.Cblk * 2u;
 
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += HALO_THREADS) s_stats[i] = 0.0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], p.bn_y ? 4 : 8); }
     for (int a = 0; a < 4; ++a) { mbar_init(&yfull_bar[a], 1); mbar_init(&yempty_bar[a], 4); }
     fence_barrier_init();
     fence_proxy_async();
@@ -677,6 +837,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   } else {
     // ================= epilogue =================
+    if (!p.bn_y) {
+#define HALO_EPI_FAST(NCH_)                                                                                                         \
+      if (p.stats) halo_epilogue_fast<NCH_, true>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_tab, warp, lane, nt, box0, box_step); \
+      else halo_epilogue_fast<NCH_, false>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_tab, warp, lane, nt, box0, box_step)
+      switch (p.BN >> 4) {
+        case 1: HALO_EPI_FAST(1); break;
+        case 2: HALO_EPI_FAST(2); break;
+        case 3: HALO_EPI_FAST(3); break;
+        default: HALO_EPI_FAST(4); break;
+      }
+#undef HALO_EPI_FAST
+    } else if (warp < 6)
     switch (p.BN >> 4) {
       case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
       case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
@@ -1074,7 +1246,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
         const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
         const uint32_t over = extent > plane ? extent - plane : 0u;             // overshoot of the very last plane
         const uint32_t tail = over > wb + 3u * ystage ? over - wb - 3u * ystage : 0u;
-        if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail > budget + (G > 1 ? 20u * 1024u : 0u)) break;
+        if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail + (uint32_t)(MT * G) * 1024u > budget + (G > 1 ? 20u * 1024u : 0u)) break;
         double cyc = 0.0;
         if (G == 1) cyc = (double)MT * ntaps * ksteps * mma_cycles(p.BN) * (resident ? 1.0 : 1.03);
         else
@@ -1141,7 +1313,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.y_box_bytes = bn ? (uint32_t)(p.NBt * p.HHs) * 8u * (uint32_t)p.BN * 2u : 0u;
   {
     const uint32_t bud = budget + (p.G > 1 ? 20u * 1024u : 0u);
-    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
+    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 1024u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
   }
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
@@ -1181,15 +1353,17 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
+  const size_t tab_bytes = (size_t)p.MT * p.G * 128 * sizeof(int2);      // per-thread block table of the fast epilogue
   const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + (size_t)p.ystages * p.y_stage_bytes + 512 + stats_bytes +
-                      256 + 1024 + 1024;
+                      256 + 1024 + 1024 + tab_bytes;
+  if (smem > 227u * 1024u) return 1;
   static bool attr = false;
   if (!attr) {
     JVAE_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
-  conv_halo_kernel<<<grid, CONV_THREADS, smem, stream>>>(tin, tw, ty, p);
+  conv_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(tin, tw, ty, p);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_CONV_HALO;
   if (bn && bn_fused) *bn_fused = 1;
