@@ -305,9 +305,11 @@ struct HaloParams {
   // W[tap (e = u - j, x)][co][ci] for every j that has such a tap.  An MMA then does count * BN columns instead of BN for the
   // same A-operand fetch, which is what bounds the N <= 64 layers.  Chunks = (plane, x, u) triples.
   int G, nck;
-  uint32_t ck_a16[HALO_MAX_CK];          // A start shift: (plane * plane_bytes + (u * HWp + x) * row bytes) / 16
-  unsigned short ck_b16[HALO_MAX_CK];    // B start shift: position of the chunk's first tap block * w_tap_bytes / 16
-  unsigned char ck_cnt[HALO_MAX_CK], ck_j0[HALO_MAX_CK], ck_fresh[HALO_MAX_CK];
+  // one 16-byte record per chunk (ONE uniform load in the issue loop; the MMA thread was issue-bound at ~12 uniform
+  // instructions per MMA when these were five byte / short tables and the instruction descriptor was rebuilt per chunk):
+  //   x = A start shift (plane * plane_bytes + (u * HWp + x) * row bytes) / 16,  y = B start shift (first tap block) / 16,
+  //   z = instruction descriptor (M = 128, N = count * BN),  w = first accumulator column (j0 * BN) | fresh << 31
+  uint4 ck[HALO_MAX_CK];
   short w_pos[CONV_MAX_TAPS];            // position of tap t's weight block in shared memory (resident weights)
 };
 
@@ -357,10 +359,11 @@ __device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0,
     const uint32_t a_m = a_lo0 + (uint32_t)m * m_step16;
     const uint32_t d_m = d0 + (uint32_t)m * gbn;
     for (int c = 0; c < p.nck; ++c) {
-      const uint32_t a_lo = a_m + p.ck_a16[c], b_lo = b_lo_base + p.ck_b16[c];
-      const uint32_t d = d_m + (uint32_t)p.ck_j0[c] * (uint32_t)p.BN;
-      const uint32_t idesc = idesc0 | ((((uint32_t)p.ck_cnt[c] * (uint32_t)p.BN) >> 3) << 17);
-      const uint32_t acc0 = p.ck_fresh[c] ? 0u : 1u;
+      const uint4 ck = p.ck[c];
+      const uint32_t a_lo = a_m + ck.x, b_lo = b_lo_base + ck.y;
+      const uint32_t d = d_m + (ck.w & 0x7fffffffu);
+      const uint32_t idesc = ck.z;
+      const uint32_t acc0 = (ck.w >> 31) ^ 1u;
 #pragma unroll
       for (int k = 0; k < KSTEPS; ++k)
         umma_bf16(d, desc64(a_hi, a_lo + 2u * k), desc64(b_hi, b_lo + 2u * k), idesc, k == 0 ? acc0 : 1u);
@@ -567,14 +570,14 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
   const int ch0 = nt * p.BN;
   const int nblk = p.MT * p.G;
   const int c_first = NCH == 1 ? 0 : set;        // chunks c_first, c_first + 2
-  if (set == 0) {
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int m = blk / p.G, j = blk - m * p.G;
-      const int slot = (m * 16 + (mrow >> 3)) * p.G + j;
-      const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
-      const bool valid = nb < p.NBt && yy < p.RT;
-      s_tab[blk * 128 + mrow] = make_int2(valid ? ((nb * p.Ho + yy * p.out_sy) * p.Wo) * p.ldc : -1, yy | (nb << 16));
-    }
+  // the table does not depend on the pixel column of a row: 16 entries (slot groups of an M-tile) per block
+  for (int i = threadIdx.x - 64; i < nblk * 16; i += 256) {
+    const int blk = i >> 4;
+    const int m = blk / p.G, j = blk - m * p.G;
+    const int slot = (m * 16 + (i & 15)) * p.G + j;
+    const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
+    const bool valid = nb < p.NBt && yy < p.RT;
+    s_tab[i] = make_int2(valid ? ((nb * p.Ho + yy * p.out_sy) * p.Wo) * p.ldc : -1, yy | (nb << 16));
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");      // the table is shared by the two warps of a lane quarter
   float s1[STATS ? LC * 16 : 1], s2[STATS ? LC * 16 : 1];
@@ -599,7 +602,7 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
     mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
     tc_fence_after();
     for (int blk = (NCH == 1 ? set : 0); blk < nblk; blk += (NCH == 1 ? 2 : 1)) {
-      const int2 e = s_tab[blk * 128 + mrow];
+      const int2 e = s_tab[blk * 16 + (mrow >> 3)];
       const bool ok = pxok && e.x >= 0 && (e.y & 0xffff) < ylim && (e.y >> 16) < nlim;
       if (!__any_sync(0xffffffffu, ok)) continue;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(blk * p.BN) + ((uint32_t)(q * 32) << 16);
@@ -719,7 +722,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (int)blockIdx.x % p.n_tiles_n;
   float* s_bn = s_bias + 64;                                               // [4][64]: mean, rstd, scale, shift (bn_y launches)
-  int2* s_tab = reinterpret_cast<int2*>(s_bn + 256);                       // [MT * G][128]: per-thread block table (fast epilogue)
+  int2* s_tab = reinterpret_cast<int2*>(s_bn + 256);                       // [MT * G][16]: block table of the fast epilogue
   for (int i = threadIdx.x; i < p.BN; i += HALO_THREADS) {
     const int ch = nt * p.BN + i;
     s_bias[i] = (p.bias && ch < p.Cout) ? p.bias[ch] : 0.f;
@@ -1246,7 +1249,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
         const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
         const uint32_t over = extent > plane ? extent - plane : 0u;             // overshoot of the very last plane
         const uint32_t tail = over > wb + 3u * ystage ? over - wb - 3u * ystage : 0u;
-        if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail + (uint32_t)(MT * G) * 1024u > budget + (G > 1 ? 20u * 1024u : 0u)) break;
+        if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail + (uint32_t)(MT * G) * 128u > budget + (G > 1 ? 20u * 1024u : 0u)) break;
         double cyc = 0.0;
         if (G == 1) cyc = (double)MT * ntaps * ksteps * mma_cycles(p.BN) * (resident ? 1.0 : 1.03);
         else
@@ -1286,9 +1289,10 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     auto add_chunk = [&](size_t ci, int u, int fresh) {
       const Col& q = cols[ci];
       const int j0 = max(0, u - q.e_hi), j1 = min(p.G - 1, u - q.e_lo);
-      p.ck_a16[nck] = ((uint32_t)q.pl * p.plane_bytes + (uint32_t)(u * p.HWp + q.x) * rb) >> 4;
-      p.ck_b16[nck] = (unsigned short)(((uint32_t)(col_base[ci] + q.e_hi - (u - j0)) * p.w_tap_bytes) >> 4);
-      p.ck_cnt[nck] = (unsigned char)(j1 - j0 + 1); p.ck_j0[nck] = (unsigned char)j0; p.ck_fresh[nck] = (unsigned char)fresh;
+      p.ck[nck].x = ((uint32_t)q.pl * p.plane_bytes + (uint32_t)(u * p.HWp + q.x) * rb) >> 4;
+      p.ck[nck].y = ((uint32_t)(col_base[ci] + q.e_hi - (u - j0)) * p.w_tap_bytes) >> 4;
+      p.ck[nck].z = make_idesc_bf16(128, (j1 - j0 + 1) * p.BN, false, false);
+      p.ck[nck].w = (uint32_t)(j0 * p.BN) | (fresh ? 0x80000000u : 0u);
       ++nck;
     };
     // fresh chunks: a disjoint cover of the G column blocks out of the first tap column
@@ -1313,7 +1317,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.y_box_bytes = bn ? (uint32_t)(p.NBt * p.HHs) * 8u * (uint32_t)p.BN * 2u : 0u;
   {
     const uint32_t bud = budget + (p.G > 1 ? 20u * 1024u : 0u);
-    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 1024u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
+    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 128u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
   }
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
@@ -1353,7 +1357,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
-  const size_t tab_bytes = (size_t)p.MT * p.G * 128 * sizeof(int2);      // per-thread block table of the fast epilogue
+  const size_t tab_bytes = (size_t)p.MT * p.G * 16 * sizeof(int2);       // block table of the fast epilogue
   const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + (size_t)p.ystages * p.y_stage_bytes + 512 + stats_bytes +
                       256 + 1024 + 1024 + tab_bytes;
   if (smem > 227u * 1024u) return 1;
