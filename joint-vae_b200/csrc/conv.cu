@@ -1009,13 +1009,22 @@ struct WHaloParams {
   int NBt, HHs, HWp, MT, strips_x, num_boxes;
   int Cblk_g, Cblk_x, ncx, Cg, Cx;          // blockIdx.z = (G channel block) * ncx + (X channel block)
   int ngroups, groups_per_cta;              // blockIdx.y selects a slice of the tap groups
-  int dymin, dxmin;                         // smallest tap offset in plane coordinates
+  int dymin, dxmin, ey;                     // smallest tap offset in plane coordinates; vertical extent of the window
   int in_stride, nplanes;                   // gathered tensor read as parity planes X_r[j] = X[s*j + r]
   short plane_ry[4], plane_rx[4];
   uint32_t plane_bytes;
-  uint32_t grp_off16[WH_MAX_GROUPS];        // descriptor start shift of the group's first tap (16-byte units)
-  unsigned char grp_ntap[WH_MAX_GROUPS];    // taps stacked in the group
-  short grp_tap[WH_MAX_GROUPS][8];          // tap index (into dW) of each stacked tap
+  uint32_t grp_off16[WH_MAX_GROUPS];        // A (gathered tensor) descriptor start shift of the group's first tap (16-byte units)
+  unsigned char grp_ntap[WH_MAX_GROUPS];    // taps stacked along M (horizontally adjacent, LBO = one pixel row)
+  // Vertical stacking on the N side (full k x k windows, stride 1): the B operand's N atoms are the gradient tile read nv times,
+  // each one slot (pixel row) further down -- LBO = SBO = one slot -- so atom j pairs gathered row s with gradient row
+  // s - ey + v0 + j, i.e. tap row dymax - v0 - j.  One MMA then covers ntap x nv taps (20 of the 25 for k = 5, 32 channels) for
+  // the same A fetch; the old form (nv = 1, the vertical shift on the A side) remains for strided / sparse windows.
+  unsigned char grp_nv[WH_MAX_GROUPS];      // N atoms (vertically stacked taps) of the group
+  uint32_t grp_boff16[WH_MAX_GROUPS];       // B descriptor start shift from (gradient box - ey slots), 16-byte units
+  uint32_t grp_idesc[WH_MAX_GROUPS];        // instruction descriptor (M = 64 / 128, N = nv * Cblk_g)
+  unsigned short grp_col[WH_MAX_GROUPS];    // first TMEM column of the group inside its CTA slice
+  short grp_tap[WH_MAX_GROUPS][8][8];       // [N atom][M block] -> tap index (into dW)
+  uint32_t g_gap_bytes;                     // zeroed bytes in front of the gradient box (>= ey slots)
   float* dw;
   int dw_ld_tap, dw_ld_co, dw_ld_cx;
   uint32_t x_stage_bytes, stage_bytes, x_box_bytes, g_box_bytes, tmem_cols;
@@ -1065,7 +1074,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         for (int pl = 0; pl < p.nplanes; ++pl)
           tma_load_4d(st + (size_t)pl * p.plane_bytes, &tmap_x, &full_bar[s], cx0, p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl],
                       p.in_stride * p.dymin + p.plane_ry[pl], nb * p.NBt);
-        tma_load_4d(st + p.x_stage_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
+        tma_load_4d(st + p.x_stage_bytes + p.g_gap_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
         if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -1076,26 +1085,27 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       // MN-major descriptors: LBO = next M block (= next stacked tap = one pixel row), SBO = next 8-pixel K group (= next slot)
       const uint32_t a_hi = (((uint32_t)p.HWp * rbx >> 4) & 0x3fffu) | (1u << 14) | (swx << 29);
       const uint32_t b_hi = (((8u * rbg) >> 4) & 0x3fffu) | (1u << 14) | (swg << 29);
-      const uint32_t a_lbo = ((rbx >> 4) & 0x3fffu) << 16, b_lbo = (((8u * rbg) >> 4) & 0x3fffu) << 16;
+      const uint32_t a_lbo = ((rbx >> 4) & 0x3fffu) << 16, b_lbo = (((8u * rbg) >> 4) & 0x3fffu) << 16;    // B atoms: one slot apart
       const uint32_t ak16 = (2u * (uint32_t)p.HWp * rbx) >> 4, bk16 = (16u * rbg) >> 4;   // one MMA = 16 pixels = 2 slots
       const uint32_t am16 = (16u * (uint32_t)p.HWp * rbx) >> 4, bm16 = (128u * rbg) >> 4;  // one M-tile = 16 slots
-      const uint32_t idesc128 = make_idesc_bf16(128, p.Cblk_g, true, true), idesc64 = make_idesc_bf16(64, p.Cblk_g, true, true);
+      const uint32_t ey_slots16 = ((uint32_t)p.ey * 8u * rbg) >> 4;
       uint32_t s = 0, ph = 0, first = 0;
       for (int box = blockIdx.x; box < p.num_boxes; box += gridDim.x) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sx_ = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t a_lo0 = ((sx_ >> 4) & 0x3fffu) | a_lbo;
-        const uint32_t b_lo0 = (((sx_ + p.x_stage_bytes) >> 4) & 0x3fffu) | b_lbo;
+        const uint32_t b_lo0 = ((((sx_ + p.x_stage_bytes + p.g_gap_bytes) >> 4) - ey_slots16) & 0x3fffu) | b_lbo;
         for (int m = 0; m < p.MT; ++m) {
           const uint32_t b_lo = b_lo0 + (uint32_t)m * bm16;
           for (int g = 0; g < ng; ++g) {
             const uint32_t a_lo = a_lo0 + (uint32_t)m * am16 + p.grp_off16[g_lo + g];
-            const uint32_t idesc = ((int)p.grp_ntap[g_lo + g] * p.Cblk_x > 64) ? idesc128 : idesc64;
-            const uint32_t d = tmem_base + (uint32_t)(g * p.Cblk_g);
+            const uint32_t bg_lo = b_lo + p.grp_boff16[g_lo + g];
+            const uint32_t idesc = p.grp_idesc[g_lo + g];
+            const uint32_t d = tmem_base + (uint32_t)p.grp_col[g_lo + g];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16(d, desc64(a_hi, a_lo + (uint32_t)k * ak16), desc64(b_hi, b_lo + (uint32_t)k * bk16), idesc,
+              umma_bf16(d, desc64(a_hi, a_lo + (uint32_t)k * ak16), desc64(b_hi, bg_lo + (uint32_t)k * bk16), idesc,
                         k == 0 ? first : 1u);
           }
           first = 1;
@@ -1119,16 +1129,19 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       const bool row_ok = m128 || lane < 16;
       const int j = row / p.Cblk_x, cx = row - j * p.Cblk_x;
       const bool live = row_ok && j < ntap && cx < Nx;
-      const int t = live ? p.grp_tap[g_lo + g][j] : 0;
-      for (int c0 = 0; c0 < p.Cblk_g; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cblk_g + c0), r);
-        tmem_ld_wait();
-        if (live) {
-          float* o = p.dw + (size_t)t * p.dw_ld_tap + (size_t)(cg0 + c0) * p.dw_ld_co + (size_t)(cx0 + cx) * p.dw_ld_cx;
+      const int nv = p.grp_nv[g_lo + g];
+      for (int jv = 0; jv < nv; ++jv) {
+        const int t = live ? p.grp_tap[g_lo + g][jv][j] : 0;
+        for (int c0 = 0; c0 < p.Cblk_g; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.grp_col[g_lo + g] + jv * p.Cblk_g + c0), r);
+          tmem_ld_wait();
+          if (live) {
+            float* o = p.dw + (size_t)t * p.dw_ld_tap + (size_t)(cg0 + c0) * p.dw_ld_co + (size_t)(cx0 + cx) * p.dw_ld_cx;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < Ng) atomicAdd(o + (size_t)i * p.dw_ld_co, __uint_as_float(r[i]));
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < Ng) atomicAdd(o + (size_t)i * p.dw_ld_co, __uint_as_float(r[i]));
+          }
         }
       }
     }
@@ -1405,43 +1418,99 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   p.ncx = (Cx + p.Cblk_x - 1) / p.Cblk_x;
   const uint32_t rbx = (uint32_t)p.Cblk_x * 2u, rbg = (uint32_t)p.Cblk_g * 2u;
   p.HWp = 8 + ex; p.HHs = Hq + ey;
-  // tap groups: runs of horizontally adjacent taps with the same dy, at most 128 / Cblk_x per group
+  // tap groups.  Full k x k windows at stride 1: runs of horizontally adjacent taps (at most 128 / Cblk_x) along M, sets of
+  // vertically adjacent taps (at most 256 / Cblk_g) along N.  Otherwise (parity planes, sparse windows): horizontal runs only,
+  // the vertical shift on the A side.
   const int tpm = 128 / p.Cblk_x;
-  std::vector<int> order(ntaps);
-  for (int t = 0; t < ntaps; ++t) order[t] = t;
-  // groups = runs of taps adjacent in x INSIDE one parity plane and one plane row
-  std::sort(order.begin(), order.end(), [&](int a, int b) {
-    if (tpl[a] != tpl[b]) return tpl[a] < tpl[b];
-    return tey[a] != tey[b] ? tey[a] < tey[b] : tex[a] < tex[b];
-  });
+  p.ey = ey;
+  std::vector<int> tap_at((size_t)(ey + 1) * (ex + 1), -1);
+  // Measured on B200 (tools/bench_layers.py, old form / stacked form): 32 -> 32 k5 at 32 x 32: 850 / 600 us; 256-channel k3 layers at
+  // 8 x 8: 142 / 117 us; but 64-channel tiles on 16 x 16 and 32 x 32 maps and the 64 -> 64 k5 layer at 8 x 8 lose (a stacked B
+  // fetch costs ~1.5x per MMA, so the form pays only when it removes most of the MMAs): enabled for 32-channel gradient tiles
+  // with at least four tap rows, and for 3 x 3 windows on maps of at most 8 x 8 with >= 128 channels.  JVAE_WGRAD_VSTACK = 0 / 1
+  // forces it off / on.
+  bool want = (cblk_of(Cg > 64 ? 64 : Cg) == 32 && ey + 1 >= 4) || (ey + 1 == 3 && Hq * Wq <= 64 && Cg >= 128);
+  if (const char* e = getenv("JVAE_WGRAD_VSTACK")) want = atoi(e) != 0;
+  bool full = want && st == 1 && p.nplanes == 1 && ntaps == (ey + 1) * (ex + 1);
+  for (int t = 0; t < ntaps && full; ++t) {
+    int& slot = tap_at[(size_t)(tey[t] - dymin) * (ex + 1) + (tex[t] - dxmin)];
+    if (slot >= 0) full = false;
+    slot = t;
+  }
   int ngr = 0;
   std::vector<int> grp_first;
-  for (int i = 0; i < ntaps;) {
-    if (ngr >= WH_MAX_GROUPS) return 1;
-    int n = 1;
-    while (i + n < ntaps && n < tpm && n < 8 && tpl[order[i + n]] == tpl[order[i]] && tey[order[i + n]] == tey[order[i]] &&
-           tex[order[i + n]] == tex[order[i]] + n)
-      ++n;
-    p.grp_ntap[ngr] = (unsigned char)n;
-    grp_first.push_back(order[i]);
-    for (int j = 0; j < n; ++j) p.grp_tap[ngr][j] = (short)order[i + j];
-    ++ngr;
-    i += n;
+  const uint32_t gslot16 = (8u * rbg) >> 4;               // one slot of the gradient tile (8 pixels), 16-byte units
+  const int E = ey;
+  if (full) {
+    int nvmax = min(ey + 1, 256 / p.Cblk_g);
+    if (const char* e = getenv("JVAE_WGRAD_NVMAX")) nvmax = max(1, min(nvmax, atoi(e)));
+    const int nsets = (ey + 1 + nvmax - 1) / nvmax;
+    for (int x0 = 0; x0 <= ex; x0 += min(tpm, 8)) {
+      const int n = min(min(tpm, 8), ex + 1 - x0);
+      for (int vs = 0, v0 = 0; vs < nsets; ++vs) {
+        const int nv = (ey + 1 - v0 + (nsets - vs) - 1) / (nsets - vs);      // balanced sets
+        if (ngr >= WH_MAX_GROUPS) return 1;
+        p.grp_ntap[ngr] = (unsigned char)n;
+        p.grp_nv[ngr] = (unsigned char)nv;
+        p.grp_off16[ngr] = ((uint32_t)x0 * rbx) >> 4;
+        p.grp_boff16[ngr] = (uint32_t)v0 * gslot16;
+        for (int jv = 0; jv < nv; ++jv)
+          for (int j = 0; j < n; ++j) p.grp_tap[ngr][jv][j] = (short)tap_at[(size_t)(ey - v0 - jv) * (ex + 1) + (x0 + j)];
+        ++ngr;
+        v0 += nv;
+      }
+    }
+  } else {
+    std::vector<int> order(ntaps);
+    for (int t = 0; t < ntaps; ++t) order[t] = t;
+    // groups = runs of taps adjacent in x INSIDE one parity plane and one plane row
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      if (tpl[a] != tpl[b]) return tpl[a] < tpl[b];
+      return tey[a] != tey[b] ? tey[a] < tey[b] : tex[a] < tex[b];
+    });
+    for (int i = 0; i < ntaps;) {
+      if (ngr >= WH_MAX_GROUPS) return 1;
+      int n = 1;
+      while (i + n < ntaps && n < tpm && n < 8 && tpl[order[i + n]] == tpl[order[i]] && tey[order[i + n]] == tey[order[i]] &&
+             tex[order[i + n]] == tex[order[i]] + n)
+        ++n;
+      p.grp_ntap[ngr] = (unsigned char)n;
+      p.grp_nv[ngr] = 1;
+      p.grp_boff16[ngr] = (uint32_t)E * gslot16;           // the gradient tile itself
+      grp_first.push_back(order[i]);
+      for (int j = 0; j < n; ++j) p.grp_tap[ngr][0][j] = (short)order[i + j];
+      ++ngr;
+      i += n;
+    }
   }
   p.ngroups = ngr;
-  p.groups_per_cta = 512 / p.Cblk_g;
+  int wmax = 0;
+  for (int gi = 0; gi < ngr; ++gi) {
+    const int M = ((int)p.grp_ntap[gi] * p.Cblk_x > 64) ? 128 : 64;
+    p.grp_idesc[gi] = make_idesc_bf16(M, (int)p.grp_nv[gi] * p.Cblk_g, true, true);
+    wmax = max(wmax, (int)p.grp_nv[gi] * p.Cblk_g);
+  }
+  p.groups_per_cta = 512 / wmax;
   if (p.groups_per_cta > ngr) p.groups_per_cta = ngr;
   const int ysplit = (ngr + p.groups_per_cta - 1) / p.groups_per_cta;
   p.groups_per_cta = (ngr + ysplit - 1) / ysplit;               // balance the slices
-  p.tmem_cols = (uint32_t)pow2_ceil(p.groups_per_cta * p.Cblk_g < 32 ? 32 : p.groups_per_cta * p.Cblk_g);
+  int cols_max = 0;
+  for (int gi = 0; gi < ngr; gi += p.groups_per_cta) {
+    int col = 0;
+    for (int k = gi; k < min(ngr, gi + p.groups_per_cta); ++k) { p.grp_col[k] = (unsigned short)col; col += (int)p.grp_nv[k] * p.Cblk_g; }
+    cols_max = max(cols_max, col);
+  }
+  p.tmem_cols = (uint32_t)pow2_ceil(cols_max < 32 ? 32 : cols_max);
+  p.g_gap_bytes = ((uint32_t)E * 8u * rbg + 1023u) & ~1023u;
+  p.ey = E;                                             // the kernel's B base sits E slots in front of the gradient box
   // images per box: best slot efficiency within the shared-memory budget
   const uint32_t budget = 200u * 1024u;
   double best = 0.0;
   for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
-    const int S = nbt * p.HHs, MT = (S - ey + 15) / 16;
+    const int S = nbt * p.HHs, MT = full ? (S + 15) / 16 : (S - ey + 15) / 16;
     const uint32_t plane = ((uint32_t)(16 * MT + ey + 1) * p.HWp * rbx + 1023u) & ~1023u;   // +1 slot: stacked-tap overrun
     const uint32_t xs = plane * (uint32_t)p.nplanes;
-    const uint32_t gs = ((uint32_t)(16 * MT > S ? 16 * MT : S) * 8u * rbg + 1023u) & ~1023u;
+    const uint32_t gs = p.g_gap_bytes + (((uint32_t)(16 * MT > S ? 16 * MT : S) * 8u * rbg + 1023u) & ~1023u);
     if (2u * (xs + gs) + 1024u > budget) break;
     if (nbt * p.HHs > 256) break;
     const double eff = (double)(nbt * Hq) / (16.0 * MT);
@@ -1451,7 +1520,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   }
   if (best <= 0.0) return 1;
   if ((size_t)p.stage_bytes >= (1u << 18)) return 1;
-  for (int gi = 0; gi < ngr; ++gi) {
+  for (int gi = 0; gi < ngr && !full; ++gi) {
     const int t0 = grp_first[gi];
     p.grp_off16[gi] = ((uint32_t)tpl[t0] * p.plane_bytes + (uint32_t)((tey[t0] - dymin) * p.HWp + (tex[t0] - dxmin)) * rbx) >> 4;
   }
