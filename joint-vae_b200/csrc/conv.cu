@@ -292,12 +292,11 @@ struct HaloParams {
   double* stats;
   int cout_pad;
   // fused BatchNorm-backward reduction (data-gradient launches): this launch's output is dL/da of the PREVIOUS layer,
-  // bn_y that layer's pre-BN output at the same pixels; stats then receives sum g*act'(z) and sum g*act'(z)*xhat
+  // bn_y that layer's pre-BN output at the same pixels (read by the epilogue threads straight from global memory); stats then
+  // receives sum g*act'(z) and sum g*act'(z)*xhat
   const __nv_bfloat16* bn_y;
   const float* bn_save; const float* bn_gamma; const float* bn_beta;
   int bn_ld, bn_act;
-  uint32_t y_stage_bytes, y_box_bytes;   // the bn_y tile of a box travels through its own TMA ring (ystages deep)
-  int ystages;
   uint32_t stage_bytes, box_bytes, w_tap_bytes, w_bytes, tmem_cols, acc_stride;
   int stages, resident, wstages;
   // Vertical tap stacking (G > 1): one M row stands for G consecutive output rows (slots) of one pixel column; the N side of an
@@ -371,185 +370,7 @@ __device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0,
   }
 }
 
-// Epilogue of one M-tile for NCH 16-column chunks (BN = 16 * NCH): bias, activation, bf16 store, and per-THREAD running
-// sums of y and y^2 in registers (reduced across the CTA once, at the end of the kernel).
-template <int NCH>
-__device__ __forceinline__ void halo_epilogue_tile(const HaloParams& p, uint32_t t_addr, bool ok, __nv_bfloat16* orow, float* orow_f, int ch0,
-                                                   const float* s_bias, const float* s_bn, const __nv_bfloat16* yrow,
-                                                   float (&s1)[NCH * 16], float (&s2)[NCH * 16]) {
-  // the BatchNorm-backward operand of every chunk is requested before the accumulator is read: one exposed global
-  // latency per tile instead of one per chunk
-  uint4 yq[NCH][2];
-  const bool bn_vec = p.bn_y && ok;
-  if (bn_vec) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      yq[c][0] = *reinterpret_cast<const uint4*>(yrow + c * 16);
-      yq[c][1] = *reinterpret_cast<const uint4*>(yrow + c * 16 + 8);
-    }
-  }
-  // accumulator chunks: all at once for narrow tiles, two at a time for 48 / 64 channels (register budget)
-  constexpr int RG = NCH <= 2 ? NCH : 2;
-  uint32_t r[RG][16];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    if (c % RG == 0) {
-#pragma unroll
-      for (int cc = 0; cc < RG; ++cc)
-        if (c + cc < NCH) tmem_ld_32x16(t_addr + (uint32_t)((c + cc) * 16), r[cc]);
-      tmem_ld_wait();
-    }
-    if (ch0 + c * 16 >= p.Cout) continue;      // warp-uniform
-    float v[16];
-    if (p.bias) {      // four 16-byte shared loads per chunk (the LSU shares the shared-memory pipe with the MMA operand fetch)
-      float bb[16];
-      const uint32_t sb = smem_u32(s_bias + c * 16);
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(sb + 4u * j));
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ok ? __uint_as_float(r[c % RG][j]) + bb[j] : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ok ? __uint_as_float(r[c % RG][j]) : 0.f;
-    }
-    if (p.bn_y) {
-      if (ok) {     // BatchNorm-backward sums of the previous layer: mask and xhat recomputed from its saved pre-BN output
-        float y[16];
-        {
-          const uint4 u0 = yq[c][0], u1 = yq[c][1];
-          y[0] = bf16_lo(u0.x); y[1] = bf16_hi(u0.x); y[2] = bf16_lo(u0.y); y[3] = bf16_hi(u0.y);
-          y[4] = bf16_lo(u0.z); y[5] = bf16_hi(u0.z); y[6] = bf16_lo(u0.w); y[7] = bf16_hi(u0.w);
-          y[8] = bf16_lo(u1.x); y[9] = bf16_hi(u1.x); y[10] = bf16_lo(u1.y); y[11] = bf16_hi(u1.y);
-          y[12] = bf16_lo(u1.z); y[13] = bf16_hi(u1.z); y[14] = bf16_lo(u1.w); y[15] = bf16_hi(u1.w);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int cc = c * 16 + j;
-          const float mean = s_bn[cc], rstd = s_bn[64 + cc], scale = s_bn[128 + cc], shift = s_bn[192 + cc];
-          const float z = fmaf(y[j], scale, shift);
-          float d = 1.f;
-          if (p.bn_act == JVAE_ACT_RELU) d = z > 0.f ? 1.f : 0.f;
-          else if (p.bn_act == JVAE_ACT_SIGMOID) { const float sg = 1.f / (1.f + __expf(-z)); d = sg * (1.f - sg); }
-          else if (p.bn_act == JVAE_ACT_LEAKY) d = z > 0.f ? 1.f : JVAE_LEAKY_SLOPE;
-          const float gz = v[j] * d;
-          s1[cc] += gz;
-          s2[cc] = fmaf(gz, (y[j] - mean) * rstd, s2[cc]);
-        }
-      }
-    } else if (p.stats) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { s1[c * 16 + j] += v[j]; s2[c * 16 + j] = fmaf(v[j], v[j], s2[c * 16 + j]); }
-    }
-    if (ok) {
-      if (p.act == JVAE_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (p.act == JVAE_ACT_SIGMOID) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-      } else if (p.act == JVAE_ACT_LEAKY) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
-      }
-      const int c0 = c * 16;
-      if (orow_f) {           // fp32 result (the 1 x k stage of the separable image head keeps full precision)
-        if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow_f + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (ch0 + c0 + j < p.ldc) orow_f[c0 + j] = ch0 + c0 + j < p.Cout ? v[j] : 0.f;
-        }
-      } else if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
-        uint4 o0, o1;
-        o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
-        o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
-        *reinterpret_cast<uint4*>(orow + c0) = o0;
-        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (ch0 + c0 + j < p.ldc) orow[c0 + j] = __float2bfloat16(ch0 + c0 + j < p.Cout ? v[j] : 0.f);
-      }
-    }
-  }
-}
-
-template <int NCH>
-__device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                   double* s_stats, const float* s_bias, const float* s_bn, const uint8_t* ysm,
-                                                   uint64_t* yfull_bar, uint64_t* yempty_bar, int warp, int lane, int nt,
-                                                   int box0, int box_step) {
-  const int q = warp & 3;
-  const int mrow = q * 32 + lane;
-  const int ch0 = nt * p.BN;
-  float s1[NCH * 16], s2[NCH * 16];
-#pragma unroll
-  for (int j = 0; j < NCH * 16; ++j) s1[j] = s2[j] = 0.f;
-  uint32_t it = 0;
-  for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
-    const uint32_t acc = it & 1;
-    int mm = box;
-    const int sx = mm % p.strips_x; mm /= p.strips_x;
-    const int by = mm % p.blocks_y; mm /= p.blocks_y;
-    const int qx = sx * 8 + (mrow & 7);
-    const int ys = it % (p.ystages > 0 ? p.ystages : 1);
-    if (p.bn_y) mbar_wait(&yfull_bar[ys], (it / p.ystages) & 1);
-    mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-    tc_fence_after();
-    for (int m = 0; m < p.MT; ++m) {
-      for (int j = 0; j < p.G; ++j) {        // G = 1: one output row per M row; G > 1: column block j of the row group
-        const int slot = (m * 16 + (mrow >> 3)) * p.G + j;
-        const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
-        const int qy = by * p.RT + yy, n = mm * p.NBt + nb;
-        const bool ok = (nb < p.NBt) && (yy < p.RT) && (qy < p.Hq) && (qx < p.Wq) && (n < p.N);
-        const int oy = qy * p.out_sy + p.out_oy, ox = qx * p.out_sx + p.out_ox;
-        const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
-        __nv_bfloat16* orow = p.out + opix * p.ldc + (size_t)ch0;
-        float* orow_f = p.out_f32 ? reinterpret_cast<float*>(p.out) + opix * p.ldc + (size_t)ch0 : nullptr;
-        // row (128 m + mrow) of the y tile in shared memory: BN channels of the pixel this thread owns (G = 1 only)
-        const __nv_bfloat16* yrow = p.bn_y ? reinterpret_cast<const __nv_bfloat16*>(ysm + (size_t)ys * p.y_stage_bytes) +
-                                                 (size_t)(m * 128 + mrow) * p.BN : nullptr;
-        const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)((m * p.G + j) * p.BN) + ((uint32_t)(q * 32) << 16);
-        halo_epilogue_tile<NCH>(p, t_addr, ok, orow, orow_f, ch0, s_bias, s_bn, yrow, s1, s2);
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&tempty_bar[acc]);
-      if (p.bn_y) mbar_arrive(&yempty_bar[ys]);
-    }
-  }
-  if (p.stats) {
-    // CTA-level reduction of the per-thread sums: warp butterfly (16 values at a time), then shared + global atomics
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float a[16], b[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { a[j] = s1[c * 16 + j]; b[j] = s2[c * 16 + j]; }
-      int chn;
-      const float t1 = warp_sum16(a, lane, &chn);
-      const float t2 = warp_sum16(b, lane, &chn);
-      if ((lane & 1) == 0 && ch0 + c * 16 + chn < p.Cout) {
-        atomicAdd(&s_stats[ch0 + c * 16 + chn], (double)t1);
-        atomicAdd(&s_stats[p.cout_pad + ch0 + c * 16 + chn], (double)t2);
-      }
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < 2 * p.cout_pad; i += 128) {
-      const int ch = i % p.cout_pad;
-      const double val = s_stats[i];
-      if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
-    }
-  }
-}
-
-// Fast epilogue (every launch without a fused BatchNorm-backward operand), run by EIGHT warps.  The ncu source view of the
+// Epilogue of the halo kernel, run by EIGHT warps.  The ncu source view of the
 // generic role above showed ~420 warp instructions per 32-channel accumulator block, of which ~90 are the work, executed by one
 // epilogue warp per scheduler at an IPC of 0.15: the accumulator drain, not the MMAs, paced the narrow layers (the MMA thread
 // spent its time waiting for a free accumulator).  Two changes:
@@ -559,10 +380,16 @@ __device__ __forceinline__ void halo_epilogue_role(const HaloParams& p, uint32_t
 //   * two warps per TMEM lane quarter (set = 0 / 1): a set takes every other 16-channel chunk of each block (every other block
 //     for 16-channel tiles), so a scheduler interleaves two independent drains and a thread keeps statistics for at most 32
 //     channels.
-template <int NCH, bool STATS>
+// MODE 0: plain; 1: BatchNorm batch statistics of the output (sum y, sum y^2); 2: BatchNorm-BACKWARD sums of the previous layer
+// (data-gradient launches whose output is dL/da of a conv-BN-activation layer): with y that layer's saved pre-BN output at the
+// same pixel (two 16-byte global loads per chunk, requested before the accumulator is read), g' = g * act'(scale y + shift),
+// the thread accumulates sum g' and sum g' y; the CTA turns them into sum g' and sum g' xhat = rstd (sum g' y - mean sum g').
+template <int NCH, int MODE>
 __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                   double* s_stats, const float* s_bias, int2* s_tab, int warp, int lane, int nt,
-                                                   int box0, int box_step) {
+                                                   double* s_stats, const float* s_bias, const float* s_bn, int2* s_tab, int warp,
+                                                   int lane, int nt, int box0, int box_step) {
+  constexpr bool STATS = MODE != 0;
+  constexpr bool BNRED = MODE == 2;
   constexpr int LC = (NCH + 1) / 2;              // chunks a thread handles at most
   const int set = (warp - 2) >> 2;               // warps 2..5: set 0, warps 6..9: set 1
   const int q = warp & 3;
@@ -577,7 +404,7 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
     const int slot = (m * 16 + (i & 15)) * p.G + j;
     const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
     const bool valid = nb < p.NBt && yy < p.RT;
-    s_tab[i] = make_int2(valid ? ((nb * p.Ho + yy * p.out_sy) * p.Wo) * p.ldc : -1, yy | (nb << 16));
+    s_tab[i] = make_int2(valid ? (nb * p.Ho + yy * p.out_sy) * p.Wo : -1, yy | (nb << 16));      // pixel offset from the box origin
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");      // the table is shared by the two warps of a lane quarter
   float s1[STATS ? LC * 16 : 1], s2[STATS ? LC * 16 : 1];
@@ -597,8 +424,8 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
     const int qx = sx * 8 + (mrow & 7);
     const bool pxok = qx < p.Wq;
     const int ylim = p.Hq - by * p.RT, nlim = p.N - mm * p.NBt;
-    const size_t base = (((size_t)(mm * p.NBt) * p.Ho + (size_t)(by * p.RT * p.out_sy + p.out_oy)) * p.Wo +
-                         (size_t)(qx * p.out_sx + p.out_ox)) * p.ldc + (size_t)ch0;
+    const size_t pix0 = ((size_t)(mm * p.NBt) * p.Ho + (size_t)(by * p.RT * p.out_sy + p.out_oy)) * p.Wo +
+                        (size_t)(qx * p.out_sx + p.out_ox);
     mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
     tc_fence_after();
     for (int blk = (NCH == 1 ? set : 0); blk < nblk; blk += (NCH == 1 ? 2 : 1)) {
@@ -606,6 +433,17 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
       const bool ok = pxok && e.x >= 0 && (e.y & 0xffff) < ylim && (e.y >> 16) < nlim;
       if (!__any_sync(0xffffffffu, ok)) continue;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(blk * p.BN) + ((uint32_t)(q * 32) << 16);
+      const size_t pix = pix0 + (size_t)(ok ? e.x : 0);
+      uint4 yq[BNRED ? LC : 1][2];
+      if (BNRED && ok) {
+#pragma unroll
+        for (int lc = 0; lc < LC; ++lc)
+          if (c_first + 2 * lc < NCH && ch0 + (c_first + 2 * lc) * 16 < p.Cout) {
+            const __nv_bfloat16* yp = p.bn_y + pix * (size_t)p.bn_ld + (size_t)(ch0 + (c_first + 2 * lc) * 16);
+            yq[lc][0] = ld_stream16(yp);
+            yq[lc][1] = ld_stream16(yp + 8);
+          }
+      }
       uint32_t r[LC][16];
 #pragma unroll
       for (int lc = 0; lc < LC; ++lc)
@@ -627,7 +465,33 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
             v[j] += b0; v[j + 1] += b1; v[j + 2] += b2; v[j + 3] += b3;
           }
         }
-        if (STATS) {
+        if (BNRED) {
+          float y[16];
+          {
+            const uint4 u0 = yq[BNRED ? lc : 0][0], u1 = yq[BNRED ? lc : 0][1];
+            y[0] = bf16_lo(u0.x); y[1] = bf16_hi(u0.x); y[2] = bf16_lo(u0.y); y[3] = bf16_hi(u0.y);
+            y[4] = bf16_lo(u0.z); y[5] = bf16_hi(u0.z); y[6] = bf16_lo(u0.w); y[7] = bf16_hi(u0.w);
+            y[8] = bf16_lo(u1.x); y[9] = bf16_hi(u1.x); y[10] = bf16_lo(u1.y); y[11] = bf16_hi(u1.y);
+            y[12] = bf16_lo(u1.z); y[13] = bf16_hi(u1.z); y[14] = bf16_lo(u1.w); y[15] = bf16_hi(u1.w);
+          }
+          const uint32_t sbn = smem_u32(s_bn);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float sc[4], sh[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sbn + 4u * (128 + c * 16 + j)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh[0]), "=f"(sh[1]), "=f"(sh[2]), "=f"(sh[3]) : "r"(sbn + 4u * (192 + c * 16 + j)));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float z = fmaf(y[j + i], sc[i], sh[i]);
+              float gz = v[j + i];
+              if (p.bn_act == JVAE_ACT_RELU) gz = z > 0.f ? gz : 0.f;
+              else if (p.bn_act == JVAE_ACT_LEAKY) gz = z > 0.f ? gz : JVAE_LEAKY_SLOPE * gz;
+              else if (p.bn_act == JVAE_ACT_SIGMOID) { const float sg = 1.f / (1.f + __expf(-z)); gz *= sg * (1.f - sg); }
+              s1[lc * 16 + j + i] += gz;
+              s2[lc * 16 + j + i] = fmaf(gz, y[j + i], s2[lc * 16 + j + i]);
+            }
+          }
+        } else if (STATS) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { s1[lc * 16 + j] += v[j]; s2[lc * 16 + j] = fmaf(v[j], v[j], s2[lc * 16 + j]); }
         }
@@ -642,7 +506,7 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
           for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
         }
         const int c0 = c * 16;
-        const size_t off = base + (size_t)e.x + (size_t)c0;
+        const size_t off = pix * (size_t)p.ldc + (size_t)(ch0 + c0);
         if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + off;
           if (ch0 + c0 + 16 <= p.ldc && vec_f32) {
@@ -693,7 +557,9 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
     const int t = threadIdx.x - 64;
     for (int i = t; i < 2 * p.cout_pad; i += 256) {
       const int ch = i % p.cout_pad;
-      const double val = s_stats[i];
+      double val = s_stats[i];
+      if (BNRED && i >= p.cout_pad && ch - ch0 >= 0 && ch - ch0 < p.BN)      // sum g' xhat = rstd (sum g' y - mean sum g')
+        val = (double)s_bn[64 + ch - ch0] * (val - (double)s_bn[ch - ch0] * s_stats[ch]);
       if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
     }
   }
@@ -702,20 +568,17 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
 constexpr int HALO_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ HaloParams p) {
+                 const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + (size_t)p.stages * p.stage_bytes;
-  uint8_t* ysm = wsm + p.w_bytes;                                           // [ystages][y_stage_bytes] (bn_y launches)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ysm + (size_t)p.ystages * p.y_stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(wsm + p.w_bytes);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* wfull_bar = empty_bar + 4;      // [wstages] (resident: only [0])
   uint64_t* wempty_bar = wfull_bar + 8;
   uint64_t* tfull_bar = wempty_bar + 8;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* yfull_bar = tempty_bar + 2;     // [4]
-  uint64_t* yempty_bar = yfull_bar + 4;     // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty_bar + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   double* s_stats = reinterpret_cast<double*>(tmem_slot + 4);              // [2][cout_pad] when p.stats (fp64 sums)
   float* s_bias = reinterpret_cast<float*>(s_stats + (p.stats ? 2 * p.cout_pad : 0));   // [BN] bias of this CTA's channel tile
 
@@ -743,8 +606,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(&wfull_bar[s], 1); mbar_init(&wempty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], p.bn_y ? 4 : 8); }
-    for (int a = 0; a < 4; ++a) { mbar_init(&yfull_bar[a], 1); mbar_init(&yempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -757,7 +619,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
-      if (p.bn_y) tma_prefetch_desc(&tmap_y);
       if (p.resident) {
         mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
         for (int t = 0; t < p.ntaps; ++t)
@@ -774,12 +635,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           tma_load_4d(smem + (size_t)s * p.stage_bytes + (size_t)pl * p.plane_bytes, &tmap_in, &full_bar[s], 0,
                       p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl], p.in_stride * (by * p.RT + p.dymin) + p.plane_ry[pl],
                       m * p.NBt);
-        if (p.bn_y) {       // the previous layer's pre-BN tile at the pixels this box writes (epilogue operand)
-          const int ys = it % p.ystages;
-          mbar_wait(&yempty_bar[ys], ((it / p.ystages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&yfull_bar[ys], p.y_box_bytes);
-          tma_load_4d(ysm + (size_t)ys * p.y_stage_bytes, &tmap_y, &yfull_bar[ys], nt * p.BN, sx * 8, by * p.RT, m * p.NBt);
-        }
       };
       uint32_t it = 0, wit = 0;
       if (box0 < p.num_boxes) load_box(box0, 0);
@@ -840,24 +695,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   } else {
     // ================= epilogue =================
-    if (!p.bn_y) {
-#define HALO_EPI_FAST(NCH_)                                                                                                         \
-      if (p.stats) halo_epilogue_fast<NCH_, true>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_tab, warp, lane, nt, box0, box_step); \
-      else halo_epilogue_fast<NCH_, false>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_tab, warp, lane, nt, box0, box_step)
-      switch (p.BN >> 4) {
-        case 1: HALO_EPI_FAST(1); break;
-        case 2: HALO_EPI_FAST(2); break;
-        case 3: HALO_EPI_FAST(3); break;
-        default: HALO_EPI_FAST(4); break;
-      }
-#undef HALO_EPI_FAST
-    } else if (warp < 6)
+#define HALO_EPI_FAST(NCH_)                                                                                                            \
+    if (p.bn_y) halo_epilogue_fast<NCH_, 2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, s_tab, warp, lane, nt, box0, box_step);    \
+    else if (p.stats) halo_epilogue_fast<NCH_, 1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, s_tab, warp, lane, nt, box0, box_step); \
+    else halo_epilogue_fast<NCH_, 0>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, s_tab, warp, lane, nt, box0, box_step)
     switch (p.BN >> 4) {
-      case 1: halo_epilogue_role<1>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
-      case 2: halo_epilogue_role<2>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
-      case 3: halo_epilogue_role<3>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
-      default: halo_epilogue_role<4>(p, tmem_base, tfull_bar, tempty_bar, s_stats, s_bias, s_bn, ysm, yfull_bar, yempty_bar, warp, lane, nt, box0, box_step); break;
+      case 1: HALO_EPI_FAST(1); break;
+      case 2: HALO_EPI_FAST(2); break;
+      case 3: HALO_EPI_FAST(3); break;
+      default: HALO_EPI_FAST(4); break;
     }
+#undef HALO_EPI_FAST
   }
   tc_fence_before();
   __syncthreads();
@@ -1223,7 +1071,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   // ---- tap rectangles per parity plane (vertical stacking needs, for every tap column, a contiguous run of tap rows)
   struct Col { int pl, x, e_lo, e_hi; };
   std::vector<Col> cols;
-  bool stackable = bn == nullptr && getenv("JVAE_CONV_NOSTACK") == nullptr;
+  bool stackable = getenv("JVAE_CONV_NOSTACK") == nullptr;
   for (int t = 0; t < ntaps && stackable; ++t) {
     const int x = tex[t] - dxmin, e = tey[t] - dymin;
     Col* c = nullptr;
@@ -1259,7 +1107,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
                                       : (((uint32_t)S * p.HWp * rb + 1023u) & ~1023u);
         const uint32_t extent = (uint32_t)(16 * MT * G + ey) * p.HWp * rb;      // bytes an M-tile sweep can touch in a plane
         const uint32_t stage = plane * (uint32_t)p.nplanes;
-        const uint32_t ystage = bn ? (((uint32_t)(S > 16 * MT ? S : 16 * MT) * 8u * (uint32_t)p.BN * 2u + 1023u) & ~1023u) : 0u;
+        const uint32_t ystage = 0u;
         const uint32_t over = extent > plane ? extent - plane : 0u;             // overshoot of the very last plane
         const uint32_t tail = over > wb + 3u * ystage ? over - wb - 3u * ystage : 0u;
         if (2u * stage + wb + stats_bytes + 1792u + 3u * ystage + tail + (uint32_t)(MT * G) * 128u > budget + (G > 1 ? 20u * 1024u : 0u)) break;
@@ -1274,7 +1122,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
         const double score = (double)(nbt * p.RT) / cyc;
         if (score > best * 1.02) {
           best = score; bestG = G; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
-          p.w_bytes = wb + tail; p.y_stage_bytes = ystage; best_extent = extent;
+          p.w_bytes = wb + tail; best_extent = extent;
         }
         found = true;
       }
@@ -1326,11 +1174,9 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     if ((((uint32_t)pos * p.w_tap_bytes) >> 4) > 0xffffu) return 1;
   }
   p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
-  p.ystages = bn ? 3 : 0;
-  p.y_box_bytes = bn ? (uint32_t)(p.NBt * p.HHs) * 8u * (uint32_t)p.BN * 2u : 0u;
   {
     const uint32_t bud = budget + (p.G > 1 ? 20u * 1024u : 0u);
-    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 128u - (uint32_t)p.ystages * p.y_stage_bytes) / p.stage_bytes);
+    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 128u) / p.stage_bytes);
   }
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
@@ -1342,17 +1188,12 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act & 0xff; p.out_f32 = (act & JVAE_OUT_F32) ? 1 : 0;
   p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
-  CUtensorMap tin, tw, ty;
-  memset(&ty, 0, sizeof(ty));
+  CUtensorMap tin, tw;
   if (bn) {
     p.bn_y = reinterpret_cast<const __nv_bfloat16*>(bn->y); p.bn_ld = bn->ld_y; p.bn_save = bn->save_mean_rstd;
     p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_act = bn->act;
     if ((bn->ld_y % 8) != 0) { set_error("jvae_conv_gather_gemm_bn: bn.ld_y must be a multiple of 8"); return JVAE_ERR_INVALID; }
-    uint64_t yd[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
-    uint64_t ysd[3] = {(uint64_t)bn->ld_y * 2, (uint64_t)Wo * bn->ld_y * 2, (uint64_t)Ho * Wo * bn->ld_y * 2};
-    uint32_t ybox[4] = {(uint32_t)p.BN, 8u, (uint32_t)p.HHs, (uint32_t)p.NBt};
-    const int rcy = make_tmap_bf16(&ty, bn->y, 4, yd, ysd, ybox, nullptr, 0);
-    if (rcy) return rcy;
+    if (!stats) { set_error("jvae_conv_gather_gemm_bn: the sums need the stats buffer"); return JVAE_ERR_INVALID; }
   }
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -1371,7 +1212,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     if (rc) return rc;
   }
   const size_t tab_bytes = (size_t)p.MT * p.G * 16 * sizeof(int2);       // block table of the fast epilogue
-  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + (size_t)p.ystages * p.y_stage_bytes + 512 + stats_bytes +
+  const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes +
                       256 + 1024 + 1024 + tab_bytes;
   if (smem > 227u * 1024u) return 1;
   static bool attr = false;
@@ -1380,7 +1221,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     attr = true;
   }
   int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
-  conv_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(tin, tw, ty, p);
+  conv_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(tin, tw, p);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_CONV_HALO;
   if (bn && bn_fused) *bn_fused = 1;
