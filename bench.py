@@ -262,7 +262,7 @@ def run_native(args, wl):
     shape = tuple(wl['ctor']['input_shape'])
     npool = 4
     xs_h, ys_h, xs, ys = train_inputs(wl, B, npool)
-    use_graph = args.graph and world == 1      # the data-parallel step (NCCL all-reduce inside) stays eager
+    use_graph = args.graph                     # N > 1: the NCCL all-reduce is a node of the captured step
     step_eager = lambda i: net.train_step(xs[i % npool], ys[i % npool])
     step_dev = lambda i: net.train_step(xs[i % npool], ys[i % npool], graph=use_graph)
 
@@ -350,8 +350,7 @@ def run_native(args, wl):
             torch.cuda.empty_cache()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     hbm, tf, which = peaks()
     L, K, D = wl['ctor']['latent_sampling'], wl['ctor']['latent_dim'], int(torch.tensor(shape).prod())
@@ -412,8 +411,22 @@ def run_native(args, wl):
                                 'sample': '2 full train steps at batch 64 after 1 warm-up, oracle/torch_model.py fp32, all host cores',
                                 'scoring_samples_per_s': vs}
     print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """End of a rank.  With N > 1 the captured data-parallel steps hold NCCL kernels inside CUDA graphs; tearing the communicator
+    down under them can block, so the rank synchronises, meets the others at a barrier and leaves without the teardown."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def run_c5(pkg, wl, C_, K_, dev, world, rank, timed, B, args):

@@ -683,10 +683,11 @@ class ClassificationVariationalNetwork(nn.Module):
 
     def _graph_ok(self, x):
         """steps a replayed graph reproduces: Philox noise (an injected tensor would be frozen into the graph), the fused
-        Adam (its state is on the device), sigma not updated from the host, a single process (the NCCL all-reduce of the
-        data-parallel step stays eager)"""
+        Adam (its state is on the device), sigma not updated from the host; the data-parallel step is captured too when its
+        all-reduce runs on NCCL (the collective becomes a node of the graph; every rank captures at the same call)"""
         opt = self.optimizer
-        return (x.is_cuda and self.encoder.sampling.injected_eps is None and opt._opt is None and opt.allreduce is None
+        dp_ok = opt.allreduce is None or getattr(opt, 'allreduce_capturable', False)
+        return (x.is_cuda and self.encoder.sampling.injected_eps is None and opt._opt is None and dp_ok
                 and not (self.sigma.decay and not self.sigma.learned) and not self.sigma.coded)
 
     def _train_step_graphed(self, x, y, kl_var_weighting, gamma_weighting, check_every, batch, current_measures):
