@@ -487,7 +487,9 @@ class ConvStep:
         bias = self.conv.bias.detach() if self.conv.bias is not None else None
         fused_act = self.act if bn is None else 0
         y = K.empty((N, self.Ho, self.Wo, self.ld_y), x)
-        stats = K.zeros((2, self.Co), x, torch.float64) if bn_train else None
+        stats = (st.pop('stats_buf', None) if bn_train else None)
+        if bn_train and stats is None:
+            stats = K.zeros((2, self.Co), x, torch.float64)
         if self.gemm1x1:
             kk = self.k * self.k
             a2 = x.view(N, x.shape[-1])
@@ -967,8 +969,18 @@ class ConvStack:
             self.plan.ensure()
         t = K.to_nhwc(x.reshape(N, C, H, W), r8(C))
         state = []
+        # the BatchNorm statistics buffers of every layer of the stack come out of ONE zeroed allocation (one fill per forward
+        # instead of one per layer)
+        bn_steps = [s for s in self.steps if isinstance(s, ConvStep) and s.bn is not None and
+                    (training or not s.bn.track_running_stats)]
+        pool, off = None, 0
+        if bn_steps:
+            pool = K.zeros((sum(2 * s.Co for s in bn_steps),), t, torch.float64)
         for s in self.steps:
             st = {}
+            if pool is not None and any(s is b for b in bn_steps):
+                st['stats_buf'] = pool[off:off + 2 * s.Co].view(2, s.Co)
+                off += 2 * s.Co
             t = s.forward(t, st, training)
             state.append(st)
         Co, Ho, Wo = self.out_shape
