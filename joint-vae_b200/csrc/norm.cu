@@ -28,6 +28,23 @@ template <> struct Vec<8> {
     *reinterpret_cast<uint4*>(p) = u;
   }
 };
+// packed loads kept raw until use (the reductions hold several of them in flight per thread)
+template <int V> struct Raw;
+template <> struct Raw<8> {
+  typedef uint4 T;
+  static __device__ __forceinline__ T load(const __nv_bfloat16* p) { return ld_stream16(p); }
+  static __device__ __forceinline__ T zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const T& u, float (&v)[8]) {
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  }
+};
+template <> struct Raw<1> {
+  typedef float T;
+  static __device__ __forceinline__ T load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ void unpack(const T& u, float (&v)[1]) { v[0] = u; }
+};
 template <> struct Vec<1> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16(v[0]); }
@@ -178,12 +195,25 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_apply_fwd_kernel(const Bn
     shift[j] = b - mean * scale[j];
   }
   if (a.training && a.num_batches && blockIdx.x == 0 && threadIdx.x == 0) *a.num_batches += 1;
-  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
-    float v[V];
-    Vec<V>::load(a.y + p * a.ld_y + chunk * V, v);
+  constexpr int U = 4;        // rows per thread and round, loads requested together
+  const size_t step = (size_t)gridDim.x * a.ppb;
+  for (size_t p0 = (size_t)blockIdx.x * a.ppb + pl; p0 < a.P; p0 += U * step) {
+    typename Raw<V>::T yr[U];
 #pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], scale[j], shift[j]), a.act);
-    Vec<V>::store(a.out + p * a.ld_out + chunk * V, v);
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      yr[u] = p < a.P ? Raw<V>::load(a.y + p * a.ld_y + chunk * V) : Raw<V>::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      if (p >= a.P) break;
+      float v[V];
+      Raw<V>::unpack(yr[u], v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], scale[j], shift[j]), a.act);
+      Vec<V>::store(a.out + p * a.ld_out + chunk * V, v);
+    }
   }
 }
 
@@ -212,29 +242,33 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS, BN_REDUCE_BLOCKS) bn_bwd_red
     scale[j] = g * rstd; shift[j] = b - mean * scale[j];
     acc[0][j] = acc[1][j] = 0.f;
   }
-  constexpr int U = 2;
+  // U pixel rows per thread and round, all 2 U loads requested (and kept packed) before the first use: ~100 KB in flight per SM
+  constexpr int U = 4;
   const size_t step = (size_t)gridDim.x * a.ppb;
   for (size_t p0 = (size_t)blockIdx.x * a.ppb + pl; p0 < a.P; p0 += U * step) {
-    float g[U][V], y[U][V];
+    typename Raw<V>::T gr[U], yr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t p = p0 + u * step;
       if (p < a.P) {
-        Vec<V>::load(a.da + p * a.ld_da + chunk * V, g[u]);
-        Vec<V>::load(a.y + p * a.ld_y + chunk * V, y[u]);
+        gr[u] = Raw<V>::load(a.da + p * a.ld_da + chunk * V);
+        yr[u] = Raw<V>::load(a.y + p * a.ld_y + chunk * V);
       } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) { g[u][j] = 0.f; y[u][j] = 0.f; }
+        gr[u] = Raw<V>::zero(); yr[u] = Raw<V>::zero();
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+      float g[V], y[V];
+      Raw<V>::unpack(gr[u], g);
+      Raw<V>::unpack(yr[u], y);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float gz = g[u][j] * act_grad_z(fmaf(y[u][j], scale[j], shift[j]), a.act);
+        const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
         acc[0][j] += gz;
-        acc[1][j] = fmaf(gz, y[u][j], acc[1][j]);
+        acc[1][j] = fmaf(gz, y[j], acc[1][j]);
       }
+    }
   }
 #pragma unroll
   for (int j = 0; j < V; ++j) {      // sum g xhat = (sum g y - mean sum g) rstd, per thread before the cross-thread reduction
@@ -261,17 +295,35 @@ __global__ void __launch_bounds__(NORM_MAX_THREADS) bn_bwd_apply_kernel(const Bn
       if (a.dgamma) a.dgamma[c] += (float)a.sums[a.C + c];
     }
   }
-  for (size_t p = (size_t)blockIdx.x * a.ppb + pl; p < a.P; p += (size_t)gridDim.x * a.ppb) {
-    float g[V], y[V];
-    Vec<V>::load(a.da + p * a.ld_da + chunk * V, g);
-    Vec<V>::load(a.y + p * a.ld_y + chunk * V, y);
+  constexpr int U = 2;        // rows per thread and round, the 2 U loads requested together
+  const size_t step = (size_t)gridDim.x * a.ppb;
+  for (size_t p0 = (size_t)blockIdx.x * a.ppb + pl; p0 < a.P; p0 += U * step) {
+    typename Raw<V>::T gr[U], yr[U];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
-      const float xh = (y[j] - mean[j]) * rstd[j];
-      g[j] = scale[j] * (gz - k1[j] - xh * k2[j]);
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      if (p < a.P) {
+        gr[u] = Raw<V>::load(a.da + p * a.ld_da + chunk * V);
+        yr[u] = Raw<V>::load(a.y + p * a.ld_y + chunk * V);
+      } else {
+        gr[u] = Raw<V>::zero(); yr[u] = Raw<V>::zero();
+      }
     }
-    Vec<V>::store(a.dy + p * a.ld_dy + chunk * V, g);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * step;
+      if (p >= a.P) break;
+      float g[V], y[V];
+      Raw<V>::unpack(gr[u], g);
+      Raw<V>::unpack(yr[u], y);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float gz = g[j] * act_grad_z(fmaf(y[j], scale[j], shift[j]), a.act);
+        const float xh = (y[j] - mean[j]) * rstd[j];
+        g[j] = scale[j] * (gz - k1[j] - xh * k2[j]);
+      }
+      Vec<V>::store(a.dy + p * a.ld_dy + chunk * V, g);
+    }
   }
 }
 
