@@ -371,7 +371,11 @@ def run_native(args, wl):
         roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, average over the launches of one
                     # step in the committed ncu --set full capture (profiles/, r02): null until re-captured for a new kernel
-                    'traffic': args.traffic, 'peak_source': which + ' (MEASURED_PEAKS.json bf16_tflops_sustained)',
+                    'traffic': args.traffic if args.traffic is not None else
+                    (1097.1e6 if (kname == 'conv_halo_kernel' and args.workload == 'c2' and B == 512) else None),
+                    'traffic_of': 'largest launch of the kernel (32 -> 32 k5 forward on 8704 x 32 x 32, 456.3 GFLOP, 1140.9 MB '
+                                  'algorithmic): profiles/r02_conv_halo_ncu_full.txt; achieved / us_per_launch average all launches',
+                    'peak_source': which + ' (MEASURED_PEAKS.json bf16_tflops_sustained)',
                     'launches_per_step': nl / args.steps, 'us_per_launch': t_s / nl * 1e6, 'flop_per_launch': fl / nl,
                     'share_of_step': t_s / (ms_plain * 1e-3) if ms_plain else None,
                     'by_kernel': {k: {'ms_per_step': v[0] / args.steps * 1e3, 'tflops': v[1] / v[0] / 1e12,
