@@ -66,6 +66,8 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc = [], None
+        self.timed = False         # rows read while the timed region runs are kept apart (mark(True) / mark(False))
+        self.rows_timed = []
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
@@ -77,7 +79,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            row = [c.strip() for c in line.split(',')]
+            self.rows.append(row)
+            if self.timed:
+                self.rows_timed.append(row)
+
+    def mark(self, on):
+        self.timed = on
 
     def stop(self):
         if self.proc is None:
@@ -87,12 +95,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        # the timed region of a short run (10 steps = 0.13 s) can fall between two 100 ms samples: then the samples of the
+        # identical warm-up steps right before it (the sampler starts with them) stand in, and the window says so
+        rows, window = (self.rows_timed, 'timed region') if self.rows_timed else (self.rows[-3:], 'warm-up steps + timed region')
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in rows)]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 def make_ctor(wl, **over):
@@ -295,10 +306,16 @@ def run_native(args, wl):
     nat.PROFILE = None
     # the published value: the same steps without per-launch events, through the public train_step (CUDA-graph replays when
     # --graph, the default on one GPU: same kernels, same arithmetic, no per-launch host cost)
-    for i in range(3):
+    clocks = ClockSampler(local)        # started ahead of the timed region: nvidia-smi needs ~0.1-0.3 s for its first row
+    # the same steps, untimed, for ~0.5 s while the sampler starts; the count comes from the (max-over-ranks) eager step time, so
+    # every rank runs the same number of data-parallel steps
+    n_w = max(3, min(100, int(500.0 / max(1e-3, ms_eager / args.steps)) + 1))
+    for i in range(n_w):
         step_dev(i)
-    clocks = ClockSampler(local)
+    torch.cuda.synchronize()
+    clocks.mark(True)
     ms = timed(step_dev, args.steps)
+    clocks.mark(False)
     clk = clocks.stop()
     ms_plain = ms_eager
     # ---- end-to-end timing through the public API with host buffers
