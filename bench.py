@@ -289,21 +289,23 @@ def run_native(args, wl):
     # (eager steps: per-launch events cannot be recorded inside a replayed graph)
     for i in range(2):          # the capture above emptied the caching allocator: let the eager pools settle again
         step_eager(i)
-    nat.PROFILE = {'conv': []}
     nat.profile_drain()
-    nat.profile_native(True)        # fused ELBO kernels: events recorded inside the library right around the launch
+    nat.CONV_FLOPS = []             # algorithmic FLOPs of every convolution call, in call order (paired with the native records)
+    nat.profile_native(True)        # events recorded inside the library right around each fused-ELBO / convolution launch
     n0 = nat.launch_count()
     ms_eager = timed(step_eager, args.steps)
     launches = nat.launch_count() - n0
     nat.profile_native(False)
     prof = nat.profile_drain()
+    conv_launches, conv_flops = prof.pop('conv_launches'), nat.CONV_FLOPS
+    nat.CONV_FLOPS = None
     conv_prof = {}
-    for a, b, flops, kname in nat.PROFILE['conv']:
-        e = conv_prof.setdefault(kname, [0.0, 0.0, 0])
-        e[0] += a.elapsed_time(b) * 1e-3
-        e[1] += flops
-        e[2] += 1
-    nat.PROFILE = None
+    if len(conv_launches) == len(conv_flops):
+        for (kname, t_ms), flops in zip(conv_launches, conv_flops):
+            e = conv_prof.setdefault(kname, [0.0, 0.0, 0])
+            e[0] += t_ms * 1e-3
+            e[1] += flops
+            e[2] += 1
     # the published value: the same steps without per-launch events, through the public train_step (CUDA-graph replays when
     # --graph, the default on one GPU: same kernels, same arithmetic, no per-launch host cost)
     clocks = ClockSampler(local)        # started ahead of the timed region: nvidia-smi needs ~0.1-0.3 s for its first row

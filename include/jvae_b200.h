@@ -396,10 +396,11 @@ int jvae_adam_step(float* p, float* m, float* v, const void* grad, int grad_dtyp
                    float weight_decay, int nseg, const int32_t* chunk_seg, const int32_t* seg_active, int32_t* seg_step,
                    float* seg_bc, float grad_scale, void* stream);
 
-/* Per-launch profile: while enabled, the fused ELBO entry points bracket their main kernel launch with CUDA events recorded
+/* Per-launch profile: while enabled, the fused ELBO and convolution entry points bracket their main kernel launch with CUDA events recorded
  * on the launching stream inside the library (tags below); jvae_profile_drain waits for them, returns (tag, milliseconds)
  * pairs and forgets them.  Enable only around eager launches (event records are not stream-capture safe). */
-enum jvae_prof_tag { JVAE_PROF_ELBO_TRAIN_FWD = 1, JVAE_PROF_ELBO_TRAIN_BWD = 2, JVAE_PROF_ELBO_EVAL_FWD = 3 };
+enum jvae_prof_tag { JVAE_PROF_ELBO_TRAIN_FWD = 1, JVAE_PROF_ELBO_TRAIN_BWD = 2, JVAE_PROF_ELBO_EVAL_FWD = 3,
+                     JVAE_PROF_CONV_HALO = 4, JVAE_PROF_CONV_TAPBOX = 5, JVAE_PROF_WGRAD_HALO = 6, JVAE_PROF_WGRAD_TAPBOX = 7 };
 int jvae_profile_enable(int on);
 int jvae_profile_drain(int32_t* tags, float* ms, int max_records);
 

@@ -190,7 +190,9 @@ _ws_cache = {}
 PROFILE = None
 
 
-PROF_TAGS = {1: 'elbo_train_fwd', 2: 'elbo_train_bwd', 3: 'elbo_eval_fwd'}
+PROF_TAGS = {1: 'elbo_train_fwd', 2: 'elbo_train_bwd', 3: 'elbo_eval_fwd', 4: 'conv_halo_kernel', 5: 'conv_gather_gemm_kernel',
+             6: 'conv_wgrad_halo_kernel', 7: 'conv_wgrad_kernel'}
+CONV_TAGS = (4, 5, 6, 7)
 
 
 def profile_native(on):
@@ -204,8 +206,13 @@ def profile_drain(max_records=1 << 16):
     ms = (ctypes.c_float * max_records)()
     n = lib().jvae_profile_drain(tags, ms, max_records)
     out = {}
+    conv = []
     for i in range(n):
         out.setdefault(PROF_TAGS.get(tags[i], str(tags[i])), []).append(float(ms[i]))
+        if tags[i] in CONV_TAGS:
+            conv.append((PROF_TAGS[tags[i]], float(ms[i])))
+    # convolution launches in call order: bench.py pairs them with the algorithmic FLOPs the Python side noted per call
+    out['conv_launches'] = conv
     return out
 
 
@@ -229,6 +236,9 @@ class _timed:
 CONV_KERNELS = {1: 'conv_halo_kernel', 2: 'conv_gather_gemm_kernel', 3: 'conv_wgrad_halo_kernel', 4: 'conv_wgrad_kernel'}
 
 
+CONV_FLOPS = None      # bench.py sets a list: algorithmic FLOPs of every convolution entry-point call, in call order
+
+
 class _timed_conv:
     """PROFILE['conv']: (start event, stop event, algorithmic FLOPs, kernel name) per convolution launch"""
 
@@ -237,6 +247,8 @@ class _timed_conv:
         self.flops = flops
 
     def __enter__(self):
+        if CONV_FLOPS is not None:
+            CONV_FLOPS.append(self.flops)
         if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)

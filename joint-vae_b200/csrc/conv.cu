@@ -1221,7 +1221,9 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     attr = true;
   }
   int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
+  void* prof = prof_begin(JVAE_PROF_CONV_HALO, stream);
   conv_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(tin, tw, p);
+  prof_end(prof, stream);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_CONV_HALO;
   if (bn && bn_fused) *bn_fused = 1;
@@ -1399,7 +1401,9 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
     JVAE_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
+  void* prof = prof_begin(JVAE_PROF_WGRAD_HALO, stream);
   conv_wgrad_halo_kernel<<<dim3(gx, ysplit, nz), CONV_THREADS, smem, stream>>>(tg, tx, p);
+  prof_end(prof, stream);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_WGRAD_HALO;
   return JVAE_OK;
@@ -1488,7 +1492,9 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   }
   ConvParams pk = p;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  void* prof = prof_begin(JVAE_PROF_CONV_TAPBOX, (cudaStream_t)stream);
   conv_gather_gemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(tin, tw, pk);
+  prof_end(prof, (cudaStream_t)stream);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_CONV_TAPBOX;
   return JVAE_OK;
@@ -1548,7 +1554,9 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
   if (rc) return rc;
   rc = act_tmap(&tx, x, N, H, W, Cin, ld_x, p.Cblk_x, p.TW, p.TH, p.NB, in_stride);
   if (rc) return rc;
+  void* prof = prof_begin(JVAE_PROF_WGRAD_TAPBOX, (cudaStream_t)stream);
   conv_wgrad_kernel<<<dim3(gx, tap_groups, nz), CONV_THREADS, smem, (cudaStream_t)stream>>>(tdy, tx, p);
+  prof_end(prof, (cudaStream_t)stream);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_WGRAD_TAPBOX;
   return JVAE_OK;
