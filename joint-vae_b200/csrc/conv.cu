@@ -279,6 +279,7 @@ struct HaloParams {
   int RT, NBt, HHs, HWp, MT;            // rows / images per box, slots per image, halo width (pixels), M-tiles per box
   int strips_x, blocks_y, blocks_n, num_boxes, n_tiles_n;
   int Cblk, ntaps, BN;
+  int nkc;                               // input-channel chunks of Cblk (wide layers: Cin > 64); 1 otherwise
   int dymin, dxmin;                      // smallest tap offset in PLANE coordinates (e = (d - r) / in_stride)
   int in_stride, nplanes;                // input stride s: the input is read as up to s*s parity planes P_r[j] = in[s*j + r]
   short plane_ry[4], plane_rx[4];
@@ -323,7 +324,8 @@ __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
 template <int KSTEPS, int MT>
 __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, uint32_t a_hi, uint32_t a_lo0, uint32_t m_step16,
                                              uint32_t b_hi, uint32_t b_lo_base, uint32_t w_tap16, uint32_t idesc,
-                                             uint64_t* wfull_bar, uint64_t* wempty_bar, uint32_t& ws, uint32_t& wph) {
+                                             uint64_t* wfull_bar, uint64_t* wempty_bar, uint32_t& ws, uint32_t& wph,
+                                             uint32_t later_chunk) {
   uint32_t b_lo = b_lo_base;
   for (int t = 0; t < p.ntaps; ++t) {
     if (!p.resident) {
@@ -332,7 +334,7 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
       b_lo = b_lo_base + ws * w_tap16;
     }
     const uint32_t a_lo = a_lo0 + p.tap_off16[t];
-    const uint32_t acc_first = t != 0;
+    const uint32_t acc_first = (t != 0) | later_chunk;      // the first tap of the first channel chunk overwrites
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -624,28 +626,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         for (int t = 0; t < p.ntaps; ++t)
           tma_load_2d(wsm + (size_t)(p.G > 1 ? p.w_pos[t] : t) * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
       }
-      auto load_box = [&](int box, uint32_t it) {
+      // one shared-memory stage per unit = (box, input-channel chunk); the unit after the current one is requested before the
+      // current unit's weights (streamed per tap when they are not resident)
+      auto load_unit = [&](int box, int kc, uint32_t iu) {
         int m = box;
         const int sx = m % p.strips_x; m /= p.strips_x;
         const int by = m % p.blocks_y; m /= p.blocks_y;
-        const int s = it % p.stages;
-        mbar_wait(&empty_bar[s], ((it / p.stages) & 1) ^ 1);
+        const int s = iu % p.stages;
+        mbar_wait(&empty_bar[s], ((iu / p.stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], p.box_bytes);
         for (int pl = 0; pl < p.nplanes; ++pl)
-          tma_load_4d(smem + (size_t)s * p.stage_bytes + (size_t)pl * p.plane_bytes, &tmap_in, &full_bar[s], 0,
+          tma_load_4d(smem + (size_t)s * p.stage_bytes + (size_t)pl * p.plane_bytes, &tmap_in, &full_bar[s], kc * p.Cblk,
                       p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl], p.in_stride * (by * p.RT + p.dymin) + p.plane_ry[pl],
                       m * p.NBt);
       };
-      uint32_t it = 0, wit = 0;
-      if (box0 < p.num_boxes) load_box(box0, 0);
-      for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
-        if (box + box_step < p.num_boxes) load_box(box + box_step, it + 1);   // one box ahead of the weights
-        if (!p.resident) {
-          for (int t = 0; t < p.ntaps; ++t, ++wit) {
-            const int ws = wit % p.wstages;
-            mbar_wait(&wempty_bar[ws], ((wit / p.wstages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&wfull_bar[ws], p.w_tap_bytes);
-            tma_load_2d(wsm + (size_t)ws * p.w_tap_bytes, &tmap_w, &wfull_bar[ws], t * p.Cblk, nt * p.BN);
+      uint32_t iu = 0, wit = 0;
+      if (box0 < p.num_boxes) load_unit(box0, 0, 0);
+      for (int box = box0; box < p.num_boxes; box += box_step) {
+        for (int kc = 0; kc < p.nkc; ++kc, ++iu) {
+          if (kc + 1 < p.nkc) load_unit(box, kc + 1, iu + 1);
+          else if (box + box_step < p.num_boxes) load_unit(box + box_step, 0, iu + 1);
+          if (!p.resident) {
+            for (int t = 0; t < p.ntaps; ++t, ++wit) {
+              const int ws = wit % p.wstages;
+              mbar_wait(&wempty_bar[ws], ((wit / p.wstages) & 1) ^ 1);
+              mbar_arrive_expect_tx(&wfull_bar[ws], p.w_tap_bytes);
+              tma_load_2d(wsm + (size_t)ws * p.w_tap_bytes, &tmap_w, &wfull_bar[ws], (t * p.nkc + kc) * p.Cblk, nt * p.BN);
+            }
           }
         }
       }
@@ -666,31 +673,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
         const uint32_t acc = it & 1;
         mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
-        mbar_wait(&full_bar[s], sph);
-        tc_fence_after();
-        const uint32_t a_lo0 = ((smem_u32(smem + (size_t)s * p.stage_bytes) >> 4) & 0x3fffu) | (1u << 16);
         const uint32_t d0 = tmem_base + acc * p.acc_stride;
         const uint32_t b_lo = ((smem_u32(wsm) >> 4) & 0x3fffu) | (1u << 16);
-#define HALO_BOX(KS, M) halo_mma_box<KS, M>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, w_tap16, idesc, wfull_bar, wempty_bar, ws, wph)
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          mbar_wait(&full_bar[s], sph);
+          tc_fence_after();
+          const uint32_t a_lo0 = ((smem_u32(smem + (size_t)s * p.stage_bytes) >> 4) & 0x3fffu) | (1u << 16);
+          const uint32_t later = kc != 0;
+#define HALO_BOX(KS, M) halo_mma_box<KS, M>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, w_tap16, idesc, wfull_bar, wempty_bar, ws, wph, later)
 #define HALO_BOX_M(KS)                                                                 \
-        switch (p.MT) {                                                                \
-          case 1: HALO_BOX(KS, 1); break;                                              \
-          case 2: HALO_BOX(KS, 2); break;                                              \
-          case 3: HALO_BOX(KS, 3); break;                                              \
-          case 4: HALO_BOX(KS, 4); break;                                              \
-          default: HALO_BOX(KS, 5); break;                                             \
-        }
-        if (p.G > 1) {
-          const uint32_t idesc0 = make_idesc_bf16(128, 0, false, false);
-          if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
-          else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
-          else halo_mma_box_g<1>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
-        } else if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
+          switch (p.MT) {                                                              \
+            case 1: HALO_BOX(KS, 1); break;                                            \
+            case 2: HALO_BOX(KS, 2); break;                                            \
+            case 3: HALO_BOX(KS, 3); break;                                            \
+            case 4: HALO_BOX(KS, 4); break;                                            \
+            default: HALO_BOX(KS, 5); break;                                           \
+          }
+          if (p.G > 1) {
+            const uint32_t idesc0 = make_idesc_bf16(128, 0, false, false);
+            if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+            else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+            else halo_mma_box_g<1>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+          } else if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
 #undef HALO_BOX_M
 #undef HALO_BOX
-        umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[s]);
+          if (++s == (uint32_t)p.stages) { s = 0; sph ^= 1; }
+        }
         umma_commit(&tfull_bar[acc]);
-        if (++s == (uint32_t)p.stages) { s = 0; sph ^= 1; }
       }
     }
   } else {
@@ -1028,7 +1038,18 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                            const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused,
                            cudaStream_t stream) {
-  if (Cin > 64 || Cout_pad > 64 || Wq < 6) return 1;      // epilogue keeps per-thread statistics for up to 64 channels
+  if (Wq < 6) return 1;
+  // wide layers (Cin > 64 or more than 64 output channels): 64-channel output tiles (the epilogue keeps per-thread statistics
+  // for at most 32 channels per warp set), the input channels in chunks of 64, weights streamed per (tap, chunk); the input
+  // box is read once per (box, chunk) instead of once per tap as in the tap-box kernel.  Opt-in (JVAE_CONV_WIDE=1, read per call
+  // so a test can switch it): measured on B200 it moves 0.71 ms of the c2 step out of the tap-box kernel and costs 0.87 ms here
+  // (N = 64 MMAs at 48 cycles against N = 256 at 128, the box re-read by each of the 2-8 channel tiles, 2.3 waves of work
+  // items on the 8 x 8 maps), so the vgg19 / ResNet bodies stay on the tap-box kernels by default.
+  const bool wide = Cin > 64 || Cout_pad > 64;
+  if (wide) {
+    const bool wide_on = getenv("JVAE_CONV_WIDE") && atoi(getenv("JVAE_CONV_WIDE")) != 0;
+    if (!wide_on || (Cout_pad > 64 && (Cout_pad % 64) != 0) || bn) return 1;
+  }
   if (bn && !(out_sy == 1 && out_sx == 1 && out_oy == 0 && out_ox == 0 && Ho == Hq && Wo == Wq)) {
     bn = nullptr; stats = nullptr;                        // phase launches: the caller runs the separate reduction
   }
@@ -1054,7 +1075,9 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   const int ey = dymax - dymin, ex = dxmax - dxmin;
   if (ey > 16 || ex > 16) return 1;
   p.N = N; p.Hq = Hq; p.Wq = Wq; p.dymin = dymin; p.dxmin = dxmin;
-  p.Cblk = cblk_of(Cin); p.ntaps = ntaps; p.BN = Cout_pad; p.n_tiles_n = 1;
+  p.Cblk = cblk_of(Cin > 64 ? 64 : Cin); p.ntaps = ntaps;
+  p.nkc = (Cin + p.Cblk - 1) / p.Cblk;
+  p.BN = Cout_pad > 64 ? 64 : Cout_pad; p.n_tiles_n = Cout_pad / p.BN;
   const uint32_t rb = (uint32_t)p.Cblk * 2u;
   p.HWp = 8 + ex;
   p.RT = Hq <= 32 ? Hq : 32;
@@ -1071,7 +1094,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   // ---- tap rectangles per parity plane (vertical stacking needs, for every tap column, a contiguous run of tap rows)
   struct Col { int pl, x, e_lo, e_hi; };
   std::vector<Col> cols;
-  bool stackable = getenv("JVAE_CONV_NOSTACK") == nullptr;
+  bool stackable = !wide && getenv("JVAE_CONV_NOSTACK") == nullptr;
   for (int t = 0; t < ntaps && stackable; ++t) {
     const int x = tex[t] - dxmin, e = tey[t] - dymin;
     Col* c = nullptr;
@@ -1093,6 +1116,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     if (G > 1 && (!stackable || G * p.BN > 256)) break;
     for (int resident = 1; resident >= 0; --resident) {
       if (G > 1 && !resident) continue;
+      if (wide && resident) continue;                      // wide layers stream their weights per (tap, chunk)
       const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
       bool found = false;
       for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
@@ -1203,7 +1227,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     if (box[1] > 256 || box[2] > 256) return 1;
     int rc = make_tmap_bf16(&tin, in, 4, dims, strides, box, es, p.Cblk * 2);
     if (rc) return rc;
-    const int Ktot = ntaps * p.Cblk;
+    const int Ktot = ntaps * p.nkc * p.Cblk;
     uint64_t wd[2] = {(uint64_t)Ktot, (uint64_t)Cout_pad};
     uint64_t ws[1] = {(uint64_t)ldw * 2};
     uint32_t wbox[2] = {(uint32_t)p.Cblk, (uint32_t)p.BN};
@@ -1220,7 +1244,8 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     JVAE_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  int grid = p.num_boxes < sm_count() ? p.num_boxes : sm_count();
+  int grid = p.num_boxes * p.n_tiles_n < sm_count() ? p.num_boxes * p.n_tiles_n : (sm_count() / p.n_tiles_n) * p.n_tiles_n;
+  if (grid < p.n_tiles_n) return 1;
   void* prof = prof_begin(JVAE_PROF_CONV_HALO, stream);
   conv_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(tin, tw, p);
   prof_end(prof, stream);

@@ -321,3 +321,25 @@ def test_im2col_matches_unfold(pkg, k, stride, H, C):
     want = want.permute(0, 2, 1).reshape(N * Hq * Hq, C * k * k)
     assert torch.equal(out[:, :C * k * k].float(), want)
     assert (out[:, C * k * k:] == 7.0).all()          # columns past C * T are left alone
+
+
+@pytest.mark.parametrize('spec,shape,N', [('vgg11', (3, 32, 32), 16), ('[x3+1]96-160-M-72', (24, 16, 16), 9)])
+def test_wide_layers_on_the_halo_kernel(pkg, spec, shape, N, monkeypatch):
+    """JVAE_CONV_WIDE=1 (opt-in): layers with more than 64 input / output channels on the halo kernel (input-channel chunk loop,
+    64-channel output tiles, streamed weights) give the results of the default tap-box kernels."""
+    from jointvae_b200 import conv_engine as ce
+    torch.manual_seed(1)
+    seq = pkg.module.vae_layers.build_de_conv_layers(shape, spec, batch_norm=True, where='input').to(DEV).train()
+    x = torch.randn(N, *shape, device=DEV)
+    outs = {}
+    for wide in ('0', '1'):
+        monkeypatch.setenv('JVAE_CONV_WIDE', wide)
+        for p in seq.parameters():
+            p.grad = None
+        xin = x.clone().requires_grad_(True)
+        torch.manual_seed(2)
+        out = ce.run(list(copy.deepcopy(seq) if wide == '1' else seq), xin)
+        out.backward(torch.ones_like(out) * 0.01)
+        outs[wide] = (out.detach().float(), xin.grad.detach().float())
+    for a, b in zip(outs['0'], outs['1']):
+        assert _rel(b, a) < 2e-2, _rel(b, a)      # two bf16 pipelines with different summation orders (values agree to an ulp of bf16)
