@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 13
+#define JVAE_ABI_VERSION 14
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -199,7 +199,9 @@ enum jvae_gemm_mode {
 /*   a, b: bf16, leading dimensions lda/ldb in elements (multiples of 8);
  *   out_bf16 / out_f32: either or both, leading dimension ldd; bias (N) f32 or NULL;
  *   col_stats (2,N) f32 or NULL: += per-column sum and sum of squares of the pre-activation
- *   (BatchNorm batch statistics, conv.py:216-217); accumulate != 0: out_f32 += result. */
+ *   (BatchNorm batch statistics, conv.py:216-217); accumulate = 1: out_f32 += result; accumulate = n >= 2: the reduction is
+ *   split into n slices (one more grid dimension) whose partial products are added to out_f32 with fp32 atomics -- for
+ *   weight gradients with few output tiles and a long reduction; no bias / activation / bf16 output then. */
 int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int lda, const void* b, int ldb,
                    const float* bias, int act, void* out_bf16, float* out_f32, int ldd,
                    float* col_stats, int accumulate, void* stream);
@@ -321,9 +323,10 @@ int jvae_cast_bf16_f32(const void* src, float* dst, size_t n, void* stream);
 /* Patch matrix of a convolution (weight gradient on small maps as ONE TN GEMM, nn.Conv2d in conv.py:189-219): row (n, y, x) of
  * out (N*Hq*Wq, ld_out) holds column ci * ntaps + t = x[n, y * in_stride + dy_t, x * in_stride + dx_t, ci], zero outside the
  * map; x is NHWC bf16 with channel stride ld_x.  The column order is torch's (Cin, kh, kw), so
- * jvae_gemm_bf16(TN, Cout, Cin * ntaps, N*Hq*Wq, dY, ld_dy, out, ld_out, ..., accumulate) adds the weight gradient to .grad */
+ * jvae_gemm_bf16(TN, Cout, Cin * ntaps, N*Hq*Wq, dY, ld_dy, out, ld_out, ..., accumulate) adds the weight gradient to .grad.
+ * tap_major != 0: column t * C + ci instead (any window of up to 64 taps; the caller permutes the small result). */
 int jvae_im2col_bf16(const void* x, int N, int H, int W, int C, int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx,
-                     int in_stride, int Hq, int Wq, void* out, int ld_out, void* stream);
+                     int in_stride, int Hq, int Wq, void* out, int ld_out, int tap_major, void* stream);
 /* NCHW f32 -> NHWC bf16 (optionally padding channels to c_pad with zeros) and back */
 int jvae_nchw_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int c_pad, void* stream);
 int jvae_nhwc_bf16_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int c_pad, void* stream);

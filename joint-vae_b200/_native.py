@@ -96,7 +96,7 @@ def lib():
     L.jvae_probe_descriptors.argtypes = [c_int]
     L.jvae_probe_poison.argtypes = [ctypes.c_uint, P]
     L.jvae_profile_enable.argtypes = [c_int]
-    L.jvae_im2col_bf16.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_int16), c_int, c_int, c_int, P, c_int, P]
+    L.jvae_im2col_bf16.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int16), ctypes.POINTER(ctypes.c_int16), c_int, c_int, c_int, P, c_int, c_int, P]
     L.jvae_profile_drain.argtypes = [P, P, c_int]
     I16P = ctypes.POINTER(ctypes.c_int16)
     L.jvae_conv_gather_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, c_int,
@@ -126,7 +126,7 @@ def lib():
     L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
-    if L.jvae_abi_version() != 13:
+    if L.jvae_abi_version() != 14:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -447,7 +447,7 @@ GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 def gemm_bf16(mode, M, N, K, a, lda, b, ldb, *, bias=None, act=0, out_bf16=None, out_f32=None, ldd=None,
               col_stats=None, accumulate=False):
     check(lib().jvae_gemm_bf16(mode, M, N, K, ptr2d(a), lda, ptr2d(b), ldb, ptr(bias), act, ptr(out_bf16), ptr(out_f32),
-                               ldd if ldd is not None else N, ptr(col_stats), int(accumulate), stream()))
+                               ldd if ldd is not None else N, ptr(col_stats), int(accumulate), stream()))     # accumulate: 0 / 1 / n >= 2 (split-K)
 
 
 def rawptr(t):
@@ -459,10 +459,20 @@ def rawptr(t):
     return c_void_p(t.data_ptr())
 
 
-def im2col(x, N, H, W, C, ld_x, taps, in_stride, Hq, Wq, out):
-    """include/jvae_b200.h: jvae_im2col_bf16; out (N*Hq*Wq, >= C*T) bf16"""
+_sm_count = {}
+
+
+def sm_count():
+    dev = torch.cuda.current_device()
+    if dev not in _sm_count:
+        _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _sm_count[dev]
+
+
+def im2col(x, N, H, W, C, ld_x, taps, in_stride, Hq, Wq, out, tap_major=False):
+    """include/jvae_b200.h: jvae_im2col_bf16; out (N*Hq*Wq, >= C*T) bf16; columns ci * T + t, or t * C + ci when tap_major"""
     check(lib().jvae_im2col_bf16(rawptr(x), N, H, W, C, ld_x, len(taps[0]), taps[0], taps[1], in_stride, Hq, Wq, rawptr(out),
-                                 out.stride(0), stream()))
+                                 out.stride(0), int(tap_major), stream()))
 
 
 def taps_arg(taps):

@@ -100,15 +100,19 @@ class NativeKernels:
         N, Hq, Wq, ld_g = g.shape
         _, H, W, ld_x = x.shape
         T = len(taps[0])
-        if (not swapped and Hq * Wq <= IM2COL_MAXPIX and Cx % 8 == 0 and Cg >= 128 and Cx >= 64 and T in (1, 4, 9, 25)
-                and dw.is_contiguous()):
-            # small maps with many channels (vgg19's 512-channel layers at 4 x 4 and 2 x 2): the per-tap kernels have no reuse
-            # there; one patch matrix in torch's (Cin, kh, kw) column order + ONE TN GEMM accumulating into .grad instead
-            P = N * Hq * Wq
+        P = N * Hq * Wq
+        small = Hq * Wq <= IM2COL_MAXPIX and Cx % 8 == 0 and Cg >= 128 and Cx >= 64 and T in (1, 4, 9, 25)
+        if not swapped and small and dw.is_contiguous():
+            # one patch matrix + ONE TN GEMM accumulating into .grad (the per-tap kernels have no operand reuse there).  With few
+            # output tiles the reduction over the pixels is split over the SMs (partial products added with fp32 atomics).
+            # (Tried for the ResNet stem too -- 7 x 7, stride 2, 3 channels, tap-major patch matrix: 122 us against ~90 us on the
+            # halo kernel, so only the small maps come here.)
             cols = torch.empty((P, Cx * T), dtype=torch.bfloat16, device=g.device)
             nat.im2col(x, N, H, W, Cx, ld_x, taps, in_stride, Hq, Wq, cols)
+            tiles = ((Cg + 127) // 128) * ((Cx * T + 127) // 128)
+            ksplit = max(1, min(nat.sm_count() // tiles, (P + 511) // 512)) if tiles < 100 else 1
             nat.gemm_bf16(2, Cg, Cx * T, P, g.view(P, ld_g), ld_g, cols, Cx * T, out_f32=dw.view(Cg, Cx * T), ldd=Cx * T,
-                          accumulate=True)
+                          accumulate=ksplit if ksplit > 1 else True)
             return
         if swapped:
             nat.conv_wgrad(g, N, Hq, Wq, Cg, ld_g, x, H, W, Cx, ld_x, taps, in_stride, dw, 1, T, Cg * T)

@@ -865,6 +865,8 @@ constexpr int WH_MAX_GROUPS = 64;
 struct WHaloParams {
   int N, Hq, Wq;
   int NBt, HHs, HWp, MT, strips_x, num_boxes;
+  int RT, blocks_y;                         // rows per box and row blocks per image (maps taller than 32 rows)
+  uint32_t g_img_bytes;                     // blocks_y > 1: the gradient tile arrives image by image (RT rows each, HHs slots apart)
   int Cblk_g, Cblk_x, ncx, Cg, Cx;          // blockIdx.z = (G channel block) * ncx + (X channel block)
   int ngroups, groups_per_cta;              // blockIdx.y selects a slice of the tap groups
   int dymin, dxmin, ey;                     // smallest tap offset in plane coordinates; vertical extent of the window
@@ -925,14 +927,24 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     if (elect_one()) {
       uint32_t s = 0, ph = 0;
       for (int box = blockIdx.x; box < p.num_boxes; box += gridDim.x) {
-        const int sx = box % p.strips_x, nb = box / p.strips_x;
+        int m = box;
+        const int sx = m % p.strips_x; m /= p.strips_x;
+        const int by = m % p.blocks_y; const int nb = m / p.blocks_y;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], p.x_box_bytes + p.g_box_bytes);
         for (int pl = 0; pl < p.nplanes; ++pl)
           tma_load_4d(st + (size_t)pl * p.plane_bytes, &tmap_x, &full_bar[s], cx0, p.in_stride * (sx * 8 + p.dxmin) + p.plane_rx[pl],
-                      p.in_stride * p.dymin + p.plane_ry[pl], nb * p.NBt);
-        tma_load_4d(st + p.x_stage_bytes + p.g_gap_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
+                      p.in_stride * (by * p.RT + p.dymin) + p.plane_ry[pl], nb * p.NBt);
+        if (p.blocks_y == 1) {
+          tma_load_4d(st + p.x_stage_bytes + p.g_gap_bytes, &tmap_g, &full_bar[s], cg0, sx * 8, 0, nb * p.NBt);
+        } else {
+          // row blocks: RT gradient rows per image, the ey halo slots behind them keep the zeros the stage was initialised with
+          // (a box of HHs rows would bring the NEXT block's rows there); rows past the image are zero-filled by TMA
+          for (int i = 0; i < p.NBt; ++i)
+            tma_load_4d(st + p.x_stage_bytes + p.g_gap_bytes + (size_t)i * p.HHs * 8u * rbg, &tmap_g, &full_bar[s], cg0, sx * 8,
+                        by * p.RT, nb * p.NBt + i);
+        }
         if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -1259,7 +1271,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
 static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
                                  int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw,
                                  int dw_ld_tap, int dw_ld_co, int dw_ld_cx, cudaStream_t stream) {
-  if (Hq > 32 || Wq < 6) return 1;
+  if (Wq < 6) return 1;
   WHaloParams p;
   memset(&p, 0, sizeof(p));
   const int st = in_stride;
@@ -1285,7 +1297,8 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   const int ncg = (Cg + p.Cblk_g - 1) / p.Cblk_g;
   p.ncx = (Cx + p.Cblk_x - 1) / p.Cblk_x;
   const uint32_t rbx = (uint32_t)p.Cblk_x * 2u, rbg = (uint32_t)p.Cblk_g * 2u;
-  p.HWp = 8 + ex; p.HHs = Hq + ey;
+  p.RT = Hq <= 32 ? Hq : 32; p.blocks_y = (Hq + p.RT - 1) / p.RT;      // taller maps: row blocks of 32
+  p.HWp = 8 + ex; p.HHs = p.RT + ey;
   // tap groups.  Full k x k windows at stride 1: runs of horizontally adjacent taps (at most 128 / Cblk_x) along M, sets of
   // vertically adjacent taps (at most 256 / Cblk_g) along N.  Otherwise (parity planes, sparse windows): horizontal runs only,
   // the vertical shift on the A side.
@@ -1381,7 +1394,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
     const uint32_t gs = p.g_gap_bytes + (((uint32_t)(16 * MT > S ? 16 * MT : S) * 8u * rbg + 1023u) & ~1023u);
     if (2u * (xs + gs) + 1024u > budget) break;
     if (nbt * p.HHs > 256) break;
-    const double eff = (double)(nbt * Hq) / (16.0 * MT);
+    const double eff = (double)(nbt * p.RT) / (16.0 * MT);
     if (eff > best + 0.02) {
       best = eff; p.NBt = nbt; p.MT = MT; p.x_stage_bytes = xs; p.stage_bytes = xs + gs; p.plane_bytes = plane;
     }
@@ -1393,18 +1406,18 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
     p.grp_off16[gi] = ((uint32_t)tpl[t0] * p.plane_bytes + (uint32_t)((tey[t0] - dymin) * p.HWp + (tex[t0] - dxmin)) * rbx) >> 4;
   }
   p.x_box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rbx;
-  p.g_box_bytes = (uint32_t)(p.NBt * p.HHs) * 8u * rbg;
+  p.g_box_bytes = (uint32_t)(p.NBt * (p.blocks_y == 1 ? p.HHs : p.RT)) * 8u * rbg;
   p.stages = (int)((budget - 1024u) / p.stage_bytes);
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return 1;
   p.strips_x = (Wq + 7) / 8;
-  p.num_boxes = p.strips_x * ((N + p.NBt - 1) / p.NBt);
+  p.num_boxes = p.strips_x * p.blocks_y * ((N + p.NBt - 1) / p.NBt);
   p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co; p.dw_ld_cx = dw_ld_cx;
   CUtensorMap tg, tx;
   {
     uint64_t dg[4] = {(uint64_t)Cg, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)N};
     uint64_t sg[3] = {(uint64_t)ld_g * 2, (uint64_t)Wq * ld_g * 2, (uint64_t)Hq * Wq * ld_g * 2};
-    uint32_t bg[4] = {(uint32_t)p.Cblk_g, 8u, (uint32_t)p.HHs, (uint32_t)p.NBt};
+    uint32_t bg[4] = {(uint32_t)p.Cblk_g, 8u, (uint32_t)(p.blocks_y == 1 ? p.HHs : p.RT), (uint32_t)(p.blocks_y == 1 ? p.NBt : 1)};
     int rc = make_tmap_bf16(&tg, g, 4, dg, sg, bg, nullptr, p.Cblk_g * 2);
     if (rc) return rc;
     uint64_t dx[4] = {(uint64_t)Cx, (uint64_t)W, (uint64_t)H, (uint64_t)N};

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(EW_THREADS) nhwc_to_nchw_kernel(const __nv_bfl
 // columns follow torch's (Cin, kh, kw) weight order, so dW = dY^T . out is the weight gradient in torch's layout (one TN GEMM
 // accumulating straight into .grad).  One thread per (row, 8 channels): T 16-byte loads, a register transpose, T 16-byte stores.
 struct TapList { short dy[32], dx[32]; };
+struct TapList64 { short dy[64], dx[64]; };
 template <int T>
 __global__ void __launch_bounds__(EW_THREADS) im2col_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int ldx,
                                                             int Hq, int Wq, int stride, const TapList taps,
@@ -84,6 +85,27 @@ __global__ void __launch_bounds__(EW_THREADS) im2col_kernel(const __nv_bfloat16*
     uint4* o = reinterpret_cast<uint4*>(out + q * (size_t)ldo + (size_t)g * 8 * T);
 #pragma unroll
     for (int t = 0; t < T; ++t) o[t] = reinterpret_cast<const uint4*>(v)[t];
+  }
+}
+
+// the same patch matrix with the columns in (tap, channel) order: column t * C + ci; any window size, one 16-byte store per tap
+__global__ void __launch_bounds__(EW_THREADS) im2col_tapmajor_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                                                     int ldx, int Hq, int Wq, int stride, int T, const TapList64 taps,
+                                                                     __nv_bfloat16* __restrict__ out, int ldo) {
+  const int cg = C >> 3;
+  const size_t total = (size_t)N * Hq * Wq * cg;
+  for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * EW_THREADS) {
+    const int g = (int)(i % cg);
+    const size_t q = i / cg;
+    const int xq = (int)(q % Wq), yq = (int)((q / Wq) % Hq), n = (int)(q / ((size_t)Wq * Hq));
+    uint4* o = reinterpret_cast<uint4*>(out + q * (size_t)ldo + (size_t)g * 8);
+    for (int t = 0; t < T; ++t) {
+      const int yy = yq * stride + taps.dy[t], xx = xq * stride + taps.dx[t];
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        u = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * ldx + (size_t)g * 8);
+      o[(size_t)t * cg] = u;
+    }
   }
 }
 
@@ -184,12 +206,23 @@ int jvae_batch_u8_to_f32(const jvae_batch_cfg* cfg, const void* src, long long n
 }
 
 int jvae_im2col_bf16(const void* x, int N, int H, int W, int C, int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx,
-                     int in_stride, int Hq, int Wq, void* out, int ld_out, void* stream) {
+                     int in_stride, int Hq, int Wq, void* out, int ld_out, int tap_major, void* stream) {
   JVAE_CHECK_ARG(x && out && tap_dy && tap_dx, "x, out and the tap lists are required");
   JVAE_CHECK_ARG(N > 0 && H > 0 && W > 0 && Hq > 0 && Wq > 0 && in_stride > 0, "bad dims");
   JVAE_CHECK_ARG(C > 0 && (C % 8) == 0 && (ld_x % 8) == 0 && ld_x >= C, "C and ld_x must be multiples of 8");
   JVAE_CHECK_ARG(ld_out >= C * ntaps && (ld_out % 8) == 0, "ld_out must cover C * ntaps columns and be a multiple of 8");
   JVAE_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) & 15) == 0, "buffers must be 16-byte aligned");
+  if (tap_major) {
+    JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= 64, "1..64 taps");
+    TapList64 tl;
+    for (int t = 0; t < ntaps; ++t) { tl.dy[t] = tap_dy[t]; tl.dx[t] = tap_dx[t]; }
+    const size_t total = (size_t)N * Hq * Wq * (C / 8);
+    im2col_tapmajor_kernel<<<ew_grid(total), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, ld_x, Hq, Wq, in_stride, ntaps, tl,
+        reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+    JVAE_LAUNCH_CHECK();
+    return JVAE_OK;
+  }
   if (ntaps != 9 && ntaps != 25 && ntaps != 1 && ntaps != 4) {
     set_error("jvae_im2col_bf16: windows of 1, 4, 9 or 25 taps only (ntaps=%d)", ntaps);
     return JVAE_ERR_UNSUPPORTED;

@@ -19,6 +19,7 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
   int M, N, K, ldd, act, accumulate;
+  int ksplit;      // > 1: gridDim.z slices of the reduction, partial results added to out_f32 with fp32 atomics
   int stages;      // ring depth actually used (<= GemmSmem::STAGES): short reductions take less shared memory, so several
                    // CTAs share an SM and their prologue / load / epilogue latencies overlap
   const float* bias;
@@ -57,7 +58,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb_all = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = p.ksplit > 1 ? (num_kb_all + p.ksplit - 1) / p.ksplit : num_kb_all;
+  const int kb_lo = (int)blockIdx.z * kb_per;
+  const int num_kb = min(kb_per, num_kb_all - kb_lo);       // k-blocks of this CTA's slice
+  if (num_kb <= 0) return;                                  // empty tail slice (uniform for the CTA, before any barrier)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -86,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* sa = smem + s * S::STAGE_BYTES;
         uint8_t* sb = sa + S::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        const int k0 = kb * GEMM_BK;
+        const int k0 = (kb_lo + kb) * GEMM_BK;
         if (!A_MN) {
           tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);            // box {64 k, 128 m}
         } else {
@@ -150,7 +155,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const size_t off = (size_t)row * p.ldd + n0 + c0;
       const bool full = (n0 + c0 + 32 <= p.N);
-      if (p.out_f32) {
+      if (p.out_f32 && p.ksplit > 1) {
+        float* o = p.out_f32 + off;
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.N) atomicAdd(o + j, v[j]);
+      } else if (p.out_f32) {
         float* o = p.out_f32 + off;
         if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -257,9 +266,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     JVAE_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_done = true;
   }
-  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN);
+  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, p.ksplit > 1 ? p.ksplit : 1);
   GemmParams q = p;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb_all = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = p.ksplit > 1 ? (num_kb_all + p.ksplit - 1) / p.ksplit : num_kb_all;
   q.stages = num_kb < S::STAGES ? (num_kb < 2 ? 2 : num_kb) : S::STAGES;
   const size_t smem = (size_t)q.stages * S::STAGE_BYTES + 256 + 1024;
   gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, q);
@@ -281,6 +291,7 @@ extern "C" int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int 
   JVAE_CHECK_ARG((((uintptr_t)a | (uintptr_t)b) & 15) == 0, "a and b must be 16-byte aligned");
   JVAE_CHECK_ARG(ldd >= N, "ldd < N");
   JVAE_CHECK_ARG(!accumulate || out_f32, "accumulate needs out_f32");
+  JVAE_CHECK_ARG(accumulate < 2 || (!out_bf16 && !bias && act == JVAE_ACT_NONE), "a split reduction only adds into out_f32");
   if (col_stats) {
     set_error("jvae_gemm_bf16: col_stats is only implemented by the convolution kernels");
     return JVAE_ERR_UNSUPPORTED;
@@ -295,7 +306,8 @@ extern "C" int jvae_gemm_bf16(int mode, int M, int N, int K, const void* a, int 
   rc = operand_tmap(&tb, b, b_mn, N, K, ldb, BN);
   if (rc) return rc;
   GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.act = act; p.accumulate = accumulate;
+  p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.act = act; p.accumulate = accumulate ? 1 : 0;
+  p.ksplit = accumulate >= 2 ? accumulate : 1;
   p.bias = bias; p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.out_f32 = out_f32;
   cudaStream_t st = (cudaStream_t)stream;
 #define JVAE_GEMM_CASE(bn, am, bm) return launch_gemm<bn, am, bm>(ta, tb, p, st)
