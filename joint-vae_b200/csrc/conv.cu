@@ -81,7 +81,8 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+constexpr int TAPBOX_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, alternating chunks)
+__global__ void __launch_bounds__(TAPBOX_THREADS, 1)
 conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -96,7 +97,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_per_tile = p.ntaps * p.nCk;
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += CONV_THREADS) s_stats[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * p.cout_pad; i += TAPBOX_THREADS) s_stats[i] = 0.0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
@@ -107,7 +108,7 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 8);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -172,8 +173,11 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     }
   } else {
     // ================= epilogue =================
-    const int q = warp & 3;
+    // two warps per TMEM lane quarter take alternate 16-channel chunks of a tile (the early vgg19 layers were drain-bound:
+    // 36 MMAs of 64 cycles against ~250 epilogue instructions per chunk on one warp per scheduler)
+    const int q = warp & 3, set = (warp - 2) >> 2;
     const int mrow = q * 32 + lane;
+    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (p.Cout & 3) == 0;
     const int tx_in = mrow % p.TW, ty_in = (mrow / p.TW) % p.TH, nb_in = mrow / (p.TW * p.TH);
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -191,18 +195,30 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
       const uint32_t t_addr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       const int ch0 = nt * p.BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      for (int c0 = set * 16; c0 < p.BN; c0 += 32) {
+        if (ch0 + c0 >= p.Cout) continue;       // warp-uniform
         uint32_t r[16];
         tmem_ld_32x16(t_addr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (ch0 + c0 >= p.Cout) continue;       // warp-uniform
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = __uint_as_float(r[j]);
-          const int ch = ch0 + c0 + j;
-          if (p.bias && ch < p.Cout) t += __ldg(&p.bias[ch]);
-          v[j] = (ok && ch < p.Cout) ? t : 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+          if (bias_vec && ch0 + c0 + 16 <= p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + c0 + j < p.Cout) v[j] += __ldg(&p.bias[ch0 + c0 + j]);
+          }
+        }
+        if (!ok || ch0 + c0 + 16 > p.Cout) {     // rows outside the image / channels past Cout contribute nothing
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (ok && ch0 + c0 + j < p.Cout) ? v[j] : 0.f;
         }
         if (p.stats) {      // batch statistics of the pre-activation (BatchNorm2d in train mode), fp32 accumulators
           float sq[16];
@@ -248,9 +264,9 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the eight epilogue warps
       const int t = threadIdx.x - 64;
-      for (int i = t; i < 2 * p.cout_pad; i += 128) {
+      for (int i = t; i < 2 * p.cout_pad; i += 256) {
         const int ch = i % p.cout_pad;
         const double val = s_stats[i];
         if (ch < p.Cout && val != 0.0) atomicAdd(&p.stats[(i / p.cout_pad) * p.Cout + ch], val);
@@ -1531,7 +1547,7 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   ConvParams pk = p;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   void* prof = prof_begin(JVAE_PROF_CONV_TAPBOX, (cudaStream_t)stream);
-  conv_gather_gemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(tin, tw, pk);
+  conv_gather_gemm_kernel<<<grid, TAPBOX_THREADS, smem, (cudaStream_t)stream>>>(tin, tw, pk);
   prof_end(prof, (cudaStream_t)stream);
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_CONV_TAPBOX;

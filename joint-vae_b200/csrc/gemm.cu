@@ -145,13 +145,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       if (!row_ok) continue;
+      // bias and activation are decided ONCE per chunk (the ncu source view of the K = 128 decoder GEMM showed ~57 instructions
+      // per output element -- a bounds test, a scalar bias load and the activation switch each -- and 19 us per 128 x 128 tile)
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        float t = __uint_as_float(r[j]);
-        if (p.bias && col < p.N) t += __ldg(&p.bias[col]);
-        v[j] = apply_act(t, p.act);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+        if (n0 + c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + n0 + c0) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) v[j] += __ldg(&p.bias[n0 + c0 + j]);
+        }
+      }
+      if (p.act == JVAE_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == JVAE_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      } else if (p.act == JVAE_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
       }
       const size_t off = (size_t)row * p.ldd + n0 + c0;
       const bool full = (n0 + c0 + 32 <= p.N);
