@@ -130,7 +130,7 @@ extern "C" int jvae_probe_descriptors(int verbose) { return jvae::probe_descript
 // ONE accumulator versus round-robin over several accumulators, operands in shared memory (contents irrelevant).
 namespace jvae {
 
-__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(int N, int nacc, int iters, int cblk, long long* out) {
+__global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(int N, int nacc, int iters, int cblk, long long* out, int M = 128) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128, 1) probe_mma_rate_kernel(int N, int nacc,
   if (warp == 0 && elect_one()) {
     const uint32_t rb = (uint32_t)cblk * 2u;
     const uint32_t swz = (cblk == 64) ? SWZ_128B : (cblk == 32 ? SWZ_64B : SWZ_32B);
-    const uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint32_t idesc = make_idesc_bf16(M, N, false, false);
     const uint64_t a_desc = make_smem_desc(smem_u32(smem), 16, 8 * rb, swz);
     const uint64_t b_desc = make_smem_desc(smem_u32(smem) + 16384, 16, 8 * rb, swz);
     const long long t0 = clock64();
@@ -188,6 +188,16 @@ int probe_mma_rate() {
       }
     }
   }
+  // N that is not a power of two, and M = 64 (tap stacking produces both)
+  for (int M : {128, 64})
+    for (int N : {32, 48, 64, 96, 128, 160, 192, 224, 256}) {
+      probe_mma_rate_kernel<<<1, 128, 64 * 1024>>>(N, 1, iters, 32, d, M);
+      probe_mma_rate_kernel<<<1, 128, 64 * 1024>>>(N, 1, iters, 32, d, M);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("[probe] mma rate: CUDA error\n"); return -1; }
+      long long h[2];
+      cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+      printf("[probe] mma M=%3d N=%3d K=16 rows=64B: complete %.1f clk/mma (M*N/256 = %d)\n", M, N, (double)h[1] / iters, M * N / 256);
+    }
   cudaFree(d);
   return 0;
 }
