@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 14
+#define JVAE_ABI_VERSION 15
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -248,6 +248,31 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
                              int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq,
                              void* out, int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                              const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused, void* stream);
+/* ALL sub-pixel phases of a stride-`out_s` ConvTranspose2d (conv.py:189-219, the imager stacks of conv-models.ini:25) or of
+ * the data gradient of a strided Conv2d in ONE launch: phase i owns phase_ntaps[i] consecutive entries of the tap table (and
+ * of wmat's [tap] blocks, same row layout as jvae_conv_gather_gemm) and writes
+ *     out[n, qy*out_s + phase_oy[i], qx*out_s + phase_ox[i], co]
+ * for every q of the (N, Hq, Wq) grid all phases share (even output sizes).  The input box is read once for all phases and
+ * the taps of different phases that read the same input shift are one MMA (their weights stacked along N).
+ * Returns JVAE_NOT_COVERED (nothing launched, no error text) when the geometry is outside what the merged kernel handles
+ * (wide layers, weights that do not fit in shared memory, JVAE_CONV_MERGE_PHASES=0): the caller then issues one
+ * jvae_conv_gather_gemm per phase, which computes the same thing. */
+#define JVAE_NOT_COVERED 1
+int jvae_conv_subpixel_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                            int nphases, const int16_t* phase_ntaps, const int16_t* phase_oy, const int16_t* phase_ox,
+                            const int16_t* tap_dy, const int16_t* tap_dx, int Hq, int Wq, void* out, int Ho, int Wo, int Cout,
+                            int ld_out, int out_s, const float* bias, int act, double* stats, void* stream);
+/* Diagnostic, HOST ONLY (no GPU, every pointer is host memory, tensors as fp32): executes the plan the halo convolution kernel
+ * would run for this geometry -- box fills, chunk records / tap table, accumulator columns, epilogue block table -- on the CPU,
+ * so the planner is testable without a device.  nphases = 0: the plan of jvae_conv_gather_gemm (ntaps / in_stride / out_o as
+ * there); nphases >= 2: the plan of jvae_conv_subpixel_gemm (out_sy = out_sx = out_s, out_o = 0).  info (8 ints, may be NULL)
+ * receives {G, phases, M-tiles per box, images per box, channel tile, chunk records, resident weights, stages}.
+ * Returns JVAE_NOT_COVERED when the halo kernel does not take the geometry. */
+int jvae_conv_halo_emulate(const float* in, int N, int H, int W, int Cin, int ld_in, const float* wmat, int Cout_pad, int ldw,
+                           int nphases, const int16_t* phase_ntaps, const int16_t* phase_oy, const int16_t* phase_ox, int ntaps,
+                           const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, float* out, int Ho, int Wo,
+                           int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
+                           int* info);
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, int dw_ld_ci, void* stream);

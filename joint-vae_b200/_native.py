@@ -107,6 +107,11 @@ def lib():
                                            c_int, P, ctypes.POINTER(BnReduce), ctypes.POINTER(c_int), P]
     L.jvae_conv_wgrad.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, I16P, I16P,
                                   c_int, P, c_int, c_int, c_int, P]
+    L.jvae_conv_subpixel_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, I16P, I16P,
+                                          I16P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P]
+    L.jvae_conv_halo_emulate.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, I16P, c_int,
+                                         I16P, I16P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, P, c_int, ctypes.POINTER(c_int)]
     L.jvae_bn_stats.argtypes = [P, c_size_t, c_int, c_int, P, P]
     L.jvae_bn_apply_fwd.argtypes = [P, c_size_t, c_int, c_int, P, P, P, c_float, c_float, P, P, P, c_int, c_int, P, c_int,
                                     P, P]
@@ -126,7 +131,7 @@ def lib():
     L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
-    if L.jvae_abi_version() != 14:
+    if L.jvae_abi_version() != 15:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -253,6 +258,13 @@ class _timed_conv:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
             self.a.record()
+        return self
+
+    def cancel(self):
+        """the entry point launched nothing (JVAE_NOT_COVERED): no record"""
+        if CONV_FLOPS is not None:
+            CONV_FLOPS.pop()
+        self.on = False
 
     def __exit__(self, *exc):
         if self.on:
@@ -503,6 +515,62 @@ def conv_gather_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, taps, in_str
                                          out_s[1], out_o[0], out_o[1], rawptr(bias), act, rawptr(stats), ctypes.byref(d),
                                          ctypes.byref(fused), stream()))
     return bool(fused.value)
+
+
+NOT_COVERED = 1
+
+
+def phases_arg(ops):
+    """gather-op dicts of the sub-pixel phases (conv_engine.deconv_form) -> the tables of jvae_conv_subpixel_gemm:
+    (taps per phase, phase_oy, phase_ox, tap_dy, tap_dx, total taps) with the taps concatenated phase by phase"""
+    A = ctypes.c_int16 * len(ops)
+    taps = [t for op in ops for t in op['taps']]
+    dy, dx = taps_arg(taps)
+    return (A(*[len(op['taps']) for op in ops]), A(*[int(op['out_o'][0]) for op in ops]), A(*[int(op['out_o'][1]) for op in ops]),
+            dy, dx, len(taps))
+
+
+def conv_subpixel_gemm(inp, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, phases, Hq, Wq, out, Ho, Wo, Cout, ld_out, out_s,
+                       bias=None, act=0, stats=None):
+    """include/jvae_b200.h: jvae_conv_subpixel_gemm.  phases = phases_arg(ops).  Returns False (nothing launched) when the
+    merged kernel does not cover the geometry: the caller then launches the phases one by one."""
+    pn, poy, pox, dy, dx, T = phases
+    with _timed_conv(2.0 * N * Hq * Wq * T * Cin * Cout) as tc:
+        rc = lib().jvae_conv_subpixel_gemm(rawptr(inp), N, H, W, Cin, ld_in, rawptr(wmat), Cout_pad, ldw, len(pn), pn, poy, pox,
+                                           dy, dx, Hq, Wq, rawptr(out), Ho, Wo, Cout, ld_out, out_s, rawptr(bias), act,
+                                           rawptr(stats), stream())
+        if rc == NOT_COVERED:
+            tc.cancel()
+    if rc == NOT_COVERED:
+        return False
+    check(rc)
+    return True
+
+
+def conv_halo_emulate(inp, Cin, wmat, Cout_pad, taps, in_stride, Hq, Wq, out, Cout, out_s=(1, 1), out_o=(0, 0), bias=None,
+                      act=0, phases=None):
+    """include/jvae_b200.h: jvae_conv_halo_emulate (HOST tensors, fp32; test aid).  inp (N,H,W,ld_in), wmat (Cout_pad, ldw),
+    out (N,Ho,Wo,ld_out) CPU float32.  Returns the info list, or None when the halo kernel does not take the geometry."""
+    for t in (inp, wmat, out):
+        assert t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous()
+    N, H, W, ld_in = inp.shape
+    _, Ho, Wo, ld_out = out.shape
+    hp = lambda t: None if t is None else c_void_p(t.data_ptr())
+    info = (c_int * 8)()
+    if phases is not None:
+        pn, poy, pox, dy, dx, T = phases
+        nph = len(pn)
+    else:
+        pn = poy = pox = None
+        dy, dx = taps
+        T, nph = len(dy), 0
+    rc = lib().jvae_conv_halo_emulate(hp(inp), N, H, W, Cin, ld_in, hp(wmat), Cout_pad, wmat.shape[1], nph, pn, poy, pox, T, dy, dx,
+                                      in_stride, Hq, Wq, hp(out), Ho, Wo, Cout, ld_out, out_s[0], out_s[1], out_o[0], out_o[1],
+                                      hp(bias), act, info)
+    if rc == NOT_COVERED:
+        return None
+    check(rc)
+    return list(info)
 
 
 def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co, dw_ld_ci=1):

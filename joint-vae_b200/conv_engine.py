@@ -124,6 +124,18 @@ class NativeKernels:
         nat.gemm_bf16(mode, M, N, K, a, a.stride(0), b, b.stride(0), bias=bias, act=act, out_bf16=out_bf16, out_f32=out_f32,
                       ldd=N)
 
+    @staticmethod
+    def phases_arg(ops):
+        return nat.phases_arg(ops)
+
+    @staticmethod
+    def subpixel(x, Cin, wmat, cout_pad, phases, Hq, Wq, out, Cout, out_s, bias, act, stats):
+        """all sub-pixel phases in one launch (jvae_conv_subpixel_gemm); False = not covered, nothing launched"""
+        N, H, W, ld_in = x.shape
+        _, Ho, Wo, ld_out = out.shape
+        return nat.conv_subpixel_gemm(x, N, H, W, Cin, ld_in, wmat, cout_pad, wmat.shape[1], phases, Hq, Wq, out, Ho, Wo, Cout,
+                                      ld_out, out_s, bias, act, stats)
+
     bn_stats = staticmethod(nat.bn_stats)
     bn_apply_fwd = staticmethod(nat.bn_apply_fwd)
     bn_bwd = staticmethod(nat.bn_bwd)
@@ -337,6 +349,13 @@ class ConvStep:
         else:
             self.fwd_ops = conv_form(k, p, s, self.Ho, self.Wo)
             self.dgrad_ops = deconv_form(k, p, s, H, W, allow_empty=True)
+        # stride-2 ConvTranspose2d with an even output: the four sub-pixel phases share their grid and run as ONE launch
+        # (jvae_conv_subpixel_gemm) on a weight matrix that lists the taps phase by phase; the per-phase launches stay as the
+        # fallback for geometries the merged kernel does not take
+        self.merged_fwd = (not self.gemm1x1) and self.transposed and s == 2 and len(self.fwd_ops) == 4 and \
+            len({(op['Hq'], op['Wq']) for op in self.fwd_ops}) == 1
+        if self.merged_fwd:
+            self.fwd_all_idx = [i for op in self.fwd_ops for i in op['idx']]
         # phases of the data gradient that no tap reaches (kernel < stride) stay zero
         self.dgrad_sparse = (not self.gemm1x1) and (not self.transposed) and len(self.dgrad_ops) < min(s, H) * min(s, W)
         self.wgrad_taps = [(i - p, j - p) for i in range(k) for j in range(k)]
@@ -387,6 +406,8 @@ class ConvStep:
         s_co, s_ci = (kk, Co * kk) if self.transposed else (Ci * kk, kk)
         sp = [gather_spec('fwd', i, Co, Ci, op['idx'], s_co, s_ci) for i, op in enumerate(self.fwd_ops)]
         sp += [gather_spec('bwd', i, Ci, Co, op['idx'], s_ci, s_co) for i, op in enumerate(self.dgrad_ops)]
+        if self.merged_fwd:
+            sp.append(gather_spec('fwd_all', None, Co, Ci, self.fwd_all_idx, s_co, s_ci))
         if self.separable:    # rows (ky, co) of the 1 x k kernel over kx taps; and [ci][kx][(ky, co)] for the data gradient
             cb = cblk_of(Ci)
             sp.append(pack_spec('sep_fwd', 'w', k * Co, Ci, range(k), s_co, s_ci, R0=Co, s_r1=k,
@@ -462,6 +483,8 @@ class ConvStep:
                 g_f = wd.permute(0, 2, 3, 1).reshape(self.Co, kk, self.Ci)
                 g_b = wd.permute(1, 2, 3, 0).reshape(self.Ci, kk, self.Co)
             d['fwd'] = [pack_gather_weights(g_f, op['idx'], self.Ci) for op in self.fwd_ops]
+            if self.merged_fwd:
+                d['fwd_all'] = pack_gather_weights(g_f, self.fwd_all_idx, self.Ci)
             if self.dense_small:     # W_eff[(q, co), (r, ci)] = W[co][ci][tap(q, r)]
                 hw = self.H * self.W
                 weff = torch.zeros((hw, self.Co, hw, self.Ci), dtype=torch.float32, device=w.device)
@@ -509,7 +532,7 @@ class ConvStep:
                 K.bn_stats(y, N * hw, self.Co, self.ld_y, stats)
         elif self.separable:
             self._sep_forward(x, pk, bias, fused_act, stats, y)
-        else:
+        elif not self._merged_forward(x, pk, y, bias, fused_act, stats):
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
                 K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
                          y, self.Co, op['out_s'], op['out_o'], bias, fused_act, stats)
@@ -529,6 +552,17 @@ class ConvStep:
             engine.bump_stats()      # the kernel wrote running_mean / running_var behind the version counters
         st['y'], st['save'], st['bn_train'] = y, save, bn_train
         return a
+
+    def _merged_forward(self, x, pk, out, bias, act, stats):
+        """the four sub-pixel phases of a stride-2 ConvTranspose2d in one launch; False: run them one by one"""
+        if not self.merged_fwd:
+            return False
+        ph = self._ctaps.get('fa')
+        if ph is None:
+            ph = self._ctaps['fa'] = K.phases_arg(self.fwd_ops)
+        wm = pk['fwd_all']
+        op = self.fwd_ops[0]
+        return K.subpixel(x, self.Ci, wm, wm.shape[0], ph, op['Hq'], op['Wq'], out, self.Co, self.s, bias, act, stats)
 
     def _sep_forward(self, x, pk, bias, act, stats, out):
         """1 x k convolution to k * Co channels (tensor cores), then the vertical shift-and-add with bias / activation / stats.
@@ -557,7 +591,7 @@ class ConvStep:
                    act=self.act, out_bf16=a.view(N, hw * self.Co))
         elif self.separable:
             self._sep_forward(x, pk, pk['b'], self.act, None, a)
-        else:
+        elif not self._merged_forward(x, pk, a, pk['b'], self.act, None):
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
                 K.gather(x, self.Ci, wm, wm.shape[0], self._taps(('f', i), op['taps']), op['in_stride'], op['Hq'], op['Wq'],
                          a, self.Co, op['out_s'], op['out_o'], pk['b'], self.act, None)

@@ -321,6 +321,13 @@ struct HaloParams {
   // W[tap (e = u - j, x)][co][ci] for every j that has such a tap.  An MMA then does count * BN columns instead of BN for the
   // same A-operand fetch, which is what bounds the N <= 64 layers.  Chunks = (plane, x, u) triples.
   int G, nck;
+  // Merged sub-pixel phases (PH > 1, G == 1; jvae_conv_subpixel_gemm): the PH phases of a stride-2 transposed convolution are
+  // computed from ONE box.  An M-tile owns PH accumulator blocks (one per phase, in the order the planner chose); a chunk is one
+  // input shift whose MMA stacks the weights of every phase that has a tap at that shift along N (a run of consecutive blocks),
+  // so the box is read once instead of once per phase launch and the epilogue writes whole output rows.  ph_oy / ph_ox: output
+  // offset of the phase that owns block position i.
+  int PH;
+  short ph_oy[4], ph_ox[4];
   // one 16-byte record per chunk (ONE uniform load in the issue loop; the MMA thread was issue-bound at ~12 uniform
   // instructions per MMA when these were five byte / short tables and the instruction descriptor was rebuilt per chunk):
   //   x = A start shift (plane * plane_bytes + (u * HWp + x) * row bytes) / 16,  y = B start shift (first tap block) / 16,
@@ -371,7 +378,7 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
 template <int KSTEPS>
 __device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0, uint32_t a_hi, uint32_t a_lo0, uint32_t m_step16,
                                                uint32_t b_hi, uint32_t b_lo_base, uint32_t idesc0) {
-  const uint32_t gbn = (uint32_t)(p.G * p.BN);
+  const uint32_t gbn = (uint32_t)(p.G * p.PH * p.BN);
   for (int m = 0; m < p.MT; ++m) {
     const uint32_t a_m = a_lo0 + (uint32_t)m * m_step16;
     const uint32_t d_m = d0 + (uint32_t)m * gbn;
@@ -413,16 +420,19 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
   const int q = warp & 3;
   const int mrow = q * 32 + lane;
   const int ch0 = nt * p.BN;
-  const int nblk = p.MT * p.G;
+  const int per = p.G * p.PH;                    // accumulator blocks of an M-tile: (row j of the group, phase)
+  const int nblk = p.MT * per;
   const int c_first = NCH == 1 ? 0 : set;        // chunks c_first, c_first + 2
   // the table does not depend on the pixel column of a row: 16 entries (slot groups of an M-tile) per block
   for (int i = threadIdx.x - 64; i < nblk * 16; i += 256) {
     const int blk = i >> 4;
-    const int m = blk / p.G, j = blk - m * p.G;
+    const int m = blk / per, r = blk - m * per;
+    const int j = r / p.PH, ph = r - j * p.PH;
     const int slot = (m * 16 + (i & 15)) * p.G + j;
     const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
     const bool valid = nb < p.NBt && yy < p.RT;
-    s_tab[i] = make_int2(valid ? (nb * p.Ho + yy * p.out_sy) * p.Wo : -1, yy | (nb << 16));      // pixel offset from the box origin
+    s_tab[i] = make_int2(valid ? (nb * p.Ho + yy * p.out_sy + p.ph_oy[ph]) * p.Wo + p.ph_ox[ph] : -1,
+                         yy | (nb << 16));      // pixel offset from the box origin
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");      // the table is shared by the two warps of a lane quarter
   float s1[STATS ? LC * 16 : 1], s2[STATS ? LC * 16 : 1];
@@ -640,7 +650,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       if (p.resident) {
         mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
         for (int t = 0; t < p.ntaps; ++t)
-          tma_load_2d(wsm + (size_t)(p.G > 1 ? p.w_pos[t] : t) * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
+          tma_load_2d(wsm + (size_t)(p.nck > 0 ? p.w_pos[t] : t) * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
       }
       // one shared-memory stage per unit = (box, input-channel chunk); the unit after the current one is requested before the
       // current unit's weights (streamed per tap when they are not resident)
@@ -705,7 +715,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             case 4: HALO_BOX(KS, 4); break;                                            \
             default: HALO_BOX(KS, 5); break;                                           \
           }
-          if (p.G > 1) {
+          if (p.nck > 0) {
             const uint32_t idesc0 = make_idesc_bf16(128, 0, false, false);
             if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
             else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
@@ -1060,12 +1070,15 @@ static int act_tmap(CUtensorMap* t, const void* base, int N, int H, int W, int C
   return make_tmap_bf16(t, base, 4, dims, strides, box, es, Cblk * 2);
 }
 
+// merged sub-pixel phases (jvae_conv_subpixel_gemm): the tap table lists the taps of phase 0, then phase 1, ...
+struct PhaseSpec { int n; const int16_t* ntaps; const int16_t* oy; const int16_t* ox; };
+
 // plans and launches the halo kernel; returns 1 if the geometry is not covered (caller falls back to the tap-box kernel)
 static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                            const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const PhaseSpec* phs = nullptr, HaloParams* plan_out = nullptr) {
   if (Wq < 6) return 1;
   // wide layers (Cin > 64 or more than 64 output channels): 64-channel output tiles (the epilogue keeps per-thread statistics
   // for at most 32 channels per warp set), the input channels in chunks of 64, weights streamed per (tap, chunk); the input
@@ -1074,6 +1087,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   // (N = 64 MMAs at 48 cycles against N = 256 at 128, the box re-read by each of the 2-8 channel tiles, 2.3 waves of work
   // items on the 8 x 8 maps), so the vgg19 / ResNet bodies stay on the tap-box kernels by default.
   const bool wide = Cin > 64 || Cout_pad > 64;
+  if (phs && (wide || in_stride != 1 || phs->n < 2 || phs->n > 4 || bn)) return 1;
   if (wide) {
     const bool wide_on = getenv("JVAE_CONV_WIDE") && atoi(getenv("JVAE_CONV_WIDE")) != 0;
     if (!wide_on || (Cout_pad > 64 && (Cout_pad % 64) != 0) || bn) return 1;
@@ -1083,6 +1097,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   }
   HaloParams p;
   memset(&p, 0, sizeof(p));
+  p.PH = 1;
   // tap offset d = s * e + r: parity plane r, offset e inside the plane (floor division for negative d)
   const int st = in_stride;
   int tey[CONV_MAX_TAPS], tex[CONV_MAX_TAPS], tpl[CONV_MAX_TAPS];
@@ -1136,11 +1151,92 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     stackable = covered == ntaps;                          // no holes, no duplicates
   }
 
+  // ---- merged phases: one chunk per (input shift, run of consecutive phase blocks that have a tap there)
+  struct Run { int shift, pos0, len, fresh; };
+  std::vector<Run> runs;
+  std::vector<int> shift_y, shift_x;
+  int tap_shift[CONV_MAX_TAPS], tap_phase[CONV_MAX_TAPS], ph_pos[4] = {0, 1, 2, 3};
+  if (phs) {
+    int t = 0;
+    for (int ph = 0; ph < phs->n; ++ph)
+      for (int i = 0; i < phs->ntaps[ph]; ++i, ++t) {
+        if (t >= ntaps) return 1;
+        tap_phase[t] = ph;
+        int sidx = -1;
+        for (size_t q = 0; q < shift_y.size(); ++q)
+          if (shift_y[q] == tey[t] && shift_x[q] == tex[t]) sidx = (int)q;
+        if (sidx < 0) { sidx = (int)shift_y.size(); shift_y.push_back(tey[t]); shift_x.push_back(tex[t]); }
+        for (int u = 0; u < t; ++u)
+          if (tap_shift[u] == sidx && tap_phase[u] == ph) return 1;      // two taps of a phase at one shift
+        tap_shift[t] = sidx;
+      }
+    if (t != ntaps) return 1;
+    // order of the phase blocks with the fewest runs (k = 5, stride 2: (0,1) (0,0) (1,0) (1,1) makes every shift ONE run)
+    auto runs_of = [&](const int* pos, std::vector<Run>* out) {
+      int count = 0;
+      for (size_t q = 0; q < shift_y.size(); ++q) {
+        bool used[4] = {false, false, false, false};
+        for (int u = 0; u < ntaps; ++u)
+          if (tap_shift[u] == (int)q) used[pos[tap_phase[u]]] = true;
+        for (int b = 0; b < phs->n;) {
+          if (!used[b]) { ++b; continue; }
+          int e = b;
+          while (e + 1 < phs->n && used[e + 1]) ++e;
+          if (out) out->push_back({(int)q, b, e - b + 1, 0});
+          ++count;
+          b = e + 1;
+        }
+      }
+      return count;
+    };
+    int perm[4] = {0, 1, 2, 3}, best_runs = 1 << 20;
+    do {
+      if (phs->n < 4 && (perm[3] != 3 || (phs->n < 3 && perm[2] != 2))) continue;      // only the first n entries move
+      const int c = runs_of(perm, nullptr);
+      if (c < best_runs) { best_runs = c; for (int i = 0; i < 4; ++i) ph_pos[i] = perm[i]; }
+    } while (std::next_permutation(perm, perm + 4));
+    runs_of(ph_pos, &runs);
+    // the fresh (overwriting) chunks: a disjoint cover of the phase blocks, longest runs first
+    std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.len > b.len; });
+    unsigned covered = 0;
+    for (auto& r : runs) {
+      const unsigned bits = ((1u << r.len) - 1u) << r.pos0;
+      if ((covered & bits) == 0) { r.fresh = 1; covered |= bits; }
+    }
+    if (covered != (1u << phs->n) - 1u) return 1;
+    std::stable_sort(runs.begin(), runs.end(), [](const Run& a, const Run& b) { return a.fresh > b.fresh; });
+    if ((int)runs.size() > HALO_MAX_CK) return 1;
+    p.PH = phs->n;
+    for (int ph = 0; ph < phs->n; ++ph) { p.ph_oy[ph_pos[ph]] = phs->oy[ph]; p.ph_ox[ph_pos[ph]] = phs->ox[ph]; }
+  }
+
   // ---- choose (G, resident, images per box): most useful output rows per modelled MMA cycle
   double best = 0.0;
   int bestG = 1;
   uint32_t best_extent = 0;
-  for (int G = 1; G <= 8; ++G) {
+  if (phs) {
+    // G = 1, resident weights; the channel tile is halved until all the taps' weights fit beside two stages
+    for (int bn_try = p.BN; bn_try >= 16 && (bn_try % 16) == 0 && (Cout_pad % bn_try) == 0; bn_try /= 2) {
+      const uint32_t wtap = (uint32_t)bn_try * rb, wb = (uint32_t)ntaps * wtap;
+      for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
+        const int S = nbt * p.HHs;
+        const int groups = S - ey, MT = (groups + 15) / 16;
+        if (nbt > 1 && p.RT < Hq) break;
+        if (pow2_ceil(2 * MT * p.PH * bn_try) > 512) break;
+        const uint32_t plane = ((uint32_t)(16 * MT + ey) * p.HWp * rb + 1023u) & ~1023u;
+        if (2u * plane + wb + stats_bytes + 1792u + (uint32_t)(MT * p.PH) * 128u > budget) break;
+        double cyc = 0.0;
+        for (auto& r : runs) cyc += (double)MT * ksteps * mma_cycles(r.len * bn_try);
+        cyc *= (double)(Cout_pad / bn_try);
+        const double score = (double)(nbt * p.RT) / cyc;
+        if (score > best * 1.02) {
+          best = score; p.NBt = nbt; p.MT = MT; p.stage_bytes = plane; p.plane_bytes = plane; p.resident = 1; p.w_bytes = wb;
+          p.BN = bn_try; p.n_tiles_n = Cout_pad / bn_try; p.w_tap_bytes = wtap;
+        }
+      }
+    }
+  }
+  for (int G = 1; G <= 8 && !phs; ++G) {
     if (G > 1 && (!stackable || G * p.BN > 256)) break;
     for (int resident = 1; resident >= 0; --resident) {
       if (G > 1 && !resident) continue;
@@ -1189,7 +1285,24 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   if (((uint32_t)(p.G * p.HWp) * rb >> 4) > 0x3fffu) return 1;                              // SBO field
   for (int t = 0; t < ntaps; ++t)
     p.tap_off16[t] = ((uint32_t)tpl[t] * p.plane_bytes + (uint32_t)((tey[t] - dymin) * p.HWp + (tex[t] - dxmin)) * rb) >> 4;
-  if (p.G > 1) {
+  if (phs) {
+    // weight blocks in shared memory: run after run, inside a run in block order (= the N rows of the run's MMA)
+    int pos = 0, nck = 0;
+    for (auto& r : runs) {
+      for (int b = 0; b < r.len; ++b)
+        for (int t = 0; t < ntaps; ++t)
+          if (tap_shift[t] == r.shift && ph_pos[tap_phase[t]] == r.pos0 + b) p.w_pos[t] = (short)(pos + b);
+      p.ck[nck].x = ((uint32_t)((shift_y[r.shift] - dymin) * p.HWp + (shift_x[r.shift] - dxmin)) * rb) >> 4;
+      p.ck[nck].y = ((uint32_t)pos * p.w_tap_bytes) >> 4;
+      p.ck[nck].z = make_idesc_bf16(128, r.len * p.BN, false, false);
+      p.ck[nck].w = (uint32_t)(r.pos0 * p.BN) | (r.fresh ? 0x80000000u : 0u);
+      ++nck;
+      pos += r.len;
+    }
+    if (pos != ntaps) return 1;
+    p.nck = nck;
+    if ((((uint32_t)pos * p.w_tap_bytes) >> 4) > 0xffffu) return 1;
+  } else if (p.G > 1) {
     // weight blocks in shared memory: per tap column, rows of taps DESCENDING (the column block j of a chunk reads tap e = u - j)
     int pos = 0, nck = 0;
     std::vector<int> col_base(cols.size());
@@ -1228,18 +1341,19 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.box_bytes = (uint32_t)p.nplanes * (uint32_t)(p.NBt * p.HHs) * p.HWp * rb;
   {
     const uint32_t bud = budget + (p.G > 1 ? 20u * 1024u : 0u);
-    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G) * 128u) / p.stage_bytes);
+    p.stages = (int)((bud - p.w_bytes - stats_bytes - 1792u - (uint32_t)(p.MT * p.G * p.PH) * 128u) / p.stage_bytes);
   }
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return 1;
-  p.acc_stride = (uint32_t)(p.MT * p.G * p.BN);
-  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.MT * p.G * p.BN < 32 ? 32 : 2 * p.MT * p.G * p.BN);
+  p.acc_stride = (uint32_t)(p.MT * p.G * p.PH * p.BN);
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
   p.strips_x = (Wq + 7) / 8; p.blocks_y = (Hq + p.RT - 1) / p.RT; p.blocks_n = (N + p.NBt - 1) / p.NBt;
   p.num_boxes = p.strips_x * p.blocks_y * p.blocks_n;
   p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.ldc = ld_out;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox;
   p.act = act & 0xff; p.out_f32 = (act & JVAE_OUT_F32) ? 1 : 0;
   p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.stats = stats; p.cout_pad = Cout_pad;
+  if (plan_out) { *plan_out = p; return JVAE_OK; }      // jvae_conv_halo_emulate: the plan only, nothing touches the device
   CUtensorMap tin, tw;
   if (bn) {
     p.bn_y = reinterpret_cast<const __nv_bfloat16*>(bn->y); p.bn_ld = bn->ld_y; p.bn_save = bn->save_mean_rstd;
@@ -1263,7 +1377,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     rc = make_tmap_bf16(&tw, wmat, 2, wd, ws, wbox, nullptr, p.Cblk * 2);
     if (rc) return rc;
   }
-  const size_t tab_bytes = (size_t)p.MT * p.G * 16 * sizeof(int2);       // block table of the fast epilogue
+  const size_t tab_bytes = (size_t)p.MT * p.G * p.PH * 16 * sizeof(int2);       // block table of the fast epilogue
   const size_t smem = (size_t)p.stages * p.stage_bytes + p.w_bytes + 512 + stats_bytes +
                       256 + 1024 + 1024 + tab_bytes;
   if (smem > 227u * 1024u) return 1;
@@ -1554,6 +1668,32 @@ int jvae_conv_gather_gemm_bn(const void* in, int N, int H, int W, int Cin, int l
   return JVAE_OK;
 }
 
+int jvae_conv_subpixel_gemm(const void* in, int N, int H, int W, int Cin, int ld_in, const void* wmat, int Cout_pad, int ldw,
+                            int nphases, const int16_t* phase_ntaps, const int16_t* phase_oy, const int16_t* phase_ox,
+                            const int16_t* tap_dy, const int16_t* tap_dx, int Hq, int Wq, void* out, int Ho, int Wo, int Cout,
+                            int ld_out, int out_s, const float* bias, int act, double* stats, void* stream) {
+  JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx && phase_ntaps && phase_oy && phase_ox, "null pointer");
+  JVAE_CHECK_ARG(nphases >= 1 && nphases <= 4, "1..4 phases");
+  int ntaps = 0;
+  for (int i = 0; i < nphases; ++i) {
+    JVAE_CHECK_ARG(phase_ntaps[i] >= 1, "every phase needs a tap");
+    JVAE_CHECK_ARG(phase_oy[i] >= 0 && phase_oy[i] < out_s && phase_ox[i] >= 0 && phase_ox[i] < out_s, "phase offset outside the stride");
+    ntaps += phase_ntaps[i];
+  }
+  JVAE_CHECK_ARG(ntaps <= CONV_MAX_TAPS, "at most 64 taps over all phases");
+  JVAE_CHECK_ARG((ld_in % 8) == 0 && (ldw % 8) == 0, "input / weight channel strides must be multiples of 8");
+  JVAE_CHECK_ARG(ld_out >= Cout, "ld_out < Cout");
+  JVAE_CHECK_ARG((Cout_pad % 16) == 0 && Cout_pad >= 16 && Cout_pad >= Cout, "Cout_pad must be a multiple of 16, >= Cout");
+  JVAE_CHECK_ARG((((uintptr_t)in | (uintptr_t)wmat | (uintptr_t)out) & 15) == 0, "16-byte alignment");
+  JVAE_CHECK_ARG(out_s >= 1 && (Hq - 1) * out_s + out_s <= Ho && (Wq - 1) * out_s + out_s <= Wo, "phase grid larger than the output");
+  static const bool off = (getenv("JVAE_CONV_V1") != nullptr) || (getenv("JVAE_CONV_MERGE_PHASES") && atoi(getenv("JVAE_CONV_MERGE_PHASES")) == 0);
+  if (off) return JVAE_NOT_COVERED;
+  PhaseSpec ps = {nphases, phase_ntaps, phase_oy, phase_ox};
+  const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, 1, Hq, Wq, out, Ho, Wo, Cout,
+                                 ld_out, out_s, out_s, 0, 0, bias, act, stats, nullptr, nullptr, (cudaStream_t)stream, &ps);
+  return rc > 0 ? JVAE_NOT_COVERED : rc;
+}
+
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, int dw_ld_ci, void* stream) {
@@ -1617,6 +1757,114 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
 }
 
 int jvae_last_conv_kernel(void) { return g_last_conv_kernel; }
+
+// ------------------------------------------------------------------------------------------------ plan emulation (host only)
+// Executes the PLAN try_launch_halo makes for a geometry on the host, step by step as conv_halo_kernel does: the TMA box fill
+// of a stage (zero outside the image, NaN where the kernel would see leftovers), the MMAs in the order of the chunk records /
+// tap table on row addresses decoded from the descriptor words, the fresh / accumulate flags, the epilogue's block table and
+// bounds.  A planning mistake (wrong shift, weight block, accumulator column, phase offset, a junk slot reaching a live row)
+// shows up as a wrong or NaN output.  No GPU is needed: the `-m "not gpu"` tests run it against torch convolutions.
+int jvae_conv_halo_emulate(const float* in, int N, int H, int W, int Cin, int ld_in, const float* wmat, int Cout_pad, int ldw,
+                           int nphases, const int16_t* phase_ntaps, const int16_t* phase_oy, const int16_t* phase_ox, int ntaps,
+                           const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, float* out, int Ho, int Wo,
+                           int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
+                           int* info) {
+  JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
+  HaloParams p;
+  PhaseSpec ps = {nphases, phase_ntaps, phase_oy, phase_ox};
+  const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho, Wo,
+                                 Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, nullptr, nullptr, nullptr, nullptr,
+                                 nphases > 0 ? &ps : nullptr, &p);
+  if (rc != 0) return rc > 0 ? JVAE_NOT_COVERED : rc;
+  if (info) { info[0] = p.G; info[1] = p.PH; info[2] = p.MT; info[3] = p.NBt; info[4] = p.BN; info[5] = p.nck; info[6] = p.resident; info[7] = p.stages; }
+  const float qnan = nanf("");
+  const uint32_t rb = (uint32_t)p.Cblk * 2u;
+  const size_t stage_rows = p.stage_bytes / rb;
+  const int per = p.G * p.PH, nblk = p.MT * per;
+  const size_t group_rows = (size_t)p.G * p.HWp;                    // SBO of the A descriptor in pixel rows
+  std::vector<float> stage(stage_rows * p.Cblk), D((size_t)nblk * 128 * p.BN);
+  std::vector<float> wsm;
+  auto a_at = [&](size_t row, int c) { return row < stage_rows ? stage[row * p.Cblk + c] : qnan; };
+  for (int nt = 0; nt < p.n_tiles_n; ++nt)
+    for (int box = 0; box < p.num_boxes; ++box) {
+      int mm = box;
+      const int sx = mm % p.strips_x; mm /= p.strips_x;
+      const int by = mm % p.blocks_y; mm /= p.blocks_y;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        // ---- TMA: the box of every plane (zero fill outside the tensor), leftovers elsewhere
+        std::fill(stage.begin(), stage.end(), qnan);
+        for (int pl = 0; pl < p.nplanes; ++pl)
+          for (int nb = 0; nb < p.NBt; ++nb)
+            for (int j = 0; j < p.HHs; ++j)
+              for (int i = 0; i < p.HWp; ++i) {
+                const size_t row = (size_t)pl * (p.plane_bytes / rb) + (size_t)(nb * p.HHs + j) * p.HWp + i;
+                const int n = mm * p.NBt + nb;
+                const int y = p.in_stride * (by * p.RT + p.dymin + j) + p.plane_ry[pl], x = p.in_stride * (sx * 8 + p.dxmin + i) + p.plane_rx[pl];
+                for (int c = 0; c < p.Cblk; ++c) {
+                  const int ci = kc * p.Cblk + c;
+                  const bool inside = n < N && y >= 0 && y < H && x >= 0 && x < W && ci < Cin;
+                  if (row < stage_rows) stage[row * p.Cblk + c] = inside ? in[(((size_t)n * H + y) * W + x) * ld_in + ci] : 0.f;
+                }
+              }
+        // ---- weights of this channel tile / chunk at their shared-memory positions
+        wsm.assign((size_t)p.ntaps * p.BN * p.Cblk, qnan);
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int pos = p.nck > 0 ? p.w_pos[t] : t;
+          for (int r = 0; r < p.BN; ++r)
+            for (int c = 0; c < p.Cblk; ++c)
+              wsm[((size_t)pos * p.BN + r) * p.Cblk + c] = wmat[(size_t)(nt * p.BN + r) * ldw + (size_t)(t * p.nkc + kc) * p.Cblk + c];
+        }
+        auto mma = [&](int m, size_t a_shift_rows, size_t w_block, int ncols, int dcol, bool overwrite) {
+          for (int r = 0; r < 128; ++r) {
+            const size_t arow = (size_t)(m * 16 + (r >> 3)) * group_rows + (size_t)(r & 7) + a_shift_rows;
+            for (int nn = 0; nn < ncols; ++nn) {
+              float acc = 0.f;
+              for (int c = 0; c < p.Cblk; ++c) acc += a_at(arow, c) * wsm[(w_block * p.BN + nn) * p.Cblk + c];
+              float& d = D[((size_t)m * 128 + r) * (size_t)(per * p.BN) + dcol + nn];
+              d = overwrite ? acc : d + acc;
+            }
+          }
+        };
+        if (kc == 0) std::fill(D.begin(), D.end(), qnan);
+        if (p.nck > 0) {
+          for (int m = 0; m < p.MT; ++m)
+            for (int c = 0; c < p.nck; ++c) {
+              const uint4 ck = p.ck[c];
+              mma(m, (size_t)ck.x * 16 / rb, (size_t)ck.y * 16 / p.w_tap_bytes, (int)((ck.z >> 17) & 0x3f) << 3, (int)(ck.w & 0x7fffffffu),
+                  (ck.w >> 31) != 0);
+            }
+        } else {
+          for (int t = 0; t < p.ntaps; ++t)
+            for (int m = 0; m < p.MT; ++m) mma(m, (size_t)p.tap_off16[t] * 16 / rb, (size_t)t, p.BN, 0, t == 0 && kc == 0);
+        }
+      }
+      // ---- epilogue: block table, bounds, phase offsets
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int m = blk / per, rr = blk - m * per;
+        const int j = rr / p.PH, ph = rr - j * p.PH;
+        for (int r = 0; r < 128; ++r) {
+          const int slot = (m * 16 + (r >> 3)) * p.G + j;
+          const int nb = slot / p.HHs, yy = slot - nb * p.HHs;
+          const int qx = sx * 8 + (r & 7);
+          if (!(nb < p.NBt && yy < p.RT) || qx >= p.Wq || yy >= p.Hq - by * p.RT || nb >= p.N - mm * p.NBt) continue;
+          const size_t pix = ((size_t)(mm * p.NBt) * p.Ho + (size_t)(by * p.RT * p.out_sy + p.out_oy)) * p.Wo + (size_t)(qx * p.out_sx + p.out_ox) +
+                             (size_t)((nb * p.Ho + yy * p.out_sy + p.ph_oy[ph]) * p.Wo + p.ph_ox[ph]);
+          for (int c = 0; c < p.BN; ++c) {
+            const int ch = nt * p.BN + c;
+            if (ch >= ld_out) continue;
+            float v = D[((size_t)m * 128 + r) * (size_t)(per * p.BN) + (size_t)blk % per * p.BN + c];
+            if (bias && ch < Cout) v += bias[ch];
+            if ((act & 0xff) == JVAE_ACT_RELU) v = v > 0.f ? v : (v != v ? v : 0.f);
+            else if ((act & 0xff) == JVAE_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+            else if ((act & 0xff) == JVAE_ACT_LEAKY) v = v > 0.f ? v : JVAE_LEAKY_SLOPE * v;
+            out[pix * ld_out + ch] = ch < Cout ? v : 0.f;
+          }
+        }
+      }
+    }
+  return JVAE_OK;
+}
+
 
 }  // extern "C"
 
@@ -1808,6 +2056,70 @@ static int conv_case(const ConvCase& c, int verbose) {
   return fails;
 }
 
+// all four sub-pixel phases of a stride-2 ConvTranspose2d (k, pad, output 2H x 2W) in one launch against the naive kernel run
+// phase by phase on the same merged weight matrix
+static int subpixel_case(int N, int H, int W, int Cin, int Cout, int k, int pad, int act, int verbose) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  std::vector<int16_t> dy, dx, pn, poy, pox;
+  for (int fy = 0; fy < 2; ++fy)
+    for (int fx = 0; fx < 2; ++fx) {
+      int cnt = 0;
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j)
+          if ((fy + pad - i) % 2 == 0 && (fx + pad - j) % 2 == 0) {
+            dy.push_back((int16_t)((fy + pad - i) / 2)); dx.push_back((int16_t)((fx + pad - j) / 2));
+            ++cnt;
+          }
+      pn.push_back((int16_t)cnt); poy.push_back((int16_t)fy); pox.push_back((int16_t)fx);
+    }
+  const int ntaps = (int)dy.size();
+  const int ld_in = r8(Cin), Cblk = cblk_of(Cin), Cout_pad = r16(Cout), ldw = ntaps * Cblk, ld_out = r8(Cout);
+  const size_t in_n = (size_t)N * H * W * ld_in, w_n = (size_t)Cout_pad * ldw, out_pix = (size_t)N * Ho * Wo;
+  __nv_bfloat16 *in, *w, *out; float *ref, *bias, *err, *stats_ref = nullptr, *stats_f = nullptr; double* stats = nullptr; short *ddy, *ddx;
+  if (act == 0) {
+    cudaMalloc(&stats, 2 * Cout * 8); cudaMalloc(&stats_ref, 2 * Cout * 4); cudaMalloc(&stats_f, 2 * Cout * 4);
+    cudaMemset(stats, 0, 2 * Cout * 8);
+  }
+  cudaMalloc(&in, in_n * 2); cudaMalloc(&w, w_n * 2); cudaMalloc(&out, out_pix * ld_out * 2);
+  cudaMalloc(&ref, out_pix * Cout * 4); cudaMalloc(&bias, Cout * 4); cudaMalloc(&err, 4);
+  cudaMalloc(&ddy, ntaps * 2); cudaMalloc(&ddx, ntaps * 2);
+  cudaMemcpy(ddy, dy.data(), ntaps * 2, cudaMemcpyHostToDevice); cudaMemcpy(ddx, dx.data(), ntaps * 2, cudaMemcpyHostToDevice);
+  conv_fill_kernel<<<128, 256>>>(in, in_n, 23u, 1.f);
+  conv_fill_kernel<<<128, 256>>>(w, w_n, 77u, 0.25f);
+  std::vector<float> hb(Cout);
+  for (int i = 0; i < Cout; ++i) hb[i] = 0.05f * (float)(i % 13) - 0.3f;
+  cudaMemcpy(bias, hb.data(), Cout * 4, cudaMemcpyHostToDevice);
+  cudaMemset(out, 0xff, out_pix * ld_out * 2); cudaMemset(ref, 0, out_pix * Cout * 4); cudaMemset(err, 0, 4);
+  int rc = jvae_conv_subpixel_gemm(in, N, H, W, Cin, ld_in, w, Cout_pad, ldw, 4, pn.data(), poy.data(), pox.data(), dy.data(), dx.data(),
+                                   H, W, out, Ho, Wo, Cout, ld_out, 2, bias, act, stats, nullptr);
+  float h_err = -1.f;
+  if (rc == 0) {
+    const size_t total = (size_t)N * H * W * Cout;
+    int first = 0;
+    for (int ph = 0; ph < 4; ++ph) {
+      conv_ref_kernel<<<(unsigned)((total + 255) / 256), 256>>>(in, N, H, W, Cin, ld_in, w + (size_t)first * Cblk, ldw, Cblk, 1, pn[ph],
+                                                               ddy + first, ddx + first, 1, H, W, ref, Ho, Wo, Cout, 2, 2, poy[ph],
+                                                               pox[ph], bias, act);
+      first += pn[ph];
+    }
+    conv_cmp_kernel<<<128, 256>>>(out, ld_out, ref, Cout, out_pix, nullptr, err);
+    if (stats) {
+      stats_ref_kernel<<<(Cout + 63) / 64, 64>>>(ref, Cout, out_pix, nullptr, stats, stats_ref, stats_f);
+      f32_cmp_kernel<<<1, 256>>>(stats_f, stats_ref, 2 * (size_t)Cout, err);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("[selftest] subpixel: CUDA error %s\n", cudaGetErrorString(e)); rc = -2; }
+    else cudaMemcpy(&h_err, err, 4, cudaMemcpyDeviceToHost);
+  }
+  const bool ok = rc == 0 && h_err >= 0.f && h_err < 2e-2f;
+  if (verbose || !ok)
+    printf("[selftest] subpixel N=%d %dx%d Cin=%d Cout=%d k=%d pad=%d act=%d: rc=%d rel_err=%g %s%s\n", N, H, W, Cin, Cout, k, pad, act, rc,
+           h_err, ok ? "OK" : (rc == JVAE_NOT_COVERED ? "NOT COVERED" : "FAIL"), rc < 0 ? jvae_last_error() : "");
+  if (stats) { cudaFree(stats); cudaFree(stats_ref); cudaFree(stats_f); }
+  cudaFree(in); cudaFree(w); cudaFree(out); cudaFree(ref); cudaFree(bias); cudaFree(err); cudaFree(ddy); cudaFree(ddx);
+  return ok ? 0 : 1;
+}
+
 int conv_selftest(int verbose) {
   const ConvCase cases[] = {
       {4, 8, 8, 64, 64, 3, 1, 1, 1, 0},     // SW128, NB=2
@@ -1831,6 +2143,13 @@ int conv_selftest(int verbose) {
   for (const auto& c : cases) {
     fails += conv_case(c, verbose);
     if (fails > 4) { printf("[selftest] conv: too many failures, stopping\n"); break; }
+  }
+  if (!(getenv("JVAE_CONV_V1") || (getenv("JVAE_CONV_MERGE_PHASES") && atoi(getenv("JVAE_CONV_MERGE_PHASES")) == 0))) {
+    fails += subpixel_case(5, 16, 16, 32, 32, 5, 2, 0, verbose);      // c2 imager 16 -> 32: one image per box, 4 x 32 columns
+    fails += subpixel_case(7, 8, 8, 64, 64, 5, 2, 0, verbose);        // c2 imager 8 -> 16: channel tile halved, 3 images per box
+    fails += subpixel_case(3, 16, 16, 32, 16, 4, 1, 1, verbose);      // k = 4 (two taps per axis and phase), relu
+    fails += subpixel_case(2, 40, 24, 16, 24, 3, 1, 0, verbose);      // two row blocks per image, ragged channel count
+    fails += subpixel_case(150, 8, 8, 16, 16, 5, 2, 0, verbose);      // more boxes than SMs
   }
   return fails;
 }

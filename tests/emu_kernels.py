@@ -90,6 +90,25 @@ class EmuKernels:
         view[..., :Cout] = acc if (act & 0x100) else acc.to(EmuKernels.store)      # JVAE_OUT_F32: no rounding of the result
         view[..., Cout:] = 0
 
+    @staticmethod
+    def phases_arg(ops):
+        return [(EmuKernels.taps_arg(op['taps']), op['out_o']) for op in ops]
+
+    @classmethod
+    def subpixel(cls, x, Cin, wmat, cout_pad, phases, Hq, Wq, out, Cout, out_s, bias, act, stats):
+        """jvae_conv_subpixel_gemm: phase i owns the next len(taps_i) [tap] blocks of the merged weight matrix"""
+        cb = _cblk(Cin)
+        w = (Cin + cb - 1) // cb * cb
+        first = 0
+        for taps, out_o in phases:
+            T = len(taps[0])
+            cls.gather(x, Cin, wmat[:, first * w:(first + T) * w].contiguous(), cout_pad, taps, 1, Hq, Wq, out, Cout,
+                       (out_s, out_s), out_o, bias, act, stats)
+            first += T
+        assert first * w == wmat.shape[1]
+        cls.launches -= len(phases) - 1
+        return True
+
     @classmethod
     def wgrad(cls, g, Cg, x, Cx, taps, in_stride, dw, swapped=False):
         cls.launches += 1

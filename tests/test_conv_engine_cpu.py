@@ -335,6 +335,7 @@ def test_c2_stack_plan(pkg, ce):
     assert [s.separable for s in convs] == [False] * 6 + [True]           # 32 -> 3 k5 head: 1 x 5 pass + row kernels
     assert convs[-1].wgrad_swapped and not any(s.wgrad_swapped for s in convs[:-1])
     assert [len(s.fwd_ops) if s.fwd_ops else 0 for s in convs] == [0, 1, 4, 1, 4, 1, 1]      # stride-2 deconvs: 4 sub-pixel phases
+    assert [s.merged_fwd for s in convs] == [False, False, True, False, True, False, False]    # ... issued as ONE merged launch
     assert not any(s.dense_small for s in convs)                          # opt-in only
     assert st.out_shape == (3, 32, 32)
     feats = build((3, 32, 32), 'vgg19', batch_norm=True, where='input')

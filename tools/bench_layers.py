@@ -32,6 +32,8 @@ def wrap(name):
         desc = ''
         if name == 'gather':
             desc = f'in{tuple(a[0].shape)} Cin={a[1]} taps={len(a[4][0])} s={a[5]} grid={a[6]}x{a[7]} Cout={a[9]}'
+        elif name == 'subpixel':
+            desc = f'in{tuple(a[0].shape)} Cin={a[1]} taps={a[4][5]} phases={len(a[4][0])} grid={a[5]}x{a[6]} Cout={a[8]}' + ('' if r else '  NOT COVERED')
         elif name == 'wgrad':
             desc = f'g{tuple(a[0].shape)} x{tuple(a[2].shape)} taps={len(a[4][0])} s={a[5]}'
         elif name == 'gemm':
@@ -39,7 +41,7 @@ def wrap(name):
         timers.append((name, desc, e0, e1))
         return r
     return staticmethod(w)
-for n in ('gather', 'wgrad', 'gemm', 'bn_apply_fwd', 'bn_bwd', 'bn_stats', 'act_bwd', 'maxpool_fwd', 'maxpool_bwd'):
+for n in ('gather', 'subpixel', 'wgrad', 'gemm', 'bn_apply_fwd', 'bn_bwd', 'bn_stats', 'act_bwd', 'maxpool_fwd', 'maxpool_bwd'):
     setattr(ce.K, n, wrap(n))
 
 for it in range(3):
