@@ -336,6 +336,12 @@ struct HaloParams {
   short w_pos[CONV_MAX_TAPS];            // position of tap t's weight block in shared memory (resident weights)
 };
 
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -442,13 +448,29 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
   }
   const bool has_bias = p.bias != nullptr;
   const uint32_t sb = smem_u32(s_bias);
+  const uint32_t stab = smem_u32(s_tab) + 8u * (uint32_t)(mrow >> 3);      // this thread's entry of block 0
   const bool vec_bf16 = (p.ldc & 7) == 0, vec_f32 = (p.ldc & 3) == 0;
   uint32_t it = 0;
+  // (strip, row block, image block) of the box, advanced by the decomposition of box_step with carries: the two runtime
+  // divisions per box were a fifth of the epilogue's stall samples on launches with few blocks per box (ncu source view)
+  int sx, by, mm, dsx, dby, dmm;
+  {
+    int t = box0;
+    sx = t % p.strips_x; t /= p.strips_x;
+    by = t % p.blocks_y; mm = t / p.blocks_y;
+    t = box_step;
+    dsx = t % p.strips_x; t /= p.strips_x;
+    dby = t % p.blocks_y; dmm = t / p.blocks_y;
+  }
   for (int box = box0; box < p.num_boxes; box += box_step, ++it) {
     const uint32_t acc = it & 1;
-    int mm = box;
-    const int sx = mm % p.strips_x; mm /= p.strips_x;
-    const int by = mm % p.blocks_y; mm /= p.blocks_y;
+    if (it != 0) {
+      sx += dsx;
+      if (sx >= p.strips_x) { sx -= p.strips_x; ++by; }
+      by += dby;
+      if (by >= p.blocks_y) { by -= p.blocks_y; ++mm; }
+      mm += dmm;
+    }
     const int qx = sx * 8 + (mrow & 7);
     const bool pxok = qx < p.Wq;
     const int ylim = p.Hq - by * p.RT, nlim = p.N - mm * p.NBt;
@@ -456,8 +478,13 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
                         (size_t)(qx * p.out_sx + p.out_ox);
     mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
     tc_fence_after();
-    for (int blk = (NCH == 1 ? set : 0); blk < nblk; blk += (NCH == 1 ? 2 : 1)) {
-      const int2 e = s_tab[blk * 16 + (mrow >> 3)];
+    constexpr int BSTEP = NCH == 1 ? 2 : 1;
+    int2 e_next = lds_int2(stab + 8u * (uint32_t)(NCH == 1 ? set : 0) * 16u);
+    for (int blk = (NCH == 1 ? set : 0); blk < nblk; blk += BSTEP) {
+      // the table entry of the NEXT block is requested now: its latency used to head the dependent chain of every block
+      // (ncu source view of the merged sub-pixel launch: the top stall after the accumulator wait)
+      const int2 e = e_next;
+      if (blk + BSTEP < nblk) e_next = lds_int2(stab + 8u * (uint32_t)(blk + BSTEP) * 16u);
       const bool ok = pxok && e.x >= 0 && (e.y & 0xffff) < ylim && (e.y >> 16) < nlim;
       if (!__any_sync(0xffffffffu, ok)) continue;
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t)(blk * p.BN) + ((uint32_t)(q * 32) << 16);
@@ -523,15 +550,17 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
 #pragma unroll
           for (int j = 0; j < 16; ++j) { s1[lc * 16 + j] += v[j]; s2[lc * 16 + j] = fmaf(v[j], v[j], s2[lc * 16 + j]); }
         }
-        if (p.act == JVAE_ACT_RELU) {
+        if (p.act != JVAE_ACT_NONE) {      // one uniform test in the common case (BatchNorm layers, data gradients)
+          if (p.act == JVAE_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (p.act == JVAE_ACT_SIGMOID) {
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == JVAE_ACT_SIGMOID) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-        } else if (p.act == JVAE_ACT_LEAKY) {
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : JVAE_LEAKY_SLOPE * v[j];
+          }
         }
         const int c0 = c * 16;
         const size_t off = pix * (size_t)p.ldc + (size_t)(ch0 + c0);
