@@ -336,6 +336,12 @@ struct HaloParams {
   short w_pos[CONV_MAX_TAPS];            // position of tap t's weight block in shared memory (resident weights)
 };
 
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
 __device__ __forceinline__ int2 lds_int2(uint32_t addr) {
   int2 v;
   asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -450,6 +456,10 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
   const uint32_t sb = smem_u32(s_bias);
   const uint32_t stab = smem_u32(s_tab) + 8u * (uint32_t)(mrow >> 3);      // this thread's entry of block 0
   const bool vec_bf16 = (p.ldc & 7) == 0, vec_f32 = (p.ldc & 3) == 0;
+  // 32-byte stores (st.global.v8.b32) when the thread's 16 channels start on a 32-byte boundary: one full sector per instruction
+  // instead of two half sectors (the scattered 16-byte stores of the sub-pixel / narrow layers kept L1TEX 67 % busy)
+  const bool al32 = (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;
+  const bool v8_bf16 = al32 && (p.ldc & 15) == 0, v8_f32 = al32 && (p.ldc & 7) == 0;
   uint32_t it = 0;
   // (strip, row block, image block) of the box, advanced by the decomposition of box_step with carries: the two runtime
   // divisions per box were a fifth of the epilogue's stall samples on launches with few blocks per box (ncu source view)
@@ -499,6 +509,21 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
             yq[lc][1] = ld_stream16(yp + 8);
           }
       }
+      // the bias of the thread's channels is requested BEFORE the accumulator (its latency hides under the TMEM load, and the
+      // sum lands in the accumulator's own registers: with the loads after the wait the compiler copied all 16 values away
+      // and back, 32 of ~145 instructions per block)
+      float bq[LC][16];
+      if (has_bias) {
+#pragma unroll
+        for (int lc = 0; lc < LC; ++lc)
+          if (c_first + 2 * lc < NCH) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(bq[lc][j]), "=f"(bq[lc][j + 1]), "=f"(bq[lc][j + 2]), "=f"(bq[lc][j + 3])
+                           : "r"(sb + 4u * ((c_first + 2 * lc) * 16 + j)));
+          }
+      }
       uint32_t r[LC][16];
 #pragma unroll
       for (int lc = 0; lc < LC; ++lc)
@@ -514,11 +539,7 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[lc][j]);
         if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float b0, b1, b2, b3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(sb + 4u * (c * 16 + j)));
-            v[j] += b0; v[j + 1] += b1; v[j + 2] += b2; v[j + 3] += b3;
-          }
+          for (int j = 0; j < 16; ++j) v[j] += bq[lc][j];
         }
         if (BNRED) {
           float y[16];
@@ -549,6 +570,9 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
         } else if (STATS) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { s1[lc * 16 + j] += v[j]; s2[lc * 16 + j] = fmaf(v[j], v[j], s2[lc * 16 + j]); }
+          // keeps the sums ahead of the activation: sunk below it they needed a second copy of the 16 values (32 moves per block)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(v[j]));
         }
         if (p.act != JVAE_ACT_NONE) {      // one uniform test in the common case (BatchNorm layers, data gradients)
           if (p.act == JVAE_ACT_RELU) {
@@ -566,7 +590,12 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
         const size_t off = pix * (size_t)p.ldc + (size_t)(ch0 + c0);
         if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + off;
-          if (ch0 + c0 + 16 <= p.ldc && vec_f32) {
+          if (ch0 + c0 + 16 <= p.ldc && v8_f32) {
+            st_global_v8(o, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]),
+                         __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            st_global_v8(o + 8, __float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]),
+                         __float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+          } else if (ch0 + c0 + 16 <= p.ldc && vec_f32) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
@@ -576,7 +605,10 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, uint32_t
           }
         } else {
           __nv_bfloat16* o = p.out + off;
-          if (ch0 + c0 + 16 <= p.ldc && vec_bf16) {
+          if (ch0 + c0 + 16 <= p.ldc && v8_bf16) {
+            st_global_v8(o, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]),
+                         pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          } else if (ch0 + c0 + 16 <= p.ldc && vec_bf16) {
             uint4 o0, o1;
             o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
             o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
