@@ -247,6 +247,9 @@ conv_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
             float* of = reinterpret_cast<float*>(p.out) + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + (size_t)nt * p.BN + c0;
             for (int j = 0; j < 16; ++j)
               if (ch0 + c0 + j < p.ldc) of[j] = v[j];
+          } else if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0) {
+            st_global_v8(orow + c0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]),
+                         pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
           } else if (ch0 + c0 + 16 <= p.ldc && (p.ldc & 7) == 0) {
             uint4 o0, o1;
             o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
@@ -335,12 +338,6 @@ struct HaloParams {
   uint4 ck[HALO_MAX_CK];
   short w_pos[CONV_MAX_TAPS];            // position of tap t's weight block in shared memory (resident weights)
 };
-
-__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
-                                             uint32_t g, uint32_t h) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               :: "l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
-}
 
 __device__ __forceinline__ int2 lds_int2(uint32_t addr) {
   int2 v;

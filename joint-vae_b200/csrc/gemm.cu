@@ -197,7 +197,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (p.out_bf16) {
         __nv_bfloat16* o = p.out_bf16 + off;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        if (full && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 16)
+            st_global_v8(o + j, pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
+                         pack_bf16(v[j + 6], v[j + 7]), pack_bf16(v[j + 8], v[j + 9]), pack_bf16(v[j + 10], v[j + 11]),
+                         pack_bf16(v[j + 12], v[j + 13]), pack_bf16(v[j + 14], v[j + 15]));
+        } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 t;
