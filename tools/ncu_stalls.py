@@ -12,7 +12,11 @@ for r in rows:
         cur['hdr'] = r
     elif cur is not None:
         cur['body'].append(r)
+seen = None
 for b in blocks:
+    if seen is not None and b['body'] == seen:      # the source page repeats each launch
+        continue
+    seen = b['body']
     h = b['hdr']; si = h.index('Warp Stall Sampling (All Samples)'); so = h.index('Source'); ex = h.index('Instructions Executed')
     stall_cols = [(i, c) for i, c in enumerate(h) if c.startswith('stall_') and 'Not Issued' not in c]
     tot = sum(int(r[si]) for r in b['body'] if r[si].isdigit())
