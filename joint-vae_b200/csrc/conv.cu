@@ -1458,7 +1458,10 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
 // plans and launches the halo weight-gradient kernel; returns 1 when the geometry is not covered
 static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
                                  int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw,
-                                 int dw_ld_tap, int dw_ld_co, int dw_ld_cx, cudaStream_t stream) {
+                                 int dw_ld_tap, int dw_ld_co, int dw_ld_cx, cudaStream_t stream, const int* tap_ids = nullptr,
+                                 bool dry_run = false) {
+  // tap_ids: position of tap t in dW when the list is a subset of the layer's taps (per-plane launches, jvae_conv_wgrad);
+  // dry_run: plan only (is the geometry covered?)
   if (Wq < 6) return 1;
   WHaloParams p;
   memset(&p, 0, sizeof(p));
@@ -1524,7 +1527,10 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
         p.grp_off16[ngr] = ((uint32_t)x0 * rbx) >> 4;
         p.grp_boff16[ngr] = (uint32_t)v0 * gslot16;
         for (int jv = 0; jv < nv; ++jv)
-          for (int j = 0; j < n; ++j) p.grp_tap[ngr][jv][j] = (short)tap_at[(size_t)(ey - v0 - jv) * (ex + 1) + (x0 + j)];
+          for (int j = 0; j < n; ++j) {
+            const int t = tap_at[(size_t)(ey - v0 - jv) * (ex + 1) + (x0 + j)];
+            p.grp_tap[ngr][jv][j] = (short)(tap_ids ? tap_ids[t] : t);
+          }
         ++ngr;
         v0 += nv;
       }
@@ -1547,7 +1553,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
       p.grp_nv[ngr] = 1;
       p.grp_boff16[ngr] = (uint32_t)E * gslot16;           // the gradient tile itself
       grp_first.push_back(order[i]);
-      for (int j = 0; j < n; ++j) p.grp_tap[ngr][0][j] = (short)order[i + j];
+      for (int j = 0; j < n; ++j) p.grp_tap[ngr][0][j] = (short)(tap_ids ? tap_ids[order[i + j]] : order[i + j]);
       ++ngr;
       i += n;
     }
@@ -1601,6 +1607,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   p.strips_x = (Wq + 7) / 8;
   p.num_boxes = p.strips_x * p.blocks_y * ((N + p.NBt - 1) / p.NBt);
   p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co; p.dw_ld_cx = dw_ld_cx;
+  if (dry_run) return JVAE_OK;
   CUtensorMap tg, tx;
   {
     uint64_t dg[4] = {(uint64_t)Cg, (uint64_t)Wq, (uint64_t)Hq, (uint64_t)N};
@@ -1764,6 +1771,29 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
     const int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, in_stride, dw,
                                          dw_ld_tap, dw_ld_co, dw_ld_ci, (cudaStream_t)stream);
     if (rc <= 0) return rc;
+    // Stride 2 with wide rows (the 64-channel stride-2 layers): the four parity planes of the gathered tensor do not fit one
+    // stage together, but each plane alone does -- one launch per plane with that plane's taps (a tap belongs to exactly one
+    // plane, so the launches add into disjoint slices of dW).  Tap-box kernel before: 375 us for the 8 -> 16 layer of c2.
+    static const bool split_off = getenv("JVAE_WGRAD_PLANE_SPLIT") && atoi(getenv("JVAE_WGRAD_PLANE_SPLIT")) == 0;
+    if (in_stride == 2 && !split_off) {
+      std::vector<int16_t> sdy[4], sdx[4];
+      std::vector<int> ids[4];
+      for (int t = 0; t < ntaps; ++t) {
+        const int pl = (((tap_dy[t] % 2) + 2) % 2) * 2 + (((tap_dx[t] % 2) + 2) % 2);
+        sdy[pl].push_back(tap_dy[t]); sdx[pl].push_back(tap_dx[t]); ids[pl].push_back(t);
+      }
+      bool covered = true;
+      for (int pass = 0; pass < 2 && covered; ++pass)      // first pass: plans only, so that either every plane launches or none
+        for (int pl = 0; pl < 4; ++pl) {
+          if (ids[pl].empty()) continue;
+          const int r2 = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, (int)ids[pl].size(), sdy[pl].data(),
+                                               sdx[pl].data(), 2, dw, dw_ld_tap, dw_ld_co, dw_ld_ci, (cudaStream_t)stream,
+                                               ids[pl].data(), pass == 0);
+          if (r2 < 0) return r2;
+          if (r2 > 0) { covered = false; break; }
+        }
+      if (covered) return JVAE_OK;
+    }
   }
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -2196,6 +2226,7 @@ int conv_selftest(int verbose) {
       {3, 32, 32, 32, 32, 5, 2, 1, 1, 0},   // halo kernel: two M-tiles per box
       {2, 40, 40, 8, 16, 3, 1, 1, 1, 0},    // halo kernel: two row blocks per image
       {9, 8, 8, 64, 64, 3, 1, 1, 2, 0},     // halo kernel: sub-pixel phase store, stacked images
+      {5, 16, 16, 64, 64, 5, 2, 2, 1, 0},   // stride 2, 64 channels: weight gradient as one halo launch per parity plane
   };
   int fails = 0;
   for (const auto& c : cases) {
