@@ -254,6 +254,7 @@ class _timed_conv:
     def __enter__(self):
         if CONV_FLOPS is not None:
             CONV_FLOPS.append(self.flops)
+            self.n0 = launch_count()
         if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
@@ -265,8 +266,16 @@ class _timed_conv:
         if CONV_FLOPS is not None:
             CONV_FLOPS.pop()
         self.on = False
+        self.cancelled = True
 
     def __exit__(self, *exc):
+        if CONV_FLOPS is not None and not getattr(self, 'cancelled', False):
+            # an entry point that launched several kernels (stride-2 weight gradients, one launch per parity plane) left one
+            # native record per launch: the call's FLOPs are spread over them
+            n = launch_count() - self.n0
+            if n > 1:
+                CONV_FLOPS.pop()
+                CONV_FLOPS.extend([self.flops / n] * n)
         if self.on:
             self.b.record()
             PROFILE['conv'].append((self.a, self.b, self.flops, CONV_KERNELS.get(int(lib().jvae_last_conv_kernel()), '?')))
