@@ -371,3 +371,50 @@ def test_im2col_tap_major_and_split_k_gemm(pkg):
         out = torch.ones((Co, 8 * T), dtype=torch.float32, device=DEV)
         nat.gemm_bf16(2, Co, 8 * T, N * Hq * Hq, g, g.stride(0), cols, 8 * T, out_f32=out, ldd=8 * T, accumulate=ks if ks > 1 else True)
         assert torch.allclose(out - 1, ref, rtol=1e-4, atol=1e-3), (ks, float((out - 1 - ref).abs().max()))
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,k,p', [(33, 8, 8, 64, 64, 5, 2), (17, 16, 16, 32, 32, 5, 2), (5, 12, 20, 16, 24, 4, 1),
+                                             (3, 40, 16, 8, 3, 3, 1)])
+def test_merged_subpixel_launch_equals_phase_launches(pkg, N, H, W, Ci, Co, k, p):
+    """jvae_conv_subpixel_gemm (all four sub-pixel phases of a stride-2 ConvTranspose2d in one launch) against one
+    jvae_conv_gather_gemm per phase on the same tensors: outputs within bf16 rounding of each other, BatchNorm sums equal
+    (module/vae_layers/conv.py:189-219; conv-models.ini:25 deconv32)"""
+    from jointvae_b200 import conv_engine as ce
+    K = ce.NativeKernels
+    torch.manual_seed(N)
+    Ho, Wo = 2 * H, 2 * W
+    ops = ce.deconv_form(k, p, 2, Ho, Wo)
+    g = (torch.randn(Co, k * k, Ci, device=DEV) * 0.2)
+    x = torch.zeros(N, H, W, ce.r8(Ci), device=DEV, dtype=torch.bfloat16)
+    x[..., :Ci] = torch.randn(N, H, W, Ci, device=DEV)
+    bias = torch.randn(Co, device=DEV)
+    w_all = ce.pack_gather_weights(g, [i for op in ops for i in op['idx']], Ci)
+    out_m = torch.full((N, Ho, Wo, ce.r8(Co)), float('nan'), device=DEV, dtype=torch.bfloat16)
+    st_m = torch.zeros(2, Co, device=DEV, dtype=torch.float64)
+    ok = K.subpixel(x, Ci, w_all, w_all.shape[0], K.phases_arg(ops), H, W, out_m, Co, 2, bias, 0, st_m)
+    assert ok, 'geometry expected to be covered by the merged kernel'
+    out_p = torch.full_like(out_m, float('nan'))
+    st_p = torch.zeros_like(st_m)
+    for op in ops:
+        wm = ce.pack_gather_weights(g, op['idx'], Ci)
+        K.gather(x, Ci, wm, wm.shape[0], K.taps_arg(op['taps']), 1, H, W, out_p, Co, op['out_s'], op['out_o'], bias, 0, st_p)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out_m.float()).any() and not torch.isnan(out_p.float()).any()
+    scale = float(out_p.float().abs().max())
+    assert float((out_m.float() - out_p.float()).abs().max()) <= 2e-2 * scale
+    assert float((out_m[..., Co:].float()).abs().max() if out_m.shape[-1] > Co else 0) == 0
+    assert torch.allclose(st_m, st_p, rtol=1e-4, atol=1e-3 * float(st_p.abs().max()))
+
+
+def test_merged_subpixel_launch_declines_wide_layers(pkg):
+    """more than 64 channels: JVAE_NOT_COVERED, nothing launched, the caller runs the phases one by one"""
+    from jointvae_b200 import conv_engine as ce
+    K = ce.NativeKernels
+    ops = ce.deconv_form(3, 1, 2, 16, 16)
+    g = torch.randn(128, 9, 128, device=DEV)
+    x = torch.randn(2, 8, 8, 128, device=DEV).to(torch.bfloat16)
+    w_all = ce.pack_gather_weights(g, [i for op in ops for i in op['idx']], 128)
+    out = torch.zeros(2, 16, 16, 128, device=DEV, dtype=torch.bfloat16)
+    n0 = pkg._native.launch_count()
+    assert K.subpixel(x, 128, w_all, w_all.shape[0], K.phases_arg(ops), 8, 8, out, 128, 2, None, 0, None) is False
+    assert pkg._native.launch_count() == n0 and float(out.float().abs().max()) == 0
