@@ -54,6 +54,10 @@ FUSE_BN_REDUCE = _os.environ.get('JVAE_FUSE_BN_REDUCE', '0') == '1'
 # maps of at most 2x2 pixels as ONE dense GEMM over (pixel, channel) pairs -- every (output pixel, input pixel) pair is exactly
 # one filter tap, so nothing is wasted on padding taps and the launch fills the machine (M = batch, N = K = pixels * channels)
 DENSE_SMALL = _os.environ.get('JVAE_CONV_DENSE_SMALL', '0') == '1'
+# the separable image head runs its FORWARD as the direct k x k convolution (tap-stacked halo kernel, one fp32 accumulation of all
+# k^2 taps, no fp32 intermediate of 16 channels per pixel): 336 us against 241 + 147 us at c2 since the second epilogue pass.  The
+# backward stays separable (data gradient 229 us against ~400 direct, weight gradient 184 against ~530).  0 restores the 1 x k pass.
+SEP_FWD_DIRECT = _os.environ.get('JVAE_HEAD_FWD_DIRECT', '1') != '0'
 # weight gradients on maps of at most this many pixels go through a patch matrix + one TN GEMM (0 disables)
 IM2COL_MAXPIX = int(_os.environ.get('JVAE_CONV_IM2COL_MAXPIX', '16'))
 
@@ -530,7 +534,7 @@ class ConvStep:
                    act=fused_act, out_bf16=y.view(N, hw * self.Co))
             if bn_train:
                 K.bn_stats(y, N * hw, self.Co, self.ld_y, stats)
-        elif self.separable:
+        elif self.separable and not SEP_FWD_DIRECT:
             self._sep_forward(x, pk, bias, fused_act, stats, y)
         elif not self._merged_forward(x, pk, y, bias, fused_act, stats):
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
@@ -589,7 +593,7 @@ class ConvStep:
             hw = self.H * self.W
             K.gemm(nat.GEMM_NT, N, hw * self.Co, hw * self.Ci, x.view(N, hw * self.Ci), pk['dense'], bias=pk['dense_bias'],
                    act=self.act, out_bf16=a.view(N, hw * self.Co))
-        elif self.separable:
+        elif self.separable and not SEP_FWD_DIRECT:
             self._sep_forward(x, pk, pk['b'], self.act, None, a)
         elif not self._merged_forward(x, pk, a, pk['b'], self.act, None):
             for i, (op, wm) in enumerate(zip(self.fwd_ops, pk['fwd'])):
