@@ -100,7 +100,7 @@ def test_stack_matches_torch_fp32(pkg, where, spec, shape, N, bn, out_act):
             assert int(m.num_batches_tracked) == 1
 
 
-@pytest.mark.parametrize('C,ld', [(32, 32), (64, 64), (512, 512), (3, 8), (200, 200), (24, 24)])
+@pytest.mark.parametrize('C,ld', [(32, 32), (64, 64), (512, 512), (3, 8), (5, 8), (200, 200), (24, 24)])
 def test_batchnorm_kernels(pkg, C, ld):
     """csrc/norm.cu against torch.nn.functional.batch_norm (+ relu) and its autograd"""
     nat = pkg._native
@@ -136,6 +136,12 @@ def test_batchnorm_kernels(pkg, C, ld):
     nat.bn_bwd(dab, ld, buf, ld, P, C, save, gamma, beta, 1, sums, dy, ld, dg, db)
     assert _rel(dy[:, :C], yr.grad) < 1e-2
     assert _rel(dg, g2.grad) < 1e-3 and _rel(db, b2.grad) < 1e-3
+    if C < 8:      # the image head: the loss gradient arrives dense (ld_da = C), y / dy in padded rows (thread-per-pixel kernels)
+        dy2 = torch.full((P, ld), float('nan'), dtype=torch.bfloat16, device=DEV)
+        dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        nat.bn_bwd(da.contiguous(), C, buf, ld, P, C, save, gamma, beta, 1, sums, dy2, ld, dg2, db2)
+        assert torch.equal(dy2, dy) and torch.equal(dg2, dg) and torch.equal(db2, db)
+        assert float(dy2[:, C:].float().abs().max()) == 0
 
 
 @pytest.mark.parametrize('C', [8, 64, 3])
