@@ -38,6 +38,7 @@ CASES = [
     ('output', '[x4+1]8x4+1:2-!3x3+1', (6, 3, 3), False, 'linear'),  # even kernel, stride 2, no output padding
     ('output', '[x3+1]24x4+0-!3x3+1', (12, 1, 1), False, 'linear'),   # 24 -> 3 image head: role-swapped weight gradient
     ('output', '[x5+2]24x4+0-24-!3x5+2', (12, 1, 1), True, 'sigmoid'),
+    ('output', '[x5+2]40x4+0-24-!3x5+2', (12, 1, 1), True, 'linear'),    # 40 -> 24 stride-1 deconv (64- / 32-channel blocks)
     # activation = leaky (config.ini:113 of the reference), with and without BatchNorm
     ('input/leaky', '[x5+2]8-8:2-16', (3, 8, 8), True, None),
     ('input/leaky', '[x3-Mx2]8-M-24', (3, 12, 12), False, None),
