@@ -1858,6 +1858,10 @@ int jvae_conv_halo_emulate(const float* in, int N, int H, int W, int Cin, int ld
                            int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
                            int* info) {
   JVAE_CHECK_ARG(in && wmat && out && tap_dy && tap_dx, "null pointer");
+  JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
+  JVAE_CHECK_ARG(nphases == 0 || (nphases >= 2 && nphases <= 4 && phase_ntaps && phase_oy && phase_ox), "0 or 2..4 phases with their tables");
+  JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
+  JVAE_CHECK_ARG((Cout_pad % 16) == 0 && Cout_pad >= Cout && ld_out >= Cout && (ld_in % 8) == 0 && (ldw % 8) == 0, "bad channel layout");
   HaloParams p;
   PhaseSpec ps = {nphases, phase_ntaps, phase_oy, phase_ox};
   const int rc = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho, Wo,
