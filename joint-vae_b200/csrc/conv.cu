@@ -386,7 +386,7 @@ __device__ __forceinline__ void halo_mma_box(const HaloParams& p, uint32_t d0, u
 // first and cover every column block of the tile exactly once (they overwrite), the others accumulate.
 template <int KSTEPS>
 __device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0, uint32_t a_hi, uint32_t a_lo0, uint32_t m_step16,
-                                               uint32_t b_hi, uint32_t b_lo_base, uint32_t idesc0) {
+                                               uint32_t b_hi, uint32_t b_lo_base, uint32_t idesc0, uint32_t later_chunk) {
   const uint32_t gbn = (uint32_t)(p.G * p.PH * p.BN);
   for (int m = 0; m < p.MT; ++m) {
     const uint32_t a_m = a_lo0 + (uint32_t)m * m_step16;
@@ -396,7 +396,7 @@ __device__ __forceinline__ void halo_mma_box_g(const HaloParams& p, uint32_t d0,
       const uint32_t a_lo = a_m + ck.x, b_lo = b_lo_base + ck.y;
       const uint32_t d = d_m + (ck.w & 0x7fffffffu);
       const uint32_t idesc = ck.z;
-      const uint32_t acc0 = (ck.w >> 31) ^ 1u;
+      const uint32_t acc0 = ((ck.w >> 31) ^ 1u) | later_chunk;      // fresh chunks overwrite only in the first channel chunk
 #pragma unroll
       for (int k = 0; k < KSTEPS; ++k)
         umma_bf16(d, desc64(a_hi, a_lo + 2u * k), desc64(b_hi, b_lo + 2u * k), idesc, k == 0 ? acc0 : 1u);
@@ -705,10 +705,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one()) {      // one elected lane (elect.sync lets the compiler keep descriptors in uniform registers)
-      if (p.resident) {
-        mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)p.ntaps * p.w_tap_bytes);
-        for (int t = 0; t < p.ntaps; ++t)
-          tma_load_2d(wsm + (size_t)(p.nck > 0 ? p.w_pos[t] : t) * p.w_tap_bytes, &tmap_w, &wfull_bar[0], t * p.Cblk, nt * p.BN);
+      if (p.resident) {      // every channel chunk's weights (nkc > 1: two 32-channel chunks of a 64-channel input)
+        mbar_arrive_expect_tx(&wfull_bar[0], (uint32_t)(p.ntaps * p.nkc) * p.w_tap_bytes);
+        for (int kc = 0; kc < p.nkc; ++kc)
+          for (int t = 0; t < p.ntaps; ++t)
+            tma_load_2d(wsm + (size_t)(kc * p.ntaps + (p.nck > 0 ? p.w_pos[t] : t)) * p.w_tap_bytes, &tmap_w, &wfull_bar[0],
+                        (t * p.nkc + kc) * p.Cblk, nt * p.BN);
       }
       // one shared-memory stage per unit = (box, input-channel chunk); the unit after the current one is requested before the
       // current unit's weights (streamed per tap when they are not resident)
@@ -775,9 +777,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
           if (p.nck > 0) {
             const uint32_t idesc0 = make_idesc_bf16(128, 0, false, false);
-            if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
-            else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
-            else halo_mma_box_g<1>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_lo, idesc0);
+            const uint32_t b_kc = b_lo + (uint32_t)(kc * p.ntaps) * w_tap16;      // this chunk's resident weights
+            if (ksteps == 2) halo_mma_box_g<2>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_kc, idesc0, later);
+            else if (ksteps == 4) halo_mma_box_g<4>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_kc, idesc0, later);
+            else halo_mma_box_g<1>(p, d0, a_hi, a_lo0, m_step16, b_hi, b_kc, idesc0, later);
           } else if (ksteps == 2) { HALO_BOX_M(2) } else if (ksteps == 4) { HALO_BOX_M(4) } else { HALO_BOX_M(1) }
 #undef HALO_BOX_M
 #undef HALO_BOX
@@ -1136,7 +1139,8 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, void* out,
                            int Ho, int Wo, int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox,
                            const float* bias, int act, double* stats, const jvae_bn_reduce* bn, int* bn_fused,
-                           cudaStream_t stream, const PhaseSpec* phs = nullptr, HaloParams* plan_out = nullptr) {
+                           cudaStream_t stream, const PhaseSpec* phs = nullptr, HaloParams* plan_out = nullptr,
+                           int force_cblk = 0, double* score_out = nullptr) {
   if (Wq < 6) return 1;
   // wide layers (Cin > 64 or more than 64 output channels): 64-channel output tiles (the epilogue keeps per-thread statistics
   // for at most 32 channels per warp set), the input channels in chunks of 64, weights streamed per (tap, chunk); the input
@@ -1152,6 +1156,22 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   }
   if (bn && !(out_sy == 1 && out_sx == 1 && out_oy == 0 && out_ox == 0 && Ho == Hq && Wo == Wq)) {
     bn = nullptr; stats = nullptr;                        // phase launches: the caller runs the separate reduction
+  }
+  // 33..64 input channels, narrow output: either ONE 64-channel chunk (128-byte rows; the resident weights then leave no room for
+  // tap stacking: N = BN MMAs bound by the A-operand fetch) or TWO 32-channel chunks per box (64-byte rows, half-size stages, the
+  // weights of both chunks resident) with tap stacking.  Both are planned, the better modelled one runs.
+  if (!phs && !wide && force_cblk == 0 && Cin > 32 && !(getenv("JVAE_CONV_KSPLIT") && atoi(getenv("JVAE_CONV_KSPLIT")) == 0)) {
+    HaloParams pa, pb;
+    double sa = 0.0, sb = 0.0;
+    const int ra = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho, Wo,
+                                   Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, nullptr, stream, nullptr, &pa, 64, &sa);
+    const int rb2 = try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho, Wo,
+                                    Cout, ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, nullptr, stream, nullptr, &pb, 32, &sb);
+    if (ra < 0) return ra;
+    const int pick = (rb2 == 0 && (ra != 0 || sb > 1.15 * sa)) ? 32 : 64;
+    if (score_out) *score_out = pick == 32 ? sb : sa;
+    return try_launch_halo(in, N, H, W, Cin, ld_in, wmat, Cout_pad, ldw, ntaps, tap_dy, tap_dx, in_stride, Hq, Wq, out, Ho, Wo, Cout,
+                           ld_out, out_sy, out_sx, out_oy, out_ox, bias, act, stats, bn, bn_fused, stream, nullptr, plan_out, pick, nullptr);
   }
   HaloParams p;
   memset(&p, 0, sizeof(p));
@@ -1176,7 +1196,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   const int ey = dymax - dymin, ex = dxmax - dxmin;
   if (ey > 16 || ex > 16) return 1;
   p.N = N; p.Hq = Hq; p.Wq = Wq; p.dymin = dymin; p.dxmin = dxmin;
-  p.Cblk = cblk_of(Cin > 64 ? 64 : Cin); p.ntaps = ntaps;
+  p.Cblk = force_cblk ? force_cblk : cblk_of(Cin > 64 ? 64 : Cin); p.ntaps = ntaps;
   p.nkc = (Cin + p.Cblk - 1) / p.Cblk;
   p.BN = Cout_pad > 64 ? 64 : Cout_pad; p.n_tiles_n = Cout_pad / p.BN;
   const uint32_t rb = (uint32_t)p.Cblk * 2u;
@@ -1186,7 +1206,8 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
   p.w_tap_bytes = (uint32_t)p.BN * rb;
   const uint32_t budget = 200u * 1024u;
   const uint32_t stats_bytes = stats ? 2u * (uint32_t)Cout_pad * 8u : 0u;
-  const uint32_t w_res = (uint32_t)ntaps * p.w_tap_bytes;
+  const uint32_t w_res = (uint32_t)ntaps * p.w_tap_bytes * (uint32_t)(wide ? 1 : p.nkc);      // every chunk's weights resident
+  const bool ksplit = !wide && p.nkc > 1;
   const int ksteps = p.Cblk >> 4;
   // modelled cycles of one 128 x n x 16 MMA with both operands in shared memory (measured: profiles/r01_umma_rate_probe.txt):
   // the tensor pipe needs n / 2, the operand fetch (4 KB of A + 32 n bytes of B at 128 B / cycle) 32 + n / 4
@@ -1299,6 +1320,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     for (int resident = 1; resident >= 0; --resident) {
       if (G > 1 && !resident) continue;
       if (wide && resident) continue;                      // wide layers stream their weights per (tap, chunk)
+      if (ksplit && (G == 1 || !resident)) continue;       // two resident chunks: only the stacked form is built
       const uint32_t wb = resident ? w_res : 4u * p.w_tap_bytes;
       bool found = false;
       for (int nbt = 1; nbt <= 16 && nbt <= N; ++nbt) {
@@ -1325,6 +1347,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
               const int j0 = max(0, u - q.e_hi), j1 = min(G - 1, u - q.e_lo);
               cyc += (double)MT * ksteps * mma_cycles((j1 - j0 + 1) * p.BN);
             }
+        cyc *= (double)p.nkc;
         const double score = (double)(nbt * p.RT) / cyc;
         if (score > best * 1.02) {
           best = score; bestG = G; p.NBt = nbt; p.MT = MT; p.stage_bytes = stage; p.plane_bytes = plane; p.resident = resident;
@@ -1336,6 +1359,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
     }
   }
   if (best <= 0.0) return 1;
+  if (score_out) *score_out = best;
   p.G = bestG;
   (void)best_extent;
   p.wstages = p.resident ? 1 : 4;
@@ -1923,7 +1947,7 @@ int jvae_conv_halo_emulate(const float* in, int N, int H, int W, int Cin, int ld
             for (int c = 0; c < p.nck; ++c) {
               const uint4 ck = p.ck[c];
               mma(m, (size_t)ck.x * 16 / rb, (size_t)ck.y * 16 / p.w_tap_bytes, (int)((ck.z >> 17) & 0x3f) << 3, (int)(ck.w & 0x7fffffffu),
-                  (ck.w >> 31) != 0);
+                  (ck.w >> 31) != 0 && kc == 0);
             }
         } else {
           for (int t = 0; t < p.ntaps; ++t)
