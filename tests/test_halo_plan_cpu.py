@@ -78,6 +78,11 @@ PLAIN = [
     (3, 32, 32, 32, 32, 5, 2, 2, False),     # stride 2: four parity planes
     (2, 40, 40, 8, 16, 3, 1, 1, False),      # two row blocks per image
     (2, 32, 32, 32, 3, 5, 2, 1, False),      # image head
+    (4, 16, 16, 64, 64, 3, 1, 1, False),     # 64 input channels: one 64-channel chunk or two stacked 32-channel chunks
+    (3, 16, 16, 48, 24, 3, 1, 1, False),     # 48 channels: the second chunk is half empty
+    (6, 8, 8, 64, 32, 5, 2, 1, True),
+    (3, 16, 16, 64, 32, 3, 1, 2, False),     # 64 channels, stride 2 (parity planes)
+    (2, 20, 12, 40, 16, 5, 2, 1, False),     # ragged strip, 40 channels
 ]
 
 
