@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JVAE_ABI_VERSION 15
+#define JVAE_ABI_VERSION 16
 
 enum jvae_status {
   JVAE_OK = 0,
@@ -273,6 +273,12 @@ int jvae_conv_halo_emulate(const float* in, int N, int H, int W, int Cin, int ld
                            const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, int Hq, int Wq, float* out, int Ho, int Wo,
                            int Cout, int ld_out, int out_sy, int out_sx, int out_oy, int out_ox, const float* bias, int act,
                            int* info);
+/* The same for the halo weight-gradient kernel (HOST ONLY, fp32 host tensors): the plan(s) jvae_conv_wgrad would run -- one, or one
+ * per parity plane for stride-2 layers whose planes do not fit a stage together -- executed on the CPU; dw += as the kernel does.
+ * *launches receives the number of kernel launches the plan stands for.  JVAE_NOT_COVERED: the tap-box kernel would run. */
+int jvae_conv_wgrad_emulate(const float* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const float* x, int H, int W, int Cin, int ld_x,
+                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
+                            int dw_ld_co, int dw_ld_ci, int* launches);
 int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const void* x, int H, int W, int Cin, int ld_x,
                     int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
                     int dw_ld_co, int dw_ld_ci, void* stream);

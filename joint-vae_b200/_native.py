@@ -109,6 +109,8 @@ def lib():
                                   c_int, P, c_int, c_int, c_int, P]
     L.jvae_conv_subpixel_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, I16P, I16P,
                                           I16P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P]
+    L.jvae_conv_wgrad_emulate.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, I16P, I16P,
+                                          c_int, P, c_int, c_int, c_int, ctypes.POINTER(c_int)]
     L.jvae_conv_halo_emulate.argtypes = [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, I16P, I16P, I16P, c_int,
                                          I16P, I16P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, P, c_int, ctypes.POINTER(c_int)]
@@ -131,7 +133,7 @@ def lib():
     L.jvae_last_conv_kernel.restype = c_int
     L.jvae_pack_job_blocks.argtypes = [ctypes.c_longlong, c_int, c_int]
     L.jvae_pack_weights.argtypes = [P, c_int, P, c_int, P]
-    if L.jvae_abi_version() != 15:
+    if L.jvae_abi_version() != 16:
         raise NativeError('ABI version mismatch between _native.py and libjvae_sm100.so')
     _lib = L
     return L
@@ -580,6 +582,23 @@ def conv_halo_emulate(inp, Cin, wmat, Cout_pad, taps, in_stride, Hq, Wq, out, Co
         return None
     check(rc)
     return list(info)
+
+
+def conv_wgrad_emulate(dy, Cout, x, Cin, taps, in_stride, dw, dw_ld_tap, dw_ld_co, dw_ld_ci=1):
+    """include/jvae_b200.h: jvae_conv_wgrad_emulate (HOST tensors, fp32; test aid).  dy (N,Hq,Wq,ld_dy), x (N,H,W,ld_x), dw fp32
+    accumulated in place.  Returns the number of launches the plan stands for, or None when the tap-box kernel would run."""
+    for t in (dy, x, dw):
+        assert t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous()
+    N, Hq, Wq, ld_dy = dy.shape
+    _, H, W, ld_x = x.shape
+    n = c_int(0)
+    rc = lib().jvae_conv_wgrad_emulate(c_void_p(dy.data_ptr()), N, Hq, Wq, Cout, ld_dy, c_void_p(x.data_ptr()), H, W, Cin, ld_x,
+                                       len(taps[0]), taps[0], taps[1], in_stride, c_void_p(dw.data_ptr()), dw_ld_tap, dw_ld_co,
+                                       dw_ld_ci, ctypes.byref(n))
+    if rc == NOT_COVERED:
+        return None
+    check(rc)
+    return n.value
 
 
 def conv_wgrad(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, taps, in_stride, dw, dw_ld_tap, dw_ld_co, dw_ld_ci=1):

@@ -1483,7 +1483,7 @@ static int try_launch_halo(const void* in, int N, int H, int W, int Cin, int ld_
 static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, int ld_g, const void* x, int H, int W, int Cx,
                                  int ld_x, int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw,
                                  int dw_ld_tap, int dw_ld_co, int dw_ld_cx, cudaStream_t stream, const int* tap_ids = nullptr,
-                                 bool dry_run = false) {
+                                 bool dry_run = false, WHaloParams* plan_out = nullptr) {
   // tap_ids: position of tap t in dW when the list is a subset of the layer's taps (per-plane launches, jvae_conv_wgrad);
   // dry_run: plan only (is the geometry covered?)
   if (Wq < 6) return 1;
@@ -1631,6 +1631,7 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   p.strips_x = (Wq + 7) / 8;
   p.num_boxes = p.strips_x * p.blocks_y * ((N + p.NBt - 1) / p.NBt);
   p.dw = dw; p.dw_ld_tap = dw_ld_tap; p.dw_ld_co = dw_ld_co; p.dw_ld_cx = dw_ld_cx;
+  if (plan_out) *plan_out = p;
   if (dry_run) return JVAE_OK;
   CUtensorMap tg, tx;
   {
@@ -1664,6 +1665,84 @@ static int try_launch_wgrad_halo(const void* g, int N, int Hq, int Wq, int Cg, i
   JVAE_LAUNCH_CHECK();
   g_last_conv_kernel = JVAE_KERNEL_WGRAD_HALO;
   return JVAE_OK;
+}
+
+
+// Host-only execution of the halo weight-gradient PLAN (try_launch_wgrad_halo), the counterpart of jvae_conv_halo_emulate: the
+// two stages (parity planes of the gathered tensor, the gradient tile behind its zeroed gap), the tap groups as MN-major
+// operands -- M = (stacked horizontal tap j, X channel) through LBO = one pixel row, N = (vertically stacked atom jv, G channel)
+// through LBO = one slot, K = 16 pixels = 2 slots per MMA -- and the scatter of D into dW through the group's tap table.
+static void wgrad_plan_emulate(const WHaloParams& p, const float* g, int ld_g, const float* x, int H, int W, int ld_x, float* dw) {
+  const int ncg = (p.Cg + p.Cblk_g - 1) / p.Cblk_g;
+  const size_t plane_rows = p.plane_bytes / ((size_t)p.Cblk_x * 2u);
+  const size_t x_rows = plane_rows * p.nplanes;
+  const int gap_slots = (int)(p.g_gap_bytes / (8u * (uint32_t)p.Cblk_g * 2u));
+  const size_t g_slots = (size_t)gap_slots + (size_t)((p.stage_bytes - p.x_stage_bytes - p.g_gap_bytes) / (8u * (uint32_t)p.Cblk_g * 2u));
+  std::vector<float> sx(x_rows * p.Cblk_x), sg(g_slots * 8 * p.Cblk_g);
+  const float qnan = nanf("");
+  for (int zg = 0; zg < ncg; ++zg)
+    for (int zx = 0; zx < p.ncx; ++zx) {
+      const int cg0 = zg * p.Cblk_g, cx0 = zx * p.Cblk_x;
+      std::vector<double> D((size_t)p.ngroups * 128 * 8 * p.Cblk_g, 0.0);      // [group][M row][N column]
+      for (int box = 0; box < p.num_boxes; ++box) {
+        int m0 = box;
+        const int bx = m0 % p.strips_x; m0 /= p.strips_x;
+        const int by = m0 % p.blocks_y; const int nb = m0 / p.blocks_y;
+        std::fill(sx.begin(), sx.end(), 0.f);      // the stage was zeroed once; the boxes always land on the same bytes
+        std::fill(sg.begin(), sg.end(), 0.f);
+        for (int pl = 0; pl < p.nplanes; ++pl)
+          for (int i = 0; i < p.NBt; ++i)
+            for (int yy = 0; yy < p.HHs; ++yy)
+              for (int xx = 0; xx < p.HWp; ++xx) {
+                const size_t row = (size_t)pl * plane_rows + (size_t)(i * p.HHs + yy) * p.HWp + xx;
+                const int n = nb * p.NBt + i;
+                const int iy = p.in_stride * (by * p.RT + p.dymin + yy) + p.plane_ry[pl], ix = p.in_stride * (bx * 8 + p.dxmin + xx) + p.plane_rx[pl];
+                for (int c = 0; c < p.Cblk_x; ++c) {
+                  const bool in = n < p.N && iy >= 0 && iy < H && ix >= 0 && ix < W && cx0 + c < p.Cx;
+                  if (row < x_rows) sx[row * p.Cblk_x + c] = in ? x[(((size_t)n * H + iy) * W + ix) * ld_x + cx0 + c] : 0.f;
+                }
+              }
+        for (int i = 0; i < p.NBt; ++i)
+          for (int yy = 0; yy < (p.blocks_y == 1 ? p.HHs : p.RT); ++yy)
+            for (int px = 0; px < 8; ++px) {
+              const size_t slot = (size_t)gap_slots + (size_t)i * p.HHs + yy;
+              const int n = nb * p.NBt + i, gy = by * p.RT + yy, gx = bx * 8 + px;
+              for (int c = 0; c < p.Cblk_g; ++c) {
+                const bool in = n < p.N && gy < p.Hq && gx < p.Wq && cg0 + c < p.Cg;
+                if (slot < g_slots) sg[(slot * 8 + px) * p.Cblk_g + c] = in ? g[(((size_t)n * p.Hq + gy) * p.Wq + gx) * ld_g + cg0 + c] : 0.f;
+              }
+            }
+        auto xa = [&](long long row, int c) { return row >= 0 && (size_t)row < x_rows ? sx[(size_t)row * p.Cblk_x + c] : qnan; };
+        auto ga = [&](long long slot, int px, int c) { return slot >= 0 && (size_t)slot < g_slots ? sg[((size_t)slot * 8 + px) * p.Cblk_g + c] : qnan; };
+        for (int m = 0; m < p.MT; ++m)
+          for (int gi = 0; gi < p.ngroups; ++gi) {
+            const long long a_rows = (long long)p.grp_off16[gi] * 16 / (p.Cblk_x * 2);
+            const long long b_slots = (long long)gap_slots - p.ey + (long long)p.grp_boff16[gi] * 16 / (8 * p.Cblk_g * 2);
+            const int ntap = p.grp_ntap[gi], nv = p.grp_nv[gi];
+            for (int k = 0; k < 8; ++k)
+              for (int kk = 0; kk < 16; ++kk) {
+                const long long s = 16 * m + 2 * k + (kk >> 3);
+                for (int j = 0; j < ntap; ++j)
+                  for (int cx = 0; cx < p.Cblk_x; ++cx) {
+                    const float a = xa(a_rows + s * p.HWp + (kk & 7) + j, cx);
+                    if (a == 0.f) continue;
+                    for (int jv = 0; jv < nv; ++jv)
+                      for (int cg = 0; cg < p.Cblk_g; ++cg)
+                        D[(((size_t)gi * 128 + (size_t)j * p.Cblk_x + cx) * 8 + jv) * p.Cblk_g + cg] += (double)a * (double)ga(b_slots + s + jv, kk & 7, cg);
+                  }
+              }
+          }
+      }
+      for (int gi = 0; gi < p.ngroups; ++gi)
+        for (int j = 0; j < p.grp_ntap[gi]; ++j)
+          for (int jv = 0; jv < p.grp_nv[gi]; ++jv) {
+            const int t = p.grp_tap[gi][jv][j];
+            for (int cx = 0; cx < p.Cblk_x && cx0 + cx < p.Cx; ++cx)
+              for (int cg = 0; cg < p.Cblk_g && cg0 + cg < p.Cg; ++cg)
+                dw[(size_t)t * p.dw_ld_tap + (size_t)(cg0 + cg) * p.dw_ld_co + (size_t)(cx0 + cx) * p.dw_ld_cx] +=
+                    (float)D[(((size_t)gi * 128 + (size_t)j * p.Cblk_x + cx) * 8 + jv) * p.Cblk_g + cg];
+          }
+    }
 }
 
 }  // namespace jvae
@@ -1869,6 +1948,48 @@ int jvae_conv_wgrad(const void* dy, int N, int Hq, int Wq, int Cout, int ld_dy, 
 }
 
 int jvae_last_conv_kernel(void) { return g_last_conv_kernel; }
+
+int jvae_conv_wgrad_emulate(const float* dy, int N, int Hq, int Wq, int Cout, int ld_dy, const float* x, int H, int W, int Cin, int ld_x,
+                            int ntaps, const int16_t* tap_dy, const int16_t* tap_dx, int in_stride, float* dw, int dw_ld_tap,
+                            int dw_ld_co, int dw_ld_ci, int* launches) {
+  JVAE_CHECK_ARG(dy && x && dw && tap_dy && tap_dx, "null pointer");
+  JVAE_CHECK_ARG(ntaps >= 1 && ntaps <= CONV_MAX_TAPS, "1..64 taps");
+  JVAE_CHECK_ARG((ld_dy % 8) == 0 && (ld_x % 8) == 0, "channel strides must be multiples of 8");
+  JVAE_CHECK_ARG(in_stride == 1 || in_stride == 2, "input stride 1 or 2");
+  if (launches) *launches = 0;
+  WHaloParams p;
+  int rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, ntaps, tap_dy, tap_dx, in_stride, dw, dw_ld_tap, dw_ld_co,
+                                 dw_ld_ci, nullptr, nullptr, true, &p);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    wgrad_plan_emulate(p, dy, ld_dy, x, H, W, ld_x, dw);
+    if (launches) *launches = 1;
+    return JVAE_OK;
+  }
+  if (in_stride != 2) return JVAE_NOT_COVERED;
+  // the per-plane split of jvae_conv_wgrad
+  std::vector<int16_t> sdy[4], sdx[4];
+  std::vector<int> ids[4];
+  for (int t = 0; t < ntaps; ++t) {
+    const int pl = (((tap_dy[t] % 2) + 2) % 2) * 2 + (((tap_dx[t] % 2) + 2) % 2);
+    sdy[pl].push_back(tap_dy[t]); sdx[pl].push_back(tap_dx[t]); ids[pl].push_back(t);
+  }
+  WHaloParams pp[4];
+  for (int pl = 0; pl < 4; ++pl) {
+    if (ids[pl].empty()) continue;
+    rc = try_launch_wgrad_halo(dy, N, Hq, Wq, Cout, ld_dy, x, H, W, Cin, ld_x, (int)ids[pl].size(), sdy[pl].data(), sdx[pl].data(), 2, dw,
+                               dw_ld_tap, dw_ld_co, dw_ld_ci, nullptr, ids[pl].data(), true, &pp[pl]);
+    if (rc < 0) return rc;
+    if (rc > 0) return JVAE_NOT_COVERED;
+  }
+  for (int pl = 0; pl < 4; ++pl) {
+    if (ids[pl].empty()) continue;
+    wgrad_plan_emulate(pp[pl], dy, ld_dy, x, H, W, ld_x, dw);
+    if (launches) ++*launches;
+  }
+  return JVAE_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------------ plan emulation (host only)
 // Executes the PLAN try_launch_halo makes for a geometry on the host, step by step as conv_halo_kernel does: the TMA box fill

@@ -108,3 +108,36 @@ def test_halo_plan_matches_torch(pkg, ce, N, H, W, Cin, Cout, k, p, s, transpose
     assert info is not None
     assert not torch.isnan(out).any()
     assert float((out[..., :Cout].permute(0, 3, 1, 2) - ref).abs().max()) < 1e-4
+
+
+# N, H, W, Cin, Cout, k, pad, stride -- Conv2d weight gradient: grid tensor dy, gathered tensor x
+WGRAD = [
+    (3, 16, 16, 32, 32, 5, 2, 1, 1),      # 32-channel gradient tile, five tap rows: vertical stacking on the N side
+    (4, 8, 8, 64, 64, 5, 2, 1, 1),        # 64 channels: horizontal runs of two taps
+    (2, 32, 32, 16, 32, 3, 1, 1, 1),
+    (5, 16, 16, 32, 32, 5, 2, 2, 1),      # stride 2: four parity planes in one stage
+    (3, 16, 16, 64, 64, 5, 2, 2, 4),      # stride 2, 64 channels: the planes do not fit together -> one launch per plane
+    (2, 40, 24, 8, 16, 3, 1, 1, 1),       # two row blocks per image
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,p,s,launches', WGRAD)
+def test_wgrad_halo_plan_matches_autograd(pkg, ce, N, H, W, Cin, Cout, k, p, s, launches):
+    """jvae_conv_wgrad_emulate executes the halo weight-gradient plan(s) on the host (MN-major operands, taps stacked along M
+    through LBO, vertically adjacent taps along N, the per-plane split of stride-2 layers) against torch's autograd"""
+    nat = pkg._native
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(Cin, Cout, k, stride=s, padding=p, bias=False)
+    x = torch.randn(N, Cin, H, W)
+    y = conv(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    want = conv.weight.grad
+    Hq, Wq = y.shape[-2:]
+    taps = [(i - p, j - p) for i in range(k) for j in range(k)]
+    dw = torch.zeros(Cout, Cin, k * k)
+    n = nat.conv_wgrad_emulate(_nhwc(dy, ce.r8(Cout)), Cout, _nhwc(x, ce.r8(Cin)), Cin, nat.taps_arg(taps), s, dw, 1, Cin * k * k, k * k)
+    assert n == launches, 'plan count'
+    assert not torch.isnan(dw).any()
+    got = dw.view(Cout, Cin, k, k)
+    assert float((got - want).abs().max()) <= 2e-4 * float(want.abs().max())
