@@ -141,3 +141,62 @@ def test_wgrad_halo_plan_matches_autograd(pkg, ce, N, H, W, Cin, Cout, k, p, s, 
     assert not torch.isnan(dw).any()
     got = dw.view(Cout, Cin, k, k)
     assert float((got - want).abs().max()) <= 2e-4 * float(want.abs().max())
+
+
+def test_random_geometries_through_both_planners(pkg, ce):
+    """seeded sweep: every plan the halo planners make for random small layers (Conv2d stride 1 / 2, forward and weight gradient;
+    stride-2 ConvTranspose2d merged) emulates to torch's result; 400 more geometries were swept when the emulators were written"""
+    import random
+    nat = pkg._native
+    rnd = random.Random(11)
+    done = 0
+    for it in range(14):
+        N = rnd.randint(1, 5); H = rnd.choice([6, 8, 9, 12, 16, 20]); W = rnd.choice([6, 8, 10, 12, 16])
+        Ci = rnd.choice([3, 8, 16, 24, 32, 40, 64]); Co = rnd.choice([3, 8, 16, 24, 32, 48, 64]); k = rnd.choice([1, 3, 5])
+        s = rnd.choice([1, 1, 2])
+        torch.manual_seed(it)
+        conv = torch.nn.Conv2d(Ci, Co, k, stride=s, padding=k // 2)
+        conv.weight.data = conv.weight.data.to(torch.bfloat16).float()
+        x = torch.randn(N, Ci, H, W)
+        y = conv(x)
+        Hq, Wq = y.shape[-2:]
+        if Wq < 6:
+            continue
+        taps = [(i - k // 2, j - k // 2) for i in range(k) for j in range(k)]
+        g = conv.weight.detach().permute(0, 2, 3, 1).reshape(Co, k * k, Ci)
+        wm = ce.pack_gather_weights(g, list(range(k * k)), Ci).float().contiguous()
+        out = torch.full((N, Hq, Wq, ce.r8(Co)), float('nan'))
+        info = nat.conv_halo_emulate(_nhwc(x, ce.r8(Ci)), Ci, wm, wm.shape[0], nat.taps_arg(taps), s, Hq, Wq, out, Co, (1, 1), (0, 0),
+                                     conv.bias.detach().contiguous(), 0)
+        if info is not None:
+            assert not torch.isnan(out).any(), (N, H, W, Ci, Co, k, s, info)
+            assert float((out[..., :Co].permute(0, 3, 1, 2) - y.detach()).abs().max()) < 1e-3, (N, H, W, Ci, Co, k, s, info)
+            done += 1
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        dw = torch.zeros(Co, Ci, k * k)
+        n = nat.conv_wgrad_emulate(_nhwc(dy, ce.r8(Co)), Co, _nhwc(x, ce.r8(Ci)), Ci, nat.taps_arg(taps), s, dw, 1, Ci * k * k, k * k)
+        if n is not None:
+            want = conv.weight.grad
+            assert float((dw.view(Co, Ci, k, k) - want).abs().max()) <= 1e-3 * float(want.abs().max()), (N, H, W, Ci, Co, k, s, n)
+            done += 1
+    for it in range(8):
+        N = rnd.randint(1, 4); H = rnd.choice([6, 8, 12, 16]); W = rnd.choice([6, 8, 12, 16])
+        Ci = rnd.choice([8, 16, 32, 48, 64]); Co = rnd.choice([3, 16, 24, 32, 64]); k = rnd.choice([2, 3, 4, 5, 6])
+        p = rnd.choice([q for q in range(k) if 0 <= 2 + 2 * q - k <= 1])
+        torch.manual_seed(100 + it)
+        conv = torch.nn.ConvTranspose2d(Ci, Co, k, stride=2, padding=p, output_padding=2 + 2 * p - k)
+        conv.weight.data = conv.weight.data.to(torch.bfloat16).float()
+        x = torch.randn(N, Ci, H, W)
+        y = conv(x).detach()
+        ops = ce.deconv_form(k, p, 2, 2 * H, 2 * W)
+        g = conv.weight.detach().permute(1, 2, 3, 0).reshape(Co, k * k, Ci)
+        wm = ce.pack_gather_weights(g, [i for op in ops for i in op['idx']], Ci).float().contiguous()
+        out = torch.full((N, 2 * H, 2 * W, ce.r8(Co)), float('nan'))
+        info = nat.conv_halo_emulate(_nhwc(x, ce.r8(Ci)), Ci, wm, wm.shape[0], None, 1, H, W, out, Co, (2, 2), (0, 0),
+                                     conv.bias.detach().contiguous(), 0, phases=nat.phases_arg(ops))
+        if info is not None:
+            assert not torch.isnan(out).any(), (N, H, W, Ci, Co, k, p, info)
+            assert float((out[..., :Co].permute(0, 3, 1, 2) - y).abs().max()) < 1e-3, (N, H, W, Ci, Co, k, p, info)
+            done += 1
+    assert done >= 20
